@@ -1,0 +1,7 @@
+"""CPU oracle for the Neighbor2Neighbor hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the shipped
+product path: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it,
+and there only as the checker / the timed CPU baseline.
+"""

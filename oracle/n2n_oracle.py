@@ -1,0 +1,321 @@
+"""CPU restatement (numpy + plain PyTorch fp32 functional ops) of the reference's
+Neighbor2Neighbor hot path.  TEST INFRASTRUCTURE — never imported by the product.
+
+Every function cites the reference file:line (paths relative to the reference
+repo ``lmh9507/image_denoising``) whose arithmetic it restates.  The restatement
+is pinned against the *unmodified* reference code by ``oracle/make_golden.py``
+(run in the build container where ``/root/reference`` is mounted); the resulting
+vectors live in ``tests/golden/`` and are re-checked by ``tests/test_oracle.py``
+on every run.  The reference itself ships no tests / golden vectors,
+so "pinned" here means "bit-equal (integer paths) or <=1e-6 (fp32 paths) to the
+reference's own code executed on the same inputs".
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------
+# a4 / a5: neighbour sub-sampler  (train.py:141-190)
+# ----------------------------------------------------------------------------
+# Cell-local positions: k = 2*ky + kx, k=0:(0,0) 1:(0,1) 2:(1,0) 3:(1,1)
+# (train.py:134-138: F.unfold channel order).  The eight admissible (k1, k2)
+# neighbour pairs, in the order the reference indexes them with rd_idx
+# (train.py:151-154).
+PAIR_TABLE = np.array(
+    [[0, 1], [0, 2], [1, 3], [2, 3], [1, 0], [2, 0], [3, 1], [3, 2]], dtype=np.int64)
+
+
+def masks_from_rd_idx(rd_idx: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """train.py:163-172 — scatter one True per 2x2 cell into two flat bool masks.
+
+    ``rd_idx`` has one entry in [0,8) per cell, cells ordered (n, i, j) row-major.
+    Returns two 1-D bool arrays of length 4*cells.
+    """
+    rd_idx = np.asarray(rd_idx, dtype=np.int64).reshape(-1)
+    cells = rd_idx.shape[0]
+    sel = PAIR_TABLE[rd_idx]                      # [cells, 2]
+    m1 = np.zeros((cells, 4), dtype=np.bool_)
+    m2 = np.zeros((cells, 4), dtype=np.bool_)
+    m1[np.arange(cells), sel[:, 0]] = True
+    m2[np.arange(cells), sel[:, 1]] = True
+    return m1.reshape(-1), m2.reshape(-1)
+
+
+def draw_rd_idx(n: int, h: int, w: int, seed: int) -> np.ndarray:
+    """train.py:155-162 with the CPU generator variant of get_generator
+    (training_script.md:4-10): a fresh generator seeded with the operation
+    counter draws randint(0, 8) per cell."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    cells = n * h // 2 * w // 2      # same left-to-right precedence as train.py:144
+    return torch.randint(0, 8, (cells,), generator=g, dtype=torch.int64).numpy()
+
+
+def subimage_from_mask(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """train.py:175-190 — out[n,c,i,j] = img[n,c,2i+k//2,2j+k%2], k = the True slot
+    of cell (n,i,j) in ``mask``; the same mask serves every channel."""
+    n, c, h, w = img.shape
+    hh, ww = h // 2, w // 2
+    m = np.asarray(mask).reshape(n, hh, ww, 4)
+    if not (m.sum(axis=-1) == 1).all():
+        raise ValueError("mask must select exactly one pixel per 2x2 cell")
+    k = m.argmax(axis=-1)                          # [n, hh, ww]
+    ky, kx = k // 2, k % 2
+    ii = 2 * np.arange(hh)[None, :, None] + ky
+    jj = 2 * np.arange(ww)[None, None, :] + kx
+    nn = np.arange(n)[:, None, None]
+    out = img[nn, :, ii, jj]                       # [n, hh, ww, c]
+    return np.ascontiguousarray(np.moveaxis(out, -1, 1))
+
+
+# ----------------------------------------------------------------------------
+# a6 / a7 / a8: UNet  (arch_unet.py:100-260, non-blindspot branch)
+# ----------------------------------------------------------------------------
+def unet_param_shapes(in_nc: int, out_nc: int, nf: int) -> "OrderedDict[str, tuple]":
+    """arch_unet.py:114-192 — registration order and shapes of the 50 tensors (25 layers)."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k)
+        s[name + ".bias"] = (co,)
+
+    def deconv(name, ci, co):
+        s[name + ".deconv.weight"] = (ci, co, 2, 2)    # ConvTranspose2d layout
+        s[name + ".deconv.bias"] = (co,)
+
+    conv("enc_conv0", nf, in_nc, 3)
+    for i in range(1, 7):
+        conv(f"enc_conv{i}", nf, nf, 3)
+    deconv("up5", nf, nf)
+    conv("dec_conv5a", 2 * nf, 2 * nf, 3)
+    conv("dec_conv5b", 2 * nf, 2 * nf, 3)
+    for lvl in (4, 3, 2):
+        deconv(f"up{lvl}", 2 * nf, 2 * nf)
+        conv(f"dec_conv{lvl}a", 2 * nf, 3 * nf, 3)
+        conv(f"dec_conv{lvl}b", 2 * nf, 2 * nf, 3)
+    deconv("up1", 2 * nf, 2 * nf)
+    conv("dec_conv1a", 96, 2 * nf + in_nc, 3)
+    conv("dec_conv1b", 96, 96, 3)
+    conv("nin_a", 96, 96, 1)
+    conv("nin_b", 96, 96, 1)
+    conv("nin_c", out_nc, 96, 1)
+    return s
+
+
+def unet_init(in_nc: int, out_nc: int, nf: int, seed: int) -> "OrderedDict[str, torch.Tensor]":
+    """arch_unet.py:24-33 — kaiming_normal(fan_in, a=0) * 0.1, zero bias.  (Not
+    RNG-stream-identical to the reference constructor; weights for parity tests
+    are always passed explicitly.)"""
+    g = torch.Generator().manual_seed(seed)
+    p = OrderedDict()
+    for name, shp in unet_param_shapes(in_nc, out_nc, nf).items():
+        if name.endswith(".bias"):
+            p[name] = torch.zeros(shp)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            std = math.sqrt(2.0 / fan_in)
+            p[name] = torch.randn(shp, generator=g) * std * 0.1
+    return p
+
+
+def unet_forward(p: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """arch_unet.py:194-260 (blindspot=False)."""
+    act = lambda t: F.leaky_relu(t, 0.2)
+    c3 = lambda t, n: F.conv2d(t, p[n + ".weight"], p[n + ".bias"], padding=1)
+    c1 = lambda t, n: F.conv2d(t, p[n + ".weight"], p[n + ".bias"])
+    up = lambda t, skip, n: torch.cat(
+        [F.conv_transpose2d(t, p[n + ".deconv.weight"], p[n + ".deconv.bias"], stride=2), skip], 1)
+    skips = [x]
+    t = act(c3(x, "enc_conv0"))
+    t = F.max_pool2d(act(c3(t, "enc_conv1")), 2)
+    skips.append(t)
+    for i in (2, 3, 4):
+        t = F.max_pool2d(act(c3(t, f"enc_conv{i}")), 2)
+        skips.append(t)
+    t = F.max_pool2d(act(c3(t, "enc_conv5")), 2)
+    t = act(c3(t, "enc_conv6"))
+    for lvl in (5, 4, 3, 2, 1):
+        t = up(t, skips[lvl - 1], f"up{lvl}")
+        t = act(c3(t, f"dec_conv{lvl}a"))
+        t = act(c3(t, f"dec_conv{lvl}b"))
+    t = act(c1(t, "nin_a"))
+    t = act(c1(t, "nin_b"))
+    return c1(t, "nin_c")
+
+
+# ----------------------------------------------------------------------------
+# a9: N2N loss and the documented training step (training_script.md:128-156)
+# ----------------------------------------------------------------------------
+def n2n_loss(out, sub2, den1, den2, lam: float):
+    """training_script.md:146-153."""
+    diff = out - sub2
+    exp_diff = den1 - den2
+    loss1 = torch.mean(diff ** 2)
+    loss2 = lam * torch.mean((diff - exp_diff) ** 2)
+    return loss1 + loss2, loss1, loss2
+
+
+def n2n_step_grads(p: Dict[str, torch.Tensor], noisy: torch.Tensor,
+                   mask1: np.ndarray, mask2: np.ndarray, lam: float):
+    """One N2N iteration up to (and including) backward: returns
+    (loss_all, loss1, loss2, grads, noisy_denoised, net_out)."""
+    params = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    nz = noisy.detach().numpy()
+    sub1 = torch.from_numpy(subimage_from_mask(nz, mask1))
+    sub2 = torch.from_numpy(subimage_from_mask(nz, mask2))
+    with torch.no_grad():
+        den = unet_forward(params, noisy)
+    den1 = torch.from_numpy(subimage_from_mask(den.numpy(), mask1))
+    den2 = torch.from_numpy(subimage_from_mask(den.numpy(), mask2))
+    out = unet_forward(params, sub1)
+    loss, l1, l2 = n2n_loss(out, sub2, den1, den2, lam)
+    loss.backward()
+    grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
+    return loss.item(), l1.item(), l2.item(), grads, den, out.detach()
+
+
+# ----------------------------------------------------------------------------
+# a10: Adam (train.py:332 — torch.optim.Adam defaults) and MultiStepLR (:333-340)
+# ----------------------------------------------------------------------------
+def adam_update(p, g, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
+    """One torch-default Adam update on float32 numpy arrays (in place).
+    step is 1-based.  denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom."""
+    m *= np.float32(b1); m += np.float32(1 - b1) * g
+    v *= np.float32(b2); v += np.float32(1 - b2) * g * g
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    denom = np.sqrt(v) / np.float32(math.sqrt(bc2)) + np.float32(eps)
+    p -= np.float32(lr / bc1) * (m / denom)
+    return p, m, v
+
+
+def multistep_lr(base_lr: float, epoch: int, n_epoch: int, gamma: float) -> float:
+    """LR in force during 1-based ``epoch`` (train.py:333-340, :346, :375):
+    milestones int(20r)-1.. with r = n_epoch/100; scheduler.step() runs at the
+    end of every epoch, so epoch e has seen e-1 scheduler steps."""
+    r = n_epoch / 100
+    ms = [int(20 * r) - 1, int(40 * r) - 1, int(60 * r) - 1, int(80 * r) - 1]
+    k = sum(1 for m_ in ms if (epoch - 1) >= m_)
+    return base_lr * gamma ** k
+
+
+# ----------------------------------------------------------------------------
+# a11 / a12: adapter and finetune loss (adapter.py:5-67, finetune.py:153-162,:283-285)
+# ----------------------------------------------------------------------------
+def adapter_forward(ap: Dict[str, torch.Tensor], noisy, base_out):
+    """adapter.py:22-26."""
+    t = torch.cat([noisy, base_out], 1)
+    t = F.relu(F.conv2d(t, ap["adapter.net.0.weight"], ap["adapter.net.0.bias"], padding=1))
+    t = F.conv2d(t, ap["adapter.net.2.weight"], ap["adapter.net.2.bias"], padding=1)
+    return base_out + t
+
+
+def finetune_loss(pred, clean, lambda_grad: float):
+    """finetune.py:153-162, :283-285."""
+    l1 = torch.mean(torch.abs(pred - clean))
+    gx = torch.mean(torch.abs((pred[..., :, 1:] - pred[..., :, :-1]) - (clean[..., :, 1:] - clean[..., :, :-1])))
+    gy = torch.mean(torch.abs((pred[..., 1:, :] - pred[..., :-1, :]) - (clean[..., 1:, :] - clean[..., :-1, :])))
+    return l1 + lambda_grad * (gx + gy), l1, gx + gy
+
+
+# ----------------------------------------------------------------------------
+# a15 / a16: PSNR / SSIM  (utils_eval.py:19-53)
+# ----------------------------------------------------------------------------
+def gaussian_taps(ksize: int = 11, sigma: float = 1.5) -> np.ndarray:
+    """cv2.getGaussianKernel(11, 1.5) (utils_eval.py:24): exp(-(i-c)^2/(2 s^2)), normalised, float64."""
+    c = (ksize - 1) / 2.0
+    k = np.exp(-((np.arange(ksize) - c) ** 2) / (2.0 * sigma * sigma))
+    return k / k.sum()
+
+
+def _valid_blur(a: np.ndarray, taps: np.ndarray) -> np.ndarray:
+    """11x11 Gaussian restricted to the interior [5:-5,5:-5] (utils_eval.py:26-31);
+    the interior of filter2D does not depend on the border mode."""
+    k = taps.shape[0]
+    h, w = a.shape
+    tmp = np.zeros((h - k + 1, w), dtype=np.float64)
+    for i in range(k):
+        tmp += taps[i] * a[i:i + h - k + 1, :]
+    out = np.zeros((h - k + 1, w - k + 1), dtype=np.float64)
+    for j in range(k):
+        out += taps[j] * tmp[:, j:j + w - k + 1]
+    return out
+
+
+def ssim_plane(a: np.ndarray, b: np.ndarray) -> float:
+    """utils_eval.py:19-33 on one 2-D plane (values on the 0..255 scale)."""
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    t = gaussian_taps()
+    mu1, mu2 = _valid_blur(a, t), _valid_blur(b, t)
+    s11 = _valid_blur(a * a, t) - mu1 * mu1
+    s22 = _valid_blur(b * b, t) - mu2 * mu2
+    s12 = _valid_blur(a * b, t) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s11 + s22 + c2))
+    return float(m.mean())
+
+
+def calculate_ssim(a: np.ndarray, b: np.ndarray) -> float:
+    """utils_eval.py:35-47."""
+    if a.shape != b.shape:
+        raise ValueError("Input images must have the same dimensions.")
+    if a.ndim == 2:
+        return ssim_plane(a, b)
+    if a.ndim == 3 and a.shape[2] == 3:
+        return float(np.mean([ssim_plane(a[:, :, i], b[:, :, i]) for i in range(3)]))
+    if a.ndim == 3 and a.shape[2] == 1:
+        return ssim_plane(a[:, :, 0], b[:, :, 0])
+    raise ValueError("Wrong input image dimensions.")
+
+
+def calculate_psnr(a: np.ndarray, b: np.ndarray) -> float:
+    """utils_eval.py:49-53 — float32 arithmetic, no mse==0 guard."""
+    d = a.astype(np.float32) - b.astype(np.float32)
+    with np.errstate(divide="ignore"):
+        return float(10.0 * np.log10(255.0 * 255.0 / np.mean(np.square(d))))
+
+
+# ----------------------------------------------------------------------------
+# a13 / a14: evaluation post-processing  (evaluation.py:73-83, evaluation_704.py:57-120)
+# ----------------------------------------------------------------------------
+def quantize_round(pred01: np.ndarray) -> np.ndarray:
+    """evaluation.py:82-83: clamp(0,1) -> clip(p*255+0.5, 0, 255) -> uint8."""
+    p = np.clip(pred01.astype(np.float32), 0.0, 1.0)
+    return np.clip(p * np.float32(255.0) + np.float32(0.5), 0, 255).astype(np.uint8)
+
+
+def tile_weight(ps: int = 352) -> np.ndarray:
+    """evaluation_704.py:62-68 — separable triangular window, float32, border == 0."""
+    y = np.linspace(0, 1, ps)
+    w1 = 1 - np.abs(y - 0.5) * 2
+    return (w1[:, None] * w1[None, :]).astype(np.float32)
+
+
+def tiled_denoise(forward, noisy_u8: np.ndarray, ps: int = 352, overlap: int = 64) -> np.ndarray:
+    """evaluation_704.py:74-120 for one 2-D uint8 image.  ``forward`` maps a
+    float32 [1,1,ps,ps] tensor to the same shape.  Returns the uint8 result
+    (truncating quantisation, no +0.5 — evaluation_704.py:120)."""
+    h, w = noisy_u8.shape
+    stride = ps - overlap
+    wm = tile_weight(ps)
+    acc = np.zeros((h, w), np.float32)
+    cnt = np.zeros((h, w), np.float32)
+    for r0 in range(0, h, stride):
+        for c0 in range(0, w, stride):
+            r1, c1 = min(r0 + ps, h), min(c0 + ps, w)
+            patch = noisy_u8[r0:r1, c0:c1].astype(np.float32) / 255.0
+            padded = np.pad(patch, ((0, ps - patch.shape[0]), (0, ps - patch.shape[1])), mode="reflect")
+            with torch.no_grad():
+                o = forward(torch.from_numpy(padded)[None, None])
+            o = o[0, 0].clamp(0, 1).numpy()[:patch.shape[0], :patch.shape[1]]
+            wv = wm[:patch.shape[0], :patch.shape[1]]
+            acc[r0:r1, c0:c1] += o * wv
+            cnt[r0:r1, c0:c1] += wv
+    cnt[cnt == 0] = 1
+    return np.clip(acc / cnt * 255.0, 0, 255).astype(np.uint8)

@@ -1,0 +1,122 @@
+"""CPU: the oracle (oracle/n2n_oracle.py) against the golden vectors produced by the
+unmodified reference code (oracle/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import n2n_oracle as O
+
+
+def _weights(in_nc, nf, seed, bias_seed):
+    p = O.unet_init(in_nc, in_nc, nf, seed)
+    g = torch.Generator().manual_seed(int(bias_seed))
+    for k in p:
+        if k.endswith(".bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.05
+    return p, g
+
+
+def _csum(t):
+    t = t.detach().double()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+
+
+def test_subsampler_matches_reference(golden):
+    z = golden("subsample")
+    for ci in range(3):
+        img = z[f"img{ci}"]
+        n, c, h, w = img.shape
+        rd = O.draw_rd_idx(n, h, w, int(z[f"seed{ci}"]))
+        assert np.array_equal(rd, z[f"rd{ci}"])
+        m1, m2 = O.masks_from_rd_idx(rd)
+        assert np.array_equal(m1, z[f"m1_{ci}"]) and np.array_equal(m2, z[f"m2_{ci}"])
+        assert np.array_equal(O.subimage_from_mask(img, m1), z[f"s1_{ci}"])
+        assert np.array_equal(O.subimage_from_mask(img, m2), z[f"s2_{ci}"])
+    img = z["const_img"]
+    for r in range(8):
+        m1, m2 = O.masks_from_rd_idx(np.full((12,), r))
+        assert np.array_equal(O.subimage_from_mask(img, m1), z[f"const_s1_{r}"])
+        assert np.array_equal(O.subimage_from_mask(img, m2), z[f"const_s2_{r}"])
+
+
+def test_subsampler_invariants():
+    rng = np.random.RandomState(0)
+    rd = rng.randint(0, 8, size=2 * 5 * 7)
+    m1, m2 = O.masks_from_rd_idx(rd)
+    a = m1.reshape(-1, 4); b = m2.reshape(-1, 4)
+    assert (a.sum(1) == 1).all() and (b.sum(1) == 1).all()
+    k1, k2 = a.argmax(1), b.argmax(1)
+    assert (k1 != k2).all()
+    # 4-adjacent, never diagonal: exactly one of (ky, kx) differs
+    assert (((k1 // 2) != (k2 // 2)) ^ ((k1 % 2) != (k2 % 2))).all()
+
+
+def test_unet_forward_matches_reference(golden):
+    z = golden("unet")
+    for tag, (in_nc, nf, seed) in {"g1": (1, 4, 3), "c3": (3, 4, 5), "nf16": (1, 16, 7)}.items():
+        p, _ = _weights(in_nc, nf, seed, z[f"{tag}_bias_seed"])
+        ws = np.stack([_csum(v) for v in p.values()])
+        assert np.allclose(ws, z[f"{tag}_wsum"], rtol=1e-12), "seeded weights differ from fixture"
+        with torch.no_grad():
+            y = O.unet_forward(p, torch.from_numpy(z[f"{tag}_x"]))
+        assert np.abs(y.numpy() - z[f"{tag}_y"]).max() < 1e-6
+
+
+def test_n2n_step_matches_reference(golden):
+    z = golden("unet")
+    p, _ = _weights(1, 4, 3, z["g1_bias_seed"])
+    loss, l1, l2, grads, _, _ = O.n2n_step_grads(
+        p, torch.from_numpy(z["step_noisy"]), z["step_mask1"], z["step_mask2"], float(z["step_lambda"]))
+    assert np.allclose([loss, l1, l2], z["step_loss"], atol=1e-7)
+    for k, g in grads.items():
+        ref = z["grad/" + k]
+        assert np.abs(g.numpy() - ref).max() <= 1e-7 + 1e-5 * np.abs(ref).max(), k
+
+
+def test_adam_and_lr_schedule(golden):
+    z = golden("adam")
+    w = z["w0"].copy(); m = np.zeros_like(w); v = np.zeros_like(w)
+    for t in range(5):
+        O.adam_update(w, z["grads"][t], m, v, t + 1, 3e-4)
+    assert np.abs(w - z["w5"]).max() < 2e-7
+    lrs = [O.multistep_lr(3e-4, e, 10, 0.5) for e in range(1, 11)]
+    assert np.allclose(lrs, z["lrs_nepoch10"], rtol=1e-12)
+
+
+def test_psnr_ssim_match_reference(golden):
+    z = golden("psnr_ssim")
+    for i in range(4):
+        assert abs(O.calculate_psnr(z[f"a{i}"], z[f"b{i}"]) - float(z[f"psnr{i}"])) < 1e-4
+        assert abs(O.calculate_ssim(z[f"a{i}"], z[f"b{i}"]) - float(z[f"ssim{i}"])) < 1e-12
+
+
+def test_adapter_and_finetune_loss_match_reference(golden):
+    z = golden("adapter")
+    base_p = O.unet_init(3, 3, 4, 21)
+    noisy = torch.from_numpy(z["noisy"]); clean = torch.from_numpy(z["clean"])
+    ap = {k[2:]: torch.from_numpy(z[k]).requires_grad_(True) for k in z.files if k.startswith("w/")}
+    with torch.no_grad():
+        bo = O.unet_forward(base_p, noisy)
+    pred = O.adapter_forward(ap, noisy, bo)
+    assert np.abs(pred.detach().numpy() - z["pred"]).max() < 1e-6
+    loss, l1, lg = O.finetune_loss(pred, clean, 0.1)
+    assert np.allclose([loss.item(), l1.item(), lg.item()], z["loss"], atol=1e-7)
+    loss.backward()
+    for k, t in ap.items():
+        ref = z["g/" + k]
+        assert np.abs(t.grad.numpy() - ref).max() <= 1e-7 + 1e-5 * np.abs(ref).max(), k
+    assert len(z["keys"]) == 54
+
+
+def test_tiled_and_whole_eval_match_reference(golden):
+    z = golden("eval")
+    p = O.unet_init(1, 1, 4, 31)
+    assert np.array_equal(O.tile_weight(352), z["weight_mask"])
+    out = O.tiled_denoise(lambda t: O.unet_forward(p, t), z["noisy_u8"])
+    assert np.array_equal(out, z["pred255"])
+    assert (out[0, :] == 0).all() and (out[:, 0] == 0).all()
+    assert abs(O.calculate_psnr(out, z["clean_u8"].astype(np.float32)) - float(z["psnr"])) < 1e-4
+    assert abs(O.calculate_ssim(out, z["clean_u8"].astype(np.float32)) - float(z["ssim"])) < 1e-10
+    x = torch.from_numpy(z["noisy_u8"][:64, :96].astype(np.float32) / 255.0)[None, None]
+    with torch.no_grad():
+        w = O.quantize_round(O.unet_forward(p, x)[0, 0].numpy())
+    assert np.array_equal(w, z["whole255"])
