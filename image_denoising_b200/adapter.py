@@ -1,0 +1,97 @@
+"""Drop-in ``adapter.OutputAdapter`` / ``adapter.DenoiserWithAdapter`` (reference adapter.py:5-67).
+
+State-dict layout is the reference's 54 keys: ``base.*`` (50) + ``adapter.net.0.weight``
+[16,2C,3,3], ``adapter.net.0.bias``, ``adapter.net.2.weight`` [C,16,3,3], ``adapter.net.2.bias``.
+The two adapter convolutions, the ReLU, the concat and the residual add run as
+n2n_adapter_forward / n2n_adapter_backward (same engines as the UNet)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _ext
+from ._ext import check, lib, ptr, ptr_array, require_cuda, stream_ptr
+
+
+class _AdapterFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, noisy, base_out, *params):
+        plan, ws = mod._plan(noisy, True)
+        out = torch.empty_like(base_out)
+        check(lib().n2n_adapter_forward(plan, ptr_array(params), ptr(noisy), ptr(base_out), ptr(out), ptr(ws), stream_ptr()))
+        ctx.plan, ctx.ws, ctx.params = plan, ws, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous().float()
+        grads = [torch.empty_like(p) for p in ctx.params]
+        check(lib().n2n_adapter_backward(ctx.plan, ptr_array(ctx.params), ptr(dout), ptr_array(grads), ptr(ctx.ws), stream_ptr()))
+        return (None, None, None) + tuple(grads)
+
+
+class OutputAdapter(nn.Module):
+    def __init__(self, in_channels: int = 1, hidden_channels: int = 16):
+        super().__init__()
+        self.in_channels = in_channels
+        self.hidden_channels = hidden_channels
+        self.net = nn.Sequential(      # parameter holders; default torch Conv2d init as in the reference
+            nn.Conv2d(2 * in_channels, hidden_channels, kernel_size=3, padding=1, bias=True),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(hidden_channels, in_channels, kernel_size=3, padding=1, bias=True),
+        )
+        self.precision = _ext.default_precision()
+        self._plans = {}
+
+    def _plan(self, x, bwd):
+        n, c, h, w = x.shape
+        key = (n, h, w, _ext.dtype_tag(self.precision), bool(bwd))
+        if key not in self._plans:
+            handle = ctypes.c_void_p()
+            check(lib().n2n_adapter_plan_create(ctypes.byref(handle), self.in_channels, self.hidden_channels,
+                                                n, h, w, key[3], int(bwd)))
+            ws = torch.empty(lib().n2n_adapter_workspace_bytes(handle), dtype=torch.uint8, device=x.device)
+            self._plans[key] = (handle, ws)
+        return self._plans[key]
+
+    def forward(self, noisy: torch.Tensor, base_out: torch.Tensor) -> torch.Tensor:
+        require_cuda(noisy, "OutputAdapter.forward")
+        noisy = noisy.contiguous().float()
+        base_out = base_out.contiguous().float()
+        params = [self.net[0].weight, self.net[0].bias, self.net[2].weight, self.net[2].bias]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _AdapterFunction.apply(self, noisy, base_out, *params)
+        plan, ws = self._plan(noisy, False)
+        out = torch.empty_like(base_out)
+        check(lib().n2n_adapter_forward(plan, ptr_array(params), ptr(noisy), ptr(base_out), ptr(out), ptr(ws), stream_ptr()))
+        return out
+
+
+class DenoiserWithAdapter(nn.Module):
+    def __init__(self, base_model: nn.Module, in_channels: int = 1, hidden_channels: int = 16,
+                 freeze_base: bool = True, use_no_grad_for_base: bool = True):
+        super().__init__()
+        self.base = base_model
+        self.in_channels = in_channels
+        self.freeze_base = freeze_base
+        self.use_no_grad_for_base = use_no_grad_for_base
+        if freeze_base:
+            for p in self.base.parameters():
+                p.requires_grad = False
+        self.adapter = OutputAdapter(in_channels=in_channels, hidden_channels=hidden_channels)
+
+    def set_precision(self, precision: str):
+        self.adapter.precision = precision
+        if hasattr(self.base, "set_precision"):
+            self.base.set_precision(precision)
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_no_grad_for_base:
+            with torch.no_grad():
+                base_out = self.base(x)
+        else:
+            base_out = self.base(x)
+        return self.adapter(x, base_out)

@@ -1,0 +1,257 @@
+// api.cu — error plumbing, engine dispatch and the single-layer C-ABI entry points
+// (NCHW fp32 at the boundary; the blocked C16 layout lives in the caller's workspace).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace n2n {
+
+static thread_local char g_err[512] = "";
+thread_local long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
+  N2N_CHECK_ARG(g.ntaps >= 1 && g.ntaps <= 9 && g.cin_blocks >= 1 && g.nout >= 16 && g.nout % 16 == 0,
+                "tapgemm: bad geometry (taps=%d cin_blocks=%d nout=%d)", g.ntaps, g.cin_blocks, g.nout);
+  if (g.dtype == N2N_BF16) return launch_tapgemm_umma(g, st);
+  return launch_tapgemm_simt(g, st);
+}
+int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
+  if (g.dtype == N2N_BF16) return launch_tapwgrad_umma(g, st);
+  return launch_tapwgrad_simt(g, st);
+}
+
+// carve a workspace
+struct Carver {
+  char* base; size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += align_up(bytes, 1024); return p; }
+};
+
+static size_t c16_bytes(int dtype, int n, int c, int h, int w) {
+  return (size_t)n * cblocks(c) * h * w * 16 * dtype_size(dtype);
+}
+
+}  // namespace n2n
+
+using namespace n2n;
+
+extern "C" const char* n2n_last_error(void) { return g_err; }
+extern "C" int n2n_version(void) { return 100; }
+extern "C" long long n2n_launch_count(void) { return g_launch_count; }
+extern "C" int n2n_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+  cudaDeviceProp p;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv2d (k in {1,3})
+// ------------------------------------------------------------------------------------------
+static LayerGeom conv_geom(int cin, int cout, int k) {
+  LayerGeom L; L.kind = k == 3 ? L_CONV3 : L_CONV1; L.cin = chan1(cin); L.cout = cout; return L;
+}
+
+struct ConvWs {
+  void *xa, *ya, *wp, *wd; float *bias, *partial, *bpartial; size_t total; int splits;
+};
+static ConvWs conv_ws(void* ws, const LayerGeom& L, int n, int h, int w, int dtype, bool deconv) {
+  Carver c(ws);
+  ConvWs r;
+  const int oh = deconv ? 2 * h : h, ow = deconv ? 2 * w : w;
+  r.splits = wgrad_default_splits(dtype, (long long)n * h * w);
+  r.xa = c.take(c16_bytes(dtype, n, L.cin.real(), h, w));
+  r.ya = c.take(c16_bytes(dtype, n, L.cout, oh, ow));
+  r.wp = c.take(L.fwd_pack_bytes(dtype));
+  r.wd = c.take(L.dgrad_pack_bytes(dtype, L.cin_blocks()));
+  r.bias = (float*)c.take(L.cout_blocks() * 16 * sizeof(float));
+  r.partial = (float*)c.take(L.partial_bytes(r.splits));
+  r.bpartial = (float*)c.take(L.bias_partial_bytes(r.splits));
+  r.total = c.off;
+  return r;
+}
+
+extern "C" size_t n2n_conv2d_workspace_bytes(int n, int cin, int cout, int h, int w, int ksize, int dtype) {
+  return conv_ws(nullptr, conv_geom(cin, cout, ksize), n, h, w, dtype, false).total;
+}
+
+#define CONV_ARGCHECK(name)                                                                                   \
+  N2N_CHECK_ARG(n > 0 && cin > 0 && cout > 0 && h > 0 && w_ > 0 && (ksize == 1 || ksize == 3),                \
+                name ": bad shape n=%d cin=%d cout=%d h=%d w=%d k=%d", n, cin, cout, h, w_, ksize);           \
+  N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, name ": bad dtype %d", dtype);                         \
+  N2N_CHECK_ARG(workspace != nullptr, name ": workspace is NULL")
+
+extern "C" int n2n_conv2d_fwd(const float* x, const float* w, const float* b, float* y, int n, int cin, int cout,
+                              int h, int w_, int ksize, float act_slope, int dtype, void* workspace, void* stream) {
+  CONV_ARGCHECK("conv2d_fwd");
+  N2N_CHECK_ARG(x && w && y, "conv2d_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = conv_geom(cin, cout, ksize);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, false);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, h, w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(x, cin, xv, dtype, st));
+  PackJob pj = make_fwd_pack(L, w, ws.wp);
+  N2N_TRY(launch_pack(&pj, 1, dtype, st));
+  BiasPadJob bj{b, ws.bias, cout, L.cout_blocks() * 16};
+  N2N_TRY(launch_bias_pad(&bj, 1, st));
+  TapGemm g = make_conv_fwd(L, dtype, xv, yv, ws.wp, ws.bias);
+  if (act_slope >= 0.f) { g.act = 1; g.slope = act_slope; }
+  N2N_TRY(launch_tapgemm(g, st));
+  return launch_c16_to_nchw(yv, dtype, y, cout, st);
+}
+
+extern "C" int n2n_conv2d_dgrad(const float* dy, const float* w, float* dx, int n, int cin, int cout, int h, int w_,
+                                int ksize, int dtype, void* workspace, void* stream) {
+  CONV_ARGCHECK("conv2d_dgrad");
+  N2N_CHECK_ARG(dy && w && dx, "conv2d_dgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = conv_geom(cin, cout, ksize);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, false);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, h, w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(dy, cout, yv, dtype, st));
+  PackJob pj = make_dgrad_pack(L, w, ws.wd, L.cin_blocks());
+  N2N_TRY(launch_pack(&pj, 1, dtype, st));
+  TapGemm g = make_conv_dgrad(L, dtype, yv, xv, ws.wd, L.cin_blocks());
+  N2N_TRY(launch_tapgemm(g, st));
+  return launch_c16_to_nchw(xv, dtype, dx, cin, st);
+}
+
+extern "C" int n2n_conv2d_wgrad(const float* x, const float* dy, float* dw, float* db, int n, int cin, int cout,
+                                int h, int w_, int ksize, int dtype, void* workspace, void* stream) {
+  CONV_ARGCHECK("conv2d_wgrad");
+  N2N_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = conv_geom(cin, cout, ksize);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, false);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, h, w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(x, cin, xv, dtype, st));
+  N2N_TRY(launch_nchw_to_c16(dy, cout, yv, dtype, st));
+  TapWgrad g = make_conv_wgrad(L, dtype, xv, yv, ws.partial, ws.bpartial, ws.splits);
+  N2N_TRY(launch_tapwgrad(g, st));
+  UnpackJob uj = make_unpack(L, ws.partial, ws.bpartial, ws.splits, dw, db);
+  return launch_unpack(&uj, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvTranspose2d(k=2, s=2)   x: [n,cin,h,w]  ->  y: [n,cout,2h,2w]
+// ------------------------------------------------------------------------------------------
+static LayerGeom deconv_geom(int cin, int cout) {
+  LayerGeom L; L.kind = L_DECONV; L.cin = chan1(cin); L.cout = cout; return L;
+}
+extern "C" size_t n2n_deconv2x2_workspace_bytes(int n, int cin, int cout, int h, int w, int dtype) {
+  return conv_ws(nullptr, deconv_geom(cin, cout), n, h, w, dtype, true).total;
+}
+#define DECONV_ARGCHECK(name)                                                                          \
+  N2N_CHECK_ARG(n > 0 && cin > 0 && cout > 0 && h > 0 && w_ > 0, name ": bad shape");                  \
+  N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, name ": bad dtype %d", dtype);                  \
+  N2N_CHECK_ARG(workspace != nullptr, name ": workspace is NULL")
+
+extern "C" int n2n_deconv2x2_fwd(const float* x, const float* w, const float* b, float* y, int n, int cin, int cout,
+                                 int h, int w_, int dtype, void* workspace, void* stream) {
+  DECONV_ARGCHECK("deconv2x2_fwd");
+  N2N_CHECK_ARG(x && w && y, "deconv2x2_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = deconv_geom(cin, cout);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, true);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, 2 * h, 2 * w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(x, cin, xv, dtype, st));
+  PackJob pj = make_fwd_pack(L, w, ws.wp);
+  N2N_TRY(launch_pack(&pj, 1, dtype, st));
+  BiasPadJob bj{b, ws.bias, cout, L.cout_blocks() * 16};
+  N2N_TRY(launch_bias_pad(&bj, 1, st));
+  for (int ab = 0; ab < 4; ++ab) {
+    TapGemm g = make_deconv_fwd(L, dtype, xv, yv, ab / 2, ab % 2, ws.wp, ws.bias);
+    N2N_TRY(launch_tapgemm(g, st));
+  }
+  return launch_c16_to_nchw(yv, dtype, y, cout, st);
+}
+
+extern "C" int n2n_deconv2x2_dgrad(const float* dy, const float* w, float* dx, int n, int cin, int cout, int h,
+                                   int w_, int dtype, void* workspace, void* stream) {
+  DECONV_ARGCHECK("deconv2x2_dgrad");
+  N2N_CHECK_ARG(dy && w && dx, "deconv2x2_dgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = deconv_geom(cin, cout);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, true);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, 2 * h, 2 * w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(dy, cout, yv, dtype, st));
+  PackJob pj = make_dgrad_pack(L, w, ws.wd, L.cin_blocks());
+  N2N_TRY(launch_pack(&pj, 1, dtype, st));
+  TapGemm g = make_deconv_dgrad(L, dtype, yv, xv, ws.wd);
+  N2N_TRY(launch_tapgemm(g, st));
+  return launch_c16_to_nchw(xv, dtype, dx, cin, st);
+}
+
+extern "C" int n2n_deconv2x2_wgrad(const float* x, const float* dy, float* dw, float* db, int n, int cin, int cout,
+                                   int h, int w_, int dtype, void* workspace, void* stream) {
+  DECONV_ARGCHECK("deconv2x2_wgrad");
+  N2N_CHECK_ARG(x && dy && dw, "deconv2x2_wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerGeom L = deconv_geom(cin, cout);
+  ConvWs ws = conv_ws(workspace, L, n, h, w_, dtype, true);
+  View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
+  View yv = make_view(ws.ya, dtype, n, 2 * h, 2 * w_, L.cout_blocks(), 0, L.cout_blocks());
+  N2N_TRY(launch_nchw_to_c16(x, cin, xv, dtype, st));
+  N2N_TRY(launch_nchw_to_c16(dy, cout, yv, dtype, st));
+  TapWgrad g = make_deconv_wgrad(L, dtype, xv, yv, ws.partial, ws.bpartial, ws.splits);
+  N2N_TRY(launch_tapwgrad(g, st));
+  UnpackJob uj = make_unpack(L, ws.partial, ws.bpartial, ws.splits, dw, db);
+  return launch_unpack(&uj, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(2)
+// ------------------------------------------------------------------------------------------
+extern "C" size_t n2n_pool_workspace_bytes(int n, int c, int h, int w, int dtype) {
+  return 2 * align_up(c16_bytes(dtype, n, c, h, w), 1024) + 2 * align_up(c16_bytes(dtype, n, c, h / 2, w / 2), 1024);
+}
+
+extern "C" int n2n_maxpool2_fwd(const float* x, float* y, int n, int c, int h, int w, int dtype, void* workspace,
+                                void* stream) {
+  N2N_CHECK_ARG(x && y && workspace && n > 0 && c > 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0,
+                "maxpool2_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  void* xa = cv.take(c16_bytes(dtype, n, c, h, w));
+  cv.take(c16_bytes(dtype, n, c, h, w));
+  void* ya = cv.take(c16_bytes(dtype, n, c, h / 2, w / 2));
+  View xv = make_view(xa, dtype, n, h, w, cblocks(c), 0, cblocks(c));
+  View yv = make_view(ya, dtype, n, h / 2, w / 2, cblocks(c), 0, cblocks(c));
+  N2N_TRY(launch_nchw_to_c16(x, c, xv, dtype, st));
+  N2N_TRY(launch_maxpool(xv, yv, dtype, st));
+  return launch_c16_to_nchw(yv, dtype, y, c, st);
+}
+
+extern "C" int n2n_maxpool2_bwd(const float* x, const float* dy, float* dx, int n, int c, int h, int w, float slope,
+                                int dtype, void* workspace, void* stream) {
+  N2N_CHECK_ARG(x && dy && dx && workspace && n > 0 && c > 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0,
+                "maxpool2_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  void* xa = cv.take(c16_bytes(dtype, n, c, h, w));
+  void* ga = cv.take(c16_bytes(dtype, n, c, h, w));
+  void* ya = cv.take(c16_bytes(dtype, n, c, h / 2, w / 2));
+  View xv = make_view(xa, dtype, n, h, w, cblocks(c), 0, cblocks(c));
+  View gv = make_view(ga, dtype, n, h, w, cblocks(c), 0, cblocks(c));
+  View yv = make_view(ya, dtype, n, h / 2, w / 2, cblocks(c), 0, cblocks(c));
+  N2N_TRY(launch_nchw_to_c16(x, c, xv, dtype, st));
+  N2N_TRY(launch_nchw_to_c16(dy, c, yv, dtype, st));
+  N2N_TRY(launch_unpool_lrelu(xv, yv, gv, slope, dtype, st));
+  return launch_c16_to_nchw(gv, dtype, dx, c, st);
+}

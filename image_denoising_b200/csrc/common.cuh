@@ -1,0 +1,241 @@
+// common.cuh — shared types for libn2n_b200.so (sm_100a only).
+//
+// Device activation layout ("C16"): [N][Cb][H][W][16] — channels are blocked by 16 so
+// that (a) every channel count of the UNet (48/96/144/in_nc) is a whole number of
+// blocks once zero-padded, (b) a (16ch x pixels) box is one contiguous run in HBM
+// for TMA, and lands in shared memory as a K-major SWIZZLE_32B UMMA operand, and
+// (c) concat is free: producers write into block ranges of the consumer's buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/n2n_b200.h"
+
+namespace n2n {
+
+void set_error(const char* fmt, ...);
+extern thread_local long long g_launch_count;   // kernels launched by this host thread (for gpu_launches)
+
+#define N2N_CHECK_ARG(cond, ...)                       \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      n2n::set_error(__VA_ARGS__);                     \
+      return N2N_ERR_ARG;                              \
+    }                                                  \
+  } while (0)
+
+#define N2N_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      n2n::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                           \
+      return N2N_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define N2N_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    ++n2n::g_launch_count;                                                          \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      n2n::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),    \
+                     __FILE__, __LINE__);                                           \
+      return N2N_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define N2N_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+constexpr int kSMs = 148;  // B200
+
+// A (possibly strided) window onto a C16 tensor.  Strides are in ELEMENTS; the 16
+// channels of one block at one pixel are always contiguous.
+struct View {
+  void* ptr = nullptr;
+  int N = 0, H = 0, W = 0, Cb = 0;
+  long long sN = 0, sCb = 0, sY = 0, sX = 0;
+};
+
+inline size_t dtype_size(int dtype) { return dtype == N2N_BF16 ? 2 : 4; }
+inline int cblocks(int c) { return (c + 15) / 16; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Dense C16 view over a buffer of Cb_total blocks, exposing blocks [cb0, cb0+cb).
+inline View make_view(void* base, int dtype, int N, int H, int W, int Cb_total, int cb0, int cb) {
+  View v;
+  v.N = N; v.H = H; v.W = W; v.Cb = cb;
+  v.sX = 16; v.sY = (long long)W * 16; v.sCb = (long long)H * W * 16;
+  v.sN = (long long)Cb_total * v.sCb;
+  v.ptr = (char*)base + (size_t)cb0 * v.sCb * dtype_size(dtype);
+  return v;
+}
+// Parity sub-view (a,b) of a dense view: pixels (2i+a, 2j+b).
+inline View parity_view(const View& v, int dtype, int a, int b) {
+  View p = v;
+  p.H = v.H / 2; p.W = v.W / 2;
+  p.sY = v.sY * 2; p.sX = v.sX * 2;
+  p.ptr = (char*)v.ptr + (size_t)(a * v.sY + b * v.sX) * dtype_size(dtype);
+  return p;
+}
+inline View sub_blocks(const View& v, int dtype, int cb0, int cb) {
+  View p = v;
+  p.Cb = cb;
+  p.ptr = (char*)v.ptr + (size_t)cb0 * v.sCb * dtype_size(dtype);
+  return p;
+}
+
+// ---- 16-element block load/store, fp32 math -------------------------------------------
+template <typename T> struct Block16;
+template <> struct Block16<float> {
+  static __device__ __forceinline__ void load(const float* p, float v[16]) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = q[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  }
+  static __device__ __forceinline__ void store(float* p, const float v[16]) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+};
+template <> struct Block16<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[16]) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint4 t = q[i];
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+        v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[16]) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      q[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+};
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+inline int grid_for(long long items, int threads, int max_waves = 8) {
+  long long blocks = (items + threads - 1) / threads;
+  long long cap = (long long)kSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- generic "tap GEMM" (conv3x3 / conv1x1 / deconv2x2 fwd+dgrad) ------------------------
+// D[p, n] = sum_t sum_c X_{view(t)}[p + (dy_t, dx_t), c] * Wp[t][n][c]
+// out = epilogue(D): v = D + bias[n] (+ addend[p,n]); act; (* (mask[p,n] > 0 ? 1 : slope)).
+struct TapGemm {
+  int dtype = N2N_F32;
+  View x[4];
+  int ntaps = 0;
+  int tap_dy[9] = {0}, tap_dx[9] = {0}, tap_view[9] = {0};
+  int tap_slab[9] = {0};          // which packed-weight slab each tap uses
+  int cin_blocks = 0;             // K per tap = 16 * cin_blocks
+  int nout = 0;                   // padded to a multiple of 16
+  const void* w = nullptr;        // packed weights (engine layout, see pack.cu)
+  const float* bias = nullptr;    // [nout] fp32 (padded) or null
+  View y;                         // output view (C16, dtype); ignored when out_nchw set
+  bool has_addend = false; View addend;
+  bool has_mask = false; View mask;
+  int act = 0;                    // 0: none, 1: leaky (slope)
+  float slope = 0.f;
+  float* out_nchw = nullptr;      // optional fp32 NCHW [N][out_c][H][W] output
+  int out_c = 0;
+};
+
+// ---- generic weight-gradient GEMM ---------------------------------------------------------
+// P[s][t][c][n] = sum_{p in split s} dY_{a(t)}[p, n] * X_{b(t)}[p + (dy_t, dx_t), c]
+// bias_partial[s][n] = sum_{p in split s} sum_{distinct dY views} dY[p, n]
+struct TapWgrad {
+  int dtype = N2N_F32;
+  View dy[4]; View x[4];
+  int npairs = 0;
+  int pair_dyv[9] = {0}, pair_xv[9] = {0}, pair_dy[9] = {0}, pair_dx[9] = {0};
+  int n_blocks = 0;               // Cout / 16 (from dY)
+  int c_blocks = 0;               // Cin / 16 (from X)
+  float* partial = nullptr;       // [splits][npairs][c_blocks*16][n_blocks*16]
+  float* bias_partial = nullptr;  // [splits][ndyviews][n_blocks*16] or null
+  int ndyviews = 1;               // how many distinct dY views feed the bias sum
+  int splits = 1;
+};
+
+// Weight pack (torch layout fp32 -> engine layout) and the inverse gradient reduce.
+struct Segs {
+  int n = 1;
+  int src0[2] = {0, 0}, cnt[2] = {0, 0}, dst0[2] = {0, 0};
+};
+struct PackJob {
+  const float* src = nullptr;     // torch-layout fp32 weights
+  void* dst = nullptr;            // engine layout
+  int ntaps = 1;
+  int nout_pad = 16, cin_blocks = 1;
+  long long s_t = 0, s_n = 0, s_c = 0;   // source element strides (tap, out-channel, in-channel)
+  Segs nseg, cseg;                // channel remaps (concat skip starts on a block boundary)
+};
+struct UnpackJob {
+  const float* partial = nullptr; // [splits][ntaps][cpad][npad]
+  const float* bias_partial = nullptr;  // [splits][npad]
+  float* dst_w = nullptr;         // torch layout grad
+  float* dst_b = nullptr;         // [nreal] or null
+  int splits = 1, ntaps = 1, npad = 16, cpad = 16;
+  int bias_rows = 1;              // rows of bias_partial to sum (= splits * ndyviews)
+  long long s_t = 0, s_n = 0, s_c = 0;
+  Segs nseg, cseg;
+};
+
+size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks);
+
+// engine entry points (host, async on stream)
+int launch_tapgemm(const TapGemm& g, cudaStream_t st);
+int launch_tapwgrad(const TapWgrad& g, cudaStream_t st);
+int wgrad_default_splits(int dtype, long long pixels);
+int launch_pack(const PackJob* jobs, int njobs, int dtype, cudaStream_t st);
+int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st);
+
+// elementwise (elementwise.cu)
+int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cudaStream_t st);
+int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream_t st);
+int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st);
+int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype, cudaStream_t st);
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// bf16 tensor-core engine (tapgemm_umma.cu / wgrad_umma.cu)
+int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st);
+int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st);
+// fp32 CUDA-core engine (tapgemm_simt.cu)
+int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st);
+int launch_tapwgrad_simt(const TapWgrad& g, cudaStream_t st);
+
+}  // namespace n2n

@@ -1,0 +1,254 @@
+// elementwise.cu — HBM-bound layout / pooling / evaluation kernels on the C16 layout.
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace n2n {
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32  <->  one C16 block (C <= 16 channels, zero padded)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_c16_kernel(const float* __restrict__ src, int C, View dst, long long items) {
+  const long long hw = (long long)dst.H * dst.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % hw;
+    const int cb = (int)((i / hw) % dst.Cb);
+    const int n = (int)(i / (hw * dst.Cb));
+    const int y = (int)(r / dst.W), x = (int)(r - (long long)y * dst.W);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int ch = cb * 16 + c;
+      v[c] = (ch < C) ? src[((long long)n * C + ch) * hw + r] : 0.f;
+    }
+    T* p = (T*)dst.ptr + n * dst.sN + cb * dst.sCb + y * dst.sY + x * dst.sX;
+    Block16<T>::store(p, v);
+  }
+}
+
+template <typename T>
+__global__ void c16_to_nchw_kernel(View src, float* __restrict__ dst, int C, long long items) {
+  const long long hw = (long long)src.H * src.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % hw;
+    const int cb = (int)((i / hw) % src.Cb);
+    const int n = (int)(i / (hw * src.Cb));
+    const int y = (int)(r / src.W), x = (int)(r - (long long)y * src.W);
+    float v[16];
+    const T* p = (const T*)src.ptr + n * src.sN + cb * src.sCb + y * src.sY + x * src.sX;
+    Block16<T>::load(p, v);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int ch = cb * 16 + c;
+      if (ch < C) dst[((long long)n * C + ch) * hw + r] = v[c];
+    }
+  }
+}
+
+int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cudaStream_t st) {
+  N2N_CHECK_ARG(C >= 1 && C <= 16 * dst.Cb, "nchw_to_c16: C=%d does not fit %d blocks", C, dst.Cb);
+  long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
+  int grid = grid_for(items, 256);
+  if (dtype == N2N_BF16) nchw_to_c16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, C, dst, items);
+  else nchw_to_c16_kernel<float><<<grid, 256, 0, st>>>(src, C, dst, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream_t st) {
+  N2N_CHECK_ARG(C >= 1 && C <= 16 * src.Cb, "c16_to_nchw: C=%d does not fit %d blocks", C, src.Cb);
+  long long items = (long long)src.N * src.Cb * src.H * src.W;
+  int grid = grid_for(items, 256);
+  if (dtype == N2N_BF16) c16_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, dst, C, items);
+  else c16_to_nchw_kernel<float><<<grid, 256, 0, st>>>(src, dst, C, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+struct BiasPadBatch { BiasPadJob j[32]; int n; };
+__global__ void bias_pad_kernel(const __grid_constant__ BiasPadBatch b) {
+  const BiasPadJob& J = b.j[blockIdx.x];
+  for (int i = threadIdx.x; i < J.npad; i += blockDim.x) J.dst[i] = (i < J.n && J.src) ? J.src[i] : 0.f;
+}
+int launch_bias_pad(const BiasPadJob* jobs, int njobs, cudaStream_t st) {
+  for (int base = 0; base < njobs; base += 32) {
+    BiasPadBatch b;
+    b.n = njobs - base < 32 ? njobs - base : 32;
+    for (int i = 0; i < b.n; ++i) b.j[i] = jobs[base + i];
+    bias_pad_kernel<<<b.n, 128, 0, st>>>(b);
+    N2N_LAUNCH_CHECK();
+  }
+  return 0;
+}
+int launch_nchw_to_c16_multi(const float* src, int C, const View& dst, int dtype, cudaStream_t st) {
+  return launch_nchw_to_c16(src, C, dst, dtype, st);
+}
+int launch_c16_to_nchw_multi(const View& src, int dtype, float* dst, int C, cudaStream_t st) {
+  return launch_c16_to_nchw(src, dtype, dst, C, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(2) forward (arch_unet.py:120-136) and fused max-pool + LeakyReLU backward.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_kernel(View src, View dst, long long items) {
+  const int Wo = dst.W, Ho = dst.H, Cb = dst.Cb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho); r /= Ho;
+    const int cb = (int)(r % Cb);
+    const int n = (int)(r / Cb);
+    const T* s = (const T*)src.ptr + n * src.sN + cb * src.sCb + (2 * y) * src.sY + (2 * x) * src.sX;
+    float a[16], b[16], c[16], d[16], o[16];
+    Block16<T>::load(s, a);
+    Block16<T>::load(s + src.sX, b);
+    Block16<T>::load(s + src.sY, c);
+    Block16<T>::load(s + src.sY + src.sX, d);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+    Block16<T>::store((T*)dst.ptr + n * dst.sN + cb * dst.sCb + y * dst.sY + x * dst.sX, o);
+  }
+}
+
+int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st) {
+  N2N_CHECK_ARG(dst.H == src.H / 2 && dst.W == src.W / 2 && dst.Cb == src.Cb && dst.N == src.N,
+                "maxpool: shape mismatch");
+  long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
+  int grid = grid_for(items, 256);
+  if (dtype == N2N_BF16) maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, dst, items);
+  else maxpool_kernel<float><<<grid, 256, 0, st>>>(src, dst, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// gact[2y+a, 2x+b] = (first max of the window at (a,b) ? gpool[y,x] : 0) * (act > 0 ? 1 : slope)
+// Tie rule: ATen keeps the first maximum in row-major window order (update only on >).
+template <typename T>
+__global__ void unpool_lrelu_kernel(View act, View gpool, View gact, float slope, long long items) {
+  const int Wo = gpool.W, Ho = gpool.H, Cb = gpool.Cb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho); r /= Ho;
+    const int cb = (int)(r % Cb);
+    const int n = (int)(r / Cb);
+    const T* s = (const T*)act.ptr + n * act.sN + cb * act.sCb + (2 * y) * act.sY + (2 * x) * act.sX;
+    float v[4][16], g[16], o[4][16];
+    Block16<T>::load(s, v[0]);
+    Block16<T>::load(s + act.sX, v[1]);
+    Block16<T>::load(s + act.sY, v[2]);
+    Block16<T>::load(s + act.sY + act.sX, v[3]);
+    Block16<T>::load((const T*)gpool.ptr + n * gpool.sN + cb * gpool.sCb + y * gpool.sY + x * gpool.sX, g);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      int best = 0; float m = v[0][k];
+      if (v[1][k] > m) { m = v[1][k]; best = 1; }
+      if (v[2][k] > m) { m = v[2][k]; best = 2; }
+      if (v[3][k] > m) { m = v[3][k]; best = 3; }
+      const float gg = g[k] * (m > 0.f ? 1.f : slope);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][k] = (q == best) ? gg : 0.f;
+    }
+    T* d = (T*)gact.ptr + n * gact.sN + cb * gact.sCb + (2 * y) * gact.sY + (2 * x) * gact.sX;
+    Block16<T>::store(d, o[0]);
+    Block16<T>::store(d + gact.sX, o[1]);
+    Block16<T>::store(d + gact.sY, o[2]);
+    Block16<T>::store(d + gact.sY + gact.sX, o[3]);
+  }
+}
+
+int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype,
+                        cudaStream_t st) {
+  N2N_CHECK_ARG(gpool.H == act.H / 2 && gpool.W == act.W / 2 && gpool.Cb == act.Cb && gact.H == act.H &&
+                    gact.W == act.W && gact.Cb == act.Cb,
+                "unpool: shape mismatch");
+  long long items = (long long)gpool.N * gpool.Cb * gpool.H * gpool.W;
+  int grid = grid_for(items, 128);
+  if (dtype == N2N_BF16) unpool_lrelu_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(act, gpool, gact, slope, items);
+  else unpool_lrelu_kernel<float><<<grid, 128, 0, st>>>(act, gpool, gact, slope, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  N2N_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Evaluation post-processing
+// ------------------------------------------------------------------------------------------
+__global__ void quantize_u8_kernel(const float* __restrict__ p, uint8_t* __restrict__ o, long long n, float bias) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = fminf(fmaxf(p[i], 0.f), 1.f);
+    // evaluation.py:83 / evaluation_704.py:120: fp32 multiply then add, clip, truncate
+    v = __fadd_rn(__fmul_rn(v, 255.0f), bias);
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    o[i] = (uint8_t)v;
+  }
+}
+
+__global__ void tile_accumulate_kernel(const float* __restrict__ tile, int ps, const float* __restrict__ wm,
+                                       float* __restrict__ acc, float* __restrict__ cnt, int W, int r0, int c0,
+                                       int th, int tw) {
+  const long long n = (long long)th * tw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / tw), x = (int)(i - (long long)y * tw);
+    const float p = fminf(fmaxf(tile[(long long)y * ps + x], 0.f), 1.f);
+    const float w = wm[(long long)y * ps + x];
+    const long long o = (long long)(r0 + y) * W + (c0 + x);
+    acc[o] = __fadd_rn(acc[o], __fmul_rn(p, w));
+    cnt[o] = __fadd_rn(cnt[o], w);
+  }
+}
+
+__global__ void tile_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
+                                     uint8_t* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float c = cnt[i];
+    if (c == 0.f) c = 1.f;
+    float v = __fmul_rn(__fdiv_rn(acc[i], c), 255.0f);
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = (uint8_t)v;
+  }
+}
+
+}  // namespace n2n
+
+using namespace n2n;
+
+extern "C" int n2n_quantize_u8(const float* pred, uint8_t* out, int64_t count, float bias, void* stream) {
+  N2N_CHECK_ARG(pred && out && count >= 0, "quantize_u8: bad arguments");
+  if (count == 0) return 0;
+  quantize_u8_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(pred, out, count, bias);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_tile_accumulate(const float* pred_tile, int ps, const float* weight_mask, float* acc,
+                                   float* cnt, int H, int W, int r0, int c0, int th, int tw, void* stream) {
+  N2N_CHECK_ARG(pred_tile && weight_mask && acc && cnt, "tile_accumulate: null pointer");
+  N2N_CHECK_ARG(th >= 0 && tw >= 0 && th <= ps && tw <= ps && r0 >= 0 && c0 >= 0 && r0 + th <= H && c0 + tw <= W,
+                "tile_accumulate: tile out of range");
+  if (th == 0 || tw == 0) return 0;
+  tile_accumulate_kernel<<<grid_for((long long)th * tw, 256), 256, 0, (cudaStream_t)stream>>>(
+      pred_tile, ps, weight_mask, acc, cnt, W, r0, c0, th, tw);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_tile_finalize_u8(const float* acc, const float* cnt, uint8_t* out, int64_t count, void* stream) {
+  N2N_CHECK_ARG(acc && cnt && out && count >= 0, "tile_finalize: bad arguments");
+  if (count == 0) return 0;
+  tile_finalize_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(acc, cnt, out, count);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}

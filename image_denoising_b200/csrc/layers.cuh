@@ -1,0 +1,162 @@
+// layers.cuh — host-side builders that turn "a conv / deconv layer on C16 views" into the
+// generic engine descriptors (TapGemm / TapWgrad / PackJob / UnpackJob).  Shared by the
+// single-layer C-ABI entry points (api.cu) and the network plans (unet_plan.cu).
+#pragma once
+#include "common.cuh"
+
+namespace n2n {
+
+// Channel segments of a (possibly concatenated) operand: real channel ranges and where each
+// starts inside the blocked layout (every segment starts on a 16-channel block boundary).
+struct ChanSegs {
+  int n = 1;
+  int cnt[2] = {0, 0};
+  int real() const { return cnt[0] + (n > 1 ? cnt[1] : 0); }
+  int blocks() const { return cblocks(cnt[0]) + (n > 1 ? cblocks(cnt[1]) : 0); }
+  Segs to_segs() const {
+    Segs s; s.n = n;
+    s.src0[0] = 0; s.cnt[0] = cnt[0]; s.dst0[0] = 0;
+    if (n > 1) { s.src0[1] = cnt[0]; s.cnt[1] = cnt[1]; s.dst0[1] = cblocks(cnt[0]) * 16; }
+    return s;
+  }
+};
+inline ChanSegs chan1(int c) { ChanSegs s; s.n = 1; s.cnt[0] = c; return s; }
+inline ChanSegs chan2(int a, int b) { ChanSegs s; s.n = 2; s.cnt[0] = a; s.cnt[1] = b; return s; }
+
+enum LayerKind { L_CONV3 = 0, L_CONV1 = 1, L_DECONV = 2 };
+
+struct LayerGeom {
+  int kind = L_CONV3;
+  ChanSegs cin;          // input channels (concat aware)
+  int cout = 0;          // real output channels
+  int ntaps() const { return kind == L_CONV3 ? 9 : (kind == L_CONV1 ? 1 : 4); }
+  int cin_blocks() const { return cin.blocks(); }
+  int cout_blocks() const { return cblocks(cout); }
+  // source strides of the PyTorch weight for (tap, out-channel, in-channel)
+  void strides(long long& s_t, long long& s_co, long long& s_ci) const {
+    const int ci = cin.real();
+    if (kind == L_CONV3) { s_t = 1; s_co = (long long)ci * 9; s_ci = 9; }
+    else if (kind == L_CONV1) { s_t = 0; s_co = ci; s_ci = 1; }
+    else { s_t = 1; s_co = 4; s_ci = (long long)cout * 4; }       // ConvTranspose2d [ci][co][2][2]
+  }
+  size_t fwd_pack_bytes(int dtype) const { return packed_weight_bytes(dtype, ntaps(), cout_blocks() * 16, cin_blocks()); }
+  size_t dgrad_pack_bytes(int dtype, int out_blocks) const { return packed_weight_bytes(dtype, ntaps(), out_blocks * 16, cout_blocks()); }
+  size_t partial_bytes(int splits) const {
+    return (size_t)splits * ntaps() * cin_blocks() * 16 * cout_blocks() * 16 * sizeof(float);
+  }
+  size_t bias_partial_bytes(int splits) const {
+    return (size_t)splits * (kind == L_DECONV ? 4 : 1) * cout_blocks() * 16 * sizeof(float);
+  }
+};
+
+inline PackJob make_fwd_pack(const LayerGeom& L, const float* w, void* dst) {
+  PackJob j;
+  j.src = w; j.dst = dst; j.ntaps = L.ntaps();
+  j.nout_pad = L.cout_blocks() * 16; j.cin_blocks = L.cin_blocks();
+  long long st, sco, sci; L.strides(st, sco, sci);
+  j.s_t = st; j.s_n = sco; j.s_c = sci;
+  j.nseg = chan1(L.cout).to_segs(); j.cseg = L.cin.to_segs();
+  return j;
+}
+inline PackJob make_dgrad_pack(const LayerGeom& L, const float* w, void* dst, int out_blocks) {
+  PackJob j;
+  j.src = w; j.dst = dst; j.ntaps = L.ntaps();
+  j.nout_pad = out_blocks * 16; j.cin_blocks = L.cout_blocks();
+  long long st, sco, sci; L.strides(st, sco, sci);
+  j.s_t = st; j.s_n = sci; j.s_c = sco;
+  j.nseg = L.cin.to_segs(); j.cseg = chan1(L.cout).to_segs();
+  return j;
+}
+inline UnpackJob make_unpack(const LayerGeom& L, const float* partial, const float* bias_partial, int splits,
+                             float* dw, float* db) {
+  UnpackJob j;
+  j.partial = partial; j.bias_partial = bias_partial; j.dst_w = dw; j.dst_b = db;
+  j.splits = splits; j.ntaps = L.ntaps(); j.npad = L.cout_blocks() * 16; j.cpad = L.cin_blocks() * 16;
+  j.bias_rows = splits * (L.kind == L_DECONV ? 4 : 1);
+  long long st, sco, sci; L.strides(st, sco, sci);
+  j.s_t = st; j.s_n = sco; j.s_c = sci;
+  j.nseg = chan1(L.cout).to_segs(); j.cseg = L.cin.to_segs();
+  return j;
+}
+
+// y = conv(x) for conv3x3 / conv1x1 (x, y same spatial size)
+inline TapGemm make_conv_fwd(const LayerGeom& L, int dtype, const View& x, const View& y, const void* wp,
+                             const float* bias_pad) {
+  TapGemm g;
+  g.dtype = dtype; g.x[0] = x; g.ntaps = L.ntaps();
+  for (int t = 0; t < g.ntaps; ++t) {
+    g.tap_dy[t] = L.kind == L_CONV3 ? t / 3 - 1 : 0;
+    g.tap_dx[t] = L.kind == L_CONV3 ? t % 3 - 1 : 0;
+    g.tap_view[t] = 0; g.tap_slab[t] = t;
+  }
+  g.cin_blocks = L.cin_blocks(); g.nout = L.cout_blocks() * 16; g.w = wp; g.bias = bias_pad; g.y = y;
+  return g;
+}
+// dx = conv_input_grad(dy): a correlation of dy with the mirrored taps and transposed weights
+inline TapGemm make_conv_dgrad(const LayerGeom& L, int dtype, const View& dy, const View& dx, const void* wp_dgrad,
+                               int out_blocks /* how many leading cin blocks to produce */) {
+  TapGemm g;
+  g.dtype = dtype; g.x[0] = dy; g.ntaps = L.ntaps();
+  for (int t = 0; t < g.ntaps; ++t) {
+    g.tap_dy[t] = L.kind == L_CONV3 ? -(t / 3 - 1) : 0;
+    g.tap_dx[t] = L.kind == L_CONV3 ? -(t % 3 - 1) : 0;
+    g.tap_view[t] = 0; g.tap_slab[t] = t;
+  }
+  g.cin_blocks = L.cout_blocks(); g.nout = out_blocks * 16; g.w = wp_dgrad; g.bias = nullptr; g.y = dx;
+  return g;
+}
+// deconv forward for output parity (a,b): y_ab = x * W_ab + bias
+inline TapGemm make_deconv_fwd(const LayerGeom& L, int dtype, const View& x, const View& y_full, int a, int b,
+                               const void* wp, const float* bias_pad) {
+  TapGemm g;
+  g.dtype = dtype; g.x[0] = x; g.ntaps = 1;
+  g.tap_dy[0] = 0; g.tap_dx[0] = 0; g.tap_view[0] = 0; g.tap_slab[0] = 2 * a + b;
+  g.cin_blocks = L.cin_blocks(); g.nout = L.cout_blocks() * 16; g.w = wp; g.bias = bias_pad;
+  g.y = parity_view(y_full, dtype, a, b);
+  return g;
+}
+inline TapGemm make_deconv_dgrad(const LayerGeom& L, int dtype, const View& dy_full, const View& dx,
+                                 const void* wp_dgrad /* packed with out_blocks == cin_blocks */) {
+  TapGemm g;
+  g.dtype = dtype; g.ntaps = 4;
+  for (int t = 0; t < 4; ++t) {
+    g.x[t] = parity_view(dy_full, dtype, t / 2, t % 2);
+    g.tap_dy[t] = 0; g.tap_dx[t] = 0; g.tap_view[t] = t; g.tap_slab[t] = t;
+  }
+  g.cin_blocks = L.cout_blocks(); g.nout = L.cin_blocks() * 16; g.w = wp_dgrad; g.bias = nullptr; g.y = dx;
+  return g;
+}
+inline TapWgrad make_conv_wgrad(const LayerGeom& L, int dtype, const View& x, const View& dy, float* partial,
+                                float* bias_partial, int splits) {
+  TapWgrad g;
+  g.dtype = dtype; g.dy[0] = dy; g.x[0] = x; g.npairs = L.ntaps();
+  for (int t = 0; t < g.npairs; ++t) {
+    g.pair_dyv[t] = 0; g.pair_xv[t] = 0;
+    g.pair_dy[t] = L.kind == L_CONV3 ? t / 3 - 1 : 0;
+    g.pair_dx[t] = L.kind == L_CONV3 ? t % 3 - 1 : 0;
+  }
+  g.n_blocks = L.cout_blocks(); g.c_blocks = L.cin_blocks();
+  g.partial = partial; g.bias_partial = bias_partial; g.ndyviews = 1; g.splits = splits;
+  return g;
+}
+inline TapWgrad make_deconv_wgrad(const LayerGeom& L, int dtype, const View& x, const View& dy_full, float* partial,
+                                  float* bias_partial, int splits) {
+  TapWgrad g;
+  g.dtype = dtype; g.x[0] = x; g.npairs = 4;
+  for (int t = 0; t < 4; ++t) {
+    g.dy[t] = parity_view(dy_full, dtype, t / 2, t % 2);
+    g.pair_dyv[t] = t; g.pair_xv[t] = 0; g.pair_dy[t] = 0; g.pair_dx[t] = 0;
+  }
+  g.n_blocks = L.cout_blocks(); g.c_blocks = L.cin_blocks();
+  g.partial = partial; g.bias_partial = bias_partial; g.ndyviews = 4; g.splits = splits;
+  return g;
+}
+
+// bias padding (one launch for up to 32 vectors)
+struct BiasPadJob { const float* src; float* dst; int n; int npad; };
+int launch_bias_pad(const BiasPadJob* jobs, int njobs, cudaStream_t st);
+// NCHW fp32 (all channels) <-> multi-block C16 view
+int launch_nchw_to_c16_multi(const float* src, int C, const View& dst, int dtype, cudaStream_t st);
+int launch_c16_to_nchw_multi(const View& src, int dtype, float* dst, int C, cudaStream_t st);
+
+}  // namespace n2n

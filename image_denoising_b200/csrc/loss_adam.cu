@@ -1,0 +1,230 @@
+// loss_adam.cu — fused N2N loss (training_script.md:146-153), fused L1 + gradient loss
+// (finetune.py:153-162, :283-285) and multi-tensor Adam (train.py:332).  All HBM-bound:
+// one pass over the operands, vector loads, deterministic two-stage reductions (per-block
+// partials in double, summed in a fixed order by the last block to finish).
+#include "common.cuh"
+
+namespace n2n {
+
+constexpr int kRedThreads = 256;
+constexpr int kMaxRedBlocks = kSMs * 4;
+
+struct RedWs {              // layout of the loss workspace
+  unsigned int counter;     // must be zero on entry; reset by the finishing block
+  unsigned int pad[3];
+  double partial[kMaxRedBlocks][4];
+};
+
+template <int NQ>
+__device__ __forceinline__ void block_reduce(double (&v)[NQ], double* smem /* [NQ][8] */) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int q = 0; q < NQ; ++q) smem[q * 8 + warp] = v[q];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < NQ; ++q) {
+      double s = 0;
+      for (int w = 0; w < kRedThreads / 32; ++w) s += smem[q * 8 + w];
+      v[q] = s;
+    }
+  }
+}
+
+// Returns true (in thread 0 of exactly one block) once every block has published its partials.
+__device__ __forceinline__ bool last_block_done(RedWs* ws) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&ws->counter, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) __threadfence();
+  }
+  __syncthreads();
+  return last;
+}
+
+// ---- N2N loss --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads)
+n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, const float* __restrict__ den1,
+                const float* __restrict__ den2, float lam, float gscale, long long count, float* __restrict__ loss3,
+                float* __restrict__ grad, RedWs* ws) {
+  __shared__ double red[2 * 8];
+  double acc[2] = {0.0, 0.0};
+  const float k = gscale * 2.0f / (float)count;
+  const long long nvec = count / 4;
+  const bool vec_ok = ((((uintptr_t)out | (uintptr_t)sub2 | (uintptr_t)den1 | (uintptr_t)den2 | (uintptr_t)grad) & 15) == 0);
+  long long start_tail = 0;
+  if (vec_ok) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float4 o = reinterpret_cast<const float4*>(out)[i];
+      const float4 s = reinterpret_cast<const float4*>(sub2)[i];
+      const float4 a = reinterpret_cast<const float4*>(den1)[i];
+      const float4 b = reinterpret_cast<const float4*>(den2)[i];
+      const float d[4] = {o.x - s.x, o.y - s.y, o.z - s.z, o.w - s.w};
+      const float e[4] = {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
+      float g[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float r = d[q] - e[q];
+        acc[0] += (double)(d[q] * d[q]);
+        acc[1] += (double)(r * r);
+        g[q] = k * (d[q] + lam * r);
+      }
+      if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    start_tail = nvec * 4;
+  }
+  for (long long i = start_tail + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float d = out[i] - sub2[i];
+    const float r = d - (den1[i] - den2[i]);
+    acc[0] += (double)(d * d);
+    acc[1] += (double)(r * r);
+    if (grad) grad[i] = k * (d + lam * r);
+  }
+  block_reduce<2>(acc, red);
+  if (threadIdx.x == 0) { ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; }
+  if (last_block_done(ws) && threadIdx.x == 0) {
+    double s0 = 0, s1 = 0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) { s0 += ws->partial[b][0]; s1 += ws->partial[b][1]; }
+    const float l1 = (float)(s0 / (double)count);
+    const float l2 = lam * (float)(s1 / (double)count);
+    loss3[0] = l1 + l2; loss3[1] = l1; loss3[2] = l2;
+    ws->counter = 0;
+  }
+}
+
+// ---- L1 + gradient-consistency loss ------------------------------------------------------
+// e = pred - target.  loss = mean|e| + lg * ( mean_x |e[x+1]-e[x]| + mean_y |e[y+1]-e[y]| )
+// d/de[y,x] = sgn(e)/M + lg/Mx * (sgn(dx[x-1]) - sgn(dx[x])) + lg/My * (sgn(dy[y-1]) - sgn(dy[y]))
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(kRedThreads)
+l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int planes, int h, int w,
+                   float lg, float gscale, float* __restrict__ loss3, float* __restrict__ grad, RedWs* ws) {
+  __shared__ double red[3 * 8];
+  double acc[3] = {0.0, 0.0, 0.0};
+  const long long hw = (long long)h * w, count = (long long)planes * hw;
+  const long long cx = (long long)planes * h * (w - 1), cy = (long long)planes * (h - 1) * w;
+  const float k1 = gscale / (float)count;
+  const float kx = cx > 0 ? gscale * lg / (float)cx : 0.f;
+  const float ky = cy > 0 ? gscale * lg / (float)cy : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % hw;
+    const int y = (int)(r / w), x = (int)(r - (long long)y * w);
+    const float e = pred[i] - tgt[i];
+    acc[0] += (double)fabsf(e);
+    float g = k1 * sgnf(e);
+    if (x + 1 < w) {
+      const float dd = (pred[i + 1] - pred[i]) - (tgt[i + 1] - tgt[i]);
+      acc[1] += (double)fabsf(dd);
+      g -= kx * sgnf(dd);
+    }
+    if (x > 0) {
+      const float dd = (pred[i] - pred[i - 1]) - (tgt[i] - tgt[i - 1]);
+      g += kx * sgnf(dd);
+    }
+    if (y + 1 < h) {
+      const float dd = (pred[i + w] - pred[i]) - (tgt[i + w] - tgt[i]);
+      acc[2] += (double)fabsf(dd);
+      g -= ky * sgnf(dd);
+    }
+    if (y > 0) {
+      const float dd = (pred[i] - pred[i - w]) - (tgt[i] - tgt[i - w]);
+      g += ky * sgnf(dd);
+    }
+    if (grad) grad[i] = g;
+  }
+  block_reduce<3>(acc, red);
+  if (threadIdx.x == 0) {
+    ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; ws->partial[blockIdx.x][2] = acc[2];
+  }
+  if (last_block_done(ws) && threadIdx.x == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) { s0 += ws->partial[b][0]; s1 += ws->partial[b][1]; s2 += ws->partial[b][2]; }
+    const float l1 = (float)(s0 / (double)count);
+    const float gx = cx > 0 ? (float)(s1 / (double)cx) : 0.f;
+    const float gy = cy > 0 ? (float)(s2 / (double)cy) : 0.f;
+    const float lgr = gx + gy;
+    loss3[0] = l1 + lg * lgr; loss3[1] = l1; loss3[2] = lgr;
+    ws->counter = 0;
+  }
+}
+
+// ---- multi-tensor Adam ---------------------------------------------------------------------
+// torch.optim.Adam (defaults, no amsgrad / weight decay), same operation order as
+// torch/optim/adam.py: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, -lr/bc1).
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ blocks, float b1, float b2,
+                  float eps, float step_size, float inv_sqrt_bc2_recip /* sqrt(bc2) */, float gscale) {
+  const int t = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
+  const long long* row = table + 5 * (long long)t;
+  float* p = reinterpret_cast<float*>(row[0]);
+  const float* g = reinterpret_cast<const float*>(row[1]);
+  float* m = reinterpret_cast<float*>(row[2]);
+  float* v = reinterpret_cast<float*>(row[3]);
+  const long long n = row[4];
+  const long long base = (long long)chunk * N2N_ADAM_CHUNK;
+  const float w1 = 1.0f - b1, w2 = 1.0f - b2;
+  for (long long i = base + threadIdx.x; i < base + N2N_ADAM_CHUNK && i < n; i += blockDim.x) {
+    const float gi = g[i] * gscale;
+    float mi = m[i], vi = v[i];
+    mi = mi + w1 * (gi - mi);
+    vi = vi * b2 + w2 * gi * gi;
+    const float denom = sqrtf(vi) / inv_sqrt_bc2_recip + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi; v[i] = vi;
+  }
+}
+
+}  // namespace n2n
+
+using namespace n2n;
+
+extern "C" size_t n2n_loss_workspace_bytes(int64_t) { return sizeof(RedWs); }
+
+extern "C" int n2n_loss_n2n_fwdbwd(const float* out, const float* sub2, const float* den1, const float* den2,
+                                   float lam, float grad_scale, int64_t count, float* loss3, float* grad,
+                                   void* workspace, void* stream) {
+  N2N_CHECK_ARG(out && sub2 && den1 && den2 && loss3 && workspace && count > 0, "loss_n2n: bad arguments");
+  int grid = grid_for(count / 4 + 1, kRedThreads, 4);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  n2n_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(out, sub2, den1, den2, lam, grad_scale, count,
+                                                                  loss3, grad, (RedWs*)workspace);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, int n, int c, int h, int w,
+                                      float lambda_grad, float grad_scale, float* loss3, float* grad,
+                                      void* workspace, void* stream) {
+  N2N_CHECK_ARG(pred && target && loss3 && workspace && n > 0 && c > 0 && h > 0 && w > 0, "loss_l1grad: bad arguments");
+  const long long count = (long long)n * c * h * w;
+  int grid = grid_for(count, kRedThreads, 4);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  l1grad_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(pred, target, n * c, h, w, lambda_grad,
+                                                                     grad_scale, loss3, grad, (RedWs*)workspace);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_adam_multi(const int64_t* table, int ntensors, const int32_t* blocks, int nblocks, float lr,
+                              float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  N2N_CHECK_ARG(table && blocks && ntensors > 0 && nblocks > 0 && step >= 1, "adam_multi: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float sqrt_bc2 = (float)sqrt(bc2);
+  adam_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, blocks, beta1, beta2, eps,
+                                                              step_size, sqrt_bc2, grad_scale);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}

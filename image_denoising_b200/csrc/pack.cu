@@ -1,0 +1,137 @@
+// pack.cu — weight repack (PyTorch fp32 layouts -> engine layouts) and the inverse reduction of
+// weight-gradient partials back into PyTorch-layout fp32 gradients.
+//
+// Engine weight layouts (one "slab" per tap t; n = GEMM output channel, c = contraction channel):
+//   fp32 engine : Wp[t][n][c]                     n < nout_pad, c < 16*cin_blocks, zero padded
+//   bf16 engine : the exact shared-memory image the tcgen05 kernel wants, so that one
+//                 cp.async.bulk per pipeline stage brings a ready-to-use B operand:
+//                 Wp[t][g][j][n][16] with g = channel-block group (3 blocks = 48 channels per
+//                 stage), j = block in group, rows of 32 bytes in the K-major SWIZZLE_32B
+//                 pattern (16-byte chunk index XOR bit 2 of the row index).
+#include "common.cuh"
+
+namespace n2n {
+
+constexpr int kGroupBlocks = 3;   // channel blocks per pipeline stage of the bf16 engine
+
+size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks) {
+  if (dtype == N2N_BF16) {
+    const int ngroups = (cin_blocks + kGroupBlocks - 1) / kGroupBlocks;
+    return (size_t)ntaps * ngroups * kGroupBlocks * nout_pad * 32;
+  }
+  return (size_t)ntaps * nout_pad * cin_blocks * 16 * sizeof(float);
+}
+
+__device__ __forceinline__ int seg_lookup(const Segs& s, int dst) {
+  for (int i = 0; i < s.n; ++i)
+    if (dst >= s.dst0[i] && dst < s.dst0[i] + s.cnt[i]) return s.src0[i] + (dst - s.dst0[i]);
+  return -1;
+}
+
+struct PackBatch { PackJob j[8]; int n; };
+struct UnpackBatch { UnpackJob j[8]; int n; };
+
+template <bool BF16>
+__global__ void pack_kernel(const __grid_constant__ PackBatch b) {
+  const PackJob& J = b.j[blockIdx.y];
+  const int cpad = J.cin_blocks * 16;
+  const long long total = (long long)J.ntaps * J.nout_pad * cpad;
+  const int ngroups = (J.cin_blocks + kGroupBlocks - 1) / kGroupBlocks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const int n = (int)((i / cpad) % J.nout_pad);
+    const int t = (int)(i / ((long long)cpad * J.nout_pad));
+    const int sn = seg_lookup(J.nseg, n), sc = seg_lookup(J.cseg, c);
+    const float v = (sn >= 0 && sc >= 0) ? J.src[t * J.s_t + sn * J.s_n + sc * J.s_c] : 0.f;
+    if (BF16) {
+      const int cb = c >> 4, e = c & 15;
+      const int g = cb / kGroupBlocks, jj = cb - g * kGroupBlocks;
+      const size_t byte = ((size_t)((t * ngroups + g) * kGroupBlocks + jj) * J.nout_pad + n) * 32 +
+                          ((((e >> 3) ^ ((n >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>((char*)J.dst + byte) = __float2bfloat16_rn(v);
+    } else {
+      ((float*)J.dst)[i] = v;
+    }
+  }
+  if (BF16) {
+    // zero the channel blocks that pad the last group (the MMA never reads them, the bulk copy does)
+    const int padb = ngroups * kGroupBlocks - J.cin_blocks;
+    if (padb > 0) {
+      const long long ptotal = (long long)J.ntaps * padb * J.nout_pad * 16;
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ptotal;
+           i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i & 15);
+        const int n = (int)((i >> 4) % J.nout_pad);
+        const int pb = (int)((i / (16LL * J.nout_pad)) % padb);
+        const int t = (int)(i / (16LL * J.nout_pad * padb));
+        const int jj = (J.cin_blocks % kGroupBlocks) + pb;
+        const size_t byte = ((size_t)((t * ngroups + (ngroups - 1)) * kGroupBlocks + jj) * J.nout_pad + n) * 32 + e * 2;
+        *reinterpret_cast<__nv_bfloat16*>((char*)J.dst + byte) = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+__global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
+  const UnpackJob& J = b.j[blockIdx.y];
+  const long long plane = (long long)J.cpad * J.npad;
+  const long long total = (long long)J.ntaps * plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % J.npad);
+    const int c = (int)((i / J.npad) % J.cpad);
+    const int t = (int)(i / plane);
+    const int sn = seg_lookup(J.nseg, n), sc = seg_lookup(J.cseg, c);
+    if (sn < 0 || sc < 0) continue;
+    float s = 0.f;
+    for (int sp = 0; sp < J.splits; ++sp) s += J.partial[(long long)sp * total + i];
+    J.dst_w[t * J.s_t + sn * J.s_n + sc * J.s_c] = s;
+  }
+  if (J.dst_b && J.bias_partial) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < J.npad; n += gridDim.x * blockDim.x) {
+      const int sn = seg_lookup(J.nseg, n);
+      if (sn < 0) continue;
+      float s = 0.f;
+      for (int sp = 0; sp < J.bias_rows; ++sp) s += J.bias_partial[(long long)sp * J.npad + n];
+      J.dst_b[sn] = s;
+    }
+  }
+}
+
+int launch_pack(const PackJob* jobs, int njobs, int dtype, cudaStream_t st) {
+  for (int base = 0; base < njobs; base += 8) {
+    PackBatch b;
+    b.n = njobs - base < 8 ? njobs - base : 8;
+    long long maxtotal = 1;
+    for (int i = 0; i < b.n; ++i) {
+      b.j[i] = jobs[base + i];
+      long long tot = (long long)b.j[i].ntaps * b.j[i].nout_pad * b.j[i].cin_blocks * 16;
+      if (tot > maxtotal) maxtotal = tot;
+    }
+    dim3 grid(grid_for(maxtotal, 256, 2), b.n);
+    if (dtype == N2N_BF16) pack_kernel<true><<<grid, 256, 0, st>>>(b);
+    else pack_kernel<false><<<grid, 256, 0, st>>>(b);
+    N2N_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st) {
+  for (int base = 0; base < njobs; base += 8) {
+    UnpackBatch b;
+    b.n = njobs - base < 8 ? njobs - base : 8;
+    long long maxtotal = 1;
+    for (int i = 0; i < b.n; ++i) {
+      b.j[i] = jobs[base + i];
+      long long tot = (long long)b.j[i].ntaps * b.j[i].npad * b.j[i].cpad;
+      if (tot > maxtotal) maxtotal = tot;
+    }
+    dim3 grid(grid_for(maxtotal, 256, 2), b.n);
+    unpack_kernel<<<grid, 256, 0, st>>>(b);
+    N2N_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace n2n

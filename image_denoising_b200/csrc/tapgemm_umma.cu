@@ -1,0 +1,371 @@
+// tapgemm_umma.cu — the bf16 tensor-core engine for the generic tap GEMM (conv3x3 / conv1x1 /
+// ConvTranspose2x2, forward and input-gradient): an implicit GEMM on tcgen05 with the accumulator
+// in TMEM, the activation operand fed by TMA straight from the C16 tensor (zero padding = TMA
+// out-of-bounds fill, no im2col buffer), and the packed weights fed by cp.async.bulk.
+//
+//   D[128 pixels, nout] = sum over (tap, 48-channel group)  A_tap[128 px, 48 ch] * W_tap[nout, 48 ch]^T
+//
+// One CTA = one 128-pixel output tile (bw x bh pixels of one image), 6 warps:
+//   warp 0 : TMA producer   (one lane): per stage one 5-D tensor load (A) + one bulk copy (B)
+//   warp 1 : MMA issuer     (one lane): <=3 tcgen05.mma (K=16 each) per stage, commit -> stage free
+//   warps 2-5: epilogue: tcgen05.ld 16 columns at a time -> bias / addend / LeakyReLU / mask ->
+//              bf16 C16 store (32 B per pixel per block, contiguous across the warp) or fp32 NCHW
+// A 4-stage mbarrier ring decouples the three roles; two CTAs fit per SM, so one tile's epilogue
+// overlaps the other's main loop.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace n2n {
+
+using namespace umma;
+
+constexpr int kStages = 4;
+constexpr int kGroupBlocks = 3;
+constexpr int kThreads = 192;
+constexpr uint32_t kStageABytes = kGroupBlocks * 128 * 32;
+
+struct UmmaGemmParams {
+  CUtensorMap tmap[4];
+  int ntaps;
+  int8_t tap_dy[9], tap_dx[9], tap_view[9], tap_slab[9];
+  int cin_blocks, ngroups, gb, nout;
+  const uint8_t* w;
+  const float* bias;
+  View y;
+  int has_addend; View addend;
+  int has_mask; View mask;
+  int act; float slope;
+  float* out_nchw; int out_c;
+  int bw, bh, tiles_x, tiles_y, rows;
+  uint32_t stage_b_bytes, tx_bytes, tmem_cols, idesc;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * kStages + 1];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kStageABytes + p.stage_b_bytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * kStages);
+
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int img = tile / p.tiles_y;
+  const int x0 = tx * p.bw, y0 = ty * p.bh;
+  const int iters = p.ntaps * p.ngroups;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int t = it / p.ngroups, g = it - t * p.ngroups;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem0 + stage * stage_bytes;
+        const uint32_t b_dst = a_dst + kStageABytes;
+        mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+        tma_load_5d(a_dst, &p.tmap[p.tap_view[t]], full_bar(stage), 0, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
+                    g * kGroupBlocks, img);
+        const uint8_t* wsrc = p.w + ((size_t)(p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * p.nout * 32;
+        bulk_load(b_dst, wsrc, (uint32_t)(p.gb * p.nout * 32), full_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t a_sub = (uint32_t)p.rows * 32u, b_sub = (uint32_t)p.nout * 32u;
+      for (int it = 0; it < iters; ++it) {
+        const int g = it % p.ngroups;
+        int nb = p.cin_blocks - g * kGroupBlocks;
+        if (nb > kGroupBlocks) nb = kGroupBlocks;
+        mbar_wait(full_bar(stage), phase);
+        fence_after_sync();
+        const uint32_t a_base = smem0 + stage * stage_bytes;
+        const uint32_t b_base = a_base + kStageABytes;
+        for (int j = 0; j < nb; ++j) {
+          const uint64_t ad = make_smem_desc(a_base + j * a_sub, 16, 256, kSwizzle32);
+          const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
+          mma_bf16(tmem_base, ad, bd, p.idesc, (it | j) != 0);
+        }
+        mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
+        if (it == iters - 1) mma_commit(tmem_full_bar);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32) ----
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int py = m / p.bw, px = m - py * p.bw;
+    const int y = y0 + py, x = x0 + px;
+    const bool valid = (m < p.rows) && (y < p.y.H) && (x < p.y.W);
+    mbar_wait(tmem_full_bar, 0);
+    fence_after_sync();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const long long ypix = (long long)img * p.y.sN + (long long)y * p.y.sY + (long long)x * p.y.sX;
+    const long long apix = (long long)img * p.addend.sN + (long long)y * p.addend.sY + (long long)x * p.addend.sX;
+    const long long mpix = (long long)img * p.mask.sN + (long long)y * p.mask.sY + (long long)x * p.mask.sX;
+    for (int cb = 0; cb < p.nout / 16; ++cb) {
+      float v[16];
+      tmem_ld16(lane_addr + cb * 16, v);
+      if (valid) {
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(b4 + q);
+            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+          }
+        }
+        if (p.has_addend) {
+          float a[16];
+          Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.addend.ptr + apix + cb * p.addend.sCb, a);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] += a[q];
+        }
+        if (p.act) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+        }
+        if (p.has_mask) {
+          float mk[16];
+          Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.mask.ptr + mpix + cb * p.mask.sCb, mk);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] *= (mk[q] > 0.f ? 1.f : p.slope);
+        }
+        if (p.out_nchw) {
+          const long long hw = (long long)p.y.H * p.y.W;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int n = cb * 16 + q;
+            if (n < p.out_c) p.out_nchw[((long long)img * p.out_c + n) * hw + (long long)y * p.y.W + x] = v[q];
+          }
+        } else {
+          Block16<__nv_bfloat16>::store((__nv_bfloat16*)p.y.ptr + ypix + cb * p.y.sCb, v);
+        }
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+int encode_c16_tensor_map(CUtensorMap* out, const View& v, int bw, int bh, int cbox) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return N2N_ERR_CUDA; }
+  cuuint64_t dims[5] = {16, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.Cb, (cuuint64_t)v.N};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sX * 2, (cuuint64_t)v.sY * 2, (cuuint64_t)v.sCb * 2, (cuuint64_t)v.sN * 2};
+  cuuint32_t box[5] = {16, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)cbox, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (v.N == 1) strides[3] = strides[2] * (cuuint64_t)(v.Cb > 0 ? v.Cb : 1);   // any valid value
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p W=%d H=%d Cb=%d N=%d strides=%lld,%lld,%lld,%lld box=%d,%d,%d",
+              (int)r, v.ptr, v.W, v.H, v.Cb, v.N, (long long)strides[0], (long long)strides[1], (long long)strides[2],
+              (long long)strides[3], bw, bh, cbox);
+    return N2N_ERR_CUDA;
+  }
+  return 0;
+}
+
+// Choose the 128-pixel tile shape (bw x bh, bw a power of two) that wastes the fewest pixels.
+void choose_tile(int H, int W, int& bw, int& bh) {
+  long long best = -1;
+  for (int cand = 128; cand >= 8; cand >>= 1) {
+    const int cb = 128 / cand;
+    const long long cost = (long long)((W + cand - 1) / cand) * cand * ((H + cb - 1) / cb) * cb;
+    if (best < 0 || cost < best) { best = cost; bw = cand; bh = cb; }
+  }
+}
+
+int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
+  N2N_CHECK_ARG(g.nout >= 16 && g.nout <= 256 && g.nout % 16 == 0, "tapgemm_umma: nout=%d unsupported", g.nout);
+  static bool attr_set = false;
+  UmmaGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int H = g.y.H, W = g.y.W;
+  int bw, bh;
+  choose_tile(H, W, bw, bh);
+  if (bh > H) bh = H;                    // 8x8 level: a single image supplies only 64 rows
+  p.bw = bw; p.bh = bh; p.rows = bw * bh;
+  p.tiles_x = (W + bw - 1) / bw; p.tiles_y = (H + bh - 1) / bh;
+  p.ntaps = g.ntaps;
+  int nviews = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.tap_dy[t] = (int8_t)g.tap_dy[t]; p.tap_dx[t] = (int8_t)g.tap_dx[t];
+    p.tap_view[t] = (int8_t)g.tap_view[t]; p.tap_slab[t] = (int8_t)g.tap_slab[t];
+    if (g.tap_view[t] + 1 > nviews) nviews = g.tap_view[t] + 1;
+  }
+  p.cin_blocks = g.cin_blocks;
+  p.ngroups = (g.cin_blocks + kGroupBlocks - 1) / kGroupBlocks;
+  p.gb = g.cin_blocks < kGroupBlocks ? g.cin_blocks : kGroupBlocks;
+  p.nout = g.nout;
+  for (int v = 0; v < 4; ++v) {
+    const View& xv = g.x[v < nviews ? v : 0];
+    N2N_CHECK_ARG(xv.H == H && xv.W == W && xv.Cb >= g.cin_blocks, "tapgemm_umma: view %d geometry mismatch", v);
+    N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, p.gb));
+  }
+  p.w = (const uint8_t*)g.w; p.bias = g.bias; p.y = g.y;
+  p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
+  p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
+  p.stage_b_bytes = (uint32_t)align_up((size_t)kGroupBlocks * g.nout * 32, 1024);
+  p.tx_bytes = (uint32_t)(p.gb * p.rows * 32 + p.gb * g.nout * 32);
+  p.tmem_cols = tmem_cols_for(g.nout);
+  p.idesc = make_idesc_bf16(128, g.nout, false, false);
+  const size_t smem = 1024 + (size_t)kStages * (kStageABytes + p.stage_b_bytes);
+  if (!attr_set) {
+    N2N_CUDA(cudaFuncSetAttribute(tapgemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;
+  N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "tapgemm_umma: bad tile count");
+  tapgemm_umma_kernel<<<(unsigned)tiles, kThreads, smem, st>>>(p);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bring-up probe: a single-CTA GEMM D[128, N] = A[128, K] * B[N, K]^T (bf16 -> fp32) whose
+// operands are written to shared memory by ordinary stores in the exact layouts the engines
+// assume.  It validates the descriptor encodings independently of TMA.
+//   variant 0: K-major  SWIZZLE_32B  ([k/16][row][32 B])            — forward / dgrad engine
+//   variant 1: MN-major SWIZZLE_32B  ([mn/16][k][32 B], LBO = atom) — weight-gradient engine
+//   variant 2: as 1 with LBO/SBO swapped (diagnostic)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                  float* __restrict__ D, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* s = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ncols = 256;
+  const uint32_t a_bytes = 128u * K * 2u;
+  uint8_t* sa = s; uint8_t* sb = s + a_bytes;
+  if (variant == 0) {
+    for (int i = threadIdx.x; i < 128 * K; i += 128) {
+      const int r = i / K, k = i % K, kb = k >> 4, e = k & 15;
+      const uint32_t off = (uint32_t)kb * 128 * 32 + r * 32 + ((((e >> 3) ^ ((r >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[i];
+    }
+    for (int i = threadIdx.x; i < N * K; i += 128) {
+      const int r = i / K, k = i % K, kb = k >> 4, e = k & 15;
+      const uint32_t off = (uint32_t)kb * N * 32 + r * 32 + ((((e >> 3) ^ ((r >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(sb + off) = B[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < 128 * K; i += 128) {
+      const int r = i / K, k = i % K, mb = r >> 4, e = r & 15;
+      const uint32_t off = (uint32_t)mb * K * 32 + k * 32 + ((((e >> 3) ^ ((k >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[i];
+    }
+    for (int i = threadIdx.x; i < N * K; i += 128) {
+      const int r = i / K, k = i % K, nb = r >> 4, e = r & 15;
+      const uint32_t off = (uint32_t)nb * K * 32 + k * 32 + ((((e >> 3) ^ ((k >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(sb + off) = B[i];
+    }
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), ncols); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) {
+    const bool mn = variant != 0;
+    const uint32_t idesc = make_idesc_bf16(128, N, mn, mn);
+    for (int kk = 0; kk < K / 16; ++kk) {
+      uint64_t ad, bd;
+      if (variant == 0) {
+        ad = make_smem_desc(smem0 + kk * 128 * 32, 16, 256, kSwizzle32);
+        bd = make_smem_desc(smem0 + a_bytes + kk * N * 32, 16, 256, kSwizzle32);
+      } else if (variant == 1) {
+        ad = make_smem_desc(smem0 + kk * 16 * 32, (uint32_t)K * 32, 256, kSwizzle32);
+        bd = make_smem_desc(smem0 + a_bytes + kk * 16 * 32, (uint32_t)K * 32, 256, kSwizzle32);
+      } else {
+        ad = make_smem_desc(smem0 + kk * 16 * 32, 256, (uint32_t)K * 32, kSwizzle32);
+        bd = make_smem_desc(smem0 + a_bytes + kk * 16 * 32, 256, (uint32_t)K * 32, kSwizzle32);
+      }
+      mma_bf16(tmem_base, ad, bd, idesc, kk != 0);
+    }
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  fence_after_sync();
+  const int m = warp * 32 + lane;
+  for (int cb = 0; cb < N / 16; ++cb) {
+    float v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 16, v);
+    for (int q = 0; q < 16; ++q) D[(long long)m * N + cb * 16 + q] = v[q];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
+}
+
+}  // namespace n2n
+
+using namespace n2n;
+
+extern "C" int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf16, float* d, int m, int n, int k,
+                              void* stream) {
+  N2N_CHECK_ARG(m == 128 && n >= 16 && n <= 256 && n % 16 == 0 && k >= 16 && k % 16 == 0 && k <= 256,
+                "probe_umma: need m=128, n%%16==0 (<=256), k%%16==0 (<=256)");
+  N2N_CHECK_ARG(variant >= 0 && variant <= 2 && a_bf16 && b_bf16 && d, "probe_umma: bad arguments");
+  const size_t smem = 1024 + (size_t)(128 + n) * k * 2;
+  N2N_CUDA(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const __nv_bfloat16*)a_bf16,
+                                                            (const __nv_bfloat16*)b_bf16, d, n, k);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,399 @@
+// unet_plan.cu — native executor for arch_unet.UNet (arch_unet.py:100-260, non-blindspot) and
+// adapter.OutputAdapter (adapter.py:5-26): one C call runs the whole forward (or backward) as a
+// fixed sequence of engine launches over C16 buffers carved out of a caller-owned workspace.
+//
+// Concat is never materialised: ConvTranspose epilogues write blocks [0, c_up) of the level's
+// concat buffer, the encoder's pool kernels write the skip blocks behind them
+// (torch.cat([upsampled, skip]) order, arch_unet.py:62), and the decoder conv reads the whole
+// buffer as one operand.
+#include <vector>
+
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace n2n {
+
+struct Buf { size_t off = 0; int Cb = 0; int lvl = 0; };
+
+enum {
+  B_CAT0, B_CAT1, B_CAT2, B_CAT3, B_CAT4,
+  B_E0, B_E1, B_E2, B_E3, B_E4, B_E5, B_P5, B_E6,
+  B_D5A, B_D5B, B_D4A, B_D4B, B_D3A, B_D3B, B_D2A, B_D2B, B_D1A, B_D1B, B_NA, B_NB, B_OUT,
+  B_COUNT
+};
+
+struct LayerIO {
+  int in_buf, in_cb0, in_cb;     // input blocks [in_cb0, in_cb0+in_cb) of in_buf
+  int out_buf, out_cb0;          // output written at block offset out_cb0 of out_buf
+  bool act;                      // LeakyReLU(0.2) after the layer
+};
+
+}  // namespace n2n
+
+using namespace n2n;
+
+struct n2n_unet_plan {
+  int in_nc, out_nc, nf, N, H, W, dtype;
+  bool bwd;
+  int nfb, c2b, inb, hb;
+  LayerGeom L[25];
+  LayerIO io[25];
+  int dgrad_blocks[25];   // how many input blocks the layer's dgrad produces (0 = none)
+  int splits[25];
+  Buf act[B_COUNT], grd[B_COUNT];
+  size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
+  size_t total = 0;
+  int fwd_launches = 0, bwd_launches = 0;
+
+  int lh(int lvl) const { return H >> lvl; }
+  int lw(int lvl) const { return W >> lvl; }
+  View view(const Buf* set, void* ws, int b, int cb0, int cb) const {
+    const Buf& B = set[b];
+    return make_view((char*)ws + B.off, dtype, N, lh(B.lvl), lw(B.lvl), B.Cb, cb0, cb);
+  }
+};
+
+static void plan_layout(n2n_unet_plan* p) {
+  const int nf = p->nf, in_nc = p->in_nc, out_nc = p->out_nc;
+  p->nfb = cblocks(nf); p->c2b = cblocks(2 * nf); p->inb = cblocks(in_nc); p->hb = cblocks(96);
+  const int nfb = p->nfb, c2b = p->c2b, inb = p->inb, hb = p->hb;
+  auto setbuf = [&](int b, int Cb, int lvl) { p->act[b].Cb = Cb; p->act[b].lvl = lvl; p->grd[b].Cb = Cb; p->grd[b].lvl = lvl; };
+  setbuf(B_CAT0, c2b + inb, 0);
+  setbuf(B_CAT1, c2b + nfb, 1); setbuf(B_CAT2, c2b + nfb, 2); setbuf(B_CAT3, c2b + nfb, 3);
+  setbuf(B_CAT4, nfb + nfb, 4);
+  setbuf(B_E0, nfb, 0); setbuf(B_E1, nfb, 0); setbuf(B_E2, nfb, 1); setbuf(B_E3, nfb, 2); setbuf(B_E4, nfb, 3);
+  setbuf(B_E5, nfb, 4); setbuf(B_P5, nfb, 5); setbuf(B_E6, nfb, 5);
+  setbuf(B_D5A, c2b, 4); setbuf(B_D5B, c2b, 4); setbuf(B_D4A, c2b, 3); setbuf(B_D4B, c2b, 3);
+  setbuf(B_D3A, c2b, 2); setbuf(B_D3B, c2b, 2); setbuf(B_D2A, c2b, 1); setbuf(B_D2B, c2b, 1);
+  setbuf(B_D1A, hb, 0); setbuf(B_D1B, hb, 0); setbuf(B_NA, hb, 0); setbuf(B_NB, hb, 0);
+  setbuf(B_OUT, cblocks(out_nc), 0);
+
+  auto conv3 = [&](int i, ChanSegs cin, int cout) { p->L[i].kind = L_CONV3; p->L[i].cin = cin; p->L[i].cout = cout; };
+  auto conv1 = [&](int i, ChanSegs cin, int cout) { p->L[i].kind = L_CONV1; p->L[i].cin = cin; p->L[i].cout = cout; };
+  auto deconv = [&](int i, int cin, int cout) { p->L[i].kind = L_DECONV; p->L[i].cin = chan1(cin); p->L[i].cout = cout; };
+  auto setio = [&](int i, int ib, int icb0, int icb, int ob, int ocb0, bool act, int dgb) {
+    p->io[i] = LayerIO{ib, icb0, icb, ob, ocb0, act};
+    p->dgrad_blocks[i] = dgb;
+  };
+  // state_dict order (arch_unet.py:114-192)
+  conv3(0, chan1(in_nc), nf);        setio(0, B_CAT0, c2b, inb, B_E0, 0, true, 0);
+  conv3(1, chan1(nf), nf);           setio(1, B_E0, 0, nfb, B_E1, 0, true, nfb);
+  conv3(2, chan1(nf), nf);           setio(2, B_CAT1, c2b, nfb, B_E2, 0, true, nfb);
+  conv3(3, chan1(nf), nf);           setio(3, B_CAT2, c2b, nfb, B_E3, 0, true, nfb);
+  conv3(4, chan1(nf), nf);           setio(4, B_CAT3, c2b, nfb, B_E4, 0, true, nfb);
+  conv3(5, chan1(nf), nf);           setio(5, B_CAT4, nfb, nfb, B_E5, 0, true, nfb);
+  conv3(6, chan1(nf), nf);           setio(6, B_P5, 0, nfb, B_E6, 0, true, nfb);
+  deconv(7, nf, nf);                 setio(7, B_E6, 0, nfb, B_CAT4, 0, false, nfb);
+  conv3(8, chan2(nf, nf), 2 * nf);   setio(8, B_CAT4, 0, 2 * nfb, B_D5A, 0, true, 2 * nfb);
+  conv3(9, chan1(2 * nf), 2 * nf);   setio(9, B_D5A, 0, c2b, B_D5B, 0, true, c2b);
+  const int cats[4] = {B_CAT3, B_CAT2, B_CAT1, B_CAT0};
+  const int das[4] = {B_D4A, B_D3A, B_D2A, B_D1A}, dbs[4] = {B_D4B, B_D3B, B_D2B, B_D1B};
+  const int prev[4] = {B_D5B, B_D4B, B_D3B, B_D2B};
+  for (int k = 0; k < 4; ++k) {
+    const int base = 10 + 3 * k;
+    const bool last = (k == 3);
+    deconv(base, 2 * nf, 2 * nf);    setio(base, prev[k], 0, c2b, cats[k], 0, false, c2b);
+    if (!last) {
+      conv3(base + 1, chan2(2 * nf, nf), 2 * nf);  setio(base + 1, cats[k], 0, c2b + nfb, das[k], 0, true, c2b + nfb);
+      conv3(base + 2, chan1(2 * nf), 2 * nf);      setio(base + 2, das[k], 0, c2b, dbs[k], 0, true, c2b);
+    } else {
+      // arch_unet.py:177-181: literal 96-wide head; the skip is the raw input.
+      conv3(base + 1, chan2(2 * nf, in_nc), 96);   setio(base + 1, cats[k], 0, c2b + inb, das[k], 0, true, c2b);
+      conv3(base + 2, chan1(96), 96);              setio(base + 2, das[k], 0, hb, dbs[k], 0, true, hb);
+    }
+  }
+  conv1(22, chan1(96), 96);          setio(22, B_D1B, 0, hb, B_NA, 0, true, hb);
+  conv1(23, chan1(96), 96);          setio(23, B_NA, 0, hb, B_NB, 0, true, hb);
+  conv1(24, chan1(96), out_nc);      setio(24, B_NB, 0, hb, B_OUT, 0, false, hb);
+
+  // ---- workspace layout ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t es = dtype_size(p->dtype);
+  for (int b = 0; b < B_COUNT; ++b) {
+    if (b == B_OUT) continue;   // forward output goes straight to the caller's NCHW tensor
+    p->act[b].off = take((size_t)p->N * p->act[b].Cb * p->lh(p->act[b].lvl) * p->lw(p->act[b].lvl) * 16 * es);
+  }
+  for (int i = 0; i < 25; ++i) {
+    p->off_wp[i] = take(p->L[i].fwd_pack_bytes(p->dtype));
+    p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
+  }
+  if (p->bwd) {
+    for (int b = 0; b < B_COUNT; ++b)
+      p->grd[b].off = take((size_t)p->N * p->grd[b].Cb * p->lh(p->grd[b].lvl) * p->lw(p->grd[b].lvl) * 16 * es);
+    for (int i = 0; i < 25; ++i) {
+      const LayerIO& io = p->io[i];
+      const long long px = (long long)p->N * p->lh(p->act[io.in_buf].lvl) * p->lw(p->act[io.in_buf].lvl);
+      p->splits[i] = wgrad_default_splits(p->dtype, px);
+      // dgrad weights are packed for the full input width so that dL/dx can be served too
+      p->off_wd[i] = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));
+      p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
+      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
+    }
+  }
+  p->total = off;
+}
+
+extern "C" int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature, int n, int h, int w,
+                                    int dtype, int with_backward) {
+  N2N_CHECK_ARG(plan != nullptr, "unet_plan_create: plan is NULL");
+  N2N_CHECK_ARG(in_nc >= 1 && in_nc <= 16 && out_nc >= 1 && out_nc <= 16, "unet_plan_create: in_nc/out_nc must be in [1,16]");
+  N2N_CHECK_ARG(n_feature >= 1 && n_feature <= 256, "unet_plan_create: n_feature out of range");
+  N2N_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0,
+                "unet_plan_create: need n>=1 and H,W multiples of 32 (got %d,%d,%d)", n, h, w);
+  N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, "unet_plan_create: bad dtype %d", dtype);
+  n2n_unet_plan* p = new n2n_unet_plan();
+  p->in_nc = in_nc; p->out_nc = out_nc; p->nf = n_feature; p->N = n; p->H = h; p->W = w; p->dtype = dtype;
+  p->bwd = with_backward != 0;
+  plan_layout(p);
+  *plan = p;
+  return 0;
+}
+extern "C" void n2n_unet_plan_destroy(n2n_unet_plan* plan) { delete plan; }
+extern "C" size_t n2n_unet_workspace_bytes(const n2n_unet_plan* plan) { return plan ? plan->total : 0; }
+extern "C" int n2n_unet_launches(const n2n_unet_plan* plan, int backward) {
+  return plan ? (backward ? plan->bwd_launches : plan->fwd_launches) : 0;
+}
+
+extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y,
+                                void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && x && y && ws, "unet_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long launches0 = g_launch_count;
+  const int dt = p->dtype;
+  // weights -> engine layout (fwd; dgrad copies too when a backward will follow)
+  {
+    std::vector<PackJob> jobs;
+    BiasPadJob bj[25];
+    for (int i = 0; i < 25; ++i) {
+      jobs.push_back(make_fwd_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
+      if (p->bwd)
+        jobs.push_back(make_dgrad_pack(p->L[i], params[2 * i], (char*)ws + p->off_wd[i], p->L[i].cin_blocks()));
+      bj[i] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), p->L[i].cout, p->L[i].cout_blocks() * 16};
+    }
+    N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
+    N2N_TRY(launch_bias_pad(bj, 25, st));
+  }
+  // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
+  N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
+
+  auto run_layer = [&](int i) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
+    const void* wp = (char*)ws + p->off_wp[i];
+    const float* bias = (const float*)((char*)ws + p->off_bias[i]);
+    if (L.kind == L_DECONV) {
+      View yfull = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      for (int ab = 0; ab < 4; ++ab) {
+        TapGemm g = make_deconv_fwd(L, dt, xin, yfull, ab / 2, ab % 2, wp, bias);
+        N2N_TRY(launch_tapgemm(g, st));
+      }
+      return 0;
+    }
+    TapGemm g;
+    if (io.out_buf == B_OUT) {
+      View dummy = p->view(p->act, ws, B_NB, 0, L.cout_blocks());   // geometry only
+      g = make_conv_fwd(L, dt, xin, dummy, wp, bias);
+      g.out_nchw = y; g.out_c = p->out_nc;
+    } else {
+      g = make_conv_fwd(L, dt, xin, p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks()), wp, bias);
+    }
+    if (io.act) { g.act = 1; g.slope = 0.2f; }
+    return launch_tapgemm(g, st);
+  };
+  auto pool = [&](int src, int dst, int dst_cb0) -> int {
+    return launch_maxpool(p->view(p->act, ws, src, 0, p->nfb), p->view(p->act, ws, dst, dst_cb0, p->nfb), dt, st);
+  };
+  N2N_TRY(run_layer(0));
+  N2N_TRY(run_layer(1)); N2N_TRY(pool(B_E1, B_CAT1, p->c2b));
+  N2N_TRY(run_layer(2)); N2N_TRY(pool(B_E2, B_CAT2, p->c2b));
+  N2N_TRY(run_layer(3)); N2N_TRY(pool(B_E3, B_CAT3, p->c2b));
+  N2N_TRY(run_layer(4)); N2N_TRY(pool(B_E4, B_CAT4, p->nfb));
+  N2N_TRY(run_layer(5)); N2N_TRY(pool(B_E5, B_P5, 0));
+  for (int i = 6; i < 25; ++i) N2N_TRY(run_layer(i));
+  p->fwd_launches = (int)(g_launch_count - launches0);
+  return 0;
+}
+
+extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, const float* dy,
+                                 float* const* grads, float* dx, void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && dy && grads && ws, "unet_backward: null argument");
+  N2N_CHECK_ARG(p->bwd, "unet_backward: plan was created without with_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long launches0 = g_launch_count;
+  const int dt = p->dtype;
+  const bool want_dx = dx != nullptr;
+
+  N2N_TRY(launch_nchw_to_c16(dy, p->out_nc, p->view(p->grd, ws, B_OUT, 0, cblocks(p->out_nc)), dt, st));
+
+  // grad of layer i's OUTPUT lives in grd[out_buf] blocks [out_cb0, +cout_blocks).
+  auto wgrad = [&](int i) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
+    View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+    float* partial = (float*)((char*)ws + p->off_partial[i]);
+    float* bpartial = (float*)((char*)ws + p->off_bpartial[i]);
+    TapWgrad g = (L.kind == L_DECONV) ? make_deconv_wgrad(L, dt, xin, gy, partial, bpartial, p->splits[i])
+                                      : make_conv_wgrad(L, dt, xin, gy, partial, bpartial, p->splits[i]);
+    return launch_tapwgrad(g, st);
+  };
+  // dgrad of layer i into grd[in_buf] (first `blocks` input blocks); mask_by_input multiplies by
+  // lrelu'(input) (valid because the input is the in-place activated output of the previous
+  // layer, arch_unet.py:113); add_existing accumulates onto what the skip path already wrote.
+  auto dgrad = [&](int i, int blocks, bool mask_by_input, bool add_existing) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+    View gx = p->view(p->grd, ws, io.in_buf, io.in_cb0, blocks);
+    const void* wd = (char*)ws + p->off_wd[i];
+    TapGemm g = (L.kind == L_DECONV) ? make_deconv_dgrad(L, dt, gy, gx, wd)
+                                     : make_conv_dgrad(L, dt, gy, gx, wd, L.cin_blocks());
+    g.nout = blocks * 16;
+    if (mask_by_input) { g.has_mask = true; g.mask = p->view(p->act, ws, io.in_buf, io.in_cb0, blocks); g.slope = 0.2f; }
+    if (add_existing) { g.has_addend = true; g.addend = gx; }
+    return launch_tapgemm(g, st);
+  };
+  auto unpool = [&](int act_buf, int gpool_buf, int gpool_cb0) -> int {
+    return launch_unpool_lrelu(p->view(p->act, ws, act_buf, 0, p->nfb), p->view(p->grd, ws, gpool_buf, gpool_cb0, p->nfb),
+                               p->view(p->grd, ws, act_buf, 0, p->nfb), 0.2f, dt, st);
+  };
+
+  // head + level-0 decoder
+  for (int i = 24; i >= 21; --i) { N2N_TRY(wgrad(i)); N2N_TRY(dgrad(i, p->L[i].cin_blocks(), true, false)); }
+  N2N_TRY(wgrad(20));
+  N2N_TRY(dgrad(20, p->c2b + p->inb, false, false));
+  // decoder levels 1..4: up{k} then dec_conv{k+1}b / a
+  for (int base = 19; base >= 10; base -= 3) {
+    N2N_TRY(wgrad(base));     N2N_TRY(dgrad(base, p->c2b, true, false));          // up_k: input is dec_conv_{k+1}b output
+    N2N_TRY(wgrad(base - 1)); N2N_TRY(dgrad(base - 1, p->c2b, true, false));      // dec_conv b
+    N2N_TRY(wgrad(base - 2)); N2N_TRY(dgrad(base - 2, p->L[base - 2].cin_blocks(), false, false));  // dec_conv a -> concat
+  }
+  N2N_TRY(wgrad(7)); N2N_TRY(dgrad(7, p->nfb, true, false));                      // up5: input is enc_conv6 output
+  N2N_TRY(wgrad(6)); N2N_TRY(dgrad(6, p->nfb, false, false));                     // enc_conv6: input is pool5 (no act)
+  N2N_TRY(unpool(B_E5, B_P5, 0));
+  // encoder: the pooled tensors also feed the skip connections, whose grads are already in the
+  // concat-grad buffers -> accumulate.
+  N2N_TRY(wgrad(5)); N2N_TRY(dgrad(5, p->nfb, false, true)); N2N_TRY(unpool(B_E4, B_CAT4, p->nfb));
+  N2N_TRY(wgrad(4)); N2N_TRY(dgrad(4, p->nfb, false, true)); N2N_TRY(unpool(B_E3, B_CAT3, p->c2b));
+  N2N_TRY(wgrad(3)); N2N_TRY(dgrad(3, p->nfb, false, true)); N2N_TRY(unpool(B_E2, B_CAT2, p->c2b));
+  N2N_TRY(wgrad(2)); N2N_TRY(dgrad(2, p->nfb, false, true)); N2N_TRY(unpool(B_E1, B_CAT1, p->c2b));
+  N2N_TRY(wgrad(1)); N2N_TRY(dgrad(1, p->nfb, true, false));
+  N2N_TRY(wgrad(0));
+  if (want_dx) {
+    N2N_TRY(dgrad(0, p->inb, false, true));
+    N2N_TRY(launch_c16_to_nchw(p->view(p->grd, ws, B_CAT0, p->c2b, p->inb), dt, dx, p->in_nc, st));
+  }
+  // partials -> PyTorch-layout fp32 gradients
+  {
+    UnpackJob jobs[25];
+    for (int i = 0; i < 25; ++i)
+      jobs[i] = make_unpack(p->L[i], (const float*)((char*)ws + p->off_partial[i]),
+                            (const float*)((char*)ws + p->off_bpartial[i]), p->splits[i], grads[2 * i], grads[2 * i + 1]);
+    N2N_TRY(launch_unpack(jobs, 25, st));
+  }
+  p->bwd_launches = (int)(g_launch_count - launches0);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Output adapter (adapter.py:5-26)
+// ------------------------------------------------------------------------------------------
+struct n2n_adapter_plan {
+  int C, hid, N, H, W, dtype; bool bwd;
+  LayerGeom L[2];
+  size_t off_cat, off_h, off_gout, off_gh, off_wp[2], off_wd1, off_bias[2], off_partial[2], off_bpartial[2];
+  int splits;
+  size_t total;
+};
+
+extern "C" int n2n_adapter_plan_create(n2n_adapter_plan** plan, int channels, int hidden, int n, int h, int w,
+                                       int dtype, int with_backward) {
+  N2N_CHECK_ARG(plan && channels >= 1 && channels <= 16 && hidden >= 1 && hidden <= 256 && n >= 1 && h >= 1 && w >= 1,
+                "adapter_plan_create: bad arguments");
+  N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, "adapter_plan_create: bad dtype");
+  n2n_adapter_plan* p = new n2n_adapter_plan();
+  p->C = channels; p->hid = hidden; p->N = n; p->H = h; p->W = w; p->dtype = dtype; p->bwd = with_backward != 0;
+  p->L[0].kind = L_CONV3; p->L[0].cin = chan2(channels, channels); p->L[0].cout = hidden;   // cat[noisy, base_out]
+  p->L[1].kind = L_CONV3; p->L[1].cin = chan1(hidden); p->L[1].cout = channels;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t px = (size_t)n * h * w * 16 * dtype_size(dtype);
+  p->off_cat = take(2 * px);
+  p->off_h = take(cblocks(hidden) * px);
+  for (int i = 0; i < 2; ++i) {
+    p->off_wp[i] = take(p->L[i].fwd_pack_bytes(dtype));
+    p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
+  }
+  p->splits = wgrad_default_splits(dtype, (long long)n * h * w);
+  if (p->bwd) {
+    p->off_gout = take(px);
+    p->off_gh = take(cblocks(hidden) * px);
+    p->off_wd1 = take(p->L[1].dgrad_pack_bytes(dtype, p->L[1].cin_blocks()));
+    for (int i = 0; i < 2; ++i) {
+      p->off_partial[i] = take(p->L[i].partial_bytes(p->splits));
+      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits));
+    }
+  }
+  p->total = off;
+  *plan = p;
+  return 0;
+}
+extern "C" void n2n_adapter_plan_destroy(n2n_adapter_plan* plan) { delete plan; }
+extern "C" size_t n2n_adapter_workspace_bytes(const n2n_adapter_plan* plan) { return plan ? plan->total : 0; }
+
+extern "C" int n2n_adapter_forward(n2n_adapter_plan* p, const float* const* params, const float* noisy,
+                                   const float* base_out, float* out, void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && noisy && base_out && out && ws, "adapter_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dt = p->dtype;
+  const int hb = cblocks(p->hid);
+  View cat = make_view((char*)ws + p->off_cat, dt, p->N, p->H, p->W, 2, 0, 2);
+  View hv = make_view((char*)ws + p->off_h, dt, p->N, p->H, p->W, hb, 0, hb);
+  PackJob pj[3];
+  int nj = 0;
+  pj[nj++] = make_fwd_pack(p->L[0], params[0], (char*)ws + p->off_wp[0]);
+  pj[nj++] = make_fwd_pack(p->L[1], params[2], (char*)ws + p->off_wp[1]);
+  if (p->bwd) pj[nj++] = make_dgrad_pack(p->L[1], params[2], (char*)ws + p->off_wd1, p->L[1].cin_blocks());
+  N2N_TRY(launch_pack(pj, nj, dt, st));
+  BiasPadJob bj[2] = {{params[1], (float*)((char*)ws + p->off_bias[0]), p->hid, hb * 16},
+                      {params[3], (float*)((char*)ws + p->off_bias[1]), p->C, 16}};
+  N2N_TRY(launch_bias_pad(bj, 2, st));
+  N2N_TRY(launch_nchw_to_c16(noisy, p->C, sub_blocks(cat, dt, 0, 1), dt, st));
+  N2N_TRY(launch_nchw_to_c16(base_out, p->C, sub_blocks(cat, dt, 1, 1), dt, st));
+  TapGemm g0 = make_conv_fwd(p->L[0], dt, cat, hv, (char*)ws + p->off_wp[0], (const float*)((char*)ws + p->off_bias[0]));
+  g0.act = 1; g0.slope = 0.f;                                   // ReLU (adapter.py:16)
+  N2N_TRY(launch_tapgemm(g0, st));
+  TapGemm g1 = make_conv_fwd(p->L[1], dt, hv, sub_blocks(cat, dt, 0, 1), (char*)ws + p->off_wp[1],
+                             (const float*)((char*)ws + p->off_bias[1]));
+  g1.has_addend = true; g1.addend = sub_blocks(cat, dt, 1, 1);  // + base_out (adapter.py:26)
+  g1.out_nchw = out; g1.out_c = p->C;
+  return launch_tapgemm(g1, st);
+}
+
+extern "C" int n2n_adapter_backward(n2n_adapter_plan* p, const float* const* params, const float* dout,
+                                    float* const* grads, void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && dout && grads && ws, "adapter_backward: null argument");
+  N2N_CHECK_ARG(p->bwd, "adapter_backward: plan was created without with_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dt = p->dtype;
+  const int hb = cblocks(p->hid);
+  View cat = make_view((char*)ws + p->off_cat, dt, p->N, p->H, p->W, 2, 0, 2);
+  View hv = make_view((char*)ws + p->off_h, dt, p->N, p->H, p->W, hb, 0, hb);
+  View gout = make_view((char*)ws + p->off_gout, dt, p->N, p->H, p->W, 1, 0, 1);
+  View gh = make_view((char*)ws + p->off_gh, dt, p->N, p->H, p->W, hb, 0, hb);
+  N2N_TRY(launch_nchw_to_c16(dout, p->C, gout, dt, st));
+  float* part[2] = {(float*)((char*)ws + p->off_partial[0]), (float*)((char*)ws + p->off_partial[1])};
+  float* bpart[2] = {(float*)((char*)ws + p->off_bpartial[0]), (float*)((char*)ws + p->off_bpartial[1])};
+  TapWgrad w1 = make_conv_wgrad(p->L[1], dt, hv, gout, part[1], bpart[1], p->splits);
+  N2N_TRY(launch_tapwgrad(w1, st));
+  TapGemm d1 = make_conv_dgrad(p->L[1], dt, gout, gh, (char*)ws + p->off_wd1, hb);
+  d1.has_mask = true; d1.mask = hv; d1.slope = 0.f;             // ReLU'
+  N2N_TRY(launch_tapgemm(d1, st));
+  TapWgrad w0 = make_conv_wgrad(p->L[0], dt, cat, gh, part[0], bpart[0], p->splits);
+  N2N_TRY(launch_tapwgrad(w0, st));
+  UnpackJob uj[2] = {make_unpack(p->L[0], part[0], bpart[0], p->splits, grads[0], grads[1]),
+                     make_unpack(p->L[1], part[1], bpart[1], p->splits, grads[2], grads[3])};
+  return launch_unpack(uj, 2, st);
+}

@@ -1,0 +1,247 @@
+"""Thin torch-tensor wrappers over the kernel-level C-ABI entry points (one Python
+function per entry point of include/n2n_b200.h).  Everything here takes and returns
+CUDA tensors; nothing falls back to PyTorch arithmetic."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _ext
+from ._ext import check, lib, ptr, require_cuda, stream_ptr
+
+_ELEM = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2, torch.float64: 8, torch.uint8: 1,
+         torch.int8: 1, torch.int16: 2, torch.int32: 4, torch.int64: 8, torch.bool: 1}
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------- sub-sampler
+def mask_pair_from_rdidx(rd_idx: torch.Tensor, want_masks: bool = True, want_packed: bool = False):
+    """train.py:151-172 from an already drawn rd_idx (int64, one value per cell)."""
+    require_cuda(rd_idx, "mask_pair_from_rdidx")
+    rd_idx = rd_idx.contiguous()
+    cells = rd_idx.numel()
+    m1 = m2 = pk = None
+    if want_masks:
+        m1 = torch.empty(cells * 4, dtype=torch.bool, device=rd_idx.device)
+        m2 = torch.empty(cells * 4, dtype=torch.bool, device=rd_idx.device)
+    if want_packed:
+        pk = torch.empty(cells, dtype=torch.uint8, device=rd_idx.device)
+    check(lib().n2n_mask_pair_from_rdidx(ptr(rd_idx), cells, ptr(m1), ptr(m2), ptr(pk), stream_ptr()))
+    return m1, m2, pk
+
+
+def subsample(img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """train.py:175-190."""
+    require_cuda(img, "generate_subimages")
+    n, c, h, w = img.shape
+    if mask.dtype != torch.bool or mask.dim() != 1 or mask.numel() != n * (h // 2) * (w // 2) * 4:
+        raise ValueError(f"mask must be a 1-D bool tensor of length {n * (h // 2) * (w // 2) * 4}, got "
+                         f"{tuple(mask.shape)} {mask.dtype}")
+    img = img.contiguous(); mask = mask.contiguous()
+    out = torch.empty((n, c, h // 2, w // 2), dtype=img.dtype, device=img.device)
+    check(lib().n2n_subsample(ptr(img), ptr(mask), ptr(out), n, c, h, w, _ELEM[img.dtype], stream_ptr()))
+    return out
+
+
+def subsample_pair(img: torch.Tensor, mask1: Optional[torch.Tensor] = None, mask2: Optional[torch.Tensor] = None,
+                   packed: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused form: both sub-images in one pass over img."""
+    require_cuda(img, "subsample_pair")
+    n, c, h, w = img.shape
+    cells = n * (h // 2) * (w // 2)
+    if packed is None:
+        for m in (mask1, mask2):
+            if m is None or m.dtype != torch.bool or m.numel() != cells * 4:
+                raise ValueError("subsample_pair needs two bool masks of 4*cells elements or a packed selector")
+        mask1 = mask1.contiguous(); mask2 = mask2.contiguous()
+    elif packed.dtype != torch.uint8 or packed.numel() != cells:
+        raise ValueError("packed selector must be uint8 with one byte per cell")
+    img = img.contiguous()
+    o1 = torch.empty((n, c, h // 2, w // 2), dtype=img.dtype, device=img.device)
+    o2 = torch.empty_like(o1)
+    check(lib().n2n_subsample_pair(ptr(img), ptr(mask1), ptr(mask2), ptr(packed), ptr(o1), ptr(o2),
+                                   n, c, h, w, _ELEM[img.dtype], stream_ptr()))
+    return o1, o2
+
+
+# ----------------------------------------------------------------------------- single layers
+def conv2d_fwd(x, w, b=None, act_slope: float = -1.0, precision: str = "fp32"):
+    require_cuda(x, "conv2d_fwd")
+    x = _f32c(x); w = _f32c(w); b = None if b is None else _f32c(b)
+    n, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    dt = _ext.dtype_tag(precision)
+    y = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().n2n_conv2d_workspace_bytes(n, cin, cout, h, wd, k, dt), x.device)
+    check(lib().n2n_conv2d_fwd(ptr(x), ptr(w), ptr(b), ptr(y), n, cin, cout, h, wd, k, act_slope, dt, ptr(ws), stream_ptr()))
+    return y
+
+
+def conv2d_dgrad(dy, w, precision: str = "fp32"):
+    require_cuda(dy, "conv2d_dgrad")
+    dy = _f32c(dy); w = _f32c(w)
+    n, cout, h, wd = dy.shape
+    _, cin, k, _ = w.shape
+    dt = _ext.dtype_tag(precision)
+    dx = torch.empty((n, cin, h, wd), dtype=torch.float32, device=dy.device)
+    ws = _ws(lib().n2n_conv2d_workspace_bytes(n, cin, cout, h, wd, k, dt), dy.device)
+    check(lib().n2n_conv2d_dgrad(ptr(dy), ptr(w), ptr(dx), n, cin, cout, h, wd, k, dt, ptr(ws), stream_ptr()))
+    return dx
+
+
+def conv2d_wgrad(x, dy, ksize: int, precision: str = "fp32"):
+    require_cuda(x, "conv2d_wgrad")
+    x = _f32c(x); dy = _f32c(dy)
+    n, cin, h, wd = x.shape
+    cout = dy.shape[1]
+    dt = _ext.dtype_tag(precision)
+    dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().n2n_conv2d_workspace_bytes(n, cin, cout, h, wd, ksize, dt), x.device)
+    check(lib().n2n_conv2d_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), n, cin, cout, h, wd, ksize, dt, ptr(ws), stream_ptr()))
+    return dw, db
+
+
+def deconv2x2_fwd(x, w, b=None, precision: str = "fp32"):
+    require_cuda(x, "deconv2x2_fwd")
+    x = _f32c(x); w = _f32c(w); b = None if b is None else _f32c(b)
+    n, cin, h, wd = x.shape
+    cout = w.shape[1]
+    dt = _ext.dtype_tag(precision)
+    y = torch.empty((n, cout, 2 * h, 2 * wd), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().n2n_deconv2x2_workspace_bytes(n, cin, cout, h, wd, dt), x.device)
+    check(lib().n2n_deconv2x2_fwd(ptr(x), ptr(w), ptr(b), ptr(y), n, cin, cout, h, wd, dt, ptr(ws), stream_ptr()))
+    return y
+
+
+def deconv2x2_dgrad(dy, w, precision: str = "fp32"):
+    require_cuda(dy, "deconv2x2_dgrad")
+    dy = _f32c(dy); w = _f32c(w)
+    n, cout, h2, w2 = dy.shape
+    cin = w.shape[0]
+    h, wd = h2 // 2, w2 // 2
+    dt = _ext.dtype_tag(precision)
+    dx = torch.empty((n, cin, h, wd), dtype=torch.float32, device=dy.device)
+    ws = _ws(lib().n2n_deconv2x2_workspace_bytes(n, cin, cout, h, wd, dt), dy.device)
+    check(lib().n2n_deconv2x2_dgrad(ptr(dy), ptr(w), ptr(dx), n, cin, cout, h, wd, dt, ptr(ws), stream_ptr()))
+    return dx
+
+
+def deconv2x2_wgrad(x, dy, precision: str = "fp32"):
+    require_cuda(x, "deconv2x2_wgrad")
+    x = _f32c(x); dy = _f32c(dy)
+    n, cin, h, wd = x.shape
+    cout = dy.shape[1]
+    dt = _ext.dtype_tag(precision)
+    dw = torch.empty((cin, cout, 2, 2), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().n2n_deconv2x2_workspace_bytes(n, cin, cout, h, wd, dt), x.device)
+    check(lib().n2n_deconv2x2_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), n, cin, cout, h, wd, dt, ptr(ws), stream_ptr()))
+    return dw, db
+
+
+def maxpool2_fwd(x, precision: str = "fp32"):
+    require_cuda(x, "maxpool2_fwd")
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    dt = _ext.dtype_tag(precision)
+    y = torch.empty((n, c, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().n2n_pool_workspace_bytes(n, c, h, w, dt), x.device)
+    check(lib().n2n_maxpool2_fwd(ptr(x), ptr(y), n, c, h, w, dt, ptr(ws), stream_ptr()))
+    return y
+
+
+def maxpool2_bwd(x, dy, slope: float = 1.0, precision: str = "fp32"):
+    require_cuda(x, "maxpool2_bwd")
+    x = _f32c(x); dy = _f32c(dy)
+    n, c, h, w = x.shape
+    dt = _ext.dtype_tag(precision)
+    dx = torch.empty_like(x)
+    ws = _ws(lib().n2n_pool_workspace_bytes(n, c, h, w, dt), x.device)
+    check(lib().n2n_maxpool2_bwd(ptr(x), ptr(dy), ptr(dx), n, c, h, w, slope, dt, ptr(ws), stream_ptr()))
+    return dx
+
+
+# ----------------------------------------------------------------------------- losses
+_loss_ws = {}
+
+
+def _loss_workspace(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    if key not in _loss_ws:
+        _loss_ws[key] = torch.zeros(lib().n2n_loss_workspace_bytes(0), dtype=torch.uint8, device=device)
+    return _loss_ws[key]
+
+
+def n2n_loss_fwdbwd(out, sub2, den1, den2, lam: float, grad_scale: float = 1.0, want_grad: bool = True):
+    """training_script.md:146-153 -> (loss3 tensor [loss_all, loss1, loss2], dloss/dout or None)."""
+    require_cuda(out, "n2n_loss")
+    out = _f32c(out); sub2 = _f32c(sub2); den1 = _f32c(den1); den2 = _f32c(den2)
+    if not (out.shape == sub2.shape == den1.shape == den2.shape):
+        raise ValueError("n2n_loss: shape mismatch")
+    loss3 = torch.empty(3, dtype=torch.float32, device=out.device)
+    grad = torch.empty_like(out) if want_grad else None
+    check(lib().n2n_loss_n2n_fwdbwd(ptr(out), ptr(sub2), ptr(den1), ptr(den2), float(lam), float(grad_scale),
+                                    out.numel(), ptr(loss3), ptr(grad), ptr(_loss_workspace(out.device)), stream_ptr()))
+    return loss3, grad
+
+
+def l1grad_loss_fwdbwd(pred, target, lambda_grad: float, grad_scale: float = 1.0, want_grad: bool = True):
+    """finetune.py:153-162, :283-285 -> (loss3 [loss, l1, grad_term], dloss/dpred or None)."""
+    require_cuda(pred, "l1grad_loss")
+    pred = _f32c(pred); target = _f32c(target)
+    if pred.shape != target.shape or pred.dim() != 4:
+        raise ValueError("l1grad_loss: need two [N,C,H,W] tensors of equal shape")
+    n, c, h, w = pred.shape
+    loss3 = torch.empty(3, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib().n2n_loss_l1grad_fwdbwd(ptr(pred), ptr(target), n, c, h, w, float(lambda_grad), float(grad_scale),
+                                       ptr(loss3), ptr(grad), ptr(_loss_workspace(pred.device)), stream_ptr()))
+    return loss3, grad
+
+
+# ----------------------------------------------------------------------------- evaluation
+def quantize_u8(pred: torch.Tensor, bias: float) -> torch.Tensor:
+    require_cuda(pred, "quantize_u8")
+    pred = _f32c(pred)
+    out = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
+    check(lib().n2n_quantize_u8(ptr(pred), ptr(out), pred.numel(), float(bias), stream_ptr()))
+    return out
+
+
+def tile_accumulate(pred_tile, weight_mask, acc, cnt, r0: int, c0: int, th: int, tw: int):
+    ps = pred_tile.shape[-1]
+    H, W = acc.shape
+    check(lib().n2n_tile_accumulate(ptr(pred_tile), ps, ptr(weight_mask), ptr(acc), ptr(cnt), H, W, r0, c0, th, tw,
+                                    stream_ptr()))
+
+
+def tile_finalize_u8(acc, cnt) -> torch.Tensor:
+    out = torch.empty(acc.shape, dtype=torch.uint8, device=acc.device)
+    check(lib().n2n_tile_finalize_u8(ptr(acc), ptr(cnt), ptr(out), acc.numel(), stream_ptr()))
+    return out
+
+
+def psnr_ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a, b: uint8 CUDA tensors [B,H,W] or [B,H,W,C] (C in {1,3}) -> float64 [B,2] = (psnr, ssim)."""
+    require_cuda(a, "psnr_ssim")
+    if a.shape != b.shape or a.dtype != torch.uint8 or b.dtype != torch.uint8:
+        raise ValueError("Input images must have the same dimensions.")
+    if a.dim() == 3:
+        a = a.unsqueeze(-1); b = b.unsqueeze(-1)
+    a = a.contiguous(); b = b.contiguous()
+    B, H, W, C = a.shape
+    res = torch.empty((B, 2), dtype=torch.float64, device=a.device)
+    ws = _ws(lib().n2n_psnr_ssim_workspace_bytes(B, H, W, C), a.device)
+    check(lib().n2n_psnr_ssim_u8(ptr(a), ptr(b), B, H, W, C, ptr(res), ptr(ws), stream_ptr()))
+    return res

@@ -1,0 +1,119 @@
+"""N2NTrainer — the fused Neighbor2Neighbor training step (training_script.md:128-156)
+driven entirely through libn2n_b200: fused sub-sampler, no-grad full-resolution UNet forward,
+half-resolution forward + backward, fused loss, (optional) NCCL gradient all-reduce and fused
+multi-tensor Adam.  All buffers are allocated once; a step issues no allocations and no host
+synchronisation.  Data parallel = one process per GPU (torch.distributed, NCCL): each rank
+takes its slice of the global batch, the flat fp32 gradient buffer (5 MB) is all-reduced and
+the 1/world factor is folded into the Adam kernel.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _ext, n2n, ops
+from ._ext import check, lib, ptr, ptr_array, stream_ptr
+from .optim import build_adam_tables
+
+
+class N2NTrainer:
+    def __init__(self, network, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, precision=None, process_group=None,
+                 buckets=2):
+        self.net = network
+        self.precision = precision or network.precision
+        network.set_precision(self.precision)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        params = list(network.parameters())
+        dev = params[0].device
+        _ext.require_cuda(params[0], "N2NTrainer")
+        sizes = [p.numel() for p in params]
+        # one flat fp32 buffer each for params / grads / exp_avg / exp_avg_sq; the module's
+        # parameters become views of the flat parameter buffer (state_dict() is unchanged).
+        self.flat_p = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_m = torch.zeros_like(self.flat_p)
+        self.flat_v = torch.zeros_like(self.flat_p)
+        off = 0
+        self.params, self.grads = [], []
+        for p, n in zip(params, sizes):
+            view = self.flat_p[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.params.append(p)
+            self.grads.append(self.flat_g[off:off + n].view(p.shape))
+            off += n
+        self.table, self.blocks = build_adam_tables([self.flat_p], [self.flat_g], [self.flat_m], [self.flat_v], dev)
+        # gradient buckets in reverse-autograd order: the head / full-resolution decoder tensors
+        # sit at the END of the state_dict order, so bucket 0 is the tail of the flat buffer.
+        total = self.flat_g.numel()
+        cut = total - sum(sizes[-10:]) if buckets > 1 else 0
+        self.bucket_slices = [(cut, total), (0, cut)] if cut > 0 else [(0, total)]
+        self._shapes = None
+        self.last_launches = 0
+        if self.world > 1:
+            torch.distributed.broadcast(self.flat_p, src=0, group=self.pg)   # once, instead of DataParallel's per-step replicate
+
+    # ------------------------------------------------------------------ buffers / plans
+    def _prepare(self, noisy):
+        n, c, h, w = noisy.shape
+        if self._shapes == (n, c, h, w):
+            return
+        net, dev = self.net, noisy.device
+        dt = _ext.dtype_tag(self.precision)
+        self._shapes = (n, c, h, w)
+        self.plan_full = ctypes.c_void_p()
+        self.plan_half = ctypes.c_void_p()
+        check(lib().n2n_unet_plan_create(ctypes.byref(self.plan_full), net.in_nc, net.out_nc, net.n_feature, n, h, w, dt, 0))
+        check(lib().n2n_unet_plan_create(ctypes.byref(self.plan_half), net.in_nc, net.out_nc, net.n_feature, n,
+                                         h // 2, w // 2, dt, 1))
+        self.ws_full = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_full), dtype=torch.uint8, device=dev)
+        self.ws_half = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_half), dtype=torch.uint8, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.den = torch.empty((n, net.out_nc, h, w), **f32)
+        half = (n, c, h // 2, w // 2)
+        self.sub1 = torch.empty(half, **f32); self.sub2 = torch.empty(half, **f32)
+        self.den1 = torch.empty((n, net.out_nc, h // 2, w // 2), **f32); self.den2 = torch.empty_like(self.den1)
+        self.out = torch.empty_like(self.den1)
+        self.dout = torch.empty_like(self.den1)
+        self.loss3 = torch.zeros(3, **f32)
+        self.packed = torch.empty(n * (h // 2) * (w // 2), dtype=torch.uint8, device=dev)
+        self.loss_ws = torch.zeros(lib().n2n_loss_workspace_bytes(0), dtype=torch.uint8, device=dev)
+        self.param_ptrs = ptr_array(self.params)
+        self.grad_ptrs = ptr_array(self.grads)
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, noisy, Lambda, rd_idx=None, lr=None):
+        """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
+        device tensor [loss_all, loss1, loss2] (no host sync).  ``rd_idx`` may carry this rank's
+        slice of a globally drawn selector (mask parity with a 1-GPU run)."""
+        noisy = noisy.contiguous()
+        self._prepare(noisy)
+        L, st = lib(), stream_ptr()
+        n, c, h, w = noisy.shape
+        launches0 = L.n2n_launch_count()
+        if rd_idx is None:
+            rd_idx = n2n.draw_rd_idx(noisy)
+        check(L.n2n_mask_pair_from_rdidx(ptr(rd_idx), rd_idx.numel(), None, None, ptr(self.packed), st))
+        check(L.n2n_subsample_pair(ptr(noisy), None, None, ptr(self.packed), ptr(self.sub1), ptr(self.sub2), n, c, h, w, 4, st))
+        check(L.n2n_unet_forward(self.plan_full, self.param_ptrs, ptr(noisy), ptr(self.den), ptr(self.ws_full), st))
+        check(L.n2n_subsample_pair(ptr(self.den), None, None, ptr(self.packed), ptr(self.den1), ptr(self.den2),
+                                   n, self.net.out_nc, h, w, 4, st))
+        check(L.n2n_unet_forward(self.plan_half, self.param_ptrs, ptr(self.sub1), ptr(self.out), ptr(self.ws_half), st))
+        check(L.n2n_loss_n2n_fwdbwd(ptr(self.out), ptr(self.sub2), ptr(self.den1), ptr(self.den2), float(Lambda), 1.0,
+                                    self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
+        check(L.n2n_unet_backward(self.plan_half, self.param_ptrs, ptr(self.dout), self.grad_ptrs, None, ptr(self.ws_half), st))
+        if self.world > 1:
+            for a, b in self.bucket_slices:
+                torch.distributed.all_reduce(self.flat_g[a:b], group=self.pg)
+        self.step_count += 1
+        check(L.n2n_adam_multi(ptr(self.table), 1, ptr(self.blocks), self.blocks.shape[0], float(lr or self.lr),
+                               float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,
+                               1.0 / self.world, st))
+        self.last_launches = L.n2n_launch_count() - launches0
+        return self.loss3

@@ -1,0 +1,219 @@
+/*
+ * n2n_b200.h — C-ABI of libn2n_b200.so: the B200 (sm_100a) kernels behind the
+ * Neighbor2Neighbor hot path of lmh9507/image_denoising.
+ *
+ * The reference is 100 % Python on stock PyTorch and has no FFI / plugin layer
+ * (SURVEY.md §0.1, §8b); its boundary is the Python call surface.  Each entry
+ * point below therefore cites the reference *Python* interface whose arithmetic
+ * it replaces (file:line into the reference repo).  The ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md and implemented in
+ * image_denoising_b200/_ext.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; n2n_last_error() gives a
+ *     thread-local message;
+ *   - the caller owns every buffer (device pointers, normally torch tensors);
+ *     the library never allocates or frees device memory: scratch comes from a
+ *     caller-provided workspace sized by the matching *_workspace_bytes query;
+ *   - every call is asynchronous on the passed stream (a cudaStream_t passed as
+ *     void*); no call synchronises the device;
+ *   - "NCHW" tensors are contiguous; dtype tags: N2N_F32 = 0, N2N_BF16 = 1
+ *     (for activations/compute), element sizes for the copy-only sub-sampler;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with an error code.
+ */
+#ifndef N2N_B200_H
+#define N2N_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define N2N_F32 0
+#define N2N_BF16 1
+
+#define N2N_OK 0
+#define N2N_ERR_ARG (-1)
+#define N2N_ERR_CUDA (-2)
+#define N2N_ERR_UNSUPPORTED (-3)
+
+const char* n2n_last_error(void);
+int n2n_version(void);
+/* 1 if a CUDA device with compute capability 10.x is present. */
+int n2n_device_ok(void);
+/* kernels launched so far by the calling host thread (bench.py's gpu_launches). */
+long long n2n_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Neighbour sub-sampler — train.py:141-190 (generate_mask_pair,
+ * generate_subimages), training_script.md:137-144.
+ * ------------------------------------------------------------------------- */
+
+/* train.py:151-172: rd_idx (int64, one value in [0,8) per 2x2 cell, cells in
+ * (n,i,j) order) -> two flat bool masks of 4*cells bytes each (one 1 per cell)
+ * and/or a packed selector (k1 | k2<<2, one byte per cell).  Any output may be
+ * NULL.  The random draw itself stays with the caller's torch generator. */
+int n2n_mask_pair_from_rdidx(const int64_t* rd_idx, int64_t cells,
+                             uint8_t* mask1, uint8_t* mask2, uint8_t* packed_sel,
+                             void* stream);
+
+/* train.py:175-190: out[n,c,i,j] = img[n,c,2i+k/2,2j+k%2], k = position of the 1
+ * in cell (n,i,j) of `mask` (flat bool, 4 bytes per cell).  elem_size in
+ * {1,2,4,8}: a pure copy, bit-exact in any dtype.  img is NCHW [n,c,h,w]
+ * contiguous, out is [n,c,h/2,w/2]. */
+int n2n_subsample(const void* img, const uint8_t* mask, void* out,
+                  int n, int c, int h, int w, int elem_size, void* stream);
+
+/* Fused pair (the form the N2N step uses): one pass over img producing both
+ * sub-images.  Selector source: either the two reference bool masks
+ * (mask1/mask2 non-NULL) or the packed selector (packed_sel non-NULL). */
+int n2n_subsample_pair(const void* img, const uint8_t* mask1, const uint8_t* mask2,
+                       const uint8_t* packed_sel, void* out1, void* out2,
+                       int n, int c, int h, int w, int elem_size, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Single layers (NCHW fp32 at the boundary; compute in `dtype`) —
+ * arch_unet.py:113-190 (nn.Conv2d 3x3 s1 p1 / 1x1, LeakyReLU(0.2) in place),
+ * arch_unet.py:57-62 (ConvTranspose2d k2 s2), arch_unet.py:120-136 (MaxPool2d(2)).
+ * These are the per-op parity surface; the network-level entry points below run
+ * the same kernels without leaving the blocked device layout.
+ * ------------------------------------------------------------------------- */
+size_t n2n_conv2d_workspace_bytes(int n, int cin, int cout, int h, int w, int ksize, int dtype);
+
+/* y = act(conv2d(x, w, b)); ksize in {1,3}, stride 1, pad ksize/2.
+ * w: [cout,cin,k,k] fp32, b: [cout] or NULL; act_slope < 0 => no activation,
+ * otherwise y = v>0 ? v : act_slope*v (0.2 LeakyReLU, 0 ReLU). */
+int n2n_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
+                   int n, int cin, int cout, int h, int w_, int ksize, float act_slope,
+                   int dtype, void* workspace, void* stream);
+/* dx = conv2d_input_grad(dy, w) (no activation handling). */
+int n2n_conv2d_dgrad(const float* dy, const float* w, float* dx,
+                     int n, int cin, int cout, int h, int w_, int ksize,
+                     int dtype, void* workspace, void* stream);
+/* dw = conv2d_weight_grad(x, dy) [cout,cin,k,k], db = sum(dy) [cout] (db may be NULL). */
+int n2n_conv2d_wgrad(const float* x, const float* dy, float* dw, float* db,
+                     int n, int cin, int cout, int h, int w_, int ksize,
+                     int dtype, void* workspace, void* stream);
+
+size_t n2n_deconv2x2_workspace_bytes(int n, int cin, int cout, int h, int w, int dtype);
+/* y[n,co,2i+a,2j+b] = b[co] + sum_ci x[n,ci,i,j] * w[ci,co,a,b]; w: [cin,cout,2,2]. */
+int n2n_deconv2x2_fwd(const float* x, const float* w, const float* b, float* y,
+                      int n, int cin, int cout, int h, int w_, int dtype, void* workspace, void* stream);
+int n2n_deconv2x2_dgrad(const float* dy, const float* w, float* dx,
+                        int n, int cin, int cout, int h, int w_, int dtype, void* workspace, void* stream);
+int n2n_deconv2x2_wgrad(const float* x, const float* dy, float* dw, float* db,
+                        int n, int cin, int cout, int h, int w_, int dtype, void* workspace, void* stream);
+
+size_t n2n_pool_workspace_bytes(int n, int c, int h, int w, int dtype);
+/* y = maxpool2x2(x);  x: [n,c,h,w] -> y: [n,c,h/2,w/2]. */
+int n2n_maxpool2_fwd(const float* x, float* y, int n, int c, int h, int w, int dtype,
+                     void* workspace, void* stream);
+/* dx = lrelu'(x; slope) * unpool(dy) with ATen's first-max tie rule; x is the
+ * (already activated) pool input.  slope = 1 gives the plain max-pool backward. */
+int n2n_maxpool2_bwd(const float* x, const float* dy, float* dx, int n, int c, int h, int w,
+                     float slope, int dtype, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * UNet — arch_unet.py:100-260 (non-blindspot).  A plan is bound to
+ * (in_nc,out_nc,n_feature,N,H,W,dtype); H and W must be multiples of 32.
+ * params/grads: the 50 tensors in state_dict order (arch_unet.py:114-192),
+ * fp32, PyTorch layouts (Conv2d [co,ci,k,k], ConvTranspose2d [ci,co,2,2]).
+ * ------------------------------------------------------------------------- */
+typedef struct n2n_unet_plan n2n_unet_plan;
+#define N2N_UNET_NUM_PARAMS 50
+
+int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature,
+                         int n, int h, int w, int dtype, int with_backward);
+void n2n_unet_plan_destroy(n2n_unet_plan* plan);
+size_t n2n_unet_workspace_bytes(const n2n_unet_plan* plan);
+/* number of kernel launches one forward / backward issues (for gpu_launches). */
+int n2n_unet_launches(const n2n_unet_plan* plan, int backward);
+/* y = UNet(x): x [N,in_nc,H,W] fp32, y [N,out_nc,H,W] fp32.  With a
+ * with_backward plan the activations needed by n2n_unet_backward stay in the
+ * workspace until the next forward on the same workspace. */
+int n2n_unet_forward(n2n_unet_plan* plan, const float* const* params, const float* x, float* y,
+                     void* workspace, void* stream);
+/* grads[i] (fp32, same shapes as params) are OVERWRITTEN with dL/dparam for the
+ * last forward; dy is dL/dy [N,out_nc,H,W].  dx (may be NULL) receives dL/dx. */
+int n2n_unet_backward(n2n_unet_plan* plan, const float* const* params, const float* dy,
+                      float* const* grads, float* dx, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Output adapter — adapter.py:5-26 (OutputAdapter.forward), :59-67.
+ * out = base_out + conv3x3(relu(conv3x3(cat[noisy, base_out]))).
+ * params/grads: net.0.weight [hid,2C,3,3], net.0.bias, net.2.weight [C,hid,3,3], net.2.bias.
+ * ------------------------------------------------------------------------- */
+typedef struct n2n_adapter_plan n2n_adapter_plan;
+int n2n_adapter_plan_create(n2n_adapter_plan** plan, int channels, int hidden,
+                            int n, int h, int w, int dtype, int with_backward);
+void n2n_adapter_plan_destroy(n2n_adapter_plan* plan);
+size_t n2n_adapter_workspace_bytes(const n2n_adapter_plan* plan);
+int n2n_adapter_forward(n2n_adapter_plan* plan, const float* const* params,
+                        const float* noisy, const float* base_out, float* out,
+                        void* workspace, void* stream);
+int n2n_adapter_backward(n2n_adapter_plan* plan, const float* const* params, const float* dout,
+                         float* const* grads, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Losses
+ * ------------------------------------------------------------------------- */
+size_t n2n_loss_workspace_bytes(int64_t count);
+/* training_script.md:146-153: diff = out-sub2, exp = den1-den2,
+ * loss = mean(diff^2) + lam*mean((diff-exp)^2).  Writes loss3 = {loss_all, loss1,
+ * loss2} (fp32, device) and, if grad != NULL, grad = grad_scale * dloss/dout. */
+int n2n_loss_n2n_fwdbwd(const float* out, const float* sub2, const float* den1, const float* den2,
+                        float lam, float grad_scale, int64_t count, float* loss3, float* grad,
+                        void* workspace, void* stream);
+/* finetune.py:153-162, :283-285: loss = L1(p,t) + lambda_grad*(L1(dx p,dx t)+L1(dy p,dy t)).
+ * loss3 = {loss, loss_l1, loss_grad}; grad (may be NULL) = grad_scale * dloss/dpred. */
+int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, int n, int c, int h, int w,
+                           float lambda_grad, float grad_scale, float* loss3, float* grad,
+                           void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Adam — train.py:332 (torch.optim.Adam defaults), finetune.py:260-263.
+ * One launch over a table of tensors.  table (device, int64) holds, per tensor t
+ * of ntensors: [p_ptr, g_ptr, m_ptr, v_ptr, numel]; blocks (device, int32) holds
+ * per CUDA block: [tensor index, chunk index] (chunk = 2048 elements).
+ * g is multiplied by grad_scale before use (1/world for data parallel).
+ * ------------------------------------------------------------------------- */
+#define N2N_ADAM_CHUNK 2048
+int n2n_adam_multi(const int64_t* table, int ntensors, const int32_t* blocks, int nblocks,
+                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                   void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Evaluation — evaluation.py:82-83, evaluation_704.py:57-120, utils_eval.py:19-53.
+ * ------------------------------------------------------------------------- */
+/* pred (fp32 planes, [count]) -> uint8: clamp(0,1) then clip(p*255 + bias, 0, 255)
+ * truncated; bias = 0.5 (evaluation.py:83) or 0 (evaluation_704.py:120). */
+int n2n_quantize_u8(const float* pred, uint8_t* out, int64_t count, float bias, void* stream);
+/* evaluation_704.py:105-112: acc[r0+y, c0+x] += clamp(pred[y,x],0,1) * wm[y,x], cnt += wm for the
+ * valid (th x tw) part of a ps x ps tile; acc/cnt are H x W fp32 planes. */
+int n2n_tile_accumulate(const float* pred_tile, int ps, const float* weight_mask,
+                        float* acc, float* cnt, int H, int W, int r0, int c0, int th, int tw,
+                        void* stream);
+/* evaluation_704.py:114-120: out = clip(acc / (cnt==0 ? 1 : cnt) * 255, 0, 255) truncated. */
+int n2n_tile_finalize_u8(const float* acc, const float* cnt, uint8_t* out, int64_t count, void* stream);
+
+size_t n2n_psnr_ssim_workspace_bytes(int batch, int h, int w, int channels);
+/* utils_eval.py:19-53 on `batch` pairs of H x W x C uint8 images (interleaved
+ * HWC as PIL/numpy hold them, C in {1,3}).  result: [batch][2] doubles =
+ * {psnr (dB, +inf when identical), ssim}. */
+int n2n_psnr_ssim_u8(const uint8_t* a, const uint8_t* b, int batch, int h, int w, int channels,
+                     double* result, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Probes (test / bring-up only): a bare tcgen05 GEMM used to validate the
+ * shared-memory descriptor encodings the convolution kernels rely on.
+ * ------------------------------------------------------------------------- */
+int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf16, float* d,
+                   int m, int n, int k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2N_B200_H */

@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box): every kernel family of libn2n_b200 against the CPU
+oracle (oracle/n2n_oracle.py) / plain PyTorch fp32 ops on the same seeded inputs, through the
+C-ABI.  Tolerances: bit-exact for the sub-sampler and the uint8 evaluation path; fp32 engine
+max-abs <= 1e-5 relative to the tensor scale; bf16 engine <= 2e-2 relative (bf16 inputs, fp32
+accumulation)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import n2n_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32", "bf16"]
+
+
+def _tol(precision):
+    return 2e-5 if precision == "fp32" else 2.5e-2
+
+
+def _rel_err(a, b):
+    a = a.detach().float().cpu(); b = b.detach().float().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+def _q(t, precision):
+    """Round operands the way the bf16 engine sees them, so that only accumulation order differs."""
+    return t.bfloat16().float() if precision == "bf16" else t
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from image_denoising_b200 import _ext
+    assert _ext.lib().n2n_device_ok() == 1, "libn2n_b200 needs an sm_100 device"
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------- sub-sampler
+def test_subsampler_golden_bit_exact(dev, golden):
+    from image_denoising_b200 import ops
+    z = golden("subsample")
+    for ci in range(3):
+        img = torch.from_numpy(z[f"img{ci}"]).to(dev)
+        rd = torch.from_numpy(z[f"rd{ci}"]).to(dev)
+        m1, m2, pk = ops.mask_pair_from_rdidx(rd, want_masks=True, want_packed=True)
+        assert np.array_equal(m1.cpu().numpy(), z[f"m1_{ci}"]) and np.array_equal(m2.cpu().numpy(), z[f"m2_{ci}"])
+        s1 = ops.subsample(img, m1); s2 = ops.subsample(img, m2)
+        assert np.array_equal(s1.cpu().numpy(), z[f"s1_{ci}"]) and np.array_equal(s2.cpu().numpy(), z[f"s2_{ci}"])
+        p1, p2 = ops.subsample_pair(img, m1, m2)
+        q1, q2 = ops.subsample_pair(img, packed=pk)
+        for t in (p1, q1):
+            assert torch.equal(t, s1)
+        for t in (p2, q2):
+            assert torch.equal(t, s2)
+    img = torch.from_numpy(z["const_img"]).to(dev)
+    for r in range(8):
+        rd = torch.full((12,), r, dtype=torch.int64, device=dev)
+        m1, m2, _ = ops.mask_pair_from_rdidx(rd)
+        assert np.array_equal(ops.subsample(img, m1).cpu().numpy(), z[f"const_s1_{r}"])
+        assert np.array_equal(ops.subsample(img, m2).cpu().numpy(), z[f"const_s2_{r}"])
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 1, 34, 50), (3, 2, 7, 9), (2, 1, 8, 24), (1, 3, 2, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64, torch.uint8])
+def test_subsampler_vs_oracle(dev, shape, dtype):
+    from image_denoising_b200 import ops
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(h * 131 + w)
+    img = (torch.rand(shape, generator=g) * 200).to(dtype)
+    rd = O.draw_rd_idx(n, h, w, seed=h + w)
+    m1, m2 = O.masks_from_rd_idx(rd)
+    host = img.view(torch.int16).numpy() if dtype == torch.bfloat16 else img.numpy()
+    ref1 = O.subimage_from_mask(host, m1)
+    ref2 = O.subimage_from_mask(host, m2)
+    gm1, gm2, pk = ops.mask_pair_from_rdidx(torch.from_numpy(rd).to(dev), want_masks=True, want_packed=True)
+    assert np.array_equal(gm1.cpu().numpy(), m1) and np.array_equal(gm2.cpu().numpy(), m2)
+    d = img.to(dev)
+    s1 = ops.subsample(d, gm1); s2 = ops.subsample(d, gm2)
+    view = (lambda t: t.cpu().view(torch.int16).numpy()) if dtype == torch.bfloat16 else (lambda t: t.cpu().numpy())
+    assert np.array_equal(view(s1), ref1) and np.array_equal(view(s2), ref2)
+    p1, p2 = ops.subsample_pair(d, packed=pk)
+    assert torch.equal(p1, s1) and torch.equal(p2, s2)
+
+
+def test_subsampler_full_size_properties(dev):
+    """C2: 32x1x512x512.  Size-independent properties: every output pixel comes from its own
+    2x2 cell and (k1,k2) are 4-adjacent; reference-form (two bool masks) == packed form."""
+    from image_denoising_b200 import n2n, ops
+    n, c, h, w = 32, 1, 512, 512
+    idx = torch.arange(n * c * h * w, dtype=torch.float32, device=dev).reshape(n, c, h, w)  # exact below 2^24
+    n2n.operation_seed_counter = 0
+    m1, m2 = n2n.generate_mask_pair(idx)
+    assert m1.dtype == torch.bool and m1.shape == (n * h // 2 * w // 2 * 4,)
+    a = m1.view(-1, 4); b = m2.view(-1, 4)
+    assert bool((a.sum(1) == 1).all()) and bool((b.sum(1) == 1).all())
+    k1 = a.int().argmax(1); k2 = b.int().argmax(1)
+    assert bool((((k1 // 2) != (k2 // 2)) ^ ((k1 % 2) != (k2 % 2))).all())
+    s1 = n2n.generate_subimages(idx, m1); s2 = n2n.generate_subimages(idx, m2)
+    for s, k in ((s1, k1), (s2, k2)):
+        flat = s.long().view(n, h // 2, w // 2)
+        yy = (flat // w) % h; xx = flat % w
+        ii = torch.arange(h // 2, device=dev)[None, :, None]; jj = torch.arange(w // 2, device=dev)[None, None, :]
+        kk = k.view(n, h // 2, w // 2)
+        assert torch.equal(yy, 2 * ii + kk // 2) and torch.equal(xx, 2 * jj + kk % 2)
+    p1, p2 = ops.subsample_pair(idx, m1, m2)
+    assert torch.equal(p1, s1) and torch.equal(p2, s2)
+
+
+def test_subsampler_errors(dev):
+    from image_denoising_b200 import ops, _ext
+    img = torch.zeros(1, 1, 4, 4, device=dev)
+    with pytest.raises(ValueError):
+        ops.subsample(img, torch.zeros(15, dtype=torch.bool, device=dev))
+    with pytest.raises(_ext.N2NError):
+        ops.subsample(img.cpu(), torch.zeros(16, dtype=torch.bool))
+    empty = torch.zeros(0, 1, 4, 4, device=dev)
+    assert ops.subsample(empty, torch.zeros(0, dtype=torch.bool, device=dev)).shape == (0, 1, 2, 2)
+
+
+# ------------------------------------------------------------------------------- single layers
+CONV_CASES = [  # (n, cin, cout, h, w, k)
+    (2, 1, 48, 32, 32, 3), (1, 48, 48, 16, 48, 3), (1, 96, 96, 24, 20, 3), (1, 144, 96, 16, 16, 3),
+    (1, 97, 96, 8, 40, 3), (2, 96, 96, 16, 16, 1), (1, 96, 1, 32, 32, 1), (1, 6, 16, 20, 12, 3), (3, 16, 3, 8, 8, 3),
+    (1, 48, 48, 8, 8, 3), (1, 20, 24, 130, 18, 3),
+]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_dgrad_wgrad(dev, case, precision):
+    from image_denoising_b200 import ops
+    n, cin, cout, h, w, k = case
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = _q(torch.randn(n, cin, h, w, generator=g), precision)
+    wt = _q(torch.randn(cout, cin, k, k, generator=g) * 0.1, precision)
+    b = torch.randn(cout, generator=g) * 0.1
+    dy = _q(torch.randn(n, cout, h, w, generator=g), precision)
+    xr = x.clone().requires_grad_(True); wr = wt.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br, padding=k // 2)
+    y_ref.backward(dy)
+    tol = _tol(precision)
+    y = ops.conv2d_fwd(x.to(dev), wt.to(dev), b.to(dev), -1.0, precision)
+    assert _rel_err(y, y_ref) < tol
+    ya = ops.conv2d_fwd(x.to(dev), wt.to(dev), b.to(dev), 0.2, precision)
+    assert _rel_err(ya, F.leaky_relu(y_ref, 0.2)) < tol
+    dx = ops.conv2d_dgrad(dy.to(dev), wt.to(dev), precision)
+    assert _rel_err(dx, xr.grad) < tol
+    dw, db = ops.conv2d_wgrad(x.to(dev), dy.to(dev), k, precision)
+    assert _rel_err(dw, wr.grad) < tol
+    assert _rel_err(db, br.grad) < tol
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", [(2, 48, 48, 8, 8), (1, 96, 96, 16, 12), (1, 8, 8, 4, 20), (1, 96, 96, 64, 64)])
+def test_deconv2x2(dev, case, precision):
+    from image_denoising_b200 import ops
+    n, cin, cout, h, w = case
+    g = torch.Generator().manual_seed(cin + 3 * cout)
+    x = _q(torch.randn(n, cin, h, w, generator=g), precision)
+    wt = _q(torch.randn(cin, cout, 2, 2, generator=g) * 0.1, precision)
+    b = torch.randn(cout, generator=g) * 0.1
+    dy = _q(torch.randn(n, cout, 2 * h, 2 * w, generator=g), precision)
+    xr = x.clone().requires_grad_(True); wr = wt.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    y_ref = F.conv_transpose2d(xr, wr, br, stride=2)
+    y_ref.backward(dy)
+    tol = _tol(precision)
+    assert _rel_err(ops.deconv2x2_fwd(x.to(dev), wt.to(dev), b.to(dev), precision), y_ref) < tol
+    assert _rel_err(ops.deconv2x2_dgrad(dy.to(dev), wt.to(dev), precision), xr.grad) < tol
+    dw, db = ops.deconv2x2_wgrad(x.to(dev), dy.to(dev), precision)
+    assert _rel_err(dw, wr.grad) < tol and _rel_err(db, br.grad) < tol
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_maxpool_fwd_bwd_with_ties(dev, precision):
+    from image_denoising_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(-2, 3, (2, 20, 12, 16), generator=g).float()     # many ties; exact in bf16
+    dy = torch.randn(2, 20, 6, 8, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    a = F.leaky_relu(xr, 0.2)
+    y_ref = F.max_pool2d(a, 2)
+    y_ref.backward(dy)
+    act = F.leaky_relu(x, 0.2)
+    y = ops.maxpool2_fwd(act.to(dev), precision)
+    assert _rel_err(y, y_ref) < (1e-6 if precision == "fp32" else 1e-2)
+    # plain pool backward (slope 1) on the activated tensor, ATen first-max tie rule
+    ar = act.clone().requires_grad_(True)
+    F.max_pool2d(ar, 2).backward(dy)
+    dx = ops.maxpool2_bwd(act.to(dev), dy.to(dev), 1.0, precision)
+    if precision == "fp32":
+        assert torch.equal(dx.cpu(), ar.grad)
+    # fused pool + LeakyReLU backward
+    dxa = ops.maxpool2_bwd(act.to(dev), dy.to(dev), 0.2, precision)
+    if precision == "fp32":
+        # x == 0 -> act == 0 -> our mask uses slope (matches in-place leaky_relu backward on the result)
+        ref = ar.grad * torch.where(act > 0, torch.ones_like(act), torch.full_like(act, 0.2))
+        assert torch.allclose(dxa.cpu(), ref, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- losses / Adam
+def test_n2n_loss_kernel(dev):
+    from image_denoising_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for shape in [(4, 1, 32, 32), (1, 3, 7, 5)]:
+        out, sub2, den1, den2 = [torch.randn(shape, generator=g) for _ in range(4)]
+        o = out.clone().requires_grad_(True)
+        loss, l1, l2 = O.n2n_loss(o, sub2, den1, den2, 0.7)
+        loss.backward()
+        loss3, grad = ops.n2n_loss_fwdbwd(out.to(dev), sub2.to(dev), den1.to(dev), den2.to(dev), 0.7)
+        assert np.allclose(loss3.cpu().numpy(), [loss.item(), l1.item(), l2.item()], rtol=1e-6, atol=1e-8)
+        assert torch.allclose(grad.cpu(), o.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_l1grad_loss_kernel(dev, golden):
+    from image_denoising_b200 import ops
+    z = golden("adapter")
+    pred = torch.from_numpy(z["pred"]); clean = torch.from_numpy(z["clean"])
+    p = pred.clone().requires_grad_(True)
+    loss, l1, lg = O.finetune_loss(p, clean, 0.1)
+    loss.backward()
+    loss3, grad = ops.l1grad_loss_fwdbwd(pred.to(dev), clean.to(dev), 0.1)
+    assert np.allclose(loss3.cpu().numpy(), z["loss"], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(grad.cpu(), p.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_fused_adam_matches_reference(dev, golden):
+    from image_denoising_b200.optim import FusedAdam
+    z = golden("adam")
+    w = torch.nn.Parameter(torch.from_numpy(z["w0"]).to(dev))
+    extra = torch.nn.Parameter(torch.zeros(5000, device=dev))      # multi-tensor / multi-chunk path
+    opt = FusedAdam([w, extra], lr=3e-4)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 3, 5, 7], gamma=0.5)
+    ew = torch.zeros(5000); em = torch.zeros(5000); ev = torch.zeros(5000)
+    gen = torch.Generator().manual_seed(1)
+    for t in range(5):
+        ge = torch.randn(5000, generator=gen)
+        w.grad = torch.from_numpy(z["grads"][t]).to(dev)
+        extra.grad = ge.to(dev)
+        opt.step()
+        O.adam_update(ew.numpy(), ge.numpy(), em.numpy(), ev.numpy(), t + 1, 3e-4)
+    assert np.abs(w.detach().cpu().numpy() - z["w5"]).max() < 3e-7
+    assert np.abs(extra.detach().cpu().numpy() - ew.numpy()).max() < 3e-7
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]["lr"]); sched.step()
+    assert np.allclose(lrs, z["lrs_nepoch10"])
+
+
+# ------------------------------------------------------------------------------- PSNR / SSIM / eval
+def test_psnr_ssim_kernel(dev, golden):
+    from image_denoising_b200 import utils_eval
+    z = golden("psnr_ssim")
+    for i in range(4):
+        a, b = z[f"a{i}"], z[f"b{i}"]
+        assert abs(utils_eval.calculate_psnr(a, b) - float(z[f"psnr{i}"])) < 1e-4
+        assert abs(utils_eval.calculate_ssim(a, b) - float(z[f"ssim{i}"])) < 1e-9
+    a = z["a0"]
+    assert utils_eval.calculate_psnr(a, a) == float("inf")
+    assert abs(utils_eval.calculate_ssim(a, a) - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        utils_eval.calculate_ssim(z["a0"], z["a1"])
+    # batched 704x704 (C4 shape) against the oracle
+    rng = np.random.RandomState(1)
+    A = rng.randint(0, 256, size=(3, 704, 704)).astype(np.uint8)
+    B = np.clip(A.astype(np.int32) + rng.randint(-30, 31, size=A.shape), 0, 255).astype(np.uint8)
+    res = utils_eval.psnr_ssim_batch(list(A), list(B))
+    for i in range(3):
+        assert abs(res[i, 0] - O.calculate_psnr(A[i], B[i])) < 1e-4
+        assert abs(res[i, 1] - O.calculate_ssim(A[i], B[i])) < 1e-9
+
+
+def test_quantize_and_tile_blend_bit_exact(dev, golden):
+    from image_denoising_b200 import ops
+    rng = np.random.RandomState(4)
+    p = (rng.rand(3, 37, 53).astype(np.float32) * 1.4 - 0.2)
+    p[0, 0, :8] = np.array([0.0, 1.0, 0.5, 127.5 / 255, 0.99999994, 254.5 / 255, 1e-8, 0.49803922], np.float32)
+    assert np.array_equal(ops.quantize_u8(torch.from_numpy(p).to(dev), 0.5).cpu().numpy(), O.quantize_round(p))
+    trunc = np.clip(np.clip(p, 0, 1) * np.float32(255.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(ops.quantize_u8(torch.from_numpy(p).to(dev), 0.0).cpu().numpy(), trunc)
