@@ -2,6 +2,8 @@
 // (NCHW fp32 at the boundary; the blocked C16 layout lives in the caller's workspace).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "layers.cuh"
 
@@ -17,13 +19,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- optional per-launch CUDA-event timing of the two GEMM kernel classes (bench.py roofline) ----
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+struct ProfScope {
+  ProfRec r; bool on; cudaStream_t st;
+  ProfScope(int cls, double flops, cudaStream_t s) : on(g_prof_on), st(s) {
+    if (!on) return;
+    r.cls = cls; r.flops = flops;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    g_prof->push_back(r);
+  }
+};
+
 int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(g.ntaps >= 1 && g.ntaps <= 9 && g.cin_blocks >= 1 && g.nout >= 16 && g.nout % 16 == 0,
                 "tapgemm: bad geometry (taps=%d cin_blocks=%d nout=%d)", g.ntaps, g.cin_blocks, g.nout);
+  // executed (padded) FLOPs of this launch: 2 * pixels * nout * taps * 16*cin_blocks
+  const double flops = 2.0 * g.y.N * g.y.H * g.y.W * (double)g.nout * g.ntaps * 16.0 * g.cin_blocks;
+  ProfScope ps(0, flops, st);
   if (g.dtype == N2N_BF16) return launch_tapgemm_umma(g, st);
   return launch_tapgemm_simt(g, st);
 }
 int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
+  const double flops = 2.0 * g.dy[0].N * g.dy[0].H * g.dy[0].W * 256.0 * g.n_blocks * g.c_blocks * g.npairs;
+  ProfScope ps(1, flops, st);
   if (g.dtype == N2N_BF16) return launch_tapwgrad_umma(g, st);
   return launch_tapwgrad_simt(g, st);
 }
@@ -46,6 +73,31 @@ using namespace n2n;
 extern "C" const char* n2n_last_error(void) { return g_err; }
 extern "C" int n2n_version(void) { return 100; }
 extern "C" long long n2n_launch_count(void) { return g_launch_count; }
+
+extern "C" int n2n_profile_begin(void) {
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  for (auto& r : *g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof->clear();
+  g_prof_on = true;
+  return 0;
+}
+// out[3*cls + {0,1,2}] = {summed milliseconds, summed executed FLOPs, launches} for cls 0 (tap GEMM:
+// conv / deconv forward + input gradient) and cls 1 (weight-gradient GEMM incl. its bias reduction).
+extern "C" int n2n_profile_end(double* out) {
+  N2N_CHECK_ARG(out != nullptr, "profile_end: out is NULL");
+  g_prof_on = false;
+  for (int i = 0; i < 6; ++i) out[i] = 0.0;
+  if (!g_prof) return 0;
+  for (auto& r : *g_prof) {
+    N2N_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    N2N_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    out[3 * r.cls] += ms; out[3 * r.cls + 1] += r.flops; out[3 * r.cls + 2] += 1.0;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof->clear();
+  return 0;
+}
 extern "C" int n2n_device_ok(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }

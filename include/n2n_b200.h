@@ -46,6 +46,12 @@ int n2n_version(void);
 int n2n_device_ok(void);
 /* kernels launched so far by the calling host thread (bench.py's gpu_launches). */
 long long n2n_launch_count(void);
+/* Per-launch CUDA-event timing of the GEMM kernel classes on the launching stream (bench.py's
+ * roofline leg): begin() arms it for the calling thread; end() stops it, waits for the recorded
+ * events and fills out[6] = {ms, executed FLOPs, launches} for the tap-GEMM kernel (conv / deconv
+ * forward + input gradient) followed by the same three for the weight-gradient kernel. */
+int n2n_profile_begin(void);
+int n2n_profile_end(double* out);
 
 /* ------------------------------------------------------------------------- *
  * Neighbour sub-sampler — train.py:141-190 (generate_mask_pair,

@@ -142,16 +142,20 @@ def test_n2n_step_nf48_vs_oracle(dev, precision):
     rt = 1e-5 if precision == "fp32" else 3e-2
     assert abs(loss3[0] - loss) <= rt * abs(loss)
     worst = 0.0
+    bad = []
     for (k, ref), gv in zip(grads.items(), tr.grads):
         ref = ref.numpy(); got = gv.cpu().numpy()
         denom = np.abs(ref).max() + 1e-12
-        worst = max(worst, np.abs(got - ref).max() / denom)
+        rel = np.abs(got - ref).max() / denom
+        worst = max(worst, rel)
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
         if precision == "fp32":
-            assert np.abs(got - ref).max() <= 2e-4 * denom + 1e-9, k
-        else:
+            if np.abs(got - ref).max() > 2e-4 * denom + 1e-9:
+                bad.append((k, rel, cos))
+        elif cos < 0.99:
             # bf16 activations/gradients, fp32 accumulation: direction must agree closely
-            cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
-            assert cos > 0.99, (k, cos)
+            bad.append((k, rel, cos))
+    assert not bad, "\n".join(f"{k}: rel {r:.3e} cos {c:.5f}" for k, r, c in bad)
     print(f"[{precision}] worst relative grad error {worst:.3e}")
 
 
