@@ -5,13 +5,15 @@
 //
 //   D[128 pixels, nout] = sum over (tap, 48-channel group)  A_tap[128 px, 48 ch] * W_tap[nout, 48 ch]^T
 //
-// One CTA = one 128-pixel output tile (bw x bh pixels of one image), 6 warps:
-//   warp 0 : TMA producer   (one lane): per stage one 5-D tensor load (A) + one bulk copy (B)
-//   warp 1 : MMA issuer     (one lane): <=3 tcgen05.mma (K=16 each) per stage, commit -> stage free
-//   warps 2-5: epilogue: tcgen05.ld 16 columns at a time -> bias / addend / LeakyReLU / mask ->
-//              bf16 C16 store (32 B per pixel per block, contiguous across the warp) or fp32 NCHW
-// A 4-stage mbarrier ring decouples the three roles; two CTAs fit per SM, so one tile's epilogue
-// overlaps the other's main loop.
+// Persistent kernel: one CTA per SM walks the 128-pixel output tiles (bw x bh pixels of one image)
+// round-robin.  6 warps:
+//   warp 0 : TMA producer (one lane): per stage one 5-D tensor load (A) [+ one bulk copy (B)];
+//            when the whole packed weight tensor fits next to >= 4 A stages it is loaded ONCE per
+//            CTA and stays resident in shared memory (L2 traffic = activations only)
+//   warp 1 : MMA issuer (one lane): <= 3 tcgen05.mma (K = 16) per stage, commit -> stage free;
+//            accumulators are double-buffered in TMEM so tile i+1's MMAs overlap tile i's epilogue
+//   warps 2-5: epilogue: tcgen05.ld -> bias / addend / LeakyReLU / mask -> bf16 C16 store
+//            (32 B per pixel per block, contiguous across the warp) or fp32 NCHW
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -19,10 +21,11 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kGroupBlocks = 3;
 constexpr int kThreads = 192;
 constexpr uint32_t kStageABytes = kGroupBlocks * 128 * 32;
+constexpr size_t kSmemBudget = 232448 - 4096;     // 227 KB per CTA minus static/alignment slack
 
 struct UmmaGemmParams {
   CUtensorMap tmap[4];
@@ -36,34 +39,91 @@ struct UmmaGemmParams {
   int has_mask; View mask;
   int act; float slope;
   float* out_nchw; int out_c;
-  int bw, bh, tiles_x, tiles_y, rows;
-  uint32_t stage_b_bytes, tx_bytes, tmem_cols, idesc;
+  int bw, bh, tiles_x, tiles_y, rows, ntiles;
+  int resident_b, nstages;
+  uint32_t b_total_bytes, b_region_bytes, stage_bytes, tx_bytes, tmem_cols, idesc;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct EpiCtx {
+  const UmmaGemmParams* p;
+  int img, y, x;
+  bool valid;
+  long long ypix, apix, mpix;
+};
+
+__device__ __forceinline__ void epilogue_block(const EpiCtx& c, int cb, const uint32_t r[16]) {
+  const UmmaGemmParams& p = *c.p;
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+  if (!c.valid) return;
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(b4 + q);
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+  }
+  if (p.has_addend) {
+    float a[16];
+    Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.addend.ptr + c.apix + cb * p.addend.sCb, a);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] += a[q];
+  }
+  if (p.act) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+  }
+  if (p.has_mask) {
+    float mk[16];
+    Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.mask.ptr + c.mpix + cb * p.mask.sCb, mk);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] *= (mk[q] > 0.f ? 1.f : p.slope);
+  }
+  if (p.out_nchw) {
+    const long long hw = (long long)p.y.H * p.y.W;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int n = cb * 16 + q;
+      if (n < p.out_c) p.out_nchw[((long long)c.img * p.out_c + n) * hw + (long long)c.y * p.y.W + c.x] = v[q];
+    }
+  } else {
+    Block16<__nv_bfloat16>::store((__nv_bfloat16*)p.y.ptr + c.ypix + cb * p.y.sCb, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * kStages + 1];
+  __shared__ uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = kStageABytes + p.stage_b_bytes;
+  const uint32_t stages0 = smem0 + p.b_region_bytes;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * kStages);
-
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y;
-  const int img = tile / p.tiles_y;
-  const int x0 = tx * p.bw, y0 = ty * p.bh;
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 1 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 3 + b); };
   const int iters = p.ntaps * p.ngroups;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(bfull_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -78,40 +138,63 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   if (warp == 0) {
     if (lane == 0) {
       for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
+      if (p.resident_b) {
+        mbar_arrive_expect_tx(bfull_bar, p.b_total_bytes);
+        const uint32_t slab = p.b_total_bytes / (uint32_t)iters;     // one (tap, group) slab per copy
+        for (int i = 0; i < iters; ++i) bulk_load(smem0 + i * slab, p.w + (size_t)i * slab, slab, bfull_bar);
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int t = it / p.ngroups, g = it - t * p.ngroups;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t a_dst = smem0 + stage * stage_bytes;
-        const uint32_t b_dst = a_dst + kStageABytes;
-        mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-        tma_load_5d(a_dst, &p.tmap[p.tap_view[t]], full_bar(stage), 0, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
-                    g * kGroupBlocks, img);
-        const uint8_t* wsrc = p.w + ((size_t)(p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * p.nout * 32;
-        bulk_load(b_dst, wsrc, (uint32_t)(p.gb * p.nout * 32), full_bar(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int r = tile;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y;
+        const int img = r / p.tiles_y;
+        const int x0 = tx * p.bw, y0 = ty * p.bh;
+        for (int it = 0; it < iters; ++it) {
+          const int t = it / p.ngroups, g = it - t * p.ngroups;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = stages0 + stage * p.stage_bytes;
+          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+          tma_load_5d(a_dst, &p.tmap[p.tap_view[t]], full_bar(stage), 0, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
+                      g * kGroupBlocks, img);
+          if (!p.resident_b) {
+            const uint8_t* wsrc = p.w + ((size_t)(p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * p.nout * 32;
+            bulk_load(a_dst + kStageABytes, wsrc, (uint32_t)(p.gb * p.nout * 32), full_bar(stage));
+          }
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t a_sub = (uint32_t)p.rows * 32u, b_sub = (uint32_t)p.nout * 32u;
-      for (int it = 0; it < iters; ++it) {
-        const int g = it % p.ngroups;
-        int nb = p.cin_blocks - g * kGroupBlocks;
-        if (nb > kGroupBlocks) nb = kGroupBlocks;
-        mbar_wait(full_bar(stage), phase);
+      if (p.resident_b) mbar_wait(bfull_bar, 0);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint32_t a_base = smem0 + stage * stage_bytes;
-        const uint32_t b_base = a_base + kStageABytes;
-        for (int j = 0; j < nb; ++j) {
-          const uint64_t ad = make_smem_desc(a_base + j * a_sub, 16, 256, kSwizzle32);
-          const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
-          mma_bf16(tmem_base, ad, bd, p.idesc, (it | j) != 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
+        for (int it = 0; it < iters; ++it) {
+          const int t = it / p.ngroups, g = it - t * p.ngroups;
+          int nb = p.cin_blocks - g * kGroupBlocks;
+          if (nb > kGroupBlocks) nb = kGroupBlocks;
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t a_base = stages0 + stage * p.stage_bytes;
+          const uint32_t b_base = p.resident_b
+                                      ? smem0 + (uint32_t)((p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * b_sub
+                                      : a_base + kStageABytes;
+          for (int j = 0; j < nb; ++j) {
+            const uint64_t ad = make_smem_desc(a_base + j * a_sub, 16, 256, kSwizzle32);
+            const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
+            mma_bf16(d_tmem, ad, bd, p.idesc, (it | j) != 0);
+          }
+          mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
-        if (it == iters - 1) mma_commit(tmem_full_bar);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        mma_commit(tfull_bar(buf));                     // accumulator ready for the epilogue
       }
     }
   } else {
@@ -119,56 +202,39 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m / p.bw, px = m - py * p.bw;
-    const int y = y0 + py, x = x0 + px;
-    const bool valid = (m < p.rows) && (y < p.y.H) && (x < p.y.W);
-    mbar_wait(tmem_full_bar, 0);
-    fence_after_sync();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const long long ypix = (long long)img * p.y.sN + (long long)y * p.y.sY + (long long)x * p.y.sX;
-    const long long apix = (long long)img * p.addend.sN + (long long)y * p.addend.sY + (long long)x * p.addend.sX;
-    const long long mpix = (long long)img * p.mask.sN + (long long)y * p.mask.sY + (long long)x * p.mask.sX;
-    for (int cb = 0; cb < p.nout / 16; ++cb) {
-      float v[16];
-      tmem_ld16(lane_addr + cb * 16, v);
-      if (valid) {
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = __ldg(b4 + q);
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-          }
-        }
-        if (p.has_addend) {
-          float a[16];
-          Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.addend.ptr + apix + cb * p.addend.sCb, a);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] += a[q];
-        }
-        if (p.act) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
-        }
-        if (p.has_mask) {
-          float mk[16];
-          Block16<__nv_bfloat16>::load((const __nv_bfloat16*)p.mask.ptr + mpix + cb * p.mask.sCb, mk);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] *= (mk[q] > 0.f ? 1.f : p.slope);
-        }
-        if (p.out_nchw) {
-          const long long hw = (long long)p.y.H * p.y.W;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int n = cb * 16 + q;
-            if (n < p.out_c) p.out_nchw[((long long)img * p.out_c + n) * hw + (long long)y * p.y.W + x] = v[q];
-          }
-        } else {
-          Block16<__nv_bfloat16>::store((__nv_bfloat16*)p.y.ptr + ypix + cb * p.y.sCb, v);
-        }
+    const int nblk = p.nout / 16;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      int r = tile;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      EpiCtx c;
+      c.p = &p;
+      c.img = r / p.tiles_y;
+      c.y = ty * p.bh + py; c.x = tx * p.bw + px;
+      c.valid = (m < p.rows) && (c.y < p.y.H) && (c.x < p.y.W);
+      c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
+      c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
+      c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
+      const int buf = lt & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      fence_after_sync();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
+      for (int cb = 0; cb < nblk; cb += 2) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_issue(lane_addr + cb * 16, r0);
+        const bool two = cb + 1 < nblk;
+        if (two) tmem_ld16_issue(lane_addr + (cb + 1) * 16, r1);
+        tmem_ld_wait();
+        epilogue_block(c, cb, r0);
+        if (two) epilogue_block(c, cb + 1, r1);
       }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));      // this warp's quarter of the accumulator is drained
     }
-    fence_before_sync();
   }
+  fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     fence_after_sync();
@@ -225,6 +291,16 @@ void choose_tile(int H, int W, int& bw, int& bh) {
   }
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+  }
+  return n;
+}
+
 int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(g.nout >= 16 && g.nout <= 256 && g.nout % 16 == 0, "tapgemm_umma: nout=%d unsupported", g.nout);
   static bool attr_set = false;
@@ -233,7 +309,7 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   const int H = g.y.H, W = g.y.W;
   int bw, bh;
   choose_tile(H, W, bw, bh);
-  if (bh > H) bh = H;                    // 8x8 level: a single image supplies only 64 rows
+  if (bh > H) bh = H;
   p.bw = bw; p.bh = bh; p.rows = bw * bh;
   p.tiles_x = (W + bw - 1) / bw; p.tiles_y = (H + bh - 1) / bh;
   p.ntaps = g.ntaps;
@@ -253,31 +329,64 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
     N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, p.gb));
   }
   p.w = (const uint8_t*)g.w; p.bias = g.bias; p.y = g.y;
+  if (g.ntaps == 1 && g.tap_slab[0] != 0) {
+    // single-tap launch on slab k of a multi-slab tensor (deconv parity): rebase so that slab order == tap order
+    p.w += (size_t)g.tap_slab[0] * p.ngroups * kGroupBlocks * g.nout * 32;
+    p.tap_slab[0] = 0;
+  }
   p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
   p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
-  p.stage_b_bytes = (uint32_t)align_up((size_t)kGroupBlocks * g.nout * 32, 1024);
-  p.tx_bytes = (uint32_t)(p.gb * p.rows * 32 + p.gb * g.nout * 32);
-  p.tmem_cols = tmem_cols_for(g.nout);
-  p.idesc = make_idesc_bf16(128, g.nout, false, false);
-  const size_t smem = 1024 + (size_t)kStages * (kStageABytes + p.stage_b_bytes);
-  if (!attr_set) {
-    N2N_CUDA(cudaFuncSetAttribute(tapgemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;
   N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "tapgemm_umma: bad tile count");
-  tapgemm_umma_kernel<<<(unsigned)tiles, kThreads, smem, st>>>(p);
+  p.ntiles = (int)tiles;
+
+  // Weights resident in shared memory when they fit beside >= 4 activation stages and every tap uses
+  // its own slab in order (so slab i of the packed tensor is (tap, group) iteration i).
+  const size_t slab_bytes = (size_t)kGroupBlocks * g.nout * 32;
+  const size_t b_total = (size_t)g.ntaps * p.ngroups * slab_bytes;
+  bool ordered = true;
+  for (int t = 0; t < g.ntaps; ++t) ordered = ordered && (p.tap_slab[t] == t);
+  const size_t stage_b = align_up(slab_bytes, 1024);
+  if (ordered && b_total + 4 * (size_t)kStageABytes <= kSmemBudget && tiles >= 2 * num_sms()) {
+    p.resident_b = 1;
+    p.b_total_bytes = (uint32_t)b_total;
+    p.b_region_bytes = (uint32_t)align_up(b_total, 1024);
+    p.stage_bytes = kStageABytes;
+    p.tx_bytes = (uint32_t)(p.gb * p.rows * 32);
+  } else {
+    p.resident_b = 0;
+    p.b_region_bytes = 0;
+    p.stage_bytes = (uint32_t)(kStageABytes + stage_b);
+    p.tx_bytes = (uint32_t)(p.gb * p.rows * 32 + p.gb * g.nout * 32);
+  }
+  int nst = (int)((kSmemBudget - p.b_region_bytes) / p.stage_bytes);
+  if (nst > kMaxStages) nst = kMaxStages;
+  N2N_CHECK_ARG(nst >= 2, "tapgemm_umma: not enough shared memory for a pipeline (nout=%d)", g.nout);
+  p.nstages = nst;
+  p.tmem_cols = tmem_cols_for(2 * g.nout);
+  p.idesc = make_idesc_bf16(128, g.nout, false, false);
+  const size_t smem = 1024 + (size_t)p.b_region_bytes + (size_t)nst * p.stage_bytes;
+  if (!attr_set) {
+    N2N_CUDA(cudaFuncSetAttribute(tapgemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_set = true;
+  }
+  const int grid = tiles < num_sms() ? (int)tiles : num_sms();
+  tapgemm_umma_kernel<<<grid, kThreads, smem, st>>>(p);
   N2N_LAUNCH_CHECK();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// Bring-up probe: a single-CTA GEMM D[128, N] = A[128, K] * B[N, K]^T (bf16 -> fp32) whose
-// operands are written to shared memory by ordinary stores in the exact layouts the engines
-// assume.  It validates the descriptor encodings independently of TMA.
-//   variant 0: K-major  SWIZZLE_32B  ([k/16][row][32 B])            — forward / dgrad engine
-//   variant 1: MN-major SWIZZLE_32B  ([mn/16][k][32 B], LBO = atom) — weight-gradient engine
-//   variant 2: as 1 with LBO/SBO swapped (diagnostic)
+// Bring-up probe: a single-CTA GEMM D[128, N] = A * B^T (bf16 -> fp32) whose operands are written
+// to shared memory by ordinary stores in the exact layouts the engines assume.  It validates the
+// descriptor encodings independently of TMA.  variant = base | shift << 8 | use_base_offset << 16
+//   base 0: K-major  SWIZZLE_32B  ([k/16][row][32 B])            — forward / dgrad engine
+//   base 1: MN-major SWIZZLE_32B  ([mn/16][k][32 B], LBO = atom) — weight-gradient engine
+//   base 2: as 1 with LBO/SBO swapped (diagnostic)
+//   base 3: as 0, but A holds 128+8 rows and the MMA starts `shift` rows (32 B each) into it:
+//           D[m] = A[m + shift] * B^T   (the dx-shifted view of one staged activation slab)
+//   base 4: as 1, but B holds K+8 pixel rows and the MMA starts `shift` rows into it:
+//           D[m][n] = sum_k A[k][m] * B[k + shift][n]   (tap-shifted X slab in the wgrad engine)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
@@ -288,13 +397,17 @@ probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_b
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* s = smem_raw + (smem0 - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = variant & 0xff, shift = (variant >> 8) & 0xff, use_bo = (variant >> 16) & 1;
   const uint32_t ncols = 256;
-  const uint32_t a_bytes = 128u * K * 2u;
-  uint8_t* sa = s; uint8_t* sb = s + a_bytes;
-  if (variant == 0) {
-    for (int i = threadIdx.x; i < 128 * K; i += 128) {
+  const int a_rows = base == 3 ? 136 : 128;          // rows of A (K-major) ...
+  const int b_krows = base == 4 ? K + 8 : K;          // ... pixel rows of B (MN-major)
+  const uint32_t a_bytes = base == 0 || base == 3 ? (uint32_t)a_rows * K * 2u : 128u * K * 2u;
+  uint8_t* sa = s; uint8_t* sb = s + ((a_bytes + 1023u) & ~1023u);
+  const uint32_t sb_addr = smem0 + ((a_bytes + 1023u) & ~1023u);
+  if (base == 0 || base == 3) {
+    for (int i = threadIdx.x; i < a_rows * K; i += 128) {
       const int r = i / K, k = i % K, kb = k >> 4, e = k & 15;
-      const uint32_t off = (uint32_t)kb * 128 * 32 + r * 32 + ((((e >> 3) ^ ((r >> 2) & 1))) << 4) + (e & 7) * 2;
+      const uint32_t off = (uint32_t)kb * a_rows * 32 + r * 32 + ((((e >> 3) ^ ((r >> 2) & 1))) << 4) + (e & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[i];
     }
     for (int i = threadIdx.x; i < N * K; i += 128) {
@@ -303,14 +416,16 @@ probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_b
       *reinterpret_cast<__nv_bfloat16*>(sb + off) = B[i];
     }
   } else {
+    // A given as [128][K] (row m, col k) -> stored [m/16][k][m%16]
     for (int i = threadIdx.x; i < 128 * K; i += 128) {
       const int r = i / K, k = i % K, mb = r >> 4, e = r & 15;
       const uint32_t off = (uint32_t)mb * K * 32 + k * 32 + ((((e >> 3) ^ ((k >> 2) & 1))) << 4) + (e & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[i];
     }
-    for (int i = threadIdx.x; i < N * K; i += 128) {
-      const int r = i / K, k = i % K, nb = r >> 4, e = r & 15;
-      const uint32_t off = (uint32_t)nb * K * 32 + k * 32 + ((((e >> 3) ^ ((k >> 2) & 1))) << 4) + (e & 7) * 2;
+    // B given as [N][b_krows] -> stored [n/16][k][n%16]
+    for (int i = threadIdx.x; i < N * b_krows; i += 128) {
+      const int r = i / b_krows, k = i % b_krows, nb = r >> 4, e = r & 15;
+      const uint32_t off = (uint32_t)nb * b_krows * 32 + k * 32 + ((((e >> 3) ^ ((k >> 2) & 1))) << 4) + (e & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(sb + off) = B[i];
     }
   }
@@ -322,19 +437,21 @@ probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_b
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   if (threadIdx.x == 0) {
-    const bool mn = variant != 0;
+    const bool mn = !(base == 0 || base == 3);
     const uint32_t idesc = make_idesc_bf16(128, N, mn, mn);
     for (int kk = 0; kk < K / 16; ++kk) {
       uint64_t ad, bd;
-      if (variant == 0) {
-        ad = make_smem_desc(smem0 + kk * 128 * 32, 16, 256, kSwizzle32);
-        bd = make_smem_desc(smem0 + a_bytes + kk * N * 32, 16, 256, kSwizzle32);
-      } else if (variant == 1) {
+      if (base == 0 || base == 3) {
+        const uint32_t a_start = smem0 + kk * a_rows * 32 + (base == 3 ? shift * 32 : 0);
+        ad = make_smem_desc(a_start, 16, 256, kSwizzle32, use_bo ? (a_start >> 7) & 7 : 0);
+        bd = make_smem_desc(sb_addr + kk * N * 32, 16, 256, kSwizzle32);
+      } else if (base == 1 || base == 4) {
+        const uint32_t b_start = sb_addr + kk * 16 * 32 + (base == 4 ? shift * 32 : 0);
         ad = make_smem_desc(smem0 + kk * 16 * 32, (uint32_t)K * 32, 256, kSwizzle32);
-        bd = make_smem_desc(smem0 + a_bytes + kk * 16 * 32, (uint32_t)K * 32, 256, kSwizzle32);
+        bd = make_smem_desc(b_start, (uint32_t)b_krows * 32, 256, kSwizzle32, use_bo ? (b_start >> 7) & 7 : 0);
       } else {
         ad = make_smem_desc(smem0 + kk * 16 * 32, 256, (uint32_t)K * 32, kSwizzle32);
-        bd = make_smem_desc(smem0 + a_bytes + kk * 16 * 32, 256, (uint32_t)K * 32, kSwizzle32);
+        bd = make_smem_desc(sb_addr + kk * 16 * 32, 256, (uint32_t)K * 32, kSwizzle32);
       }
       mma_bf16(tmem_base, ad, bd, idesc, kk != 0);
     }
@@ -361,8 +478,9 @@ extern "C" int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf1
                               void* stream) {
   N2N_CHECK_ARG(m == 128 && n >= 16 && n <= 256 && n % 16 == 0 && k >= 16 && k % 16 == 0 && k <= 256,
                 "probe_umma: need m=128, n%%16==0 (<=256), k%%16==0 (<=256)");
-  N2N_CHECK_ARG(variant >= 0 && variant <= 2 && a_bf16 && b_bf16 && d, "probe_umma: bad arguments");
-  const size_t smem = 1024 + (size_t)(128 + n) * k * 2;
+  const int base = variant & 0xff;
+  N2N_CHECK_ARG(base >= 0 && base <= 4 && ((variant >> 8) & 0xff) <= 8 && a_bf16 && b_bf16 && d, "probe_umma: bad arguments");
+  const size_t smem = 4096 + (size_t)136 * k * 2 + (size_t)n * (k + 8) * 2;
   N2N_CUDA(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const __nv_bfloat16*)a_bf16,
                                                             (const __nv_bfloat16*)b_bf16, d, n, k);

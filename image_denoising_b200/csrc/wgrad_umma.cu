@@ -161,39 +161,48 @@ tapwgrad_umma_kernel(const __grid_constant__ UmmaWgradParams p) {
   if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
-// Bias gradient: bias_partial[row][n] = sum over the row's pixel range of dY[p, n].
-// One block per (split, dY view); HBM-bound single pass over dY.
+// Bias gradient: bias_partial[row = split * ndyviews + view][n] = sum over the split's pixel range
+// of dY_view[p, n].  One block per (row, 16-channel block): consecutive threads read consecutive
+// pixels (32 B each -> 1 KB per warp, fully coalesced); HBM-bound single pass over dY.
 __global__ void __launch_bounds__(256)
-bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, int splits, long long pixels,
-                 long long per_split, float* __restrict__ bias_partial, int npad) {
-  __shared__ float acc[256];
+bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, long long pixels, long long per_split,
+                 float* __restrict__ bias_partial, int npad) {
+  __shared__ float red[8][16];
+  const int cb = blockIdx.y;
   const int split = blockIdx.x / ndyviews, vi = blockIdx.x - split * ndyviews;
   const View& dv = vi == 0 ? dy0 : vi == 1 ? dy1 : vi == 2 ? dy2 : dy3;
-  for (int i = threadIdx.x; i < npad; i += 256) acc[i] = 0.f;
-  __syncthreads();
   const long long p0 = (long long)split * per_split;
   long long p1 = p0 + per_split;
   if (p1 > pixels) p1 = pixels;
-  const int tpc = 256 / dv.Cb;                   // pixel lanes; each thread stays on one channel block
-  const int cb_mine = threadIdx.x % dv.Cb, plane = threadIdx.x / dv.Cb;
-  if (plane < tpc) {
-    float s[16];
+  float s[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) s[q] = 0.f;
-    for (long long pp = p0 + plane; pp < p1; pp += tpc) {
-      const int x = (int)(pp % dv.W);
-      const int y = (int)((pp / dv.W) % dv.H);
-      const int img = (int)(pp / ((long long)dv.W * dv.H));
-      float v[16];
-      Block16<__nv_bfloat16>::load((const __nv_bfloat16*)dv.ptr + img * dv.sN + cb_mine * dv.sCb + y * dv.sY + x * dv.sX, v);
+  for (int q = 0; q < 16; ++q) s[q] = 0.f;
+  const long long hw = (long long)dv.W * dv.H;
+  for (long long pp = p0 + threadIdx.x; pp < p1; pp += 256) {
+    const int img = (int)(pp / hw);
+    const long long r = pp - (long long)img * hw;
+    const int y = (int)(r / dv.W), x = (int)(r - (long long)y * dv.W);
+    float v[16];
+    Block16<__nv_bfloat16>::load((const __nv_bfloat16*)dv.ptr + img * dv.sN + cb * dv.sCb + y * dv.sY + x * dv.sX, v);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) s[q] += v[q];
-    }
+    for (int q = 0; q < 16; ++q) s[q] += v[q];
+  }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) atomicAdd(&acc[cb_mine * 16 + q], s[q]);
+  for (int q = 0; q < 16; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) red[warp][q] = s[q];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npad; i += 256) bias_partial[(long long)blockIdx.x * npad + i] = acc[i];
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    bias_partial[(long long)blockIdx.x * npad + cb * 16 + threadIdx.x] = t;
+  }
 }
 
 void choose_tile(int H, int W, int& bw, int& bh);
@@ -262,8 +271,9 @@ int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st) {
   if (g.bias_partial) {
     const long long pixels = (long long)g.dy[0].N * g.dy[0].H * g.dy[0].W;
     const long long per_split = (pixels + splits - 1) / splits;
-    bias_grad_kernel<<<splits * g.ndyviews, 256, 0, st>>>(g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, splits, pixels,
-                                                          per_split, g.bias_partial, g.n_blocks * 16);
+    dim3 bgrid(splits * g.ndyviews, g.n_blocks);
+    bias_grad_kernel<<<bgrid, 256, 0, st>>>(g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, pixels, per_split,
+                                            g.bias_partial, g.n_blocks * 16);
     N2N_LAUNCH_CHECK();
   }
   return 0;
