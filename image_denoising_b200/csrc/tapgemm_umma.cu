@@ -24,14 +24,26 @@ using namespace umma;
 constexpr int kMaxStages = 8;
 constexpr int kGroupBlocks = 3;
 constexpr int kThreads = 192;
-constexpr uint32_t kStageABytes = kGroupBlocks * 128 * 32;
+constexpr int kSlabRows = 136;                    // 128 pixels + left/right halo, padded to a multiple of 8 rows
+constexpr int kMaxEntries = 32;
 constexpr size_t kSmemBudget = 232448 - 4096;     // 227 KB per CTA minus static/alignment slack
+
+// One pipeline stage of the main loop: one staged activation tile (<= 3 channel blocks of one view
+// at row offset dy) and the `ndx` horizontally shifted taps that consume it.  In slab mode
+// (128-pixel single-row tiles) the staged tile is 136 pixels wide and the three dx taps are views
+// of it that start 0 / 1 / 2 rows (32 B) into the slab, so every input pixel crosses L2->SMEM
+// three times per 3x3 conv instead of nine; otherwise ndx == 1 and the tile is exactly the tap.
+struct Entry {
+  int8_t view, dy, dx0, ndx;
+  int8_t cb0, nb, pad0, pad1;
+  uint32_t b_off[3];          // byte offsets (in the packed weight tensor) of the B sub-tiles, per dx tap
+};
 
 struct UmmaGemmParams {
   CUtensorMap tmap[4];
-  int ntaps;
-  int8_t tap_dy[9], tap_dx[9], tap_view[9], tap_slab[9];
-  int cin_blocks, ngroups, gb, nout;
+  Entry e[kMaxEntries];
+  int nentries;
+  int nout;
   const uint8_t* w;
   const float* bias;
   View y;
@@ -41,7 +53,10 @@ struct UmmaGemmParams {
   float* out_nchw; int out_c;
   int bw, bh, tiles_x, tiles_y, rows, ntiles;
   int resident_b, nstages;
-  uint32_t b_total_bytes, b_region_bytes, stage_bytes, tx_bytes, tmem_cols, idesc;
+  uint32_t a_sub;             // bytes between channel-block sub-tiles of a staged A tile
+  uint32_t a_tx[4];           // bytes one TMA box of each view delivers
+  uint32_t a_stage_bytes;     // offset of the streamed-B area inside a stage
+  uint32_t b_total_bytes, b_region_bytes, stage_bytes, tmem_cols, idesc;
 };
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
@@ -118,7 +133,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 1 + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 3 + b); };
-  const int iters = p.ntaps * p.ngroups;
+  const uint32_t b_sub = (uint32_t)p.nout * 32u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -140,8 +155,10 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
       for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
       if (p.resident_b) {
         mbar_arrive_expect_tx(bfull_bar, p.b_total_bytes);
-        const uint32_t slab = p.b_total_bytes / (uint32_t)iters;     // one (tap, group) slab per copy
-        for (int i = 0; i < iters; ++i) bulk_load(smem0 + i * slab, p.w + (size_t)i * slab, slab, bfull_bar);
+        for (uint32_t off = 0; off < p.b_total_bytes; off += 16384u) {
+          const uint32_t n = p.b_total_bytes - off < 16384u ? p.b_total_bytes - off : 16384u;
+          bulk_load(smem0 + off, p.w + off, n, bfull_bar);
+        }
       }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -150,16 +167,18 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         const int ty = r % p.tiles_y;
         const int img = r / p.tiles_y;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
-        for (int it = 0; it < iters; ++it) {
-          const int t = it / p.ngroups, g = it - t * p.ngroups;
+        for (int ei = 0; ei < p.nentries; ++ei) {
+          const Entry& e = p.e[ei];
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = stages0 + stage * p.stage_bytes;
-          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-          tma_load_5d(a_dst, &p.tmap[p.tap_view[t]], full_bar(stage), 0, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
-                      g * kGroupBlocks, img);
+          uint32_t tx_bytes = p.a_tx[e.view];
+          if (!p.resident_b) tx_bytes += (uint32_t)e.ndx * e.nb * b_sub;
+          mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+          tma_load_5d(a_dst, &p.tmap[e.view], full_bar(stage), 0, x0 + e.dx0, y0 + e.dy, e.cb0, img);
           if (!p.resident_b) {
-            const uint8_t* wsrc = p.w + ((size_t)(p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * p.nout * 32;
-            bulk_load(a_dst + kStageABytes, wsrc, (uint32_t)(p.gb * p.nout * 32), full_bar(stage));
+            for (int i = 0; i < e.ndx; ++i)
+              bulk_load(a_dst + p.a_stage_bytes + i * kGroupBlocks * b_sub, p.w + e.b_off[i], (uint32_t)e.nb * b_sub,
+                        full_bar(stage));
           }
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
@@ -168,7 +187,6 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t a_sub = (uint32_t)p.rows * 32u, b_sub = (uint32_t)p.nout * 32u;
       if (p.resident_b) mbar_wait(bfull_bar, 0);
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
@@ -176,20 +194,21 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
-        for (int it = 0; it < iters; ++it) {
-          const int t = it / p.ngroups, g = it - t * p.ngroups;
-          int nb = p.cin_blocks - g * kGroupBlocks;
-          if (nb > kGroupBlocks) nb = kGroupBlocks;
+        bool first = true;
+        for (int ei = 0; ei < p.nentries; ++ei) {
+          const Entry& e = p.e[ei];
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
           const uint32_t a_base = stages0 + stage * p.stage_bytes;
-          const uint32_t b_base = p.resident_b
-                                      ? smem0 + (uint32_t)((p.tap_slab[t] * p.ngroups + g) * kGroupBlocks) * b_sub
-                                      : a_base + kStageABytes;
-          for (int j = 0; j < nb; ++j) {
-            const uint64_t ad = make_smem_desc(a_base + j * a_sub, 16, 256, kSwizzle32);
-            const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
-            mma_bf16(d_tmem, ad, bd, p.idesc, (it | j) != 0);
+          for (int i = 0; i < e.ndx; ++i) {
+            const uint32_t b_base = p.resident_b ? smem0 + e.b_off[i] : a_base + p.a_stage_bytes + i * kGroupBlocks * b_sub;
+            for (int j = 0; j < e.nb; ++j) {
+              // dx tap i of a slab = the same staged tile, started i rows (32 B) further in
+              const uint64_t ad = make_smem_desc(a_base + j * p.a_sub + i * 32u, 16, 256, kSwizzle32);
+              const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
+              mma_bf16(d_tmem, ad, bd, p.idesc, !first);
+              first = false;
+            }
           }
           mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
@@ -312,52 +331,80 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   if (bh > H) bh = H;
   p.bw = bw; p.bh = bh; p.rows = bw * bh;
   p.tiles_x = (W + bw - 1) / bw; p.tiles_y = (H + bh - 1) / bh;
-  p.ntaps = g.ntaps;
-  int nviews = 0;
-  for (int t = 0; t < g.ntaps; ++t) {
-    p.tap_dy[t] = (int8_t)g.tap_dy[t]; p.tap_dx[t] = (int8_t)g.tap_dx[t];
-    p.tap_view[t] = (int8_t)g.tap_view[t]; p.tap_slab[t] = (int8_t)g.tap_slab[t];
-    if (g.tap_view[t] + 1 > nviews) nviews = g.tap_view[t] + 1;
-  }
-  p.cin_blocks = g.cin_blocks;
-  p.ngroups = (g.cin_blocks + kGroupBlocks - 1) / kGroupBlocks;
-  p.gb = g.cin_blocks < kGroupBlocks ? g.cin_blocks : kGroupBlocks;
   p.nout = g.nout;
+  const int ngroups = (g.cin_blocks + kGroupBlocks - 1) / kGroupBlocks;
+  const uint32_t b_sub = (uint32_t)g.nout * 32u;
+  const size_t slab_bytes = (size_t)kGroupBlocks * b_sub;               // one (tap, group) slab of the packed tensor
+  auto slab_off = [&](int slab, int grp) { return (uint32_t)(((size_t)slab * ngroups + grp) * slab_bytes); };
+
+  // slab mode: plain 3x3 tap pattern on one view, single-row 128-pixel tiles
+  bool slab = (g.ntaps == 9 && bw == 128 && bh == 1);
+  for (int t = 0; t < g.ntaps && slab; ++t)
+    slab = g.tap_view[t] == 0 && g.tap_dx[t] == (t % 3 - 1) * (g.tap_dx[1] - g.tap_dx[0] == 1 ? 1 : -1) &&
+           g.tap_dy[t] == g.tap_dy[3 * (t / 3)];
+  int ne = 0;
+  if (slab) {
+    // taps come dy-major; within a dy row dx is ascending (forward) or descending (input gradient)
+    const bool asc = g.tap_dx[0] == -1;
+    for (int r = 0; r < 3; ++r)
+      for (int grp = 0; grp < ngroups; ++grp) {
+        Entry& e = p.e[ne++];
+        e.view = 0; e.dy = (int8_t)g.tap_dy[3 * r]; e.dx0 = -1; e.ndx = 3;
+        e.cb0 = (int8_t)(grp * kGroupBlocks);
+        const int nb = g.cin_blocks - grp * kGroupBlocks;
+        e.nb = (int8_t)(nb < kGroupBlocks ? nb : kGroupBlocks);
+        for (int i = 0; i < 3; ++i) {               // i-th view of the slab = tap with dx = i - 1
+          const int t = 3 * r + (asc ? i : 2 - i);
+          e.b_off[i] = slab_off(g.tap_slab[t], grp);
+        }
+      }
+  } else {
+    N2N_CHECK_ARG(g.ntaps * ngroups <= kMaxEntries, "tapgemm_umma: too many pipeline entries");
+    for (int t = 0; t < g.ntaps; ++t)
+      for (int grp = 0; grp < ngroups; ++grp) {
+        Entry& e = p.e[ne++];
+        e.view = (int8_t)g.tap_view[t]; e.dy = (int8_t)g.tap_dy[t]; e.dx0 = (int8_t)g.tap_dx[t]; e.ndx = 1;
+        e.cb0 = (int8_t)(grp * kGroupBlocks);
+        const int nb = g.cin_blocks - grp * kGroupBlocks;
+        e.nb = (int8_t)(nb < kGroupBlocks ? nb : kGroupBlocks);
+        e.b_off[0] = slab_off(g.tap_slab[t], grp);
+      }
+  }
+  p.nentries = ne;
+  const int boxw = slab ? kSlabRows : bw;
+  const int gb = g.cin_blocks < kGroupBlocks ? g.cin_blocks : kGroupBlocks;
+  p.a_sub = (uint32_t)(boxw * bh * 32);
+  int nviews = 0;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.tap_view[t] + 1 > nviews) nviews = g.tap_view[t] + 1;
   for (int v = 0; v < 4; ++v) {
     const View& xv = g.x[v < nviews ? v : 0];
     N2N_CHECK_ARG(xv.H == H && xv.W == W && xv.Cb >= g.cin_blocks, "tapgemm_umma: view %d geometry mismatch", v);
-    N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, p.gb));
+    N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, boxw, bh, gb));
+    p.a_tx[v] = (uint32_t)(gb * boxw * bh * 32);
   }
   p.w = (const uint8_t*)g.w; p.bias = g.bias; p.y = g.y;
-  if (g.ntaps == 1 && g.tap_slab[0] != 0) {
-    // single-tap launch on slab k of a multi-slab tensor (deconv parity): rebase so that slab order == tap order
-    p.w += (size_t)g.tap_slab[0] * p.ngroups * kGroupBlocks * g.nout * 32;
-    p.tap_slab[0] = 0;
-  }
   p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
   p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
   const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;
   N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "tapgemm_umma: bad tile count");
   p.ntiles = (int)tiles;
 
-  // Weights resident in shared memory when they fit beside >= 4 activation stages and every tap uses
-  // its own slab in order (so slab i of the packed tensor is (tap, group) iteration i).
-  const size_t slab_bytes = (size_t)kGroupBlocks * g.nout * 32;
-  const size_t b_total = (size_t)g.ntaps * p.ngroups * slab_bytes;
-  bool ordered = true;
-  for (int t = 0; t < g.ntaps; ++t) ordered = ordered && (p.tap_slab[t] == t);
-  const size_t stage_b = align_up(slab_bytes, 1024);
-  if (ordered && b_total + 4 * (size_t)kStageABytes <= kSmemBudget && tiles >= 2 * num_sms()) {
+  // Weights stay resident in shared memory when the packed tensor (all slabs this launch may
+  // touch) fits beside >= 4 activation stages and there are enough tiles per CTA to amortise it.
+  int max_slab = 0;
+  for (int t = 0; t < g.ntaps; ++t) if (g.tap_slab[t] > max_slab) max_slab = g.tap_slab[t];
+  const size_t b_total = (size_t)(max_slab + 1) * ngroups * slab_bytes;
+  p.a_stage_bytes = (uint32_t)align_up((size_t)kGroupBlocks * boxw * bh * 32, 1024);
+  if (b_total + 4 * (size_t)p.a_stage_bytes <= kSmemBudget && tiles >= 2 * num_sms()) {
     p.resident_b = 1;
     p.b_total_bytes = (uint32_t)b_total;
     p.b_region_bytes = (uint32_t)align_up(b_total, 1024);
-    p.stage_bytes = kStageABytes;
-    p.tx_bytes = (uint32_t)(p.gb * p.rows * 32);
+    p.stage_bytes = p.a_stage_bytes;
   } else {
     p.resident_b = 0;
     p.b_region_bytes = 0;
-    p.stage_bytes = (uint32_t)(kStageABytes + stage_b);
-    p.tx_bytes = (uint32_t)(p.gb * p.rows * 32 + p.gb * g.nout * 32);
+    p.stage_bytes = (uint32_t)(p.a_stage_bytes + (slab ? 3 : 1) * align_up(slab_bytes, 1024));
   }
   int nst = (int)((kSmemBudget - p.b_region_bytes) / p.stage_bytes);
   if (nst > kMaxStages) nst = kMaxStages;

@@ -127,6 +127,10 @@ CONV_CASES = [  # (n, cin, cout, h, w, k)
     (1, 48, 48, 8, 8, 3), (1, 20, 24, 130, 18, 3),
     # several 128-pixel chunks per weight-gradient CTA (split-K accumulation across chunks)
     (4, 48, 48, 8, 8, 3), (3, 48, 96, 4, 4, 3), (4, 16, 16, 64, 64, 3), (2, 96, 48, 2, 2, 1),
+    # 128-pixel single-row tiles: the "slab" path (three dx taps share one staged 136-pixel row),
+    # with resident weights once there are >= 2 tiles per SM
+    (1, 96, 96, 5, 128, 3), (2, 48, 48, 3, 256, 3), (1, 144, 96, 2, 384, 3), (1, 97, 96, 3, 128, 3),
+    (2, 96, 96, 160, 256, 3), (1, 48, 96, 320, 128, 3), (1, 96, 96, 300, 128, 1),
 ]
 
 
