@@ -55,6 +55,7 @@ _SIGS = {
     "n2n_launch_count": (ctypes.c_longlong, []),
     "n2n_profile_begin": (c_int, []),
     "n2n_profile_end": (c_int, [POINTER(c_double)]),
+    "n2n_profile_end_list": (c_int, [POINTER(c_double), c_int]),
     "n2n_mask_pair_from_rdidx": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_subsample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "n2n_subsample_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

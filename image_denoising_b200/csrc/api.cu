@@ -98,6 +98,22 @@ extern "C" int n2n_profile_end(double* out) {
   g_prof->clear();
   return 0;
 }
+// Per-launch form of n2n_profile_end: rows of {class, ms, executed FLOPs} in launch order.
+extern "C" int n2n_profile_end_list(double* out, int max_rows) {
+  N2N_CHECK_ARG(out != nullptr && max_rows >= 0, "profile_end_list: bad arguments");
+  g_prof_on = false;
+  int n = 0;
+  if (!g_prof) return 0;
+  for (auto& r : *g_prof) {
+    N2N_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    N2N_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (n < max_rows) { out[3 * n] = r.cls; out[3 * n + 1] = ms; out[3 * n + 2] = r.flops; ++n; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof->clear();
+  return n;
+}
 extern "C" int n2n_device_ok(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }

@@ -52,6 +52,8 @@ long long n2n_launch_count(void);
  * forward + input gradient) followed by the same three for the weight-gradient kernel. */
 int n2n_profile_begin(void);
 int n2n_profile_end(double* out);
+/* Per-launch variant: fills rows of {class, ms, executed FLOPs} in launch order, returns the row count. */
+int n2n_profile_end_list(double* out, int max_rows);
 
 /* ------------------------------------------------------------------------- *
  * Neighbour sub-sampler — train.py:141-190 (generate_mask_pair,
