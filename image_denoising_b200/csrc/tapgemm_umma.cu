@@ -14,6 +14,8 @@
 //            accumulators are double-buffered in TMEM so tile i+1's MMAs overlap tile i's epilogue
 //   warps 2-5: epilogue: tcgen05.ld -> bias / addend / LeakyReLU / mask -> bf16 C16 store
 //            (32 B per pixel per block, contiguous across the warp) or fp32 NCHW
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -35,7 +37,7 @@ constexpr size_t kSmemBudget = 232448 - 4096;     // 227 KB per CTA minus static
 // three times per 3x3 conv instead of nine; otherwise ndx == 1 and the tile is exactly the tap.
 struct Entry {
   int8_t view, dy, dx0, ndx;
-  int8_t cb0, nb, pad0, pad1;
+  int8_t cb0, nb, pf, pad1;      // pf: issue an L2 prefetch for this entry's box of a future tile
   uint32_t b_off[3];          // byte offsets (in the packed weight tensor) of the B sub-tiles, per dx tap
 };
 
@@ -52,7 +54,7 @@ struct UmmaGemmParams {
   int act; float slope;
   float* out_nchw; int out_c;
   int bw, bh, tiles_x, tiles_y, rows, ntiles;
-  int resident_b, nstages;
+  int resident_b, nstages, prefetch_dist;
   uint32_t a_sub;             // bytes between channel-block sub-tiles of a staged A tile
   uint32_t a_tx[4];           // bytes one TMA box of each view delivers
   uint32_t a_stage_bytes;     // offset of the streamed-B area inside a stage
@@ -167,8 +169,19 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         const int ty = r % p.tiles_y;
         const int img = r / p.tiles_y;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
+        // L2 prefetch of the tile this CTA will process `prefetch_dist` rounds from now
+        const int ptile = tile + p.prefetch_dist * (int)gridDim.x;
+        int pimg = 0, px0 = 0, py0 = 0;
+        const bool do_pf = p.prefetch_dist > 0 && ptile < p.ntiles;
+        if (do_pf) {
+          int q = ptile;
+          px0 = (q % p.tiles_x) * p.bw; q /= p.tiles_x;
+          py0 = (q % p.tiles_y) * p.bh;
+          pimg = q / p.tiles_y;
+        }
         for (int ei = 0; ei < p.nentries; ++ei) {
           const Entry& e = p.e[ei];
+          if (do_pf && e.pf) tma_prefetch_l2_5d(&p.tmap[e.view], 0, px0 + e.dx0, py0 + e.dy, e.cb0, pimg);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = stages0 + stage * p.stage_bytes;
           uint32_t tx_bytes = p.a_tx[e.view];
@@ -353,6 +366,7 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
         e.cb0 = (int8_t)(grp * kGroupBlocks);
         const int nb = g.cin_blocks - grp * kGroupBlocks;
         e.nb = (int8_t)(nb < kGroupBlocks ? nb : kGroupBlocks);
+        e.pf = 1;
         for (int i = 0; i < 3; ++i) {               // i-th view of the slab = tap with dx = i - 1
           const int t = 3 * r + (asc ? i : 2 - i);
           e.b_off[i] = slab_off(g.tap_slab[t], grp);
@@ -368,9 +382,14 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
         const int nb = g.cin_blocks - grp * kGroupBlocks;
         e.nb = (int8_t)(nb < kGroupBlocks ? nb : kGroupBlocks);
         e.b_off[0] = slab_off(g.tap_slab[t], grp);
+        e.pf = (g.tap_dx[t] == 0) ? 1 : 0;          // the dx = +-1 boxes touch the same lines as dx = 0
       }
   }
   p.nentries = ne;
+  {
+    const char* pd = getenv("N2N_PREFETCH_DIST");
+    p.prefetch_dist = pd ? atoi(pd) : 2;
+  }
   const int boxw = slab ? kSlabRows : bw;
   const int gb = g.cin_blocks < kGroupBlocks ? g.cin_blocks : kGroupBlocks;
   p.a_sub = (uint32_t)(boxw * bh * 32);
