@@ -536,6 +536,48 @@ probe_umma_kernel(int variant, const __nv_bfloat16* __restrict__ A, const __nv_b
   if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
 }
 
+// Throughput probe: every SM issues `iters` back-to-back tcgen05.mma (M=128, N, K=16, bf16) on
+// shared-memory operands in the given K-major layout (contents irrelevant) and reports cycles.
+//   layout 0: SWIZZLE_32B rows of 32 B (one 16-channel block per row)   [what the conv engine uses]
+//   layout 1: SWIZZLE_128B rows of 128 B, the MMA consuming 32 B slices of them (k advances inside the row)
+//   layout 2: SWIZZLE_64B rows of 64 B
+__global__ void __launch_bounds__(128)
+probe_mma_rate_kernel(int layout, int N, int iters, int naccum, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 60 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (smem0 - smem_u32(smem_raw)))[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint32_t rowb = layout == 0 ? 32u : (layout == 1 ? 128u : 64u);
+    const uint32_t sw = layout == 0 ? kSwizzle32 : (layout == 1 ? kSwizzle128 : kSwizzle64);
+    const uint32_t ksteps = rowb / 32u;                       // K=16 slices per staged row
+    const uint32_t a0 = smem0, b0 = smem0 + 128u * rowb;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t kk = (uint32_t)it % ksteps;
+      const uint64_t ad = make_smem_desc(a0 + kk * 32u, 16, 8u * rowb, sw);
+      const uint64_t bd = make_smem_desc(b0 + kk * 32u, 16, 8u * rowb, sw);
+      mma_bf16(tmem_base + (uint32_t)((it % naccum) * N), ad, bd, idesc, it >= naccum);
+    }
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace n2n
 
 using namespace n2n;
@@ -550,6 +592,15 @@ extern "C" int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf1
   N2N_CUDA(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const __nv_bfloat16*)a_bf16,
                                                             (const __nv_bfloat16*)b_bf16, d, n, k);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_probe_mma_rate(int layout, int n, int iters, int naccum, long long* cycles_dev, int nblocks, void* stream) {
+  N2N_CHECK_ARG(layout >= 0 && layout <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && naccum >= 1 &&
+                    naccum * n <= 512 && cycles_dev && nblocks > 0, "probe_mma_rate: bad arguments");
+  N2N_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  probe_mma_rate_kernel<<<nblocks, 128, 62 * 1024, (cudaStream_t)stream>>>(layout, n, iters, naccum, cycles_dev);
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -220,6 +220,10 @@ int n2n_psnr_ssim_u8(const uint8_t* a, const uint8_t* b, int batch, int h, int w
  * ------------------------------------------------------------------------- */
 int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf16, float* d,
                    int m, int n, int k, void* stream);
+/* tcgen05.mma issue-rate probe: cycles for `iters` back-to-back M=128 x N x K=16 bf16 MMAs per CTA
+ * on shared-memory operands in K-major layout 0 (SWIZZLE_32B), 1 (SWIZZLE_128B) or 2 (SWIZZLE_64B),
+ * round-robin over `naccum` accumulators.  cycles_dev: int64[nblocks]. */
+int n2n_probe_mma_rate(int layout, int n, int iters, int naccum, long long* cycles_dev, int nblocks, void* stream);
 
 #ifdef __cplusplus
 }
