@@ -201,26 +201,38 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       if (p.resident_b) mbar_wait(bfull_bar, 0);
+      const uint32_t dhi = desc_hi(256, kSwizzle32);
+      const uint32_t a_sub16 = p.a_sub >> 4, b_sub16 = b_sub >> 4;
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
-        bool first = true;
+        uint32_t acc = 0;
         for (int ei = 0; ei < p.nentries; ++ei) {
-          const Entry& e = p.e[ei];
+          const int ndx = p.e[ei].ndx, nb = p.e[ei].nb;
+          const uint32_t bo0 = p.e[ei].b_off[0], bo1 = p.e[ei].b_off[1], bo2 = p.e[ei].b_off[2];
+          const uint32_t a_base = stages0 + stage * p.stage_bytes;
+          const uint32_t a_lo = desc_lo(a_base, 16);
+          const uint32_t bs = a_base + p.a_stage_bytes;       // streamed-B area of this stage
+          const uint32_t b_lo0 = desc_lo(p.resident_b ? smem0 + bo0 : bs, 16);
+          const uint32_t b_lo1 = desc_lo(p.resident_b ? smem0 + bo1 : bs + kGroupBlocks * b_sub, 16);
+          const uint32_t b_lo2 = desc_lo(p.resident_b ? smem0 + bo2 : bs + 2 * kGroupBlocks * b_sub, 16);
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
-          const uint32_t a_base = stages0 + stage * p.stage_bytes;
-          for (int i = 0; i < e.ndx; ++i) {
-            const uint32_t b_base = p.resident_b ? smem0 + e.b_off[i] : a_base + p.a_stage_bytes + i * kGroupBlocks * b_sub;
-            for (int j = 0; j < e.nb; ++j) {
-              // dx tap i of a slab = the same staged tile, started i rows (32 B) further in
-              const uint64_t ad = make_smem_desc(a_base + j * p.a_sub + i * 32u, 16, 256, kSwizzle32);
-              const uint64_t bd = make_smem_desc(b_base + j * b_sub, 16, 256, kSwizzle32);
-              mma_bf16(d_tmem, ad, bd, p.idesc, !first);
-              first = false;
+          // dx tap i of a slab = the same staged tile started i rows (32 B = 2 descriptor units) further in
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (i < ndx) {
+              const uint32_t bl = i == 0 ? b_lo0 : (i == 1 ? b_lo1 : b_lo2);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                if (j < nb) {
+                  mma_bf16_lo(d_tmem, a_lo + j * a_sub16 + 2u * i, bl + j * b_sub16, dhi, p.idesc, acc);
+                  acc = 1;
+                }
+              }
             }
           }
           mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
@@ -562,12 +574,17 @@ probe_mma_rate_kernel(int layout, int N, int iters, int naccum, long long* __res
     const uint32_t sw = layout == 0 ? kSwizzle32 : (layout == 1 ? kSwizzle128 : kSwizzle64);
     const uint32_t ksteps = rowb / 32u;                       // K=16 slices per staged row
     const uint32_t a0 = smem0, b0 = smem0 + 128u * rowb;
+    const uint32_t hi = desc_hi(8u * rowb, sw);
+    const uint32_t a_lo = desc_lo(a0, 16), b_lo = desc_lo(b0, 16);
+    const uint32_t d1 = tmem_base + (naccum > 1 ? (uint32_t)N : 0u);
+    (void)ksteps;
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      const uint32_t kk = (uint32_t)it % ksteps;
-      const uint64_t ad = make_smem_desc(a0 + kk * 32u, 16, 8u * rowb, sw);
-      const uint64_t bd = make_smem_desc(b0 + kk * 32u, 16, 8u * rowb, sw);
-      mma_bf16(tmem_base + (uint32_t)((it % naccum) * N), ad, bd, idesc, it >= naccum);
+    mma_bf16_lo(tmem_base, a_lo, b_lo, hi, idesc, 0);
+    mma_bf16_lo(d1, a_lo, b_lo, hi, idesc, 0);
+    for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        mma_bf16_lo((u & 1) ? d1 : tmem_base, a_lo + ((u & (ksteps - 1)) << 1), b_lo + ((u & (ksteps - 1)) << 1), hi, idesc, 1);
     }
     mma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
