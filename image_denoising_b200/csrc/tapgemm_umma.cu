@@ -59,6 +59,7 @@ struct UmmaGemmParams {
   uint32_t a_tx[4];           // bytes one TMA box of each view delivers
   uint32_t a_stage_bytes;     // offset of the streamed-B area inside a stage
   uint32_t b_total_bytes, b_region_bytes, stage_bytes, tmem_cols, idesc;
+  long long* dbg;             // optional stall counters (CTA 0): see n2n_debug_stall_buffer
 };
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
@@ -163,6 +164,8 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         }
       }
       int stage = 0; uint32_t phase = 0;
+      long long st_prod = 0;
+      const long long k0 = clock64();
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int r = tile;
         const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -182,7 +185,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         for (int ei = 0; ei < p.nentries; ++ei) {
           const Entry& e = p.e[ei];
           if (do_pf && e.pf) tma_prefetch_l2_5d(&p.tmap[e.view], 0, px0 + e.dx0, py0 + e.dy, e.cb0, pimg);
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          { const long long w0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u); st_prod += clock64() - w0; }
           const uint32_t a_dst = stages0 + stage * p.stage_bytes;
           uint32_t tx_bytes = p.a_tx[e.view];
           if (!p.resident_b) tx_bytes += (uint32_t)e.ndx * e.nb * b_sub;
@@ -196,6 +199,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_prod; p.dbg[1] = clock64() - k0; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -203,10 +207,12 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
       if (p.resident_b) mbar_wait(bfull_bar, 0);
       const uint32_t dhi = desc_hi(256, kSwizzle32);
       const uint32_t a_sub16 = p.a_sub >> 4, b_sub16 = b_sub >> 4;
+      long long st_full = 0, st_tempty = 0;
+      const long long k0 = clock64();
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
-        mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        { const long long w0 = clock64(); mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u); st_tempty += clock64() - w0; }
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
         uint32_t acc = 0;
@@ -219,7 +225,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
           const uint32_t b_lo0 = desc_lo(p.resident_b ? smem0 + bo0 : bs, 16);
           const uint32_t b_lo1 = desc_lo(p.resident_b ? smem0 + bo1 : bs + kGroupBlocks * b_sub, 16);
           const uint32_t b_lo2 = desc_lo(p.resident_b ? smem0 + bo2 : bs + 2 * kGroupBlocks * b_sub, 16);
-          mbar_wait(full_bar(stage), phase);
+          { const long long w0 = clock64(); mbar_wait(full_bar(stage), phase); st_full += clock64() - w0; }
           fence_after_sync();
           // dx tap i of a slab = the same staged tile started i rows (32 B = 2 descriptor units) further in
 #pragma unroll
@@ -240,6 +246,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         }
         mma_commit(tfull_bar(buf));                     // accumulator ready for the epilogue
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[2] = st_full; p.dbg[3] = st_tempty; p.dbg[4] = clock64() - k0; p.dbg[5] = lt; }
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32) ----
@@ -247,6 +254,8 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
     const int m = quarter * 32 + lane;
     const int py = m / p.bw, px = m - py * p.bw;
     const int nblk = p.nout / 16;
+    long long st_tfull = 0;
+    const long long k0 = clock64();
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
       int r = tile;
@@ -261,7 +270,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
       c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
       c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
       const int buf = lt & 1;
-      mbar_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      { const long long w0 = clock64(); mbar_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u); st_tfull += clock64() - w0; }
       fence_after_sync();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
       for (int cb = 0; cb < nblk; cb += 2) {
@@ -277,6 +286,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));      // this warp's quarter of the accumulator is drained
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] = st_tfull; p.dbg[7] = clock64() - k0; }
   }
   fence_before_sync();
   __syncthreads();
@@ -344,6 +354,9 @@ static int num_sms() {
   }
   return n;
 }
+
+static long long* g_dbg_buf = nullptr;
+void set_debug_stall_buffer(long long* p) { g_dbg_buf = p; }
 
 int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(g.nout >= 16 && g.nout <= 256 && g.nout % 16 == 0, "tapgemm_umma: nout=%d unsupported", g.nout);
@@ -441,6 +454,8 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   if (nst > kMaxStages) nst = kMaxStages;
   N2N_CHECK_ARG(nst >= 2, "tapgemm_umma: not enough shared memory for a pipeline (nout=%d)", g.nout);
   p.nstages = nst;
+  p.dbg = g_dbg_buf;
+  { const char* ns = getenv("N2N_STAGES"); if (ns && atoi(ns) >= 2 && atoi(ns) < nst) p.nstages = nst = atoi(ns); }
   p.tmem_cols = tmem_cols_for(2 * g.nout);
   p.idesc = make_idesc_bf16(128, g.nout, false, false);
   const size_t smem = 1024 + (size_t)p.b_region_bytes + (size_t)nst * p.stage_bytes;
@@ -619,5 +634,13 @@ extern "C" int n2n_probe_mma_rate(int layout, int n, int iters, int naccum, long
   N2N_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   probe_mma_rate_kernel<<<nblocks, 128, 62 * 1024, (cudaStream_t)stream>>>(layout, n, iters, naccum, cycles_dev);
   N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// Diagnostic: 8 int64 counters written by CTA 0 of every tap-GEMM launch (cycles): [0] producer waiting
+// for a free stage, [1] producer total, [2] MMA thread waiting for data, [3] MMA thread waiting for a
+// free accumulator, [4] MMA thread total, [5] tiles, [6] epilogue waiting for an accumulator, [7] epilogue total.
+extern "C" int n2n_debug_stall_buffer(long long* dev_counters) {
+  n2n::set_debug_stall_buffer(dev_counters);
   return 0;
 }

@@ -223,6 +223,10 @@ int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf16, float* d
 /* tcgen05.mma issue-rate probe: cycles for `iters` back-to-back M=128 x N x K=16 bf16 MMAs per CTA
  * on shared-memory operands in K-major layout 0 (SWIZZLE_32B), 1 (SWIZZLE_128B) or 2 (SWIZZLE_64B),
  * round-robin over `naccum` accumulators.  cycles_dev: int64[nblocks]. */
+/* Diagnostic: device int64[8] that CTA 0 of every subsequent bf16 tap-GEMM launch fills with stall
+ * cycle counters (NULL disables): producer-wait, producer-total, mma-wait-data, mma-wait-accumulator,
+ * mma-total, tiles, epilogue-wait, epilogue-total. */
+int n2n_debug_stall_buffer(long long* dev_counters);
 int n2n_probe_mma_rate(int layout, int n, int iters, int naccum, long long* cycles_dev, int nblocks, void* stream);
 
 #ifdef __cplusplus
