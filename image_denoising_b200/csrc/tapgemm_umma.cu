@@ -154,7 +154,8 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues ----
+    if (elect_one_sync()) {
       for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
       if (p.resident_b) {
         mbar_arrive_expect_tx(bfull_bar, p.b_total_bytes);
@@ -163,71 +164,82 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
           bulk_load(smem0 + off, p.w + off, n, bfull_bar);
         }
       }
-      int stage = 0; uint32_t phase = 0;
-      long long st_prod = 0;
-      const long long k0 = clock64();
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        int r = tile;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y;
-        const int img = r / p.tiles_y;
-        const int x0 = tx * p.bw, y0 = ty * p.bh;
-        // L2 prefetch of the tile this CTA will process `prefetch_dist` rounds from now
-        const int ptile = tile + p.prefetch_dist * (int)gridDim.x;
-        int pimg = 0, px0 = 0, py0 = 0;
-        const bool do_pf = p.prefetch_dist > 0 && ptile < p.ntiles;
-        if (do_pf) {
-          int q = ptile;
-          px0 = (q % p.tiles_x) * p.bw; q /= p.tiles_x;
-          py0 = (q % p.tiles_y) * p.bh;
-          pimg = q / p.tiles_y;
-        }
-        for (int ei = 0; ei < p.nentries; ++ei) {
-          const Entry& e = p.e[ei];
-          if (do_pf && e.pf) tma_prefetch_l2_5d(&p.tmap[e.view], 0, px0 + e.dx0, py0 + e.dy, e.cb0, pimg);
-          { const long long w0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u); st_prod += clock64() - w0; }
-          const uint32_t a_dst = stages0 + stage * p.stage_bytes;
-          uint32_t tx_bytes = p.a_tx[e.view];
-          if (!p.resident_b) tx_bytes += (uint32_t)e.ndx * e.nb * b_sub;
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    long long st_prod = 0;
+    const long long k0 = clock64();
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int r = tile;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int img = r / p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh;
+      // L2 prefetch of the tile this CTA will process `prefetch_dist` rounds from now
+      const int ptile = tile + p.prefetch_dist * (int)gridDim.x;
+      int pimg = 0, px0 = 0, py0 = 0;
+      const bool do_pf = p.prefetch_dist > 0 && ptile < p.ntiles;
+      if (do_pf) {
+        int q = ptile;
+        px0 = (q % p.tiles_x) * p.bw; q /= p.tiles_x;
+        py0 = (q % p.tiles_y) * p.bh;
+        pimg = q / p.tiles_y;
+      }
+      for (int ei = 0; ei < p.nentries; ++ei) {
+        const int view = p.e[ei].view, dy = p.e[ei].dy, dx0 = p.e[ei].dx0, ndx = p.e[ei].ndx, cb0 = p.e[ei].cb0,
+                  nb = p.e[ei].nb, pf = p.e[ei].pf;
+        if (p.dbg) { const long long w0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u); st_prod += clock64() - w0; }
+        else mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = stages0 + stage * p.stage_bytes;
+        uint32_t tx_bytes = p.a_tx[view];
+        if (!p.resident_b) tx_bytes += (uint32_t)(ndx * nb) * b_sub;
+        if (elect_one_sync()) {
+          if (do_pf && pf) tma_prefetch_l2_5d(&p.tmap[view], 0, px0 + dx0, py0 + dy, cb0, pimg);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-          tma_load_5d(a_dst, &p.tmap[e.view], full_bar(stage), 0, x0 + e.dx0, y0 + e.dy, e.cb0, img);
+          tma_load_5d(a_dst, &p.tmap[view], full_bar(stage), 0, x0 + dx0, y0 + dy, cb0, img);
           if (!p.resident_b) {
-            for (int i = 0; i < e.ndx; ++i)
-              bulk_load(a_dst + p.a_stage_bytes + i * kGroupBlocks * b_sub, p.w + e.b_off[i], (uint32_t)e.nb * b_sub,
+            for (int i = 0; i < ndx; ++i)
+              bulk_load(a_dst + p.a_stage_bytes + i * kGroupBlocks * b_sub, p.w + p.e[ei].b_off[i], (uint32_t)nb * b_sub,
                         full_bar(stage));
           }
-          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
       }
-      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_prod; p.dbg[1] = clock64() - k0; }
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = st_prod; p.dbg[1] = clock64() - k0; }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      if (p.resident_b) mbar_wait(bfull_bar, 0);
-      const uint32_t dhi = desc_hi(256, kSwizzle32);
-      const uint32_t a_sub16 = p.a_sub >> 4, b_sub16 = b_sub >> 4;
-      long long st_full = 0, st_tempty = 0;
-      const long long k0 = clock64();
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        { const long long w0 = clock64(); mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u); st_tempty += clock64() - w0; }
+    // ---- MMA issuer: whole warp converged, one elected lane issues tcgen05.mma / commit ----
+    int stage = 0; uint32_t phase = 0;
+    if (p.resident_b) mbar_wait(bfull_bar, 0);
+    const uint32_t dhi = desc_hi(256, kSwizzle32);
+    const uint32_t a_sub16 = p.a_sub >> 4, b_sub16 = b_sub >> 4;
+    const uint32_t idesc = p.idesc;
+    long long st_full = 0, st_tempty = 0;
+    const long long k0 = clock64();
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      if (p.dbg) { const long long w0 = clock64(); mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u); st_tempty += clock64() - w0; }
+      else mbar_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
+      uint32_t acc = 0;
+      for (int ei = 0; ei < p.nentries; ++ei) {
+        const int ndx = p.e[ei].ndx, nb = p.e[ei].nb;
+        const uint32_t bo0 = p.e[ei].b_off[0], bo1 = p.e[ei].b_off[1], bo2 = p.e[ei].b_off[2];
+        const uint32_t a_base = stages0 + stage * p.stage_bytes;
+        const uint32_t a_lo = desc_lo(a_base, 16);
+        const uint32_t bs = a_base + p.a_stage_bytes;       // streamed-B area of this stage
+        const uint32_t b_lo0 = desc_lo(p.resident_b ? smem0 + bo0 : bs, 16);
+        const uint32_t b_lo1 = desc_lo(p.resident_b ? smem0 + bo1 : bs + kGroupBlocks * b_sub, 16);
+        const uint32_t b_lo2 = desc_lo(p.resident_b ? smem0 + bo2 : bs + 2 * kGroupBlocks * b_sub, 16);
+        if (p.dbg) { const long long w0 = clock64(); mbar_wait(full_bar(stage), phase); st_full += clock64() - w0; }
+        else mbar_wait(full_bar(stage), phase);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
-        uint32_t acc = 0;
-        for (int ei = 0; ei < p.nentries; ++ei) {
-          const int ndx = p.e[ei].ndx, nb = p.e[ei].nb;
-          const uint32_t bo0 = p.e[ei].b_off[0], bo1 = p.e[ei].b_off[1], bo2 = p.e[ei].b_off[2];
-          const uint32_t a_base = stages0 + stage * p.stage_bytes;
-          const uint32_t a_lo = desc_lo(a_base, 16);
-          const uint32_t bs = a_base + p.a_stage_bytes;       // streamed-B area of this stage
-          const uint32_t b_lo0 = desc_lo(p.resident_b ? smem0 + bo0 : bs, 16);
-          const uint32_t b_lo1 = desc_lo(p.resident_b ? smem0 + bo1 : bs + kGroupBlocks * b_sub, 16);
-          const uint32_t b_lo2 = desc_lo(p.resident_b ? smem0 + bo2 : bs + 2 * kGroupBlocks * b_sub, 16);
-          { const long long w0 = clock64(); mbar_wait(full_bar(stage), phase); st_full += clock64() - w0; }
-          fence_after_sync();
+        if (elect_one_sync()) {
           // dx tap i of a slab = the same staged tile started i rows (32 B = 2 descriptor units) further in
+          uint32_t a1 = acc;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             if (i < ndx) {
@@ -235,19 +247,22 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 if (j < nb) {
-                  mma_bf16_lo(d_tmem, a_lo + j * a_sub16 + 2u * i, bl + j * b_sub16, dhi, p.idesc, acc);
-                  acc = 1;
+                  mma_bf16_lo(d_tmem, a_lo + j * a_sub16 + 2u * i, bl + j * b_sub16, dhi, idesc, a1);
+                  a1 = 1;
                 }
               }
             }
           }
           mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs finish
-          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(tfull_bar(buf));                     // accumulator ready for the epilogue
+        __syncwarp();
+        acc = 1;
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
       }
-      if (p.dbg && blockIdx.x == 0) { p.dbg[2] = st_full; p.dbg[3] = st_tempty; p.dbg[4] = clock64() - k0; p.dbg[5] = lt; }
+      if (elect_one_sync()) mma_commit(tfull_bar(buf)); // accumulator ready for the epilogue
+      __syncwarp();
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = st_full; p.dbg[3] = st_tempty; p.dbg[4] = clock64() - k0; p.dbg[5] = lt; }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32) ----
     const int quarter = warp & 3;
