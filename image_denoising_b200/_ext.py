@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libn2n_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "subsample.cu", "loss_adam.cu", "metrics.cu", "pack.cu",
-           "tapgemm_simt.cu", "tapgemm_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
+           "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -30,21 +30,46 @@ def _newest_source_mtime() -> float:
     m = 0.0
     for root in (CSRC, os.path.join(os.path.dirname(_HERE), "include")):
         for f in os.listdir(root):
-            m = max(m, os.path.getmtime(os.path.join(root, f)))
+            if os.path.isfile(os.path.join(root, f)):
+                m = max(m, os.path.getmtime(os.path.join(root, f)))
     return m
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into libn2n_b200.so (in-tree)."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
+    """Compile every CUDA source for sm_100a into libn2n_b200.so (in-tree).  Each translation unit
+    is compiled to csrc/_obj/<name>.o in parallel (only when stale), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    src_m = _newest_source_mtime()
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= src_m:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_m = max(os.path.getmtime(os.path.join(root, f))
+                for root in (CSRC, os.path.join(os.path.dirname(_HERE), "include"))
+                for f in os.listdir(root) if f.endswith((".h", ".cuh")))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        spath = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(spath), hdr_m):
+            return obj, None
+        cmd = [nvcc] + flags + ["-c", "-o", obj, spath]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (r.stdout + r.stderr if r.returncode != 0 else None)
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    errs = [e for _, e in results if e]
+    if errs:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + [o for o, _ in results]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 

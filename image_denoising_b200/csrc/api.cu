@@ -45,8 +45,15 @@ int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
   // executed (padded) FLOPs of this launch: 2 * pixels * nout * taps * 16*cin_blocks
   const double flops = 2.0 * g.y.N * g.y.H * g.y.W * (double)g.nout * g.ntaps * 16.0 * g.cin_blocks;
   ProfScope ps(0, flops, st);
-  if (g.dtype == N2N_BF16) return launch_tapgemm_umma(g, st);
-  return launch_tapgemm_simt(g, st);
+  if (g.dtype == N2N_BF16) {
+    const int r = launch_slabgemm_umma(g, st);
+    if (r != kSgNotEligible) return r;
+    N2N_TRY(launch_tapgemm_umma(g, st));
+  } else {
+    N2N_TRY(launch_tapgemm_simt(g, st));
+  }
+  if (g.has_pool) return launch_maxpool(g.y, g.pool, g.dtype, st);
+  return 0;
 }
 int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
   const double flops = 2.0 * g.dy[0].N * g.dy[0].H * g.dy[0].W * 256.0 * g.n_blocks * g.c_blocks * g.npairs;

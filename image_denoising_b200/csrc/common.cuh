@@ -173,6 +173,8 @@ struct TapGemm {
   float slope = 0.f;
   float* out_nchw = nullptr;      // optional fp32 NCHW [N][out_c][H][W] output
   int out_c = 0;
+  bool store_y = true;            // false: the un-pooled output is not needed (no-grad pass), only `pool`
+  bool has_pool = false; View pool;   // also write maxpool2x2(out) here (fused in the epilogue when possible)
 };
 
 // ---- generic weight-gradient GEMM ---------------------------------------------------------
@@ -234,6 +236,9 @@ int launch_fill_zero(void* p, size_t bytes, cudaStream_t st);
 // bf16 tensor-core engine (tapgemm_umma.cu / wgrad_umma.cu)
 int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st);
 int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st);
+// 8x16-tile slab engine (slabgemm_umma.cu): 0 = launched, kSgNotEligible = use the row-slab engine
+constexpr int kSgNotEligible = 1;
+int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st);
 // fp32 CUDA-core engine (tapgemm_simt.cu)
 int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st);
 int launch_tapwgrad_simt(const TapWgrad& g, cudaStream_t st);

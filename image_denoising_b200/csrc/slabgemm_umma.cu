@@ -1,0 +1,478 @@
+// slabgemm_umma.cu — second-generation bf16 tensor-core engine for the tap GEMM (conv3x3 / conv1x1 /
+// ConvTranspose2x2, forward and input gradient).  Same contract as tapgemm_umma.cu (TapGemm in,
+// C16 tensor out), different geometry:
+//
+//   * output tile = 8 x 16 pixels (M = 128, pixel m = 8*y + x).  One TMA box brings the tile's whole
+//     halo'd input window — 10 x 18 pixels x <= 3 channel blocks — into shared memory ONCE, and all
+//     nine taps of a 3x3 conv are tcgen05 operand views of that one box: tap (dy, dx) starts
+//     (10*dy + dx) * 32 B into it, the eight pixels of an image row are the eight rows of a
+//     SWIZZLE_32B group, and the descriptor's stride-byte-offset (320 B) walks the image rows.
+//     Every input pixel crosses L2 -> SMEM 1.4 times per conv (9 in a tap-by-tap implicit GEMM,
+//     3.2 in the row-slab engine).
+//   * the packed weights of the layer stay resident in shared memory for the whole persistent CTA;
+//   * the per-tile MMA schedule (A / B descriptor offsets of every tcgen05.mma) is tabulated in
+//     shared memory once per CTA, so the issuing lane does one LDS + two adds per MMA;
+//   * accumulators are double-buffered in TMEM; the epilogue (4 warps) fuses bias, LeakyReLU /
+//     ReLU, the input-gradient's activation mask and skip-gradient addend, the 2x2 max-pool
+//     (a 2x2 cell is lanes {l, l^1, l^8} of one warp -> two shuffles), the bf16 C16 store and the
+//     fp32 NCHW store of the network head.
+//
+// Layers whose weights do not fit beside >= 2 pipeline slots (Cin = 144) or whose images are
+// smaller than a tile (the 8x8 / 4x4 levels) return kSgNotEligible and run on the row-slab engine.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace n2n {
+
+using namespace umma;
+
+constexpr int kSgThreads = 192;
+constexpr int kSgMaxStages = 12;          // pipeline stages (TMA boxes) per tile
+constexpr int kSgMaxRing = 8;
+constexpr int kSgGroup = 3;               // channel blocks per stage = one packed-weight group
+constexpr int kTileW = 8, kTileH = 16;
+constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
+constexpr size_t kSgSmemMax = 232448;     // 227 KB per CTA (static + dynamic)
+constexpr size_t kSgStaticSlack = 6144;   // static shared memory of the kernel, rounded up
+
+struct SgStage {
+  int16_t view, cb0, nb, ox, oy, ntaps;
+  uint16_t cb_bytes16;       // bytes/16 between channel blocks inside the staged box
+  uint16_t sbo16;            // bytes/16 between image rows of the box (A descriptor stride-byte-offset)
+  uint16_t a_off16[9];       // start of each tap's operand view inside the box (bytes/16)
+  uint16_t pad;
+  uint32_t b_off16[9];       // start of each tap's weight slab inside the resident weights (bytes/16)
+  uint32_t tx_bytes;         // bytes the TMA box delivers
+};
+
+struct SgParams {
+  // hot (epilogue / loop) fields first: they stay in the first constant-cache lines
+  int nst, nout, ring, dbg_flags;
+  int tiles_x, tiles_y, ntiles;
+  int act; float slope;
+  int store_y, has_addend, has_mask, has_pool, out_c;
+  uint32_t slot_bytes, tmem_cols, idesc, w_bytes, w_region;
+  const uint8_t* w;
+  const float* bias;
+  float* out_nchw;
+  View y, addend, mask, pool;
+  CUtensorMap tmap[4];
+  SgStage st[kSgMaxStages];
+};
+
+// Bounded wait without clock reads: a protocol bug becomes a trap, never a hang.
+__device__ __forceinline__ void sg_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void sg_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      );
+}
+
+__device__ __forceinline__ void sg_ld16(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// One pixel's 16-channel block (32 B) moves as a single 256-bit access (full 32 B sectors).
+__device__ __forceinline__ void st_global_32B(void* ptr, const uint32_t w[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_32B(const void* ptr, uint32_t w[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(ptr)
+               : "memory");
+}
+__device__ __forceinline__ void unpack_bf16x16(const uint32_t w[8], float v[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+struct SgPix {
+  int img, y, x;
+  long long ypix, apix, mpix, ppix;
+};
+
+// One 16-channel block of one pixel: accumulator -> bias -> (+addend) -> act -> (*mask) -> stores.
+__device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix& c, int cb, const uint32_t r[16],
+                                                  int lane, const float* s_bias) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+  if (!(p.dbg_flags & 8)) {
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb * 16);   // shared-memory broadcast
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = b4[q];
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+  }
+  if (p.has_addend) {
+    uint32_t aw[8]; float t[16];
+    ld_global_32B((const __nv_bfloat16*)p.addend.ptr + c.apix + cb * p.addend.sCb, aw);
+    unpack_bf16x16(aw, t);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] += t[q];
+  }
+  if (p.act && !(p.dbg_flags & 16)) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+  }
+  if (p.has_mask) {
+    uint32_t aw[8]; float t[16];
+    ld_global_32B((const __nv_bfloat16*)p.mask.ptr + c.mpix + cb * p.mask.sCb, aw);
+    unpack_bf16x16(aw, t);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] *= (t[q] > 0.f ? 1.f : p.slope);
+  }
+  if (p.out_nchw) {
+    const long long hw = (long long)p.y.H * p.y.W;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int n = cb * 16 + q;
+      if (n < p.out_c) p.out_nchw[((long long)c.img * p.out_c + n) * hw + (long long)c.y * p.y.W + c.x] = v[q];
+    }
+    return;
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if (p.store_y && !(p.dbg_flags & 32)) st_global_32B((__nv_bfloat16*)p.y.ptr + c.ypix + cb * p.y.sCb, w);
+  if (p.has_pool) {
+    // 2x2 max over lanes {l, l^1 (x neighbour), l^8 (y neighbour)}; max commutes with bf16 rounding
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+      uint32_t o = __shfl_xor_sync(0xffffffffu, w[j], 1);
+      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+      uint32_t aw = *reinterpret_cast<uint32_t*>(&a);
+      o = __shfl_xor_sync(0xffffffffu, aw, 8);
+      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+      w[j] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    if ((lane & 9) == 0) st_global_32B((__nv_bfloat16*)p.pool.ptr + c.ppix + cb * p.pool.sCb, w);
+  }
+}
+
+__global__ void __launch_bounds__(kSgThreads, 1)
+slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * kSgMaxRing + 5];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) uint2 s_tap[kSgMaxStages * 10];  // per (stage, tap): (A offset, B offset) in 16-byte units
+  __shared__ int4 s_ld[kSgMaxStages];                 // per stage: view, cb0, ox | oy << 16, tx_bytes
+  __shared__ uint4 s_mm[kSgMaxStages];
+  __shared__ __align__(16) float s_bias[256];                // per stage: ntaps, nb, cb_bytes16, A descriptor high word
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t slots0 = smem0 + p.w_region;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kSgMaxRing + s); };
+  const uint32_t wfull_bar = bar0 + 8u * (2 * kSgMaxRing);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 1 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 3 + b); };
+  const uint32_t b_sub16 = (uint32_t)p.nout * 2u;     // nout rows x 32 B, in 16-byte units
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(wfull_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    fence_barrier_init();
+  }
+  // per-CTA schedule tables
+  for (int i = threadIdx.x; i < p.nst * 10; i += kSgThreads) {
+    const int s = i / 10, t = i - s * 10;
+    const SgStage& S = p.st[s];
+    s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t], S.b_off16[t]) : make_uint2(0u, 0u);
+  }
+  for (int i = threadIdx.x; i < p.nout; i += kSgThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  if (threadIdx.x < p.nst) {
+    const SgStage& S = p.st[threadIdx.x];
+    s_ld[threadIdx.x] = make_int4(S.view, S.cb0, (int)(uint16_t)S.ox | ((int)(uint16_t)S.oy << 16), (int)S.tx_bytes);
+    s_mm[threadIdx.x] = make_uint4((uint32_t)S.ntaps, (uint32_t)S.nb, (uint32_t)S.cb_bytes16,
+                                   (uint32_t)S.sbo16 | (1u << 14) | (kSwizzle32 << 29));
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ---- TMA producer (whole warp walks the loop, one elected lane issues) ----
+    if (elect_one_sync()) {
+      for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
+      mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
+      for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
+        const uint32_t n = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
+        bulk_load(smem0 + off, p.w + off, n, wfull_bar);
+      }
+    }
+    __syncwarp();
+    int slot = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int r = tile - img * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      for (int s = 0; s < p.nst; ++s) {
+        const int4 ld = s_ld[s];
+        sg_wait(empty_bar(slot), phase ^ 1u);
+        if (elect_one_sync()) {
+          if (p.dbg_flags & 1) {
+            mbar_arrive(full_bar(slot));
+          } else {
+            mbar_arrive_expect_tx(full_bar(slot), (uint32_t)ld.w);
+            tma_load_5d(slots0 + slot * p.slot_bytes, &p.tmap[ld.x], full_bar(slot), 0, x0 + (int)(int16_t)(ld.z & 0xffff),
+                        y0 + (int)(int16_t)(ld.z >> 16), ld.y, img);
+          }
+        }
+        __syncwarp();
+        if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    int slot = 0; uint32_t phase = 0;
+    sg_wait(wfull_bar, 0);
+    const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
+    const uint32_t w_lo = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t idesc = p.idesc;
+    const bool skip = (p.dbg_flags & 2) != 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      sg_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
+      uint32_t acc = 0;
+      for (int s = 0; s < p.nst; ++s) {
+        const uint4 mm = s_mm[s];                            // ntaps, nb, cb_bytes16, a_hi
+        const uint32_t a_lo = (((slots0 + slot * p.slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        // the stage's tap table goes to registers up front (5 LDS.128), so the issue loop below is
+        // two integer adds per tcgen05.mma
+        uint2 tp[10];
+        {
+          const uint4* t4 = reinterpret_cast<const uint4*>(&s_tap[s * 10]);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const uint4 t = t4[q];
+            tp[2 * q] = make_uint2(t.x, t.y); tp[2 * q + 1] = make_uint2(t.z, t.w);
+          }
+        }
+        sg_wait(full_bar(slot), phase);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          if (!skip) {
+            uint32_t a1 = acc;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (t < (int)mm.x) {
+                const uint32_t al = a_lo + tp[t].x, bl = w_lo + tp[t].y;
+                sg_mma(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
+                if (mm.y > 1) sg_mma(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                if (mm.y > 2) sg_mma(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                a1 = 1;
+              }
+            }
+          }
+          mma_commit(empty_bar(slot));
+        }
+        __syncwarp();
+        acc = 1;
+        if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+      }
+      if (elect_one_sync()) mma_commit(tfull_bar(buf));
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile ----
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    const int nblk = p.nout >> 4;
+    const bool skip = (p.dbg_flags & 4) != 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      SgPix c;
+      c.img = tile / tiles_per_img;
+      const int r = tile - c.img * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      c.y = ty * kTileH + py; c.x = tx * kTileW + px;
+      c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
+      c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
+      c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
+      c.ppix = (long long)c.img * p.pool.sN + (long long)(c.y >> 1) * p.pool.sY + (long long)(c.x >> 1) * p.pool.sX;
+      const int buf = lt & 1;
+      sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      fence_after_sync();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
+      for (int cb = 0; cb < nblk; cb += 2) {
+        uint32_t r0[16], r1[16];
+        sg_ld16(lane_addr + cb * 16, r0);
+        const bool two = cb + 1 < nblk;
+        if (two) sg_ld16(lane_addr + (cb + 1) * 16, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (skip) continue;
+        sg_epilogue_block(p, c, cb, r0, lane, s_bias);
+        if (two) sg_epilogue_block(p, c, cb + 1, r1, lane, s_bias);
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int sg_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+  }
+  return n;
+}
+
+// Returns 0 when launched, kSgNotEligible when this geometry belongs to the row-slab engine, < 0 on error.
+int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
+  static bool attr_set = false;
+  if (g.dtype != N2N_BF16 || g.nout < 16 || g.nout > 256 || g.nout % 16) return kSgNotEligible;
+  const int H = g.y.H, W = g.y.W;
+  if (H % kTileH || W % kTileW || H < kTileH || W < kTileW) return kSgNotEligible;
+  { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return kSgNotEligible; }
+  const int ngroups = (g.cin_blocks + kSgGroup - 1) / kSgGroup;
+  const uint32_t b_sub = (uint32_t)g.nout * 32u;
+  const size_t slab_bytes = (size_t)kSgGroup * b_sub;
+  int max_slab = 0, nviews = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.tap_slab[t] > max_slab) max_slab = g.tap_slab[t];
+    if (g.tap_view[t] + 1 > nviews) nviews = g.tap_view[t] + 1;
+    if (g.tap_dy[t] < -1 || g.tap_dy[t] > 1 || g.tap_dx[t] < -1 || g.tap_dx[t] > 1) return kSgNotEligible;
+  }
+  if (nviews > 4) return kSgNotEligible;
+  const size_t w_bytes = (size_t)(max_slab + 1) * ngroups * slab_bytes;
+
+  SgParams p;
+  memset(&p, 0, sizeof(p));
+  const int gb = g.cin_blocks < kSgGroup ? g.cin_blocks : kSgGroup;
+  int nst = 0;
+  size_t slot_bytes = 0;
+  for (int v = 0; v < nviews; ++v) {
+    bool halo = false; int nt = 0;
+    for (int t = 0; t < g.ntaps; ++t)
+      if (g.tap_view[t] == v) { ++nt; if (g.tap_dy[t] || g.tap_dx[t]) halo = true; }
+    if (nt == 0) continue;
+    const View& xv = g.x[v];
+    if (xv.H != H || xv.W != W || xv.Cb < g.cin_blocks) return kSgNotEligible;
+    const int bw = halo ? kHaloW : kTileW, bh = halo ? kHaloH : kTileH;
+    N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, gb));
+    const uint32_t cb_bytes = (uint32_t)(bw * bh * 32);
+    for (int grp = 0; grp < ngroups; ++grp) {
+      if (nst >= kSgMaxStages) return kSgNotEligible;
+      SgStage& S = p.st[nst++];
+      S.view = (int16_t)v; S.cb0 = (int16_t)(grp * kSgGroup);
+      const int nb = g.cin_blocks - grp * kSgGroup;
+      S.nb = (int16_t)(nb < kSgGroup ? nb : kSgGroup);
+      S.ox = S.oy = (int16_t)(halo ? -1 : 0);
+      S.cb_bytes16 = (uint16_t)(cb_bytes >> 4);
+      S.sbo16 = (uint16_t)((bw * 32) >> 4);
+      S.tx_bytes = (uint32_t)gb * cb_bytes;
+      int k = 0;
+      for (int t = 0; t < g.ntaps; ++t) {
+        if (g.tap_view[t] != v) continue;
+        const int oy = halo ? g.tap_dy[t] + 1 : 0, ox = halo ? g.tap_dx[t] + 1 : 0;
+        S.a_off16[k] = (uint16_t)(((oy * bw + ox) * 32) >> 4);
+        S.b_off16[k] = (uint32_t)((((size_t)g.tap_slab[t] * ngroups + grp) * slab_bytes) >> 4);
+        ++k;
+      }
+      S.ntaps = (int16_t)k;
+      if ((size_t)gb * cb_bytes > slot_bytes) slot_bytes = (size_t)gb * cb_bytes;
+    }
+  }
+  for (int v = 0; v < 4; ++v)      // unused descriptor slots must still be valid for prefetch.tensormap
+    if (v >= nviews) p.tmap[v] = p.tmap[0];
+  slot_bytes = align_up(slot_bytes, 1024);
+  const size_t w_region = align_up(w_bytes, 1024);
+  const size_t budget = kSgSmemMax - kSgStaticSlack - 1024;
+  if (w_region + 2 * slot_bytes > budget) return kSgNotEligible;
+  int ring = (int)((budget - w_region) / slot_bytes);
+  if (ring > kSgMaxRing) ring = kSgMaxRing;
+  { const char* e = getenv("N2N_SG_RING"); if (e && atoi(e) >= 2 && atoi(e) < ring) ring = atoi(e); }
+
+  p.nst = nst; p.nout = g.nout;
+  p.w = (const uint8_t*)g.w; p.w_bytes = (uint32_t)w_bytes; p.w_region = (uint32_t)w_region;
+  p.bias = g.bias; p.y = g.y; p.store_y = g.store_y ? 1 : 0;
+  p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
+  p.has_pool = g.has_pool; p.pool = g.pool;
+  p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
+  p.tiles_x = W / kTileW; p.tiles_y = H / kTileH;
+  const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;
+  N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "slabgemm: bad tile count");
+  p.ntiles = (int)tiles;
+  p.ring = ring; p.slot_bytes = (uint32_t)slot_bytes;
+  p.tmem_cols = tmem_cols_for(2 * g.nout);
+  p.idesc = make_idesc_bf16(128, g.nout, false, false);
+  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
+  const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
+  if (!attr_set) {
+    N2N_CUDA(cudaFuncSetAttribute(slabgemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kSgSmemMax - kSgStaticSlack)));
+    attr_set = true;
+  }
+  const int grid = tiles < sg_num_sms() ? (int)tiles : sg_num_sms();
+  slabgemm_umma_kernel<<<grid, kSgThreads, smem, st>>>(p);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace n2n

@@ -60,6 +60,7 @@ struct UmmaGemmParams {
   uint32_t a_stage_bytes;     // offset of the streamed-B area inside a stage
   uint32_t b_total_bytes, b_region_bytes, stage_bytes, tmem_cols, idesc;
   long long* dbg;             // optional stall counters (CTA 0): see n2n_debug_stall_buffer
+  int dbg_flags;              // diagnostic (N2N_DBG_FLAGS): 1 skip TMA loads, 2 skip MMA issue, 4 skip epilogue stores
 };
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
@@ -193,7 +194,9 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         const uint32_t a_dst = stages0 + stage * p.stage_bytes;
         uint32_t tx_bytes = p.a_tx[view];
         if (!p.resident_b) tx_bytes += (uint32_t)(ndx * nb) * b_sub;
-        if (elect_one_sync()) {
+        if (p.dbg_flags & 1) {
+          if (elect_one_sync()) mbar_arrive(full_bar(stage));
+        } else if (elect_one_sync()) {
           if (do_pf && pf) tma_prefetch_l2_5d(&p.tmap[view], 0, px0 + dx0, py0 + dy, cb0, pimg);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           tma_load_5d(a_dst, &p.tmap[view], full_bar(stage), 0, x0 + dx0, y0 + dy, cb0, img);
@@ -246,7 +249,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
               const uint32_t bl = i == 0 ? b_lo0 : (i == 1 ? b_lo1 : b_lo2);
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                if (j < nb) {
+                if (j < nb && !(p.dbg_flags & 2)) {
                   mma_bf16_lo(d_tmem, a_lo + j * a_sub16 + 2u * i, bl + j * b_sub16, dhi, idesc, a1);
                   a1 = 1;
                 }
@@ -294,6 +297,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
         const bool two = cb + 1 < nblk;
         if (two) tmem_ld16_issue(lane_addr + (cb + 1) * 16, r1);
         tmem_ld_wait();
+        if (p.dbg_flags & 4) continue;
         epilogue_block(c, cb, r0);
         if (two) epilogue_block(c, cb + 1, r1);
       }
@@ -470,6 +474,7 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(nst >= 2, "tapgemm_umma: not enough shared memory for a pipeline (nout=%d)", g.nout);
   p.nstages = nst;
   p.dbg = g_dbg_buf;
+  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   { const char* ns = getenv("N2N_STAGES"); if (ns && atoi(ns) >= 2 && atoi(ns) < nst) p.nstages = nst = atoi(ns); }
   p.tmem_cols = tmem_cols_for(2 * g.nout);
   p.idesc = make_idesc_bf16(128, g.nout, false, false);

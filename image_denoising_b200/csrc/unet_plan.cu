@@ -177,7 +177,7 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
   N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
 
-  auto run_layer = [&](int i) -> int {
+  auto run_layer = [&](int i, int pool_buf = -1, int pool_cb0 = 0) -> int {
     const LayerIO& io = p->io[i];
     const LayerGeom& L = p->L[i];
     View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
@@ -200,17 +200,20 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
       g = make_conv_fwd(L, dt, xin, p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks()), wp, bias);
     }
     if (io.act) { g.act = 1; g.slope = 0.2f; }
+    if (pool_buf >= 0) {
+      // MaxPool2d(2) fused behind the conv (arch_unet.py:203-219); the un-pooled activation is only
+      // kept when a backward pass will need it (max routing + LeakyReLU sign)
+      g.has_pool = true; g.pool = p->view(p->act, ws, pool_buf, pool_cb0, p->nfb);
+      g.store_y = p->bwd;
+    }
     return launch_tapgemm(g, st);
   };
-  auto pool = [&](int src, int dst, int dst_cb0) -> int {
-    return launch_maxpool(p->view(p->act, ws, src, 0, p->nfb), p->view(p->act, ws, dst, dst_cb0, p->nfb), dt, st);
-  };
   N2N_TRY(run_layer(0));
-  N2N_TRY(run_layer(1)); N2N_TRY(pool(B_E1, B_CAT1, p->c2b));
-  N2N_TRY(run_layer(2)); N2N_TRY(pool(B_E2, B_CAT2, p->c2b));
-  N2N_TRY(run_layer(3)); N2N_TRY(pool(B_E3, B_CAT3, p->c2b));
-  N2N_TRY(run_layer(4)); N2N_TRY(pool(B_E4, B_CAT4, p->nfb));
-  N2N_TRY(run_layer(5)); N2N_TRY(pool(B_E5, B_P5, 0));
+  N2N_TRY(run_layer(1, B_CAT1, p->c2b));
+  N2N_TRY(run_layer(2, B_CAT2, p->c2b));
+  N2N_TRY(run_layer(3, B_CAT3, p->c2b));
+  N2N_TRY(run_layer(4, B_CAT4, p->nfb));
+  N2N_TRY(run_layer(5, B_P5, 0));
   for (int i = 6; i < 25; ++i) N2N_TRY(run_layer(i));
   p->fwd_launches = (int)(g_launch_count - launches0);
   return 0;
