@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libn2n_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "subsample.cu", "loss_adam.cu", "metrics.cu", "pack.cu",
-           "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
+           "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -79,6 +79,7 @@ _SIGS = {
     "n2n_device_ok": (c_int, []),
     "n2n_launch_count": (ctypes.c_longlong, []),
     "n2n_profile_begin": (c_int, []),
+    "n2n_profile_active": (c_int, []),
     "n2n_profile_end": (c_int, [POINTER(c_double)]),
     "n2n_profile_end_list": (c_int, [POINTER(c_double), c_int]),
     "n2n_mask_pair_from_rdidx": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -122,6 +123,11 @@ _SIGS = {
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_adam_multi": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_float, c_float, c_int,
                                c_float, c_void_p]),
+    "n2n_set_step_scalars": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p]),
+    "n2n_loss_n2n_fwdbwd_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_adam_multi_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_float, c_float,
+                                   c_float, c_void_p]),
     "n2n_quantize_u8": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "n2n_tile_accumulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),

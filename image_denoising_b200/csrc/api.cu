@@ -58,7 +58,11 @@ int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
 int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
   const double flops = 2.0 * g.dy[0].N * g.dy[0].H * g.dy[0].W * 256.0 * g.n_blocks * g.c_blocks * g.npairs;
   ProfScope ps(1, flops, st);
-  if (g.dtype == N2N_BF16) return launch_tapwgrad_umma(g, st);
+  if (g.dtype == N2N_BF16) {
+    const int r = launch_wgrad_slab_umma(g, st);
+    if (r != kSgNotEligible) return r;
+    return launch_tapwgrad_umma(g, st);
+  }
   return launch_tapwgrad_simt(g, st);
 }
 
@@ -80,6 +84,8 @@ using namespace n2n;
 extern "C" const char* n2n_last_error(void) { return g_err; }
 extern "C" int n2n_version(void) { return 100; }
 extern "C" long long n2n_launch_count(void) { return g_launch_count; }
+
+extern "C" int n2n_profile_active(void) { return g_prof_on ? 1 : 0; }
 
 extern "C" int n2n_profile_begin(void) {
   if (!g_prof) g_prof = new std::vector<ProfRec>();

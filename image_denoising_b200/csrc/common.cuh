@@ -239,6 +239,7 @@ int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st);
 // 8x16-tile slab engine (slabgemm_umma.cu): 0 = launched, kSgNotEligible = use the row-slab engine
 constexpr int kSgNotEligible = 1;
 int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st);
+int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st);
 // fp32 CUDA-core engine (tapgemm_simt.cu)
 int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st);
 int launch_tapwgrad_simt(const TapWgrad& g, cudaStream_t st);

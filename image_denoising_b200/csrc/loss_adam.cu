@@ -52,8 +52,9 @@ __device__ __forceinline__ bool last_block_done(RedWs* ws) {
 __global__ void __launch_bounds__(kRedThreads)
 n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, const float* __restrict__ den1,
                 const float* __restrict__ den2, float lam, float gscale, long long count, float* __restrict__ loss3,
-                float* __restrict__ grad, RedWs* ws) {
+                float* __restrict__ grad, RedWs* ws, const float* __restrict__ dev_scalars) {
   __shared__ double red[2 * 8];
+  if (dev_scalars) lam = dev_scalars[0];      // graph-replayed steps read Lambda from device memory
   double acc[2] = {0.0, 0.0};
   const float k = gscale * 2.0f / (float)count;
   const long long nvec = count / 4;
@@ -164,7 +165,9 @@ l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
 // denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, -lr/bc1).
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ blocks, float b1, float b2,
-                  float eps, float step_size, float inv_sqrt_bc2_recip /* sqrt(bc2) */, float gscale) {
+                  float eps, float step_size, float inv_sqrt_bc2_recip /* sqrt(bc2) */, float gscale,
+                  const float* __restrict__ dev_scalars) {
+  if (dev_scalars) { step_size = dev_scalars[1]; inv_sqrt_bc2_recip = dev_scalars[2]; }
   const int t = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
   const long long* row = table + 5 * (long long)t;
   float* p = reinterpret_cast<float*>(row[0]);
@@ -198,7 +201,20 @@ extern "C" int n2n_loss_n2n_fwdbwd(const float* out, const float* sub2, const fl
   int grid = grid_for(count / 4 + 1, kRedThreads, 4);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   n2n_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(out, sub2, den1, den2, lam, grad_scale, count,
-                                                                  loss3, grad, (RedWs*)workspace);
+                                                                  loss3, grad, (RedWs*)workspace, nullptr);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// Graph-friendly form: Lambda comes from dev_scalars[0] (see n2n_set_step_scalars).
+extern "C" int n2n_loss_n2n_fwdbwd_dev(const float* out, const float* sub2, const float* den1, const float* den2,
+                                       const float* dev_scalars, float grad_scale, int64_t count, float* loss3,
+                                       float* grad, void* workspace, void* stream) {
+  N2N_CHECK_ARG(out && sub2 && den1 && den2 && loss3 && workspace && dev_scalars && count > 0, "loss_n2n_dev: bad arguments");
+  int grid = grid_for(count / 4 + 1, kRedThreads, 4);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  n2n_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(out, sub2, den1, den2, 0.f, grad_scale, count,
+                                                                  loss3, grad, (RedWs*)workspace, dev_scalars);
   N2N_LAUNCH_CHECK();
   return 0;
 }
@@ -224,7 +240,34 @@ extern "C" int n2n_adam_multi(const int64_t* table, int ntensors, const int32_t*
   const float step_size = (float)((double)lr / bc1);
   const float sqrt_bc2 = (float)sqrt(bc2);
   adam_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, blocks, beta1, beta2, eps,
-                                                              step_size, sqrt_bc2, grad_scale);
+                                                              step_size, sqrt_bc2, grad_scale, nullptr);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// Graph-friendly form: lr / bias-correction terms come from dev_scalars[1..2].
+extern "C" int n2n_adam_multi_dev(const int64_t* table, int ntensors, const int32_t* blocks, int nblocks,
+                                  const float* dev_scalars, float beta1, float beta2, float eps, float grad_scale,
+                                  void* stream) {
+  N2N_CHECK_ARG(table && blocks && dev_scalars && ntensors > 0 && nblocks > 0, "adam_multi_dev: bad arguments");
+  adam_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, blocks, beta1, beta2, eps,
+                                                              0.f, 1.f, grad_scale, dev_scalars);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void set_step_scalars_kernel(float* dst, float lam, float step_size, float sqrt_bc2) {
+  dst[0] = lam; dst[1] = step_size; dst[2] = sqrt_bc2; dst[3] = 0.f;
+}
+
+// dev_scalars[4] = {Lambda, lr / (1 - beta1^step), sqrt(1 - beta2^step), 0}: the per-step values a
+// captured CUDA graph of the training step cannot carry as kernel arguments.
+extern "C" int n2n_set_step_scalars(float* dev_scalars, float lam, float lr, float beta1, float beta2, int step,
+                                    void* stream) {
+  N2N_CHECK_ARG(dev_scalars && step >= 1, "set_step_scalars: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  set_step_scalars_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_scalars, lam, (float)((double)lr / bc1), (float)sqrt(bc2));
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -125,8 +125,10 @@ struct SgPix {
 };
 
 // One 16-channel block of one pixel: accumulator -> bias -> (+addend) -> act -> (*mask) -> stores.
+// `aux` (when non-null) holds the block's mask words (or addend words when there is no mask), loaded
+// from global memory before the accumulator wait so that their DRAM latency is off the critical path.
 __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix& c, int cb, const uint32_t r[16],
-                                                  int lane, const float* s_bias) {
+                                                  int lane, const float* s_bias, const uint32_t* aux) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
@@ -140,7 +142,12 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   }
   if (p.has_addend) {
     uint32_t aw[8]; float t[16];
-    ld_global_32B((const __nv_bfloat16*)p.addend.ptr + c.apix + cb * p.addend.sCb, aw);
+    if (aux && !p.has_mask) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aw[q] = aux[q];
+    } else {
+      ld_global_32B((const __nv_bfloat16*)p.addend.ptr + c.apix + cb * p.addend.sCb, aw);
+    }
     unpack_bf16x16(aw, t);
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] += t[q];
@@ -151,7 +158,12 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   }
   if (p.has_mask) {
     uint32_t aw[8]; float t[16];
-    ld_global_32B((const __nv_bfloat16*)p.mask.ptr + c.mpix + cb * p.mask.sCb, aw);
+    if (aux) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aw[q] = aux[q];
+    } else {
+      ld_global_32B((const __nv_bfloat16*)p.mask.ptr + c.mpix + cb * p.mask.sCb, aw);
+    }
     unpack_bf16x16(aw, t);
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] *= (t[q] > 0.f ? 1.f : p.slope);
@@ -344,18 +356,38 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
       c.ppix = (long long)c.img * p.pool.sN + (long long)(c.y >> 1) * p.pool.sY + (long long)(c.x >> 1) * p.pool.sX;
       const int buf = lt & 1;
+      // The epilogue's global operand (activation mask, else skip-gradient addend): warm L2 with the
+      // whole tile's worth now, while this tile's MMAs still run, and keep the register loads one
+      // block pair ahead of their use, so their latency stays off the critical path.
+      const bool pre = (p.has_mask || p.has_addend) && !skip;
+      const __nv_bfloat16* ab = p.has_mask ? (const __nv_bfloat16*)p.mask.ptr + c.mpix : (const __nv_bfloat16*)p.addend.ptr + c.apix;
+      const long long as = p.has_mask ? p.mask.sCb : p.addend.sCb;
+      uint32_t ax0[8], ax1[8];
+      if (pre) {
+        for (int cb = 2; cb < nblk; ++cb)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ab + cb * as));
+        ld_global_32B(ab, ax0);
+        if (nblk > 1) ld_global_32B(ab + as, ax1);
+      }
       sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
       fence_after_sync();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
+#pragma unroll 1
       for (int cb = 0; cb < nblk; cb += 2) {
-        uint32_t r0[16], r1[16];
+        uint32_t r0[16], r1[16], nx0[8], nx1[8];
         sg_ld16(lane_addr + cb * 16, r0);
         const bool two = cb + 1 < nblk;
         if (two) sg_ld16(lane_addr + (cb + 1) * 16, r1);
+        if (pre && cb + 2 < nblk) {
+          ld_global_32B(ab + (cb + 2) * as, nx0);
+          if (cb + 3 < nblk) ld_global_32B(ab + (cb + 3) * as, nx1);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (skip) continue;
-        sg_epilogue_block(p, c, cb, r0, lane, s_bias);
-        if (two) sg_epilogue_block(p, c, cb + 1, r1, lane, s_bias);
+        sg_epilogue_block(p, c, cb, r0, lane, s_bias, pre ? ax0 : nullptr);
+        if (two) sg_epilogue_block(p, c, cb + 1, r1, lane, s_bias, pre ? ax1 : nullptr);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ax0[q] = nx0[q]; ax1[q] = nx1[q]; }
       }
       fence_before_sync();
       __syncwarp();

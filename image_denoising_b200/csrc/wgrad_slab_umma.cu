@@ -1,0 +1,305 @@
+// wgrad_slab_umma.cu — second-generation bf16 tensor-core engine for the weight-gradient GEMM
+//   P[t][c][n] = sum_p dY_a(t)[p, n] * X_b(t)[p + (dy_t, dx_t), c]          (K = the pixel axis)
+// in the 8 x 16-pixel tile geometry of slabgemm_umma.cu.
+//
+// Per tile a CTA stages ONE "common" box (conv: the dY tile, 8 x 16 pixels; deconv: the X tile) and
+// the "variant" boxes of its tap group (conv: the halo'd 10 x 18 X window — all nine taps are
+// operand views of it, tap (dy, dx) starting (10*dy + dx) * 32 B further in; deconv: one dY parity
+// tile per tap).  Both operands are consumed MN-major straight from the C16 boxes: the 16 channels
+// of a block are the contiguous M/N run (leading-byte-offset = one block of the box), the eight
+// pixels of an image row are the eight K rows of a SWIZZLE_32B group and the stride-byte-offset
+// (256 B for a tile, 320 B for a halo'd window) walks the image rows; one tcgen05.mma covers
+// K = 16 pixels = two image rows, so a tile is 8 K-steps per tap.
+//
+// Grid = (pixel splits) x (tap groups): a CTA owns a contiguous range of tiles and as many taps as
+// fit in TMEM (512 / (16 * variant blocks) accumulators of [128 x N] fp32); it accumulates over its
+// whole tile range in TMEM and stores its fp32 partial once at the end (pack.cu's unpack kernel
+// reduces the splits in a fixed order -> deterministic).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace n2n {
+
+using namespace umma;
+
+constexpr int kWsThreads = 192;
+constexpr int kWsMaxRing = 4;
+constexpr int kWsTileW = 8, kWsTileH = 16;
+constexpr size_t kWsSmemMax = 232448;
+constexpr size_t kWsStaticSlack = 2048;
+
+struct WsParams {
+  int npairs, taps_per_cta, tgroups;
+  int m_blocks, n_blocks, swap;
+  int npad, cpad;
+  int tiles_x, tiles_y;
+  long long tiles, tiles_per_split;
+  int ring, halo, box_per_tap;           // box_per_tap: 1 = every tap has its own variant box (deconv), 0 = one shared box
+  uint32_t slot_bytes, a_bytes, var_box_bytes, tmem_cols, idesc;
+  uint32_t a_lbo, a_hi, a_kstep16;       // LBO field (already << 16) of the A descriptor low word; high word; K-step (bytes/16)
+  uint32_t b_lbo, b_hi, b_kstep16;
+  float* partial;
+  uint16_t tap_off16[12];                // start of each tap's view inside its variant box (bytes/16)
+  int8_t tap_view[12];                   // tensor map of the tap's variant view
+  CUtensorMap tmap_common;
+  CUtensorMap tmap_var[4];
+};
+
+__device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void ws_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * kWsMaxRing + 1];
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kWsMaxRing + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * kWsMaxRing);
+
+  const int split = blockIdx.x / p.tgroups, tg = blockIdx.x - split * p.tgroups;
+  const int tap0 = tg * p.taps_per_cta;
+  int ntap = p.npairs - tap0;
+  if (ntap > p.taps_per_cta) ntap = p.taps_per_cta;
+  const long long tile_begin = (long long)split * p.tiles_per_split;
+  long long tile_end = tile_begin + p.tiles_per_split;
+  if (tile_end > p.tiles) tile_end = p.tiles;
+  const bool has_work = tile_end > tile_begin;
+  const int ncols = p.n_blocks * 16;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int nbox = p.box_per_tap ? ntap : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWsMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (elect_one_sync()) {
+      prefetch_tensormap(&p.tmap_common);
+      for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap_var[v]);
+    }
+    __syncwarp();
+    const uint32_t tx = p.a_bytes + (uint32_t)nbox * p.var_box_bytes;
+    const int org = p.halo ? -1 : 0;
+    int slot = 0; uint32_t phase = 0;
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const int img = (int)(tile / tiles_per_img);
+      const int r = (int)(tile - (long long)img * tiles_per_img);
+      const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
+      const int x0 = txi * kWsTileW, y0 = ty * kWsTileH;
+      ws_wait(empty_bar(slot), phase ^ 1u);
+      if (elect_one_sync()) {
+        const uint32_t dst = smem0 + slot * p.slot_bytes;
+        mbar_arrive_expect_tx(full_bar(slot), tx);
+        tma_load_5d(dst, &p.tmap_common, full_bar(slot), 0, x0, y0, 0, img);
+        for (int i = 0; i < nbox; ++i)
+          tma_load_5d(dst + p.a_bytes + i * p.var_box_bytes, &p.tmap_var[p.tap_view[tap0 + i]], full_bar(slot), 0,
+                      x0 + org, y0 + org, 0, img);
+      }
+      __syncwarp();
+      if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    if (has_work) {
+      // per-tap B start offsets (16-byte units, relative to the slot's variant area) in registers
+      uint32_t boff[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+        boff[i] = i < ntap ? (uint32_t)p.tap_off16[tap0 + i] + (p.box_per_tap ? (uint32_t)i * (p.var_box_bytes >> 4) : 0u) : 0u;
+      const uint32_t a_hi = p.a_hi, b_hi = p.b_hi, idesc = p.idesc;
+      int slot = 0; uint32_t phase = 0;
+      uint32_t acc = 0;
+      for (long long tile = tile_begin; tile < tile_end; ++tile) {
+        const uint32_t s0 = smem0 + slot * p.slot_bytes;
+        const uint32_t a_lo0 = ((s0 & 0x3FFFFu) >> 4) | p.a_lbo;
+        const uint32_t b_lo0 = (((s0 + p.a_bytes) & 0x3FFFFu) >> 4) | p.b_lbo;
+        ws_wait(full_bar(slot), phase);
+        fence_after_sync();
+        if (elect_one_sync()) {
+#pragma unroll 1
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t a_lo = a_lo0 + kk * p.a_kstep16;
+            const uint32_t b_lok = b_lo0 + kk * p.b_kstep16;
+            const uint32_t a1 = (acc | (uint32_t)kk) ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < 10; ++i)
+              if (i < ntap) ws_mma(tmem_base + (uint32_t)(i * ncols), a_lo, a_hi, b_lok + boff[i], b_hi, idesc, a1);
+          }
+          mma_commit(empty_bar(slot));
+        }
+        __syncwarp();
+        acc = 1;
+        if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+      }
+      if (elect_one_sync()) mma_commit(tfull_bar);
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue (once): TMEM -> fp32 partial ----
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    if (has_work) {
+      ws_wait(tfull_bar, 0);
+      fence_after_sync();
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool row_ok = m < p.m_blocks * 16;
+    for (int i = 0; i < ntap; ++i) {
+      const int t = tap0 + i;
+      float* P = p.partial + ((long long)split * p.npairs + t) * p.cpad * p.npad;
+      for (int cb = 0; cb < p.n_blocks; ++cb) {
+        float v[16];
+        if (has_work) {
+          tmem_ld16(lane_addr + i * ncols + cb * 16, v);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        }
+        if (row_ok) {
+          if (p.swap == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) P[(long long)(cb * 16 + q) * p.npad + m] = v[q];
+          } else {
+            float4* dst = reinterpret_cast<float4*>(P + (long long)m * p.npad + cb * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+int launch_bias_grad(const TapWgrad& g, cudaStream_t st);
+
+// Returns 0 when launched, kSgNotEligible when this geometry belongs to the first-generation engine.
+int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
+  static bool attr_set = false;
+  { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return kSgNotEligible; }
+  const bool swap = g.ndyviews > 1;       // deconv: common = X, variants = dY parity views
+  const View& common = swap ? g.x[0] : g.dy[0];
+  const int m_blocks = swap ? g.c_blocks : g.n_blocks;
+  const int n_blocks = swap ? g.n_blocks : g.c_blocks;
+  if (g.dtype != N2N_BF16 || m_blocks < 1 || m_blocks > 8 || n_blocks < 1 || n_blocks > 16) return kSgNotEligible;
+  if (g.npairs < 1 || g.npairs > 9) return kSgNotEligible;
+  const int H = common.H, W = common.W;
+  if (H % kWsTileH || W % kWsTileW) return kSgNotEligible;
+  bool halo = false;
+  int nvar = 0;
+  for (int t = 0; t < g.npairs; ++t) {
+    if (g.pair_dy[t] < -1 || g.pair_dy[t] > 1 || g.pair_dx[t] < -1 || g.pair_dx[t] > 1) return kSgNotEligible;
+    if (g.pair_dy[t] || g.pair_dx[t]) halo = true;
+    const int vi = swap ? g.pair_dyv[t] : g.pair_xv[t];
+    if (vi + 1 > nvar) nvar = vi + 1;
+    if ((swap ? g.pair_xv[t] : g.pair_dyv[t]) != 0) return kSgNotEligible;
+  }
+  if (nvar > 4) return kSgNotEligible;
+  // conv: every tap is a view of ONE variant tensor; deconv: one variant tensor per tap, no offsets
+  const bool box_per_tap = nvar > 1;
+  if (box_per_tap && (halo || nvar != g.npairs)) return kSgNotEligible;
+
+  WsParams p;
+  memset(&p, 0, sizeof(p));
+  p.npairs = g.npairs; p.m_blocks = m_blocks; p.n_blocks = n_blocks; p.swap = swap ? 1 : 0;
+  p.npad = g.n_blocks * 16; p.cpad = g.c_blocks * 16;
+  p.partial = g.partial;
+  p.halo = halo ? 1 : 0; p.box_per_tap = box_per_tap ? 1 : 0;
+  const int bw = halo ? kWsTileW + 2 : kWsTileW, bh = halo ? kWsTileH + 2 : kWsTileH;
+  p.a_bytes = (uint32_t)(m_blocks * kWsTileW * kWsTileH * 32);
+  p.var_box_bytes = (uint32_t)(n_blocks * bw * bh * 32);
+  // taps per CTA: bounded by TMEM columns, and (deconv) by the shared memory one slot may take
+  int tpc = 512 / (n_blocks * 16);
+  if (tpc > g.npairs) tpc = g.npairs;
+  if (tpc > 10) tpc = 10;
+  const size_t budget = kWsSmemMax - kWsStaticSlack - 1024;
+  auto slot_for = [&](int taps) { return align_up((size_t)p.a_bytes + (size_t)(box_per_tap ? taps : 1) * p.var_box_bytes, 1024); };
+  while (tpc > 1 && 2 * slot_for(tpc) > budget) --tpc;
+  if (tpc < 1 || 2 * slot_for(tpc) > budget) return kSgNotEligible;
+  p.taps_per_cta = tpc;
+  p.tgroups = (g.npairs + tpc - 1) / tpc;
+  p.slot_bytes = (uint32_t)slot_for(tpc);
+  int ring = (int)(budget / p.slot_bytes);
+  if (ring > kWsMaxRing) ring = kWsMaxRing;
+  p.ring = ring;
+  p.tiles_x = W / kWsTileW; p.tiles_y = H / kWsTileH;
+  p.tiles = (long long)common.N * p.tiles_x * p.tiles_y;
+  const int splits = g.splits;
+  p.tiles_per_split = (p.tiles + splits - 1) / splits;
+  p.tmem_cols = tmem_cols_for(tpc * n_blocks * 16);
+  p.idesc = make_idesc_bf16(128, n_blocks * 16, true, true);
+  // MN-major descriptors: LBO = bytes between 16-channel blocks of a box, SBO = bytes between image rows
+  const uint32_t a_blk = (uint32_t)(kWsTileW * kWsTileH * 32), b_blk = (uint32_t)(bw * bh * 32);
+  p.a_lbo = ((a_blk >> 4) & 0x3FFFu) << 16;
+  p.b_lbo = ((b_blk >> 4) & 0x3FFFu) << 16;
+  p.a_hi = (((uint32_t)(kWsTileW * 32) >> 4) & 0x3FFFu) | (1u << 14) | (kSwizzle32 << 29);
+  p.b_hi = (((uint32_t)(bw * 32) >> 4) & 0x3FFFu) | (1u << 14) | (kSwizzle32 << 29);
+  p.a_kstep16 = (uint32_t)(2 * kWsTileW * 32) >> 4;
+  p.b_kstep16 = (uint32_t)(2 * bw * 32) >> 4;
+  for (int t = 0; t < g.npairs; ++t) {
+    const int oy = halo ? g.pair_dy[t] + 1 : 0, ox = halo ? g.pair_dx[t] + 1 : 0;
+    p.tap_off16[t] = (uint16_t)(((oy * bw + ox) * 32) >> 4);
+    p.tap_view[t] = (int8_t)(swap ? g.pair_dyv[t] : g.pair_xv[t]);
+  }
+  N2N_TRY(encode_c16_tensor_map(&p.tmap_common, common, kWsTileW, kWsTileH, m_blocks));
+  for (int v = 0; v < 4; ++v) {
+    const View& vv = swap ? g.dy[v < nvar ? v : 0] : g.x[v < nvar ? v : 0];
+    if (vv.H != H || vv.W != W) return kSgNotEligible;
+    N2N_TRY(encode_c16_tensor_map(&p.tmap_var[v], vv, bw, bh, n_blocks));
+  }
+  // the M = 128 MMA always walks 8 channel blocks of the common tile: keep that window inside the allocation
+  size_t smem = 1024 + (size_t)ring * p.slot_bytes;
+  const size_t window = 1024 + (size_t)(ring - 1) * p.slot_bytes + 8u * a_blk + 1024;
+  if (smem < window) smem = window;
+  if (smem > kWsSmemMax - kWsStaticSlack) return kSgNotEligible;
+  if (!attr_set) {
+    N2N_CUDA(cudaFuncSetAttribute(wgrad_slab_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kWsSmemMax - kWsStaticSlack)));
+    attr_set = true;
+  }
+  wgrad_slab_umma_kernel<<<splits * p.tgroups, kWsThreads, smem, st>>>(p);
+  N2N_LAUNCH_CHECK();
+  if (g.bias_partial) return launch_bias_grad(g, st);
+  return 0;
+}
+
+}  // namespace n2n

@@ -207,6 +207,19 @@ bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, long long
 
 void choose_tile(int H, int W, int& bw, int& bh);
 
+// HBM-bound bias-gradient pass shared by both weight-gradient engines.
+int launch_bias_grad(const TapWgrad& g, cudaStream_t st) {
+  if (!g.bias_partial) return 0;
+  const int splits = g.splits;
+  const long long pixels = (long long)g.dy[0].N * g.dy[0].H * g.dy[0].W;
+  const long long per_split = (pixels + splits - 1) / splits;
+  dim3 bgrid(splits * g.ndyviews, g.n_blocks);
+  bias_grad_kernel<<<bgrid, 256, 0, st>>>(g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, pixels, per_split,
+                                          g.bias_partial, g.n_blocks * 16);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st) {
   static bool attr_set = false;
   // conv: common = dY (view 0), variants = X shifted; deconv (ndyviews == 4): common = X, variants = dY parity views
@@ -268,15 +281,7 @@ int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st) {
   dim3 grid(splits, tgroups);
   tapwgrad_umma_kernel<<<grid, kThreadsW, smem, st>>>(p);
   N2N_LAUNCH_CHECK();
-  if (g.bias_partial) {
-    const long long pixels = (long long)g.dy[0].N * g.dy[0].H * g.dy[0].W;
-    const long long per_split = (pixels + splits - 1) / splits;
-    dim3 bgrid(splits * g.ndyviews, g.n_blocks);
-    bias_grad_kernel<<<bgrid, 256, 0, st>>>(g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, pixels, per_split,
-                                            g.bias_partial, g.n_blocks * 16);
-    N2N_LAUNCH_CHECK();
-  }
-  return 0;
+  return launch_bias_grad(g, st);
 }
 
 }  // namespace n2n

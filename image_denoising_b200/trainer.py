@@ -9,6 +9,7 @@ the 1/world factor is folded into the Adam kernel.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -19,7 +20,7 @@ from .optim import build_adam_tables
 
 class N2NTrainer:
     def __init__(self, network, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, precision=None, process_group=None,
-                 buckets=2):
+                 buckets=2, use_graph=None):
         self.net = network
         self.precision = precision or network.precision
         network.set_precision(self.precision)
@@ -56,6 +57,13 @@ class N2NTrainer:
         self.bucket_slices = [(cut, total), (0, cut)] if cut > 0 else [(0, total)]
         self._shapes = None
         self.last_launches = 0
+        # CUDA-graph replay of the whole iteration (one graph launch instead of ~190 kernel launches);
+        # N2N_NO_GRAPH=1 keeps the eager launch sequence (used by the per-launch profiling hooks).
+        if use_graph is None:
+            use_graph = os.environ.get("N2N_NO_GRAPH", "0") != "1"
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._eager_steps = 0
         if self.world > 1:
             torch.distributed.broadcast(self.flat_p, src=0, group=self.pg)   # once, instead of DataParallel's per-step replicate
 
@@ -88,32 +96,79 @@ class N2NTrainer:
         self.grad_ptrs = ptr_array(self.grads)
 
     # ------------------------------------------------------------------ one iteration
-    def step(self, noisy, Lambda, rd_idx=None, lr=None):
-        """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
-        device tensor [loss_all, loss1, loss2] (no host sync).  ``rd_idx`` may carry this rank's
-        slice of a globally drawn selector (mask parity with a 1-GPU run, SURVEY.md §8e)."""
-        noisy = noisy.contiguous()
-        self._prepare(noisy)
+    def _launch_sequence(self, noisy, rd_idx, lam, lr, dev_scalars):
+        """The launch sequence of one iteration on the current stream.  With ``dev_scalars`` the
+        per-step scalars (Lambda, Adam step size / bias correction) are read from device memory, so
+        the same sequence can be replayed as a CUDA graph."""
         L, st = lib(), stream_ptr()
         n, c, h, w = noisy.shape
-        launches0 = L.n2n_launch_count()
-        if rd_idx is None:
-            rd_idx = n2n.draw_rd_idx(noisy)
         check(L.n2n_mask_pair_from_rdidx(ptr(rd_idx), rd_idx.numel(), None, None, ptr(self.packed), st))
         check(L.n2n_subsample_pair(ptr(noisy), None, None, ptr(self.packed), ptr(self.sub1), ptr(self.sub2), n, c, h, w, 4, st))
         check(L.n2n_unet_forward(self.plan_full, self.param_ptrs, ptr(noisy), ptr(self.den), ptr(self.ws_full), st))
         check(L.n2n_subsample_pair(ptr(self.den), None, None, ptr(self.packed), ptr(self.den1), ptr(self.den2),
                                    n, self.net.out_nc, h, w, 4, st))
         check(L.n2n_unet_forward(self.plan_half, self.param_ptrs, ptr(self.sub1), ptr(self.out), ptr(self.ws_half), st))
-        check(L.n2n_loss_n2n_fwdbwd(ptr(self.out), ptr(self.sub2), ptr(self.den1), ptr(self.den2), float(Lambda), 1.0,
-                                    self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
+        if dev_scalars is None:
+            check(L.n2n_loss_n2n_fwdbwd(ptr(self.out), ptr(self.sub2), ptr(self.den1), ptr(self.den2), float(lam), 1.0,
+                                        self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
+        else:
+            check(L.n2n_loss_n2n_fwdbwd_dev(ptr(self.out), ptr(self.sub2), ptr(self.den1), ptr(self.den2), ptr(dev_scalars),
+                                            1.0, self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
         check(L.n2n_unet_backward(self.plan_half, self.param_ptrs, ptr(self.dout), self.grad_ptrs, None, ptr(self.ws_half), st))
         if self.world > 1:
             for a, b in self.bucket_slices:
                 torch.distributed.all_reduce(self.flat_g[a:b], group=self.pg)
+        if dev_scalars is None:
+            check(L.n2n_adam_multi(ptr(self.table), 1, ptr(self.blocks), self.blocks.shape[0], float(lr),
+                                   float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,
+                                   1.0 / self.world, st))
+        else:
+            check(L.n2n_adam_multi_dev(ptr(self.table), 1, ptr(self.blocks), self.blocks.shape[0], ptr(dev_scalars),
+                                       float(self.betas[0]), float(self.betas[1]), float(self.eps), 1.0 / self.world, st))
+
+    def _capture(self):
+        """Capture the iteration once (static input / selector / scalar buffers)."""
+        self.in_static = torch.empty(self._shapes, dtype=torch.float32, device=self.flat_p.device)
+        n, c, h, w = self._shapes
+        self.rd_static = torch.zeros(n * (h // 2) * (w // 2), dtype=torch.int64, device=self.flat_p.device)
+        self.dev_scalars = torch.zeros(4, dtype=torch.float32, device=self.flat_p.device)
+        # a capture must not change the optimiser state: snapshot, capture (the captured launches do
+        # not execute), nothing to restore
+        g = torch.cuda.CUDAGraph()
+        launches0 = lib().n2n_launch_count()
+        with torch.cuda.graph(g):
+            self._launch_sequence(self.in_static, self.rd_static, 0.0, self.lr, self.dev_scalars)
+        self.graph_launches = lib().n2n_launch_count() - launches0
+        self._graph = g
+
+    def step(self, noisy, Lambda, rd_idx=None, lr=None):
+        """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
+        device tensor [loss_all, loss1, loss2] (no host sync).  ``rd_idx`` may carry this rank's
+        slice of a globally drawn selector (mask parity with a 1-GPU run, SURVEY.md §8e)."""
+        noisy = noisy.contiguous()
+        shapes_before = self._shapes
+        self._prepare(noisy)
+        if shapes_before != self._shapes:
+            self._graph = None
+            self._eager_steps = 0
+        L = lib()
+        launches0 = L.n2n_launch_count()
+        if rd_idx is None:
+            rd_idx = n2n.draw_rd_idx(noisy)
         self.step_count += 1
-        check(L.n2n_adam_multi(ptr(self.table), 1, ptr(self.blocks), self.blocks.shape[0], float(lr or self.lr),
-                               float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,
-                               1.0 / self.world, st))
+        lr = float(lr or self.lr)
+        profiling = L.n2n_profile_active() == 1
+        if self.use_graph and not profiling and self._eager_steps >= 1:
+            if self._graph is None:
+                self._capture()
+            self.in_static.copy_(noisy, non_blocking=True)
+            self.rd_static.copy_(rd_idx, non_blocking=True)
+            check(L.n2n_set_step_scalars(ptr(self.dev_scalars), float(Lambda), lr, float(self.betas[0]),
+                                         float(self.betas[1]), self.step_count, stream_ptr()))
+            self._graph.replay()
+            self.last_launches = self.graph_launches + 1
+            return self.loss3
+        self._launch_sequence(noisy, rd_idx, Lambda, lr, None)
+        self._eager_steps += 1
         self.last_launches = L.n2n_launch_count() - launches0
         return self.loss3

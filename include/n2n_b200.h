@@ -51,6 +51,7 @@ long long n2n_launch_count(void);
  * events and fills out[6] = {ms, executed FLOPs, launches} for the tap-GEMM kernel (conv / deconv
  * forward + input gradient) followed by the same three for the weight-gradient kernel. */
 int n2n_profile_begin(void);
+int n2n_profile_active(void);   /* 1 between begin() and end() on the calling thread */
 int n2n_profile_end(double* out);
 /* Per-launch variant: fills rows of {class, ms, executed FLOPs} in launch order, returns the row count. */
 int n2n_profile_end_list(double* out, int max_rows);
@@ -192,6 +193,19 @@ int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, int n, int c,
 int n2n_adam_multi(const int64_t* table, int ntensors, const int32_t* blocks, int nblocks,
                    float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                    void* stream);
+
+/* CUDA-graph forms of the two per-step kernels whose scalars change every iteration
+ * (Lambda = epoch/n_epoch*ratio, training_script.md:148; Adam's bias corrections, train.py:368):
+ * a captured training step reads them from dev_scalars[4] = {Lambda, lr/(1-beta1^step),
+ * sqrt(1-beta2^step), 0}, which n2n_set_step_scalars refreshes before each replay. */
+int n2n_set_step_scalars(float* dev_scalars, float lam, float lr, float beta1, float beta2, int step,
+                         void* stream);
+int n2n_loss_n2n_fwdbwd_dev(const float* out, const float* sub2, const float* den1, const float* den2,
+                            const float* dev_scalars, float grad_scale, int64_t count, float* loss3,
+                            float* grad, void* workspace, void* stream);
+int n2n_adam_multi_dev(const int64_t* table, int ntensors, const int32_t* blocks, int nblocks,
+                       const float* dev_scalars, float beta1, float beta2, float eps, float grad_scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Evaluation — evaluation.py:82-83, evaluation_704.py:57-120, utils_eval.py:19-53.

@@ -29,6 +29,6 @@ for i in range(n):
     if cls == 0 and k < 2 * len(names_fwd):
         tag = ("full:" if k < len(names_fwd) else "half:") + names_fwd[k % len(names_fwd)]
         k += 1
-    if ms > 0.03:
+    if ms > 0.0:
         print(f"{i:3d} cls={cls} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TF/s(exec) {tag}")
 print("totals ms:", tot)
