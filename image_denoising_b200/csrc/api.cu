@@ -55,6 +55,12 @@ int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
   if (g.has_pool) return launch_maxpool(g.y, g.pool, g.dtype, st);
   return 0;
 }
+int launch_head_chain(const HeadChain& h, cudaStream_t st) {
+  const double px = (double)h.x.N * h.x.H * h.x.W;
+  const double flops = 2.0 * px * 16.0 * h.mid_blocks * (16.0 * h.in_blocks + 16.0 * h.mid_blocks + h.out_nc);
+  ProfScope ps(0, flops, st);
+  return launch_head_chain_umma(h, st);
+}
 int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
   const double flops = 2.0 * g.dy[0].N * g.dy[0].H * g.dy[0].W * 256.0 * g.n_blocks * g.c_blocks * g.npairs;
   ProfScope ps(1, flops, st);
@@ -151,7 +157,7 @@ static ConvWs conv_ws(void* ws, const LayerGeom& L, int n, int h, int w, int dty
   Carver c(ws);
   ConvWs r;
   const int oh = deconv ? 2 * h : h, ow = deconv ? 2 * w : w;
-  r.splits = wgrad_default_splits(dtype, (long long)n * h * w);
+  r.splits = layer_wgrad_splits(L, dtype, n, h, w);
   r.xa = c.take(c16_bytes(dtype, n, L.cin.real(), h, w));
   r.ya = c.take(c16_bytes(dtype, n, L.cout, oh, ow));
   r.wp = c.take(L.fwd_pack_bytes(dtype));

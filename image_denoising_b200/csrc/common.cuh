@@ -177,6 +177,24 @@ struct TapGemm {
   bool has_pool = false; View pool;   // also write maxpool2x2(out) here (fused in the epilogue when possible)
 };
 
+// ---- fused 1x1 head: y = Wc * lrelu(Wb * lrelu(Wa * x + ba) + bb) + bc  (arch_unet.py:257-259) -----
+struct HeadChain {
+  View x;                          // input activations (dec_conv1b output), in_blocks blocks
+  int in_blocks = 0, mid_blocks = 0, mid_channels = 0, out_nc = 0;
+  const void* wa = nullptr;        // packed bf16 1x1 weights (engine layout) of nin_a / nin_b
+  const void* wb = nullptr;
+  const float* bias_a = nullptr;   // padded fp32
+  const float* bias_b = nullptr;
+  const float* wc = nullptr;       // nin_c weight, torch layout fp32 [out_nc][mid_channels]
+  const float* bias_c = nullptr;   // [out_nc]
+  float slope = 0.2f;
+  bool has_save = false;           // training pass: also store the two intermediate activations
+  View save_a, save_b;
+  float* out_nchw = nullptr;       // fp32 [N][out_nc][H][W]
+};
+int launch_head_chain(const HeadChain& h, cudaStream_t st);        // api.cu (profiling scope + dispatch)
+int launch_head_chain_umma(const HeadChain& h, cudaStream_t st);   // head_umma.cu
+
 // ---- generic weight-gradient GEMM ---------------------------------------------------------
 // P[s][t][c][n] = sum_{p in split s} dY_{a(t)}[p, n] * X_{b(t)}[p + (dy_t, dx_t), c]
 // bias_partial[s][n] = sum_{p in split s} sum_{distinct dY views} dY[p, n]

@@ -1,0 +1,359 @@
+// head_umma.cu — the UNet's 1x1 head (nin_a -> LeakyReLU -> nin_b -> LeakyReLU -> nin_c,
+// arch_unet.py:186-190 / :257-259) as ONE persistent tcgen05 kernel.  Unfused, the chain is three
+// HBM round trips over a full-resolution 96-channel tensor (the largest in the network) for 13
+// MFLOP/pixel; fused, the tile of dec_conv1b's output is read once and only the out_nc-channel
+// fp32 result leaves the SM (plus, in a training pass, the two bf16 activations the backward needs).
+//
+// Per 8 x 16-pixel tile (M = 128):
+//   warp 0     TMA: the X tile [in_blocks][128 px][16 ch] (K-major SWIZZLE_32B operand) -> ring slot
+//   warp 1     MMA-1: D1 = X * Wa^T            (TMEM, double buffered)
+//              MMA-2: D2 = H1 * Wb^T           (H1 = shared-memory operand written by stage E1)
+//   warps 2-5  E1: D1 -> +bias_a -> LeakyReLU -> bf16 -> H1 tile in shared memory, in exactly the
+//              swizzled K-major layout MMA-2 wants (16-byte chunk XOR address bit 7), then
+//              fence.proxy.async so the tensor core sees it
+//   warps 6-9  E2: D2 -> +bias_b -> LeakyReLU -> dot with nin_c's rows (fp32, registers) -> +bias_c ->
+//              fp32 NCHW store
+// E1 and E2 work on different tiles at the same time; both weight matrices stay resident in
+// shared memory; nin_c's weights are broadcast reads of a small shared-memory table.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace n2n {
+
+using namespace umma;
+
+constexpr int kHdThreads = 320;
+constexpr int kHdRing = 3;
+constexpr int kHdMaxOut = 4;
+
+struct HdParams {
+  int in_blocks, mid_blocks, out_nc;
+  int tiles_x, tiles_y, ntiles;
+  int has_save;
+  float slope;
+  uint32_t wa_bytes, wb_bytes, x_bytes, h_bytes, tmem_cols, idesc;
+  const uint8_t *wa, *wb;
+  const float *bias_a, *bias_b, *wc, *bias_c;
+  float* out_nchw;
+  View x, save_a, save_b;
+  CUtensorMap tmap_x;
+};
+
+__device__ __forceinline__ void hd_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void hd_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate));
+}
+
+__device__ __forceinline__ void hd_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void hd_st_global_32B(void* ptr, const uint32_t w[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kHdThreads, 1)
+head_chain_umma_kernel(const __grid_constant__ HdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // barriers: x_full[3] x_empty[3] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[2] d2_empty[2] w_full
+  __shared__ uint64_t bars[2 * kHdRing + 12 + 1];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t wa0 = smem0, wb0 = wa0 + p.wa_bytes;
+  const uint32_t x0s = wb0 + p.wb_bytes;                     // X ring
+  const uint32_t h0s = x0s + kHdRing * p.x_bytes;            // H1 double buffer
+  const uint32_t bar0 = smem_u32(bars);
+  auto x_full = [&](int s) { return bar0 + 8u * s; };
+  auto x_empty = [&](int s) { return bar0 + 8u * (kHdRing + s); };
+  auto d1_full = [&](int b) { return bar0 + 8u * (2 * kHdRing + b); };
+  auto d1_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 2 + b); };
+  auto h_full = [&](int b) { return bar0 + 8u * (2 * kHdRing + 4 + b); };
+  auto h_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 6 + b); };
+  auto d2_full = [&](int b) { return bar0 + 8u * (2 * kHdRing + 8 + b); };
+  auto d2_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 10 + b); };
+  const uint32_t w_full = bar0 + 8u * (2 * kHdRing + 12);
+  const int nmid = p.mid_blocks * 16;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHdRing; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4);
+      mbar_init(h_full(b), 4);  mbar_init(h_empty(b), 1);
+      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += kHdThreads) {
+    s_ba[i] = i < nmid ? p.bias_a[i] : 0.f;
+    s_bb[i] = i < nmid ? p.bias_b[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kHdMaxOut * 128; i += kHdThreads) {
+    const int oc = i >> 7, c = i & 127;
+    s_wc[i] = (oc < p.out_nc && c < nmid) ? p.wc[oc * nmid + c] : 0.f;
+  }
+  if (threadIdx.x < kHdMaxOut) s_bc[threadIdx.x] = threadIdx.x < p.out_nc ? p.bias_c[threadIdx.x] : 0.f;
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (elect_one_sync()) {
+      prefetch_tensormap(&p.tmap_x);
+      mbar_arrive_expect_tx(w_full, p.wa_bytes + p.wb_bytes);
+      bulk_load(wa0, p.wa, p.wa_bytes, w_full);
+      bulk_load(wb0, p.wb, p.wb_bytes, w_full);
+    }
+    __syncwarp();
+    int slot = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int r = tile - img * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      hd_wait(x_empty(slot), phase ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(x_full(slot), p.x_bytes);
+        tma_load_5d(x0s + slot * p.x_bytes, &p.tmap_x, x_full(slot), 0, tx * 8, ty * 16, 0, img);
+      }
+      __syncwarp();
+      if (++slot == kHdRing) { slot = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: MMA-1 of tile i+1 is issued before MMA-2 of tile i so E1 never starves ----
+    hd_wait(w_full, 0);
+    const uint32_t idesc = p.idesc;
+    const uint32_t ba16 = (uint32_t)nmid * 2u;              // bytes/16 of one K block of Wa / Wb (nmid rows x 32 B)
+    auto mma1 = [&](int lt, int slot, uint32_t xph) {
+      const int b = lt & 1;
+      hd_wait(d1_empty(b), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      hd_wait(x_full(slot), xph);
+      fence_after_sync();
+      if (elect_one_sync()) {
+        const uint32_t a_lo = (((x0s + slot * p.x_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = ((wa0 & 0x3FFFFu) >> 4) | (1u << 16);
+        for (int cb = 0; cb < p.in_blocks; ++cb)
+          hd_mma(tmem_base + (uint32_t)(b * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+        mma_commit(x_empty(slot));
+        mma_commit(d1_full(b));
+      }
+      __syncwarp();
+    };
+    auto mma2 = [&](int lt) {
+      const int b = lt & 1;
+      hd_wait(d2_empty(b), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      hd_wait(h_full(b), ((uint32_t)lt >> 1) & 1u);
+      fence_after_sync();
+      if (elect_one_sync()) {
+        const uint32_t a_lo = (((h0s + b * p.h_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = ((wb0 & 0x3FFFFu) >> 4) | (1u << 16);
+        for (int cb = 0; cb < p.mid_blocks; ++cb)
+          hd_mma(tmem_base + (uint32_t)((2 + b) * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+        mma_commit(h_empty(b));
+        mma_commit(d2_full(b));
+      }
+      __syncwarp();
+    };
+    int slot = 0; uint32_t xph = 0;
+    int lt = 0;
+    const int first = blockIdx.x;
+    if (first < p.ntiles) {
+      mma1(0, slot, xph);
+      if (++slot == kHdRing) { slot = 0; xph ^= 1u; }
+    }
+    for (int tile = first; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      if (tile + (int)gridDim.x < p.ntiles) {
+        mma1(lt + 1, slot, xph);
+        if (++slot == kHdRing) { slot = 0; xph ^= 1u; }
+      }
+      mma2(lt);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    const bool is_e1 = warp < 6;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+      const int img = tile / tiles_per_img;
+      const int r = tile - img * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * 16 + py, x = tx * 8 + px;
+      const int b = lt & 1;
+      const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      if (is_e1) {
+        // ---- E1: D1 -> H1 (shared-memory operand of MMA-2) ----
+        hd_wait(d1_full(b), par);
+        hd_wait(h_empty(b), par ^ 1u);
+        fence_after_sync();
+        const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
+        for (int cb = 0; cb < p.mid_blocks; ++cb) {
+          float v[16];
+          hd_ld16(lane_base + (uint32_t)(b * nmid + cb * 16), v);
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = v[2 * j] + s_ba[cb * 16 + 2 * j], a1 = v[2 * j + 1] + s_ba[cb * 16 + 2 * j + 1];
+            a0 = a0 > 0.f ? a0 : a0 * p.slope;
+            a1 = a1 > 0.f ? a1 : a1 * p.slope;
+            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
+          const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
+          const uint32_t sw = ((h0s + off) >> 7) & 1u;
+          uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
+          dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+        }
+        fence_before_sync();
+        fence_proxy_async();                 // generic-proxy writes of H1 -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(d1_empty(b)); mbar_arrive(h_full(b)); }
+      } else {
+        // ---- E2: D2 -> nin_c -> fp32 NCHW ----
+        hd_wait(d2_full(b), par);
+        fence_after_sync();
+        const long long spix = p.has_save ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
+        float o[kHdMaxOut];
+#pragma unroll
+        for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
+        for (int cb = 0; cb < p.mid_blocks; ++cb) {
+          float v[16];
+          hd_ld16(lane_base + (uint32_t)((2 + b) * nmid + cb * 16), v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float a = v[q] + s_bb[cb * 16 + q];
+            v[q] = a > 0.f ? a : a * p.slope;
+          }
+          if (p.has_save) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+              // the backward (and nin_c) see the bf16-rounded activation, as in the unfused path
+              v[2 * j] = __uint_as_float(w[j] << 16);
+              v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            }
+            hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = __bfloat162float(__float2bfloat16_rn(v[q]));
+          }
+#pragma unroll
+          for (int oc = 0; oc < kHdMaxOut; ++oc) {
+            if (oc < p.out_nc) {
+              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 wv = wr[q];
+                o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
+              }
+            }
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty(b));
+        const long long hw = (long long)p.x.H * p.x.W;
+#pragma unroll
+        for (int oc = 0; oc < kHdMaxOut; ++oc)
+          if (oc < p.out_nc) p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// Returns 0 when launched, kSgNotEligible when the geometry is not covered (caller runs the three
+// layers one by one).
+int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
+  static bool attr_set = false;
+  { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
+  if (h.in_blocks < 1 || h.in_blocks > 8 || h.mid_blocks < 1 || h.mid_blocks > 8 || h.out_nc < 1 || h.out_nc > kHdMaxOut)
+    return kSgNotEligible;
+  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16) return kSgNotEligible;
+  HdParams p;
+  memset(&p, 0, sizeof(p));
+  p.in_blocks = h.in_blocks; p.mid_blocks = h.mid_blocks; p.out_nc = h.out_nc;
+  p.tiles_x = h.x.W / 8; p.tiles_y = h.x.H / 16;
+  const long long tiles = (long long)h.x.N * p.tiles_x * p.tiles_y;
+  N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "head_chain: bad tile count");
+  p.ntiles = (int)tiles;
+  p.has_save = h.has_save ? 1 : 0; p.slope = h.slope;
+  const int nmid = h.mid_blocks * 16;
+  // packed 1x1 weights: [group][3 blocks][nmid rows][32 B]; block cb sits at cb * nmid * 32
+  p.wa_bytes = (uint32_t)(((h.in_blocks + 2) / 3) * 3 * nmid * 32);
+  p.wb_bytes = (uint32_t)(((h.mid_blocks + 2) / 3) * 3 * nmid * 32);
+  p.x_bytes = (uint32_t)(h.in_blocks * 4096);
+  p.h_bytes = (uint32_t)(h.mid_blocks * 4096);
+  p.tmem_cols = tmem_cols_for(4 * nmid);
+  if (4 * nmid > 512) return kSgNotEligible;
+  p.idesc = make_idesc_bf16(128, nmid, false, false);
+  p.wa = (const uint8_t*)h.wa; p.wb = (const uint8_t*)h.wb;
+  p.bias_a = h.bias_a; p.bias_b = h.bias_b; p.wc = h.wc; p.bias_c = h.bias_c;
+  p.out_nchw = h.out_nchw; p.x = h.x; p.save_a = h.save_a; p.save_b = h.save_b;
+  N2N_TRY(encode_c16_tensor_map(&p.tmap_x, h.x, 8, 16, h.in_blocks));
+  const size_t smem = 1024 + (size_t)p.wa_bytes + p.wb_bytes + (size_t)kHdRing * p.x_bytes + 2 * (size_t)p.h_bytes;
+  if (smem > 220 * 1024) return kSgNotEligible;
+  if (!attr_set) {
+    N2N_CUDA(cudaFuncSetAttribute(head_chain_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int nsm = 0, dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = kSMs;
+  const int grid = tiles < nsm ? (int)tiles : nsm;
+  head_chain_umma_kernel<<<grid, kHdThreads, smem, st>>>(p);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace n2n

@@ -123,8 +123,7 @@ static void plan_layout(n2n_unet_plan* p) {
       p->grd[b].off = take((size_t)p->N * p->grd[b].Cb * p->lh(p->grd[b].lvl) * p->lw(p->grd[b].lvl) * 16 * es);
     for (int i = 0; i < 25; ++i) {
       const LayerIO& io = p->io[i];
-      const long long px = (long long)p->N * p->lh(p->act[io.in_buf].lvl) * p->lw(p->act[io.in_buf].lvl);
-      p->splits[i] = wgrad_default_splits(p->dtype, px);
+      p->splits[i] = layer_wgrad_splits(p->L[i], p->dtype, p->N, p->lh(p->act[io.in_buf].lvl), p->lw(p->act[io.in_buf].lvl));
       // dgrad weights are packed for the full input width so that dL/dx can be served too
       p->off_wd[i] = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));
       p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
@@ -214,7 +213,25 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
   N2N_TRY(run_layer(3, B_CAT3, p->c2b));
   N2N_TRY(run_layer(4, B_CAT4, p->nfb));
   N2N_TRY(run_layer(5, B_P5, 0));
-  for (int i = 6; i < 25; ++i) N2N_TRY(run_layer(i));
+  for (int i = 6; i < 22; ++i) N2N_TRY(run_layer(i));
+  // nin_a -> nin_b -> nin_c: one fused kernel on the bf16 engine (the intermediates are only
+  // written when a backward pass will read them)
+  int head = kSgNotEligible;
+  if (dt == N2N_BF16) {
+    HeadChain h;
+    h.x = p->view(p->act, ws, B_D1B, 0, p->hb);
+    h.in_blocks = p->hb; h.mid_blocks = p->hb; h.mid_channels = 96; h.out_nc = p->out_nc;
+    h.wa = (char*)ws + p->off_wp[22]; h.wb = (char*)ws + p->off_wp[23];
+    h.bias_a = (const float*)((char*)ws + p->off_bias[22]); h.bias_b = (const float*)((char*)ws + p->off_bias[23]);
+    h.wc = params[2 * 24]; h.bias_c = params[2 * 24 + 1];
+    h.slope = 0.2f; h.has_save = p->bwd;
+    h.save_a = p->view(p->act, ws, B_NA, 0, p->hb); h.save_b = p->view(p->act, ws, B_NB, 0, p->hb);
+    h.out_nchw = y;
+    head = launch_head_chain(h, st);
+    if (head < 0) return head;
+  }
+  if (head == kSgNotEligible)
+    for (int i = 22; i < 25; ++i) N2N_TRY(run_layer(i));
   p->fwd_launches = (int)(g_launch_count - launches0);
   return 0;
 }
@@ -307,7 +324,7 @@ struct n2n_adapter_plan {
   int C, hid, N, H, W, dtype; bool bwd;
   LayerGeom L[2];
   size_t off_cat, off_h, off_gout, off_gh, off_wp[2], off_wd1, off_bias[2], off_partial[2], off_bpartial[2];
-  int splits;
+  int splits[2];
   size_t total;
 };
 
@@ -329,14 +346,14 @@ extern "C" int n2n_adapter_plan_create(n2n_adapter_plan** plan, int channels, in
     p->off_wp[i] = take(p->L[i].fwd_pack_bytes(dtype));
     p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
   }
-  p->splits = wgrad_default_splits(dtype, (long long)n * h * w);
+  for (int i = 0; i < 2; ++i) p->splits[i] = layer_wgrad_splits(p->L[i], dtype, n, h, w);
   if (p->bwd) {
     p->off_gout = take(px);
     p->off_gh = take(cblocks(hidden) * px);
     p->off_wd1 = take(p->L[1].dgrad_pack_bytes(dtype, p->L[1].cin_blocks()));
     for (int i = 0; i < 2; ++i) {
-      p->off_partial[i] = take(p->L[i].partial_bytes(p->splits));
-      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits));
+      p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
+      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
     }
   }
   p->total = off;
@@ -389,14 +406,14 @@ extern "C" int n2n_adapter_backward(n2n_adapter_plan* p, const float* const* par
   N2N_TRY(launch_nchw_to_c16(dout, p->C, gout, dt, st));
   float* part[2] = {(float*)((char*)ws + p->off_partial[0]), (float*)((char*)ws + p->off_partial[1])};
   float* bpart[2] = {(float*)((char*)ws + p->off_bpartial[0]), (float*)((char*)ws + p->off_bpartial[1])};
-  TapWgrad w1 = make_conv_wgrad(p->L[1], dt, hv, gout, part[1], bpart[1], p->splits);
+  TapWgrad w1 = make_conv_wgrad(p->L[1], dt, hv, gout, part[1], bpart[1], p->splits[1]);
   N2N_TRY(launch_tapwgrad(w1, st));
   TapGemm d1 = make_conv_dgrad(p->L[1], dt, gout, gh, (char*)ws + p->off_wd1, hb);
   d1.has_mask = true; d1.mask = hv; d1.slope = 0.f;             // ReLU'
   N2N_TRY(launch_tapgemm(d1, st));
-  TapWgrad w0 = make_conv_wgrad(p->L[0], dt, cat, gh, part[0], bpart[0], p->splits);
+  TapWgrad w0 = make_conv_wgrad(p->L[0], dt, cat, gh, part[0], bpart[0], p->splits[0]);
   N2N_TRY(launch_tapwgrad(w0, st));
-  UnpackJob uj[2] = {make_unpack(p->L[0], part[0], bpart[0], p->splits, grads[0], grads[1]),
-                     make_unpack(p->L[1], part[1], bpart[1], p->splits, grads[2], grads[3])};
+  UnpackJob uj[2] = {make_unpack(p->L[0], part[0], bpart[0], p->splits[0], grads[0], grads[1]),
+                     make_unpack(p->L[1], part[1], bpart[1], p->splits[1], grads[2], grads[3])};
   return launch_unpack(uj, 2, st);
 }

@@ -212,6 +212,32 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
 
 int launch_bias_grad(const TapWgrad& g, cudaStream_t st);
 
+static int ws_taps_per_cta(int npairs, int variant_blocks, int common_blocks, bool box_per_tap, bool halo) {
+  const int bw = halo ? kWsTileW + 2 : kWsTileW, bh = halo ? kWsTileH + 2 : kWsTileH;
+  const size_t a_bytes = (size_t)common_blocks * kWsTileW * kWsTileH * 32;
+  const size_t var_box = (size_t)variant_blocks * bw * bh * 32;
+  int tpc = 512 / (variant_blocks * 16);
+  if (tpc > npairs) tpc = npairs;
+  if (tpc > 10) tpc = 10;
+  const size_t budget = kWsSmemMax - kWsStaticSlack - 1024;
+  auto slot_for = [&](int taps) { return align_up(a_bytes + (size_t)(box_per_tap ? taps : 1) * var_box, 1024); };
+  while (tpc > 1 && 2 * slot_for(tpc) > budget) --tpc;
+  if (tpc < 1 || 2 * slot_for(tpc) > budget) return 0;
+  return tpc;
+}
+
+// How many pixel splits fill the chip exactly once given the tap grouping (0 = geometry not eligible).
+int wgrad_slab_splits(int npairs, int variant_blocks, int common_blocks, bool box_per_tap, long long tiles) {
+  if (variant_blocks < 1 || variant_blocks > 16 || common_blocks < 1 || common_blocks > 8 || tiles < 1) return 0;
+  const int tpc = ws_taps_per_cta(npairs, variant_blocks, common_blocks, box_per_tap, !box_per_tap && npairs > 1);
+  if (tpc < 1) return 0;
+  const int tg = (npairs + tpc - 1) / tpc;
+  long long s = kSMs / tg;
+  if (s > tiles) s = tiles;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
 // Returns 0 when launched, kSgNotEligible when this geometry belongs to the first-generation engine.
 int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   static bool attr_set = false;
@@ -248,13 +274,10 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.a_bytes = (uint32_t)(m_blocks * kWsTileW * kWsTileH * 32);
   p.var_box_bytes = (uint32_t)(n_blocks * bw * bh * 32);
   // taps per CTA: bounded by TMEM columns, and (deconv) by the shared memory one slot may take
-  int tpc = 512 / (n_blocks * 16);
-  if (tpc > g.npairs) tpc = g.npairs;
-  if (tpc > 10) tpc = 10;
+  const int tpc = ws_taps_per_cta(g.npairs, n_blocks, m_blocks, box_per_tap, halo);
+  if (tpc < 1) return kSgNotEligible;
   const size_t budget = kWsSmemMax - kWsStaticSlack - 1024;
   auto slot_for = [&](int taps) { return align_up((size_t)p.a_bytes + (size_t)(box_per_tap ? taps : 1) * p.var_box_bytes, 1024); };
-  while (tpc > 1 && 2 * slot_for(tpc) > budget) --tpc;
-  if (tpc < 1 || 2 * slot_for(tpc) > budget) return kSgNotEligible;
   p.taps_per_cta = tpc;
   p.tgroups = (g.npairs + tpc - 1) / tpc;
   p.slot_bytes = (uint32_t)slot_for(tpc);
