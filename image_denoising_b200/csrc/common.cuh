@@ -160,9 +160,10 @@ struct TapGemm {
   int dtype = N2N_F32;
   View x[4];
   int ntaps = 0;
-  int tap_dy[9] = {0}, tap_dx[9] = {0}, tap_view[9] = {0};
-  int tap_slab[9] = {0};          // which packed-weight slab each tap uses
+  int tap_dy[12] = {0}, tap_dx[12] = {0}, tap_view[12] = {0};
+  int tap_slab[12] = {0};         // which packed-weight slab each tap uses
   int cin_blocks = 0;             // K per tap = 16 * cin_blocks
+  int view_blocks[4] = {0, 0, 0, 0};   // per-view override of cin_blocks (0 = cin_blocks); slab engine only
   int nout = 0;                   // padded to a multiple of 16
   const void* w = nullptr;        // packed weights (engine layout, see pack.cu)
   const float* bias = nullptr;    // [nout] fp32 (padded) or null
@@ -217,6 +218,10 @@ struct Segs {
   int src0[2] = {0, 0}, cnt[2] = {0, 0}, dst0[2] = {0, 0};
 };
 struct PackJob {
+  // im2col mode (im2col_nc > 0): the GEMM's contraction index k of the single tap decodes as
+  // (3x3 tap k / nc, input channel im2col_c0 + k % nc) of a conv3x3 weight — the layout of the
+  // network input's 9-tap im2col block.
+  int im2col_nc = 0, im2col_c0 = 0;
   const float* src = nullptr;     // torch-layout fp32 weights
   void* dst = nullptr;            // engine layout
   int ntaps = 1;
@@ -225,6 +230,7 @@ struct PackJob {
   Segs nseg, cseg;                // channel remaps (concat skip starts on a block boundary)
 };
 struct UnpackJob {
+  int im2col_nc = 0, im2col_c0 = 0;   // see PackJob
   const float* partial = nullptr; // [splits][ntaps][cpad][npad]
   const float* bias_partial = nullptr;  // [splits][npad]
   float* dst_w = nullptr;         // torch layout grad
@@ -246,6 +252,9 @@ int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st);
 
 // elementwise (elementwise.cu)
 int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cudaStream_t st);
+// dst[p, (ky*3+kx)*C + c] = src[c, y+ky-1, x+kx-1] (zero outside the image): the 3x3 im2col of a
+// C-channel NCHW image as ceil(9C/16) C16 blocks, so that a 3x3 conv over it is ONE K = 16 (32) GEMM step
+int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, cudaStream_t st);
 int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream_t st);
 int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st);
 int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype, cudaStream_t st);

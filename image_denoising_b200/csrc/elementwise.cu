@@ -47,6 +47,43 @@ __global__ void c16_to_nchw_kernel(View src, float* __restrict__ dst, int C, lon
   }
 }
 
+template <typename T>
+__global__ void nchw_to_im2col9_kernel(const float* __restrict__ src, int C, View dst, long long items) {
+  const int H = dst.H, W = dst.W;
+  const long long hw = (long long)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % hw;
+    const int cb = (int)((i / hw) % dst.Cb);
+    const int n = (int)(i / (hw * dst.Cb));
+    const int y = (int)(r / W), x = (int)(r - (long long)y * W);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int k = cb * 16 + c;
+      const int tap = k / C, ch = k - tap * C;
+      float val = 0.f;
+      if (tap < 9) {
+        const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) val = src[((long long)n * C + ch) * hw + (long long)sy * W + sx];
+      }
+      v[c] = val;
+    }
+    T* p = (T*)dst.ptr + n * dst.sN + cb * dst.sCb + y * dst.sY + x * dst.sX;
+    Block16<T>::store(p, v);
+  }
+}
+
+int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, cudaStream_t st) {
+  N2N_CHECK_ARG(C >= 1 && 9 * C <= 16 * dst.Cb, "nchw_to_im2col9: 9*%d channels do not fit %d blocks", C, dst.Cb);
+  long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
+  int grid = grid_for(items, 256);
+  if (dtype == N2N_BF16) nchw_to_im2col9_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, C, dst, items);
+  else nchw_to_im2col9_kernel<float><<<grid, 256, 0, st>>>(src, C, dst, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cudaStream_t st) {
   N2N_CHECK_ARG(C >= 1 && C <= 16 * dst.Cb, "nchw_to_c16: C=%d does not fit %d blocks", C, dst.Cb);
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;

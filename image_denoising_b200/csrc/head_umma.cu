@@ -80,6 +80,20 @@ __device__ __forceinline__ void hd_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive accumulator columns (two 16-channel blocks) per instruction; completion via hd_ld_wait
+__device__ __forceinline__ void hd_ld32_issue(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void hd_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void hd_st_global_32B(void* ptr, const uint32_t w[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
@@ -230,25 +244,42 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         hd_wait(h_empty(b), par ^ 1u);
         fence_after_sync();
         const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
-        for (int cb = 0; cb < p.mid_blocks; ++cb) {
-          float v[16];
-          hd_ld16(lane_base + (uint32_t)(b * nmid + cb * 16), v);
-          uint32_t w[8];
+        // accumulator reads are issued one block pair ahead of the arithmetic that consumes them
+        uint32_t rr[32];
+        hd_ld32_issue(lane_base + (uint32_t)(b * nmid), rr);
+#pragma unroll 1
+        for (int pr = 0; 2 * pr < p.mid_blocks; ++pr) {
+          {
+            uint32_t cur[32];
+            hd_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a0 = v[2 * j] + s_ba[cb * 16 + 2 * j], a1 = v[2 * j + 1] + s_ba[cb * 16 + 2 * j + 1];
-            a0 = a0 > 0.f ? a0 : a0 * p.slope;
-            a1 = a1 > 0.f ? a1 : a1 * p.slope;
-            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-            w[j] = *reinterpret_cast<uint32_t*>(&h);
+            for (int q = 0; q < 32; ++q) cur[q] = rr[q];
+            if (2 * pr + 2 < p.mid_blocks) hd_ld32_issue(lane_base + (uint32_t)(b * nmid + (2 * pr + 2) * 16), rr);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int cb = 2 * pr + h2;
+              const uint32_t* rv = &cur[16 * h2];
+              uint32_t w[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 bb = *reinterpret_cast<const float4*>(&s_ba[cb * 16 + 4 * q]);
+                float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
+                float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
+                a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
+                a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+                w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+                w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+              }
+              // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
+              const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
+              const uint32_t sw = ((h0s + off) >> 7) & 1u;
+              uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
+              dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+              dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+              if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+            }
           }
-          // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
-          const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-          const uint32_t sw = ((h0s + off) >> 7) & 1u;
-          uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
-          dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-          dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
         }
         fence_before_sync();
         fence_proxy_async();                 // generic-proxy writes of H1 -> visible to the tensor core
@@ -262,37 +293,47 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         float o[kHdMaxOut];
 #pragma unroll
         for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
-        for (int cb = 0; cb < p.mid_blocks; ++cb) {
-          float v[16];
-          hd_ld16(lane_base + (uint32_t)((2 + b) * nmid + cb * 16), v);
+        uint32_t rr[32];
+        hd_ld32_issue(lane_base + (uint32_t)((2 + b) * nmid), rr);
+#pragma unroll 1
+        for (int pr = 0; 2 * pr < p.mid_blocks; ++pr) {
+          {
+            uint32_t cur[32];
+            hd_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            float a = v[q] + s_bb[cb * 16 + q];
-            v[q] = a > 0.f ? a : a * p.slope;
-          }
-          if (p.has_save) {
-            uint32_t w[8];
+            for (int q = 0; q < 32; ++q) cur[q] = rr[q];
+            if (2 * pr + 2 < p.mid_blocks) hd_ld32_issue(lane_base + (uint32_t)((2 + b) * nmid + (2 * pr + 2) * 16), rr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              w[j] = *reinterpret_cast<uint32_t*>(&h);
-              // the backward (and nin_c) see the bf16-rounded activation, as in the unfused path
-              v[2 * j] = __uint_as_float(w[j] << 16);
-              v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-            }
-            hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = __bfloat162float(__float2bfloat16_rn(v[q]));
-          }
-#pragma unroll
-          for (int oc = 0; oc < kHdMaxOut; ++oc) {
-            if (oc < p.out_nc) {
-              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int cb = 2 * pr + h2;
+              const uint32_t* rv = &cur[16 * h2];
+              float v[16];
+              uint32_t w[8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 wv = wr[q];
-                o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
+                const float4 bb = *reinterpret_cast<const float4*>(&s_bb[cb * 16 + 4 * q]);
+                float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
+                float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
+                a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
+                a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
+                // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+                w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+                w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+                v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
+                v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
+              }
+              if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+#pragma unroll
+              for (int oc = 0; oc < kHdMaxOut; ++oc) {
+                if (oc < p.out_nc) {
+                  const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 wv = wr[q];
+                    o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
+                  }
+                }
               }
             }
           }
@@ -319,7 +360,7 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
   if (h.in_blocks < 1 || h.in_blocks > 8 || h.mid_blocks < 1 || h.mid_blocks > 8 || h.out_nc < 1 || h.out_nc > kHdMaxOut)
     return kSgNotEligible;
-  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16) return kSgNotEligible;
+  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16 || (h.mid_blocks & 1)) return kSgNotEligible;
   HdParams p;
   memset(&p, 0, sizeof(p));
   p.in_blocks = h.in_blocks; p.mid_blocks = h.mid_blocks; p.out_nc = h.out_nc;

@@ -42,8 +42,15 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
     const int c = (int)(i % cpad);
     const int n = (int)((i / cpad) % J.nout_pad);
     const int t = (int)(i / ((long long)cpad * J.nout_pad));
-    const int sn = seg_lookup(J.nseg, n), sc = seg_lookup(J.cseg, c);
-    const float v = (sn >= 0 && sc >= 0) ? J.src[t * J.s_t + sn * J.s_n + sc * J.s_c] : 0.f;
+    const int sn = seg_lookup(J.nseg, n);
+    float v = 0.f;
+    if (J.im2col_nc > 0) {
+      const int tap = c / J.im2col_nc, ch = c - tap * J.im2col_nc;
+      if (sn >= 0 && tap < 9) v = J.src[tap * J.s_t + sn * J.s_n + (long long)(J.im2col_c0 + ch) * J.s_c];
+    } else {
+      const int sc = seg_lookup(J.cseg, c);
+      if (sn >= 0 && sc >= 0) v = J.src[t * J.s_t + sn * J.s_n + sc * J.s_c];
+    }
     if (BF16) {
       const int cb = c >> 4, e = c & 15;
       const int g = cb / kGroupBlocks, jj = cb - g * kGroupBlocks;
@@ -82,11 +89,21 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
     const int n = (int)(i % J.npad);
     const int c = (int)((i / J.npad) % J.cpad);
     const int t = (int)(i / plane);
-    const int sn = seg_lookup(J.nseg, n), sc = seg_lookup(J.cseg, c);
-    if (sn < 0 || sc < 0) continue;
+    const int sn = seg_lookup(J.nseg, n);
+    if (sn < 0) continue;
+    long long dst;
+    if (J.im2col_nc > 0) {
+      const int tap = c / J.im2col_nc, ch = c - tap * J.im2col_nc;
+      if (tap >= 9) continue;
+      dst = tap * J.s_t + sn * J.s_n + (long long)(J.im2col_c0 + ch) * J.s_c;
+    } else {
+      const int sc = seg_lookup(J.cseg, c);
+      if (sc < 0) continue;
+      dst = t * J.s_t + sn * J.s_n + sc * J.s_c;
+    }
     float s = 0.f;
     for (int sp = 0; sp < J.splits; ++sp) s += J.partial[(long long)sp * total + i];
-    J.dst_w[t * J.s_t + sn * J.s_n + sc * J.s_c] = s;
+    J.dst_w[dst] = s;
   }
   if (J.dst_b && J.bias_partial) {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < J.npad; n += gridDim.x * blockDim.x) {

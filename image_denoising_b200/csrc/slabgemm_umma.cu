@@ -432,11 +432,10 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
     if (g.tap_dy[t] < -1 || g.tap_dy[t] > 1 || g.tap_dx[t] < -1 || g.tap_dx[t] > 1) return kSgNotEligible;
   }
   if (nviews > 4) return kSgNotEligible;
-  const size_t w_bytes = (size_t)(max_slab + 1) * ngroups * slab_bytes;
+  size_t w_bytes = 0;   // = end of the last weight byte any tap reads (set below)
 
   SgParams p;
   memset(&p, 0, sizeof(p));
-  const int gb = g.cin_blocks < kSgGroup ? g.cin_blocks : kSgGroup;
   int nst = 0;
   size_t slot_bytes = 0;
   for (int v = 0; v < nviews; ++v) {
@@ -445,15 +444,18 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
       if (g.tap_view[t] == v) { ++nt; if (g.tap_dy[t] || g.tap_dx[t]) halo = true; }
     if (nt == 0) continue;
     const View& xv = g.x[v];
-    if (xv.H != H || xv.W != W || xv.Cb < g.cin_blocks) return kSgNotEligible;
+    const int vblocks = g.view_blocks[v] ? g.view_blocks[v] : g.cin_blocks;   // channel blocks this view contributes
+    if (xv.H != H || xv.W != W || xv.Cb < vblocks || vblocks > g.cin_blocks) return kSgNotEligible;
+    const int gb = vblocks < kSgGroup ? vblocks : kSgGroup;
+    const int vgroups = (vblocks + kSgGroup - 1) / kSgGroup;
     const int bw = halo ? kHaloW : kTileW, bh = halo ? kHaloH : kTileH;
     N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, gb));
     const uint32_t cb_bytes = (uint32_t)(bw * bh * 32);
-    for (int grp = 0; grp < ngroups; ++grp) {
+    for (int grp = 0; grp < vgroups; ++grp) {
       if (nst >= kSgMaxStages) return kSgNotEligible;
       SgStage& S = p.st[nst++];
       S.view = (int16_t)v; S.cb0 = (int16_t)(grp * kSgGroup);
-      const int nb = g.cin_blocks - grp * kSgGroup;
+      const int nb = vblocks - grp * kSgGroup;
       S.nb = (int16_t)(nb < kSgGroup ? nb : kSgGroup);
       S.ox = S.oy = (int16_t)(halo ? -1 : 0);
       S.cb_bytes16 = (uint16_t)(cb_bytes >> 4);
@@ -464,7 +466,9 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
         if (g.tap_view[t] != v) continue;
         const int oy = halo ? g.tap_dy[t] + 1 : 0, ox = halo ? g.tap_dx[t] + 1 : 0;
         S.a_off16[k] = (uint16_t)(((oy * bw + ox) * 32) >> 4);
-        S.b_off16[k] = (uint32_t)((((size_t)g.tap_slab[t] * ngroups + grp) * slab_bytes) >> 4);
+        const size_t boff = ((size_t)g.tap_slab[t] * ngroups + grp) * slab_bytes;
+        S.b_off16[k] = (uint32_t)(boff >> 4);
+        if (boff + (size_t)S.nb * b_sub > w_bytes) w_bytes = boff + (size_t)S.nb * b_sub;
         ++k;
       }
       S.ntaps = (int16_t)k;

@@ -6,6 +6,8 @@
 // concat buffer, the encoder's pool kernels write the skip blocks behind them
 // (torch.cat([upsampled, skip]) order, arch_unet.py:62), and the decoder conv reads the whole
 // buffer as one operand.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -35,6 +37,11 @@ using namespace n2n;
 struct n2n_unet_plan {
   int in_nc, out_nc, nf, N, H, W, dtype;
   bool bwd;
+  // bf16 engine: the network input is kept as its 3x3 im2col (kb = ceil(9*in_nc/16) blocks), so
+  // enc_conv0 and the raw-input part of dec_conv1a's concat are ONE K = 16*kb GEMM step each
+  // instead of nine taps over a 16-channel block with in_nc real channels.
+  bool im2col; int kb, skipb;
+  size_t off_partial_skip = 0, off_wd20_full = 0; int splits_skip = 1;
   int nfb, c2b, inb, hb;
   LayerGeom L[25];
   LayerIO io[25];
@@ -58,7 +65,13 @@ static void plan_layout(n2n_unet_plan* p) {
   p->nfb = cblocks(nf); p->c2b = cblocks(2 * nf); p->inb = cblocks(in_nc); p->hb = cblocks(96);
   const int nfb = p->nfb, c2b = p->c2b, inb = p->inb, hb = p->hb;
   auto setbuf = [&](int b, int Cb, int lvl) { p->act[b].Cb = Cb; p->act[b].lvl = lvl; p->grd[b].Cb = Cb; p->grd[b].lvl = lvl; };
-  setbuf(B_CAT0, c2b + inb, 0);
+  {
+    const char* e1 = getenv("N2N_NO_SLAB"); const char* e2 = getenv("N2N_NO_IM2COL");
+    p->im2col = p->dtype == N2N_BF16 && !(e1 && atoi(e1)) && !(e2 && atoi(e2));
+    p->kb = cblocks(9 * in_nc);
+    p->skipb = p->im2col ? p->kb : inb;
+  }
+  setbuf(B_CAT0, c2b + p->skipb, 0);
   setbuf(B_CAT1, c2b + nfb, 1); setbuf(B_CAT2, c2b + nfb, 2); setbuf(B_CAT3, c2b + nfb, 3);
   setbuf(B_CAT4, nfb + nfb, 4);
   setbuf(B_E0, nfb, 0); setbuf(B_E1, nfb, 0); setbuf(B_E2, nfb, 1); setbuf(B_E3, nfb, 2); setbuf(B_E4, nfb, 3);
@@ -126,6 +139,20 @@ static void plan_layout(n2n_unet_plan* p) {
       p->splits[i] = layer_wgrad_splits(p->L[i], p->dtype, p->N, p->lh(p->act[io.in_buf].lvl), p->lw(p->act[io.in_buf].lvl));
       // dgrad weights are packed for the full input width so that dL/dx can be served too
       p->off_wd[i] = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));
+      if (p->im2col && (i == 0 || i == 20)) {
+        // im2col forms: layer 0 is one pair over kb blocks; layer 20 = nine pairs over the c2b
+        // upsampled blocks + one pair over the kb im2col blocks (own partial buffer)
+        LayerGeom G = p->L[i];
+        if (i == 0) { G.kind = L_CONV1; G.cin = chan1(16 * p->kb); }
+        else G.cin = chan1(2 * nf);
+        p->splits[i] = layer_wgrad_splits(G, p->dtype, p->N, p->H, p->W);
+        if (i == 20) {
+          LayerGeom S = p->L[i]; S.kind = L_CONV1; S.cin = chan1(16 * p->kb);
+          p->splits_skip = layer_wgrad_splits(S, p->dtype, p->N, p->H, p->W);
+          p->off_partial_skip = take(S.partial_bytes(p->splits_skip));
+          p->off_wd20_full = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));   // only used when dL/dx is wanted
+        }
+      }
       p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
       p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
     }
@@ -165,16 +192,33 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     std::vector<PackJob> jobs;
     BiasPadJob bj[25];
     for (int i = 0; i < 25; ++i) {
-      jobs.push_back(make_fwd_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
-      if (p->bwd)
-        jobs.push_back(make_dgrad_pack(p->L[i], params[2 * i], (char*)ws + p->off_wd[i], p->L[i].cin_blocks()));
+      if (p->im2col && i == 0) {
+        PackJob j = make_fwd_pack(p->L[0], params[0], (char*)ws + p->off_wp[0]);
+        j.ntaps = 1; j.cin_blocks = p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = 0;
+        jobs.push_back(j);
+      } else if (p->im2col && i == 20) {
+        PackJob j = make_fwd_pack(p->L[20], params[40], (char*)ws + p->off_wp[20]);
+        j.cin_blocks = p->c2b; j.cseg = chan1(2 * p->nf).to_segs();          // the nine taps over the upsampled channels
+        jobs.push_back(j);
+        PackJob k = j;                                                         // + the im2col tap (slab 9, group 0)
+        const int mg = (p->c2b + 2) / 3;
+        k.dst = (char*)ws + p->off_wp[20] + (size_t)9 * mg * 3 * j.nout_pad * 32;
+        k.ntaps = 1; k.cin_blocks = p->kb; k.im2col_nc = p->in_nc; k.im2col_c0 = 2 * p->nf;
+        jobs.push_back(k);
+      } else {
+        jobs.push_back(make_fwd_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
+      }
+      if (p->bwd)   // im2col mode: dec_conv1a's input gradient is only needed for the upsampled blocks
+        jobs.push_back(make_dgrad_pack(p->L[i], params[2 * i], (char*)ws + p->off_wd[i],
+                                       (p->im2col && i == 20) ? p->c2b : p->L[i].cin_blocks()));
       bj[i] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), p->L[i].cout, p->L[i].cout_blocks() * 16};
     }
     N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
     N2N_TRY(launch_bias_pad(bj, 25, st));
   }
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
-  N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
+  if (p->im2col) N2N_TRY(launch_nchw_to_im2col9(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->kb), dt, st));
+  else N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
 
   auto run_layer = [&](int i, int pool_buf = -1, int pool_cb0 = 0) -> int {
     const LayerIO& io = p->io[i];
@@ -182,6 +226,22 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
     const void* wp = (char*)ws + p->off_wp[i];
     const float* bias = (const float*)((char*)ws + p->off_bias[i]);
+    if (p->im2col && (i == 0 || i == 20)) {
+      TapGemm g;
+      g.dtype = dt; g.nout = L.cout_blocks() * 16; g.w = wp; g.bias = bias;
+      g.y = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      g.act = 1; g.slope = 0.2f;
+      View skip = p->view(p->act, ws, B_CAT0, p->c2b, p->kb);
+      if (i == 0) {
+        g.x[0] = skip; g.ntaps = 1; g.cin_blocks = p->kb;                 // tap 0 = (0, 0), slab 0
+      } else {
+        g.x[0] = p->view(p->act, ws, B_CAT0, 0, p->c2b); g.x[1] = skip;
+        g.ntaps = 10; g.cin_blocks = p->c2b; g.view_blocks[1] = p->kb;
+        for (int t = 0; t < 9; ++t) { g.tap_dy[t] = t / 3 - 1; g.tap_dx[t] = t % 3 - 1; g.tap_view[t] = 0; g.tap_slab[t] = t; }
+        g.tap_view[9] = 1; g.tap_slab[9] = 9;
+      }
+      return launch_tapgemm(g, st);
+    }
     if (L.kind == L_DECONV) {
       View yfull = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
       for (int ab = 0; ab < 4; ++ab) {
@@ -255,6 +315,14 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
     View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
     float* partial = (float*)((char*)ws + p->off_partial[i]);
     float* bpartial = (float*)((char*)ws + p->off_bpartial[i]);
+    if (p->im2col && (i == 0 || i == 20)) {
+      View skip = p->view(p->act, ws, B_CAT0, p->c2b, p->kb);
+      LayerGeom S = L; S.kind = L_CONV1; S.cin = chan1(16 * p->kb);          // one (0,0) pair over the im2col blocks
+      if (i == 0) return launch_tapwgrad(make_conv_wgrad(S, dt, skip, gy, partial, bpartial, p->splits[0]), st);
+      LayerGeom M = L; M.cin = chan1(2 * p->nf);                             // nine pairs over the upsampled blocks
+      N2N_TRY(launch_tapwgrad(make_conv_wgrad(M, dt, p->view(p->act, ws, B_CAT0, 0, p->c2b), gy, partial, bpartial, p->splits[20]), st));
+      return launch_tapwgrad(make_conv_wgrad(S, dt, skip, gy, (float*)((char*)ws + p->off_partial_skip), nullptr, p->splits_skip), st);
+    }
     TapWgrad g = (L.kind == L_DECONV) ? make_deconv_wgrad(L, dt, xin, gy, partial, bpartial, p->splits[i])
                                       : make_conv_wgrad(L, dt, xin, gy, partial, bpartial, p->splits[i]);
     return launch_tapwgrad(g, st);
@@ -268,6 +336,12 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
     View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
     View gx = p->view(p->grd, ws, io.in_buf, io.in_cb0, blocks);
     const void* wd = (char*)ws + p->off_wd[i];
+    if (p->im2col && i == 20 && blocks != p->c2b) {
+      // dL/dx requested: repack dec_conv1a's transposed weights for all input blocks (raw-input block included)
+      PackJob j = make_dgrad_pack(L, params[2 * i], (char*)ws + p->off_wd20_full, L.cin_blocks());
+      N2N_TRY(launch_pack(&j, 1, dt, st));
+      wd = (char*)ws + p->off_wd20_full;
+    }
     TapGemm g = (L.kind == L_DECONV) ? make_deconv_dgrad(L, dt, gy, gx, wd)
                                      : make_conv_dgrad(L, dt, gy, gx, wd, L.cin_blocks());
     g.nout = blocks * 16;
@@ -283,7 +357,7 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   // head + level-0 decoder
   for (int i = 24; i >= 21; --i) { N2N_TRY(wgrad(i)); N2N_TRY(dgrad(i, p->L[i].cin_blocks(), true, false)); }
   N2N_TRY(wgrad(20));
-  N2N_TRY(dgrad(20, p->c2b + p->inb, false, false));
+  N2N_TRY(dgrad(20, (want_dx || !p->im2col) ? p->c2b + p->inb : p->c2b, false, false));
   // decoder levels 1..4: up{k} then dec_conv{k+1}b / a
   for (int base = 19; base >= 10; base -= 3) {
     N2N_TRY(wgrad(base));     N2N_TRY(dgrad(base, p->c2b, true, false));          // up_k: input is dec_conv_{k+1}b output
@@ -307,11 +381,23 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   }
   // partials -> PyTorch-layout fp32 gradients
   {
-    UnpackJob jobs[25];
-    for (int i = 0; i < 25; ++i)
-      jobs[i] = make_unpack(p->L[i], (const float*)((char*)ws + p->off_partial[i]),
-                            (const float*)((char*)ws + p->off_bpartial[i]), p->splits[i], grads[2 * i], grads[2 * i + 1]);
-    N2N_TRY(launch_unpack(jobs, 25, st));
+    UnpackJob jobs[26];
+    int nj = 0;
+    for (int i = 0; i < 25; ++i) {
+      UnpackJob j = make_unpack(p->L[i], (const float*)((char*)ws + p->off_partial[i]),
+                                (const float*)((char*)ws + p->off_bpartial[i]), p->splits[i], grads[2 * i], grads[2 * i + 1]);
+      if (p->im2col && i == 0) {
+        j.ntaps = 1; j.cpad = 16 * p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = 0;
+      } else if (p->im2col && i == 20) {
+        j.cpad = 16 * p->c2b; j.cseg = chan1(2 * p->nf).to_segs();
+        UnpackJob k = j;
+        k.partial = (const float*)((char*)ws + p->off_partial_skip); k.bias_partial = nullptr; k.dst_b = nullptr;
+        k.splits = p->splits_skip; k.ntaps = 1; k.cpad = 16 * p->kb; k.im2col_nc = p->in_nc; k.im2col_c0 = 2 * p->nf;
+        jobs[nj++] = k;
+      }
+      jobs[nj++] = j;
+    }
+    N2N_TRY(launch_unpack(jobs, nj, st));
   }
   p->bwd_launches = (int)(g_launch_count - launches0);
   return 0;
