@@ -28,7 +28,7 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kSgThreads = 192;
+constexpr int kSgThreads = 320;           // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kSgMaxStages = 12;          // pipeline stages (TMA boxes) per tile
 constexpr int kSgMaxRing = 8;
 constexpr int kSgGroup = 3;               // channel blocks per stage = one packed-weight group
@@ -224,7 +224,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
@@ -338,11 +338,14 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       __syncwarp();
     }
   } else {
-    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile ----
+    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile;
+    //      the two warps of a lane quarter split the tile's channel blocks between them ----
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
-    const int nblk = p.nout >> 4;
+    const int nblk_all = p.nout >> 4;
+    const int cb_lo = (warp >= 6) ? (nblk_all + 1) / 2 : 0;
+    const int nblk = (warp >= 6) ? nblk_all : (nblk_all + 1) / 2;     // this warp handles blocks [cb_lo, nblk)
     const bool skip = (p.dbg_flags & 4) != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
@@ -364,16 +367,16 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       const long long as = p.has_mask ? p.mask.sCb : p.addend.sCb;
       uint32_t ax0[8], ax1[8];
       if (pre) {
-        for (int cb = 2; cb < nblk; ++cb)
+        for (int cb = cb_lo + 2; cb < nblk; ++cb)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ab + cb * as));
-        ld_global_32B(ab, ax0);
-        if (nblk > 1) ld_global_32B(ab + as, ax1);
+        if (cb_lo < nblk) ld_global_32B(ab + cb_lo * as, ax0);
+        if (cb_lo + 1 < nblk) ld_global_32B(ab + (cb_lo + 1) * as, ax1);
       }
       sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
       fence_after_sync();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
 #pragma unroll 1
-      for (int cb = 0; cb < nblk; cb += 2) {
+      for (int cb = cb_lo; cb < nblk; cb += 2) {
         uint32_t r0[16], r1[16], nx0[8], nx1[8];
         sg_ld16(lane_addr + cb * 16, r0);
         const bool two = cb + 1 < nblk;
