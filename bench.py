@@ -47,42 +47,81 @@ def _peaks():
     return dict(bf16=1400.0, hbm=6650.0, src="fallback")
 
 
+def _traffic_note():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region (NVML; falls back to nvidia-smi)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, reasons bitmask or None, [nvidia-smi reason strings])
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((sm, self.max_sm, mask, None))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            self.samples.append((float(f[0]), float(f[1]), None, f[2:6]))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        # NVML clocks-event-reason bits: SW power cap 0x4, HW slowdown 0x8, SW thermal 0x20, HW thermal 0x40
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        sm, mx, reasons = [], 0.0, set()
         for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
+            sm.append(s[0]); mx = max(mx, s[1])
+            if s[2] is not None:
+                for n, b in bits.items():
+                    if s[2] & b:
+                        reasons.add(n)
+            elif s[3]:
+                for n, v in zip(names, s[3]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
-            except Exception:
-                continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
@@ -128,6 +167,52 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def inference_704(dev, precision, world, rank, dist, total_images=128, per_launch=8, reps=2):
+    """BASELINE configs[3]: evaluation.py semantics on 128 synthetic 704x704 grayscale images sharded over
+    the ranks (no collective): pinned uint8 H2D -> /255 -> whole-image UNet forward -> clamp/quantise ->
+    PSNR/SSIM kernel -> D2H of the metrics.  Returns whole-job images/s (device timing, max over ranks)."""
+    import torch
+    from image_denoising_b200 import UNet, ops
+    torch.manual_seed(4321)
+    net = UNet(in_nc=1, out_nc=1, n_feature=NF).to(dev).set_precision(precision)
+    mine = total_images // world
+    g = torch.Generator().manual_seed(2025 + rank)
+    clean = (torch.rand((per_launch, 704, 704), generator=g) * 255).to(torch.uint8)
+    noisy = (clean.float() + torch.randn(clean.shape, generator=g) * 25.0).clamp(0, 255).to(torch.uint8)
+    clean_h, noisy_h = clean.pin_memory(), noisy.pin_memory()
+    res_h = torch.empty((per_launch, 2), dtype=torch.float64).pin_memory()
+    clean_d = torch.empty_like(clean, device=dev); noisy_d = torch.empty_like(noisy, device=dev)
+
+    def one_pass():
+        for _ in range(0, mine, per_launch):
+            noisy_d.copy_(noisy_h, non_blocking=True); clean_d.copy_(clean_h, non_blocking=True)
+            with torch.no_grad():
+                pred = net((noisy_d.float() / 255.0).unsqueeze(1))
+            q = ops.quantize_u8(pred, 0.5).squeeze(1)
+            res_h.copy_(ops.psnr_ssim_u8(q, clean_d), non_blocking=True)
+
+    one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ips = world * mine * reps / (ms / 1e3)
+    return {"metric": "inference_images_per_s_704x704_whole_image", "value": ips, "unit": "images/s",
+            "images": world * mine, "per_launch": per_launch, "psnr_first": float(res_h[0, 0]),
+            "gflop_per_image": 291.71, "tflops": ips * 291.71 / 1e3,
+            "note": "e2e: pinned uint8 H2D + forward + quantise + PSNR/SSIM kernel + D2H of metrics; random-init weights"}
 
 
 def run_b200(args):
@@ -224,14 +309,22 @@ def run_b200(args):
         tap_ms, tap_flops_exec, tap_n, wg_ms, wg_flops_exec, wg_n = [float(x) for x in out]
         alg_flops = GFLOP_TAPGEMM_PER_PATCH * 1e9 * B * psteps
         achieved = alg_flops / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "tapgemm_umma_kernel (conv/deconv fwd + dgrad, %d launches/step)" % round(tap_n / psteps),
+        roof = {"bound": "tensor",
+                "kernel": "slabgemm_umma_kernel (+ head_chain_umma / tapgemm_umma for the shapes it declines): conv/deconv "
+                          "forward + input gradient, %d launches/step" % round(tap_n / psteps),
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
-                "traffic": None, "peak_source": pk["src"],
+                "traffic": _traffic_note(), "peak_source": pk["src"],
                 "share_of_step": tap_ms / psteps / (ms / args.steps),
                 "executed_tflops_incl_padding": tap_flops_exec / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0,
                 "wgrad_kernel": {"achieved": (GFLOP_WGRAD_PER_PATCH * 1e9 * B * psteps) / (wg_ms / 1e3) / 1e12 if wg_ms > 0 else 0.0,
                                  "unit": "TFLOP/s", "ms_per_step": wg_ms / psteps, "launches_per_step": round(wg_n / psteps)},
                 "ms_per_step": tap_ms / psteps}
+
+    infer = None
+    if not args.no_inference:
+        del trainer
+        torch.cuda.empty_cache()
+        infer = inference_704(dev, args.precision, world, rank, dist)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -254,6 +347,7 @@ def run_b200(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "step_tflops": GFLOP_PER_PATCH * B * 1e9 / (ms / args.steps / 1e3) / 1e12,
+            "inference_704": infer,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -264,12 +358,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -5,6 +5,7 @@ PSNR/SSIM evaluation, all executed by hand-written CUDA kernels behind the C-ABI
 include/n2n_b200.h.  No CPU or PyTorch-arithmetic fallback exists: importing is cheap, but
 every compute entry point needs libn2n_b200.so and a CUDA device."""
 from . import _ext  # noqa: F401
+from . import dp  # noqa: F401
 from .arch_unet import UNet  # noqa: F401
 from .adapter import DenoiserWithAdapter, OutputAdapter  # noqa: F401
 from .n2n import (AugmentNoise, checkpoint, generate_mask_pair, generate_packed_selector,  # noqa: F401

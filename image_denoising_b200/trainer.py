@@ -13,7 +13,7 @@ import os
 
 import torch
 
-from . import _ext, n2n, ops
+from . import _ext, dp, n2n, ops
 from ._ext import check, lib, ptr, ptr_array, stream_ptr
 from .optim import build_adam_tables
 
@@ -52,9 +52,7 @@ class N2NTrainer:
         self.table, self.blocks = build_adam_tables([self.flat_p], [self.flat_g], [self.flat_m], [self.flat_v], dev)
         # gradient buckets in reverse-autograd order: the head / full-resolution decoder tensors
         # sit at the END of the state_dict order, so bucket 0 is the tail of the flat buffer.
-        total = self.flat_g.numel()
-        cut = total - sum(sizes[-10:]) if buckets > 1 else 0
-        self.bucket_slices = [(cut, total), (0, cut)] if cut > 0 else [(0, total)]
+        self.bucket_slices = dp.bucket_slices(sizes, buckets)
         self._shapes = None
         self.last_launches = 0
         # CUDA-graph replay of the whole iteration (one graph launch instead of ~190 kernel launches);
@@ -65,7 +63,7 @@ class N2NTrainer:
         self._graph = None
         self._eager_steps = 0
         if self.world > 1:
-            torch.distributed.broadcast(self.flat_p, src=0, group=self.pg)   # once, instead of DataParallel's per-step replicate
+            dp.broadcast_params(self.flat_p, 0, self.pg)
 
     # ------------------------------------------------------------------ buffers / plans
     def _prepare(self, noisy):
@@ -116,8 +114,7 @@ class N2NTrainer:
                                             1.0, self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
         check(L.n2n_unet_backward(self.plan_half, self.param_ptrs, ptr(self.dout), self.grad_ptrs, None, ptr(self.ws_half), st))
         if self.world > 1:
-            for a, b in self.bucket_slices:
-                torch.distributed.all_reduce(self.flat_g[a:b], group=self.pg)
+            dp.allreduce_buckets(self.flat_g, self.bucket_slices, self.pg)
         if dev_scalars is None:
             check(L.n2n_adam_multi(ptr(self.table), 1, ptr(self.blocks), self.blocks.shape[0], float(lr),
                                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,

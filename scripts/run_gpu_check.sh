@@ -1,3 +1,3 @@
 RUN_BENCH=0 bash scripts/gpu_tests.sh
 python scripts/layer_times.py > gpurun_out/layers.log 2>&1; tail -1 gpurun_out/layers.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_dev.json 2> gpurun_out/bench_dev.err; tail -c 1500 gpurun_out/bench_dev.json; tail -3 gpurun_out/bench_dev.err
+python bench.py > gpurun_out/bench_dev.json 2> gpurun_out/bench_dev.err; tail -c 2500 gpurun_out/bench_dev.json; tail -3 gpurun_out/bench_dev.err

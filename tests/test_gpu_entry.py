@@ -1,0 +1,41 @@
+"""The reference-flag entry points (entry/train.py, entry/finetune.py, entry/evaluation.py) run end to end
+on synthetic data and write the reference's checkpoint / metrics file names."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _run(args, cwd):
+    r = subprocess.run([sys.executable] + args, cwd=cwd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return r.stdout
+
+
+def test_train_finetune_eval_roundtrip(tmp_path):
+    out = str(tmp_path)
+    _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "4", "--patch", "64", "--batchsize", "2", "--n_epoch", "2",
+          "--save_model_path", out, "--log_name", "UNET_test"], ROOT)
+    ckpts = sorted(glob.glob(os.path.join(out, "UNET_test", "*", "epoch_model_*.pth")))
+    assert [os.path.basename(c) for c in ckpts] == ["epoch_model_000.pth", "epoch_model_001.pth", "epoch_model_002.pth"]
+    sd = torch.load(ckpts[-1], map_location="cpu")
+    assert len(sd) == 50 and sd["dec_conv1a.weight"].shape == (96, 97, 3, 3) and all(v.dtype == torch.float32 for v in sd.values())
+    assert all(torch.isfinite(v).all() for v in sd.values())
+    assert not torch.equal(sd["nin_c.weight"], torch.load(ckpts[0], map_location="cpu")["nin_c.weight"])    # it trained
+
+    _run([os.path.join(ROOT, "entry", "finetune.py"), "--synthetic", "2", "--pretrained_ckpt", ckpts[-1], "--n_epoch", "1",
+          "--batchsize", "2", "--patch_size", "64", "--patches_per_image", "2", "--save_model_path", out, "--log_name", "ft"], ROOT)
+    ad = torch.load(os.path.join(out, "ft", "epoch_adapter_001.pth"), map_location="cpu")
+    assert len(ad) == 54 and "adapter.net.0.weight" in ad and "base.enc_conv0.weight" in ad
+
+    ev = os.path.join(out, "eval")
+    _run([os.path.join(ROOT, "entry", "evaluation.py"), "--synthetic", "2", "--checkpoint", ckpts[-1], "--save_dir", ev], ROOT)
+    txt = open(os.path.join(ev, "metrics.txt")).read()
+    assert txt.count("PSNR=") == 3 and "AVG" in txt
+    _run([os.path.join(ROOT, "entry", "evaluation.py"), "--synthetic", "1", "--checkpoint", ckpts[-1], "--save_dir", ev, "--tiled"], ROOT)
