@@ -78,7 +78,7 @@ def main():
                 cb[j] = clean[i][:, top:top + ps, left:left + ps]; nb[j] = noise[i][:, top:top + ps, left:left + ps]
             c = torch.from_numpy(cb).to(dev) / 255.0; n = torch.from_numpy(nb).to(dev) / 255.0
             opt.zero_grad(set_to_none=True)
-            loss, _loss_l1, _loss_grad = l1_grad_loss(model(n), c, args.lambda_grad)
+            loss, _loss3 = l1_grad_loss(model(n), c, args.lambda_grad)
             loss.backward()
             opt.step()
             tot += float(loss)
