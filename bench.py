@@ -229,7 +229,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L = _ext.lib()
     assert L.n2n_device_ok() == 1, "libn2n_b200 needs an sm_100 device"
 
@@ -297,14 +298,16 @@ def run_b200(args):
     e2e_value = world * B * args.steps / e2e_s
 
     # ---- roofline leg: per-launch CUDA events around the GEMM kernels, same steps, same stream ----
+    # every rank runs the same eager steps (they contain the gradient all-reduce); rank 0 reports
     roof = None
+    psteps = max(1, min(3, args.steps))
+    L.n2n_profile_begin()
+    for i in range(psteps):
+        one_step(i)
+    out = (ctypes.c_double * 6)()
+    _ext.check(L.n2n_profile_end(out))
+    barrier()
     if rank == 0:
-        psteps = max(1, min(3, args.steps))
-        L.n2n_profile_begin()
-        for i in range(psteps):
-            one_step(i)
-        out = (ctypes.c_double * 6)()
-        _ext.check(L.n2n_profile_end(out))
         pk = _peaks()
         tap_ms, tap_flops_exec, tap_n, wg_ms, wg_flops_exec, wg_n = [float(x) for x in out]
         alg_flops = GFLOP_TAPGEMM_PER_PATCH * 1e9 * B * psteps

@@ -50,6 +50,7 @@ int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
   if (g.dtype == N2N_BF16) {
     const int r = launch_slabgemm_umma(g, st);
     if (r != kSgNotEligible) return r;
+    N2N_CHECK_ARG(g.n_split == 0 && g.view_blocks[1] == 0, "tapgemm: this launch form needs the slab engine (geometry not eligible)");
     N2N_TRY(launch_tapgemm_umma(g, st));
   } else {
     N2N_TRY(launch_tapgemm_simt(g, st));

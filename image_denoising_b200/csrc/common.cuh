@@ -174,6 +174,10 @@ struct TapGemm {
   float slope = 0.f;
   float* out_nchw = nullptr;      // optional fp32 NCHW [N][out_c][H][W] output
   int out_c = 0;
+  // Column split (slab engine only): output columns [n_split*16*b, n_split*16*(b+1)) are the n_split
+  // channel blocks of output pixel p + b*split_stride (elements) — ConvTranspose2x2 computes the two
+  // horizontally adjacent output pixels of one input pixel as ONE N = 2*Cout GEMM.
+  int n_split = 0; long long split_stride = 0;
   bool store_y = true;            // false: the un-pooled output is not needed (no-grad pass), only `pool`
   bool has_pool = false; View pool;   // also write maxpool2x2(out) here (fused in the epilogue when possible)
 };
@@ -216,6 +220,7 @@ struct TapWgrad {
 struct Segs {
   int n = 1;
   int src0[2] = {0, 0}, cnt[2] = {0, 0}, dst0[2] = {0, 0};
+  long long off[2] = {0, 0};      // extra source-element offset of the segment (pack only)
 };
 struct PackJob {
   // im2col mode (im2col_nc > 0): the GEMM's contraction index k of the single tap decodes as

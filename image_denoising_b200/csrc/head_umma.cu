@@ -8,10 +8,10 @@
 //   warp 0     TMA: the X tile [in_blocks][128 px][16 ch] (K-major SWIZZLE_32B operand) -> ring slot
 //   warp 1     MMA-1: D1 = X * Wa^T            (TMEM, double buffered)
 //              MMA-2: D2 = H1 * Wb^T           (H1 = shared-memory operand written by stage E1)
-//   warps 2-5  E1: D1 -> +bias_a -> LeakyReLU -> bf16 -> H1 tile in shared memory, in exactly the
+//   warps 2-9  E1: D1 -> +bias_a -> LeakyReLU -> bf16 -> H1 tile in shared memory, in exactly the
 //              swizzled K-major layout MMA-2 wants (16-byte chunk XOR address bit 7), then
 //              fence.proxy.async so the tensor core sees it
-//   warps 6-9  E2: D2 -> +bias_b -> LeakyReLU -> dot with nin_c's rows (fp32, registers) -> +bias_c ->
+//   warps 10-17 E2: D2 -> +bias_b -> LeakyReLU -> dot with nin_c's rows (fp32, registers) -> +bias_c ->
 //              fp32 NCHW store
 // E1 and E2 work on different tiles at the same time; both weight matrices stay resident in
 // shared memory; nin_c's weights are broadcast reads of a small shared-memory table.
@@ -24,7 +24,7 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kHdThreads = 320;
+constexpr int kHdThreads = 576;            // TMA warp, MMA warp, 8 warps for stage E1, 8 for stage E2
 constexpr int kHdRing = 3;
 constexpr int kHdMaxOut = 4;
 
@@ -92,6 +92,14 @@ __device__ __forceinline__ void hd_ld32_issue(uint32_t taddr, uint32_t r[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void hd_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void hd_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void hd_st_global_32B(void* ptr, const uint32_t w[8]) {
@@ -106,7 +114,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   // barriers: x_full[3] x_empty[3] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[2] d2_empty[2] w_full
   __shared__ uint64_t bars[2 * kHdRing + 12 + 1];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
+  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut], s_part[kHdMaxOut * 128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -129,9 +137,9 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHdRing; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4);
-      mbar_init(h_full(b), 4);  mbar_init(h_empty(b), 1);
-      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
+      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 8);
+      mbar_init(h_full(b), 8);  mbar_init(h_empty(b), 1);
+      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 8);
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -225,10 +233,15 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       mma2(lt);
     }
   } else {
+    // warps 2-9: stage E1, warps 10-17: stage E2; the two warps that share a TMEM lane quarter split
+    // the channel blocks of the tile between them
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
-    const bool is_e1 = warp < 6;
+    const bool is_e1 = warp < 10;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int cb_lo = half ? (p.mid_blocks + 1) / 2 : 0;
+    const int cb_hi = half ? p.mid_blocks : (p.mid_blocks + 1) / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
       const int img = tile / tiles_per_img;
@@ -244,42 +257,34 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         hd_wait(h_empty(b), par ^ 1u);
         fence_after_sync();
         const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
-        // accumulator reads are issued one block pair ahead of the arithmetic that consumes them
-        uint32_t rr[32];
-        hd_ld32_issue(lane_base + (uint32_t)(b * nmid), rr);
+        uint32_t rr[16];
+        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), rr);
 #pragma unroll 1
-        for (int pr = 0; 2 * pr < p.mid_blocks; ++pr) {
-          {
-            uint32_t cur[32];
-            hd_ld_wait();
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
+          uint32_t rv[16];
+          hd_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 32; ++q) cur[q] = rr[q];
-            if (2 * pr + 2 < p.mid_blocks) hd_ld32_issue(lane_base + (uint32_t)(b * nmid + (2 * pr + 2) * 16), rr);
+          for (int q = 0; q < 16; ++q) rv[q] = rr[q];
+          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 1) * 16), rr);   // one block ahead
+          uint32_t w[8];
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int cb = 2 * pr + h2;
-              const uint32_t* rv = &cur[16 * h2];
-              uint32_t w[8];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 bb = *reinterpret_cast<const float4*>(&s_ba[cb * 16 + 4 * q]);
-                float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
-                float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
-                a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
-                a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
-                __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-                w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
-                w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
-              }
-              // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
-              const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-              const uint32_t sw = ((h0s + off) >> 7) & 1u;
-              uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
-              dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-              dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-              if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
-            }
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s_ba[cb * 16 + 4 * q]);
+            float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
+            float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
+            a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
+            a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
+            __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+            w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
           }
+          // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
+          const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
+          const uint32_t sw = ((h0s + off) >> 7) & 1u;
+          uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
+          dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
         }
         fence_before_sync();
         fence_proxy_async();                 // generic-proxy writes of H1 -> visible to the tensor core
@@ -292,48 +297,41 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         const long long spix = p.has_save ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
         float o[kHdMaxOut];
 #pragma unroll
-        for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
-        uint32_t rr[32];
-        hd_ld32_issue(lane_base + (uint32_t)((2 + b) * nmid), rr);
+        for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = half ? 0.f : s_bc[oc];
+        uint32_t rr[16];
+        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + cb_lo * 16), rr);
 #pragma unroll 1
-        for (int pr = 0; 2 * pr < p.mid_blocks; ++pr) {
-          {
-            uint32_t cur[32];
-            hd_ld_wait();
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
+          uint32_t rv[16];
+          hd_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 32; ++q) cur[q] = rr[q];
-            if (2 * pr + 2 < p.mid_blocks) hd_ld32_issue(lane_base + (uint32_t)((2 + b) * nmid + (2 * pr + 2) * 16), rr);
+          for (int q = 0; q < 16; ++q) rv[q] = rr[q];
+          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 1) * 16), rr);
+          float v[16];
+          uint32_t w[8];
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int cb = 2 * pr + h2;
-              const uint32_t* rv = &cur[16 * h2];
-              float v[16];
-              uint32_t w[8];
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s_bb[cb * 16 + 4 * q]);
+            float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
+            float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
+            a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
+            a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
+            // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
+            __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+            w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+            v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
+            v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
+          }
+          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+#pragma unroll
+          for (int oc = 0; oc < kHdMaxOut; ++oc) {
+            if (oc < p.out_nc) {
+              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 bb = *reinterpret_cast<const float4*>(&s_bb[cb * 16 + 4 * q]);
-                float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
-                float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
-                a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
-                a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
-                // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
-                __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-                w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
-                w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
-                v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
-                v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
-              }
-              if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
-#pragma unroll
-              for (int oc = 0; oc < kHdMaxOut; ++oc) {
-                if (oc < p.out_nc) {
-                  const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float4 wv = wr[q];
-                    o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
-                  }
-                }
+                const float4 wv = wr[q];
+                o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
               }
             }
           }
@@ -341,10 +339,20 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(d2_empty(b));
-        const long long hw = (long long)p.x.H * p.x.W;
+        // combine the two half-sums of this lane quarter (named barrier 1 + quarter, 64 threads)
+        if (half) {
 #pragma unroll
-        for (int oc = 0; oc < kHdMaxOut; ++oc)
-          if (oc < p.out_nc) p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc];
+          for (int oc = 0; oc < kHdMaxOut; ++oc) s_part[oc * 128 + m] = o[oc];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (!half) {
+          const long long hw = (long long)p.x.H * p.x.W;
+#pragma unroll
+          for (int oc = 0; oc < kHdMaxOut; ++oc)
+            if (oc < p.out_nc)
+              p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc] + s_part[oc * 128 + m];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
       }
     }
   }
@@ -360,7 +368,7 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
   if (h.in_blocks < 1 || h.in_blocks > 8 || h.mid_blocks < 1 || h.mid_blocks > 8 || h.out_nc < 1 || h.out_nc > kHdMaxOut)
     return kSgNotEligible;
-  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16 || (h.mid_blocks & 1)) return kSgNotEligible;
+  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16 ) return kSgNotEligible;
   HdParams p;
   memset(&p, 0, sizeof(p));
   p.in_blocks = h.in_blocks; p.mid_blocks = h.mid_blocks; p.out_nc = h.out_nc;

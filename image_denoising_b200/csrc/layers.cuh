@@ -115,6 +115,34 @@ inline TapGemm make_deconv_fwd(const LayerGeom& L, int dtype, const View& x, con
   g.y = parity_view(y_full, dtype, a, b);
   return g;
 }
+// Pair form (slab engine): output row parity a, both column parities in one GEMM with N = 2*Cout_pad.
+// Weights: slab a = rows [b][co] of W[ci][co][a][b]  (make_deconv_pair_pack).
+inline PackJob make_deconv_pair_pack(const LayerGeom& L, const float* w, void* dst) {
+  PackJob j;
+  j.src = w; j.dst = dst; j.ntaps = 2;
+  const int cp = L.cout_blocks() * 16;
+  j.nout_pad = 2 * cp; j.cin_blocks = L.cin_blocks();
+  j.s_t = 2; j.s_n = 4; j.s_c = (long long)L.cout * 4;          // ConvTranspose2d [ci][co][a][b]
+  j.nseg.n = 2;
+  j.nseg.src0[0] = 0; j.nseg.cnt[0] = L.cout; j.nseg.dst0[0] = 0; j.nseg.off[0] = 0;
+  j.nseg.src0[1] = 0; j.nseg.cnt[1] = L.cout; j.nseg.dst0[1] = cp; j.nseg.off[1] = 1;
+  j.cseg = L.cin.to_segs();
+  return j;
+}
+inline TapGemm make_deconv_fwd_pair(const LayerGeom& L, int dtype, const View& x, const View& y_full, int a,
+                                    const void* wp_pair, const float* bias_pad) {
+  TapGemm g;
+  g.dtype = dtype; g.x[0] = x; g.ntaps = 1;
+  g.tap_dy[0] = 0; g.tap_dx[0] = 0; g.tap_view[0] = 0; g.tap_slab[0] = a;
+  g.cin_blocks = L.cin_blocks(); g.nout = 2 * L.cout_blocks() * 16; g.w = wp_pair; g.bias = bias_pad;
+  g.y = parity_view(y_full, dtype, a, 0);
+  g.n_split = L.cout_blocks(); g.split_stride = y_full.sX;       // column parity 1 = the next output pixel
+  return g;
+}
+bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_blocks);
+bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo);
+bool slab_geometry_ok(int dtype, int h, int w);
+
 inline TapGemm make_deconv_dgrad(const LayerGeom& L, int dtype, const View& dy_full, const View& dx,
                                  const void* wp_dgrad /* packed with out_blocks == cin_blocks */) {
   TapGemm g;

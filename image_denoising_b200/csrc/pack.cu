@@ -22,9 +22,12 @@ size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks) {
   return (size_t)ntaps * nout_pad * cin_blocks * 16 * sizeof(float);
 }
 
-__device__ __forceinline__ int seg_lookup(const Segs& s, int dst) {
+__device__ __forceinline__ int seg_lookup(const Segs& s, int dst, long long* extra = nullptr) {
   for (int i = 0; i < s.n; ++i)
-    if (dst >= s.dst0[i] && dst < s.dst0[i] + s.cnt[i]) return s.src0[i] + (dst - s.dst0[i]);
+    if (dst >= s.dst0[i] && dst < s.dst0[i] + s.cnt[i]) {
+      if (extra) *extra = s.off[i];
+      return s.src0[i] + (dst - s.dst0[i]);
+    }
   return -1;
 }
 
@@ -42,14 +45,15 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
     const int c = (int)(i % cpad);
     const int n = (int)((i / cpad) % J.nout_pad);
     const int t = (int)(i / ((long long)cpad * J.nout_pad));
-    const int sn = seg_lookup(J.nseg, n);
+    long long noff = 0;
+    const int sn = seg_lookup(J.nseg, n, &noff);
     float v = 0.f;
     if (J.im2col_nc > 0) {
       const int tap = c / J.im2col_nc, ch = c - tap * J.im2col_nc;
       if (sn >= 0 && tap < 9) v = J.src[tap * J.s_t + sn * J.s_n + (long long)(J.im2col_c0 + ch) * J.s_c];
     } else {
       const int sc = seg_lookup(J.cseg, c);
-      if (sn >= 0 && sc >= 0) v = J.src[t * J.s_t + sn * J.s_n + sc * J.s_c];
+      if (sn >= 0 && sc >= 0) v = J.src[t * J.s_t + sn * J.s_n + sc * J.s_c + noff];
     }
     if (BF16) {
       const int cb = c >> 4, e = c & 15;

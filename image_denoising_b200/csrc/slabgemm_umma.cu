@@ -52,7 +52,8 @@ struct SgParams {
   int nst, nout, ring, dbg_flags;
   int tiles_x, tiles_y, ntiles;
   int act; float slope;
-  int store_y, has_addend, has_mask, has_pool, out_c;
+  int store_y, has_addend, has_mask, has_pool, out_c, n_split;
+  long long split_stride;
   uint32_t slot_bytes, tmem_cols, idesc, w_bytes, w_region;
   const uint8_t* w;
   const float* bias;
@@ -183,7 +184,12 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     w[j] = *reinterpret_cast<uint32_t*>(&h);
   }
-  if (p.store_y && !(p.dbg_flags & 32)) st_global_32B((__nv_bfloat16*)p.y.ptr + c.ypix + cb * p.y.sCb, w);
+  if (p.store_y && !(p.dbg_flags & 32)) {
+    long long o = c.ypix;
+    int cbr = cb;
+    if (p.n_split && cb >= p.n_split) { cbr = cb - p.n_split; o += p.split_stride; }
+    st_global_32B((__nv_bfloat16*)p.y.ptr + o + cbr * p.y.sCb, w);
+  }
   if (p.has_pool) {
     // 2x2 max over lanes {l, l^1 (x neighbour), l^8 (y neighbour)}; max commutes with bf16 rounding
 #pragma unroll
@@ -233,7 +239,8 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const SgStage& S = p.st[s];
     s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t], S.b_off16[t]) : make_uint2(0u, 0u);
   }
-  for (int i = threadIdx.x; i < p.nout; i += kSgThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.nout; i += kSgThreads)
+    s_bias[i] = p.bias ? p.bias[(p.n_split && i >= p.n_split * 16) ? i - p.n_split * 16 : i] : 0.f;
   if (threadIdx.x < p.nst) {
     const SgStage& S = p.st[threadIdx.x];
     s_ld[threadIdx.x] = make_int4(S.view, S.cb0, (int)(uint16_t)S.ox | ((int)(uint16_t)S.oy << 16), (int)S.tx_bytes);
@@ -418,6 +425,33 @@ static int sg_num_sms() {
   return n;
 }
 
+// Do the packed weights of a conv (taps x cin_blocks x nout) fit resident beside two pipeline slots?
+bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo) {
+  const int ngroups = (cin_blocks + kSgGroup - 1) / kSgGroup;
+  const size_t w_bytes = (size_t)ntaps * ngroups * kSgGroup * nout * 32;
+  const int gb = cin_blocks < kSgGroup ? cin_blocks : kSgGroup;
+  const size_t slot = align_up((size_t)gb * (halo ? kHaloW * kHaloH : kTileW * kTileH) * 32, 1024);
+  return align_up(w_bytes, 1024) + 2 * slot <= kSgSmemMax - kSgStaticSlack - 1024;
+}
+bool slab_geometry_ok(int dtype, int h, int w) {
+  { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return false; }
+  return dtype == N2N_BF16 && h % kTileH == 0 && w % kTileW == 0 && h >= kTileH && w >= kTileW;
+}
+
+// Can ConvTranspose2x2 run as two N = 2*Cout launches on this engine?  (geometry + shared-memory fit)
+bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_blocks) {
+  { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return false; }
+  { const char* e = getenv("N2N_NO_DECONV_PAIR"); if (e && atoi(e)) return false; }
+  if (dtype != N2N_BF16 || h % kTileH || w % kTileW || h < kTileH || w < kTileW) return false;
+  const int nout = 2 * cout_blocks * 16;
+  if (nout > 256) return false;
+  const int ngroups = (cin_blocks + kSgGroup - 1) / kSgGroup;
+  const size_t w_bytes = (size_t)2 * ngroups * kSgGroup * nout * 32;
+  const int gb = cin_blocks < kSgGroup ? cin_blocks : kSgGroup;
+  const size_t slot = align_up((size_t)gb * kTileW * kTileH * 32, 1024);
+  return align_up(w_bytes, 1024) + 2 * slot <= kSgSmemMax - kSgStaticSlack - 1024;
+}
+
 // Returns 0 when launched, kSgNotEligible when this geometry belongs to the row-slab engine, < 0 on error.
 int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   static bool attr_set = false;
@@ -448,9 +482,9 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
     if (nt == 0) continue;
     const View& xv = g.x[v];
     const int vblocks = g.view_blocks[v] ? g.view_blocks[v] : g.cin_blocks;   // channel blocks this view contributes
-    if (xv.H != H || xv.W != W || xv.Cb < vblocks || vblocks > g.cin_blocks) return kSgNotEligible;
-    const int gb = vblocks < kSgGroup ? vblocks : kSgGroup;
     const int vgroups = (vblocks + kSgGroup - 1) / kSgGroup;
+    if (xv.H != H || xv.W != W || xv.Cb < vblocks || vgroups > ngroups) return kSgNotEligible;
+    const int gb = vblocks < kSgGroup ? vblocks : kSgGroup;
     const int bw = halo ? kHaloW : kTileW, bh = halo ? kHaloH : kTileH;
     N2N_TRY(encode_c16_tensor_map(&p.tmap[v], xv, bw, bh, gb));
     const uint32_t cb_bytes = (uint32_t)(bw * bh * 32);
@@ -493,6 +527,8 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   p.bias = g.bias; p.y = g.y; p.store_y = g.store_y ? 1 : 0;
   p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
   p.has_pool = g.has_pool; p.pool = g.pool;
+  p.n_split = g.n_split; p.split_stride = g.split_stride;
+  if (g.n_split && (g.has_pool || g.has_mask || g.has_addend || g.out_nchw || 2 * g.n_split * 16 != g.nout)) return kSgNotEligible;
   p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
   p.tiles_x = W / kTileW; p.tiles_y = H / kTileH;
   const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;

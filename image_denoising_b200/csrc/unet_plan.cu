@@ -47,6 +47,11 @@ struct n2n_unet_plan {
   LayerIO io[25];
   int dgrad_blocks[25];   // how many input blocks the layer's dgrad produces (0 = none)
   int splits[25];
+  // 3x3 convs over a two-segment concat whose packed weights exceed shared memory (Cin = 2nf + nf):
+  // forward = two launches over the K segments (the second adds the first's bf16 partial), input
+  // gradient = two launches over the N segments; each half keeps its weights resident on the slab engine.
+  bool ksplit[25];
+  bool deconv_pair[25];   // ConvTranspose layers that run as two N = 2*Cout launches on the slab engine
   Buf act[B_COUNT], grd[B_COUNT];
   size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
   size_t total = 0;
@@ -119,6 +124,21 @@ static void plan_layout(n2n_unet_plan* p) {
   conv1(23, chan1(96), 96);          setio(23, B_NA, 0, hb, B_NB, 0, true, hb);
   conv1(24, chan1(96), out_nc);      setio(24, B_NB, 0, hb, B_OUT, 0, false, hb);
 
+  for (int i = 0; i < 25; ++i) {
+    const LayerGeom& G = p->L[i];
+    const int lv = p->act[p->io[i].in_buf].lvl;
+    const char* eks = getenv("N2N_NO_KSPLIT");
+    p->ksplit[i] = !(eks && atoi(eks)) && G.kind == L_CONV3 && G.cin.n == 2 && slab_geometry_ok(p->dtype, p->lh(lv), p->lw(lv)) &&
+                   !slab_weights_fit(9, G.cin_blocks(), G.cout_blocks() * 16, true) &&
+                   slab_weights_fit(9, cblocks(G.cin.cnt[0]), G.cout_blocks() * 16, true) &&
+                   slab_weights_fit(9, cblocks(G.cin.cnt[1]), G.cout_blocks() * 16, true) &&
+                   slab_weights_fit(9, G.cout_blocks(), cblocks(G.cin.cnt[0]) * 16, true) && !(p->im2col && i == 20);
+    p->deconv_pair[i] = false;
+    if (p->L[i].kind == L_DECONV) {
+      const int lvl = p->act[p->io[i].in_buf].lvl;
+      p->deconv_pair[i] = slab_deconv_pair_ok(p->dtype, p->lh(lvl), p->lw(lvl), p->L[i].cin_blocks(), p->L[i].cout_blocks());
+    }
+  }
   // ---- workspace layout ----
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
@@ -205,10 +225,30 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
         k.dst = (char*)ws + p->off_wp[20] + (size_t)9 * mg * 3 * j.nout_pad * 32;
         k.ntaps = 1; k.cin_blocks = p->kb; k.im2col_nc = p->in_nc; k.im2col_c0 = 2 * p->nf;
         jobs.push_back(k);
+      } else if (p->ksplit[i]) {
+        const LayerGeom& G = p->L[i];
+        const int b0 = cblocks(G.cin.cnt[0]), b1 = cblocks(G.cin.cnt[1]);
+        PackJob j = make_fwd_pack(G, params[2 * i], (char*)ws + p->off_wp[i]);
+        j.cin_blocks = b0; j.cseg = chan1(G.cin.cnt[0]).to_segs();
+        jobs.push_back(j);
+        PackJob k = make_fwd_pack(G, params[2 * i], (char*)ws + p->off_wp[i] + packed_weight_bytes(dt, 9, j.nout_pad, b0));
+        k.cin_blocks = b1; k.cseg.n = 1; k.cseg.src0[0] = G.cin.cnt[0]; k.cseg.cnt[0] = G.cin.cnt[1]; k.cseg.dst0[0] = 0;
+        jobs.push_back(k);
+      } else if (p->deconv_pair[i]) {
+        jobs.push_back(make_deconv_pair_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
       } else {
         jobs.push_back(make_fwd_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
       }
-      if (p->bwd)   // im2col mode: dec_conv1a's input gradient is only needed for the upsampled blocks
+      if (p->bwd && p->ksplit[i]) {
+        const LayerGeom& G = p->L[i];
+        const int b0 = cblocks(G.cin.cnt[0]), b1 = cblocks(G.cin.cnt[1]);
+        PackJob j = make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i], b0);      // rows = first segment's channels
+        j.nseg = chan1(G.cin.cnt[0]).to_segs();
+        jobs.push_back(j);
+        PackJob k = make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i] + packed_weight_bytes(dt, 9, b0 * 16, G.cout_blocks()), b1);
+        k.nseg.n = 1; k.nseg.src0[0] = G.cin.cnt[0]; k.nseg.cnt[0] = G.cin.cnt[1]; k.nseg.dst0[0] = 0;
+        jobs.push_back(k);
+      } else if (p->bwd)   // im2col mode: dec_conv1a's input gradient is only needed for the upsampled blocks
         jobs.push_back(make_dgrad_pack(p->L[i], params[2 * i], (char*)ws + p->off_wd[i],
                                        (p->im2col && i == 20) ? p->c2b : p->L[i].cin_blocks()));
       bj[i] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), p->L[i].cout, p->L[i].cout_blocks() * 16};
@@ -244,11 +284,28 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     }
     if (L.kind == L_DECONV) {
       View yfull = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      if (p->deconv_pair[i]) {
+        for (int a = 0; a < 2; ++a) N2N_TRY(launch_tapgemm(make_deconv_fwd_pair(L, dt, xin, yfull, a, wp, bias), st));
+        return 0;
+      }
       for (int ab = 0; ab < 4; ++ab) {
         TapGemm g = make_deconv_fwd(L, dt, xin, yfull, ab / 2, ab % 2, wp, bias);
         N2N_TRY(launch_tapgemm(g, st));
       }
       return 0;
+    }
+    if (p->ksplit[i]) {
+      const int b0 = cblocks(L.cin.cnt[0]), b1 = cblocks(L.cin.cnt[1]);
+      View yv = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      LayerGeom A = L; A.cin = chan1(L.cin.cnt[0]);
+      LayerGeom B = L; B.cin = chan1(L.cin.cnt[1]);
+      TapGemm g0 = make_conv_fwd(A, dt, p->view(p->act, ws, io.in_buf, io.in_cb0, b0), yv, wp, bias);     // partial (+bias), no act
+      N2N_TRY(launch_tapgemm(g0, st));
+      TapGemm g1 = make_conv_fwd(B, dt, p->view(p->act, ws, io.in_buf, io.in_cb0 + b0, b1), yv,
+                                 (const char*)wp + packed_weight_bytes(dt, 9, L.cout_blocks() * 16, b0), nullptr);
+      g1.has_addend = true; g1.addend = yv;
+      if (io.act) { g1.act = 1; g1.slope = 0.2f; }
+      return launch_tapgemm(g1, st);
     }
     TapGemm g;
     if (io.out_buf == B_OUT) {
@@ -341,6 +398,14 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
       PackJob j = make_dgrad_pack(L, params[2 * i], (char*)ws + p->off_wd20_full, L.cin_blocks());
       N2N_TRY(launch_pack(&j, 1, dt, st));
       wd = (char*)ws + p->off_wd20_full;
+    }
+    if (p->ksplit[i] && blocks == L.cin_blocks() && !mask_by_input && !add_existing) {
+      const int b0 = cblocks(L.cin.cnt[0]), b1 = cblocks(L.cin.cnt[1]);
+      TapGemm g0 = make_conv_dgrad(L, dt, gy, p->view(p->grd, ws, io.in_buf, io.in_cb0, b0), wd, b0);
+      N2N_TRY(launch_tapgemm(g0, st));
+      TapGemm g1 = make_conv_dgrad(L, dt, gy, p->view(p->grd, ws, io.in_buf, io.in_cb0 + b0, b1),
+                                   (const char*)wd + packed_weight_bytes(dt, 9, b0 * 16, L.cout_blocks()), b1);
+      return launch_tapgemm(g1, st);
     }
     TapGemm g = (L.kind == L_DECONV) ? make_deconv_dgrad(L, dt, gy, gx, wd)
                                      : make_conv_dgrad(L, dt, gy, gx, wd, L.cin_blocks());
