@@ -47,10 +47,10 @@ __device__ __forceinline__ void hd_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     if (done) return;
   }
@@ -114,7 +114,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   // barriers: x_full[3] x_empty[3] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[2] d2_empty[2] w_full
   __shared__ uint64_t bars[2 * kHdRing + 12 + 1];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut], s_part[kHdMaxOut * 128];
+  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,9 +137,9 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHdRing; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 8);
-      mbar_init(h_full(b), 8);  mbar_init(h_empty(b), 1);
-      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 8);
+      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4);
+      mbar_init(h_full(b), 4);  mbar_init(h_empty(b), 1);
+      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -233,17 +233,16 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       mma2(lt);
     }
   } else {
-    // warps 2-9: stage E1, warps 10-17: stage E2; the two warps that share a TMEM lane quarter split
-    // the channel blocks of the tile between them
+    // warps 2-9: stage E1, warps 10-17: stage E2; each stage has two groups of four warps that take
+    // alternate tiles (group g <-> buffer g of D1 / H1 / D2), so both buffers are worked on at once
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
     const bool is_e1 = warp < 10;
-    const int half = ((warp - 2) >> 2) & 1;
-    const int cb_lo = half ? (p.mid_blocks + 1) / 2 : 0;
-    const int cb_hi = half ? p.mid_blocks : (p.mid_blocks + 1) / 2;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+    const int group = ((warp - 2) >> 2) & 1;
+    const int cb_lo = 0, cb_hi = p.mid_blocks;
+    int lt = group;
+    for (int tile = blockIdx.x + group * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, lt += 2) {
       const int img = tile / tiles_per_img;
       const int r = tile - img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -297,7 +296,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         const long long spix = p.has_save ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
         float o[kHdMaxOut];
 #pragma unroll
-        for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = half ? 0.f : s_bc[oc];
+        for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
         uint32_t rr[16];
         if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + cb_lo * 16), rr);
 #pragma unroll 1
@@ -339,20 +338,10 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(d2_empty(b));
-        // combine the two half-sums of this lane quarter (named barrier 1 + quarter, 64 threads)
-        if (half) {
+        const long long hw = (long long)p.x.H * p.x.W;
 #pragma unroll
-          for (int oc = 0; oc < kHdMaxOut; ++oc) s_part[oc * 128 + m] = o[oc];
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        if (!half) {
-          const long long hw = (long long)p.x.H * p.x.W;
-#pragma unroll
-          for (int oc = 0; oc < kHdMaxOut; ++oc)
-            if (oc < p.out_nc)
-              p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc] + s_part[oc * 128 + m];
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        for (int oc = 0; oc < kHdMaxOut; ++oc)
+          if (oc < p.out_nc) p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc];
       }
     }
   }

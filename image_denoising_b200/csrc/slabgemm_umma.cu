@@ -70,10 +70,10 @@ __device__ __forceinline__ void sg_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     if (done) return;
   }
@@ -230,7 +230,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
@@ -346,16 +346,17 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     }
   } else {
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile;
-    //      the two warps of a lane quarter split the tile's channel blocks between them ----
+    //      two groups of four warps take alternate tiles (group g <-> accumulator buffer g), so the
+    //      per-tile bookkeeping is paid once per group and both accumulators drain concurrently ----
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
-    const int nblk_all = p.nout >> 4;
-    const int cb_lo = (warp >= 6) ? (nblk_all + 1) / 2 : 0;
-    const int nblk = (warp >= 6) ? nblk_all : (nblk_all + 1) / 2;     // this warp handles blocks [cb_lo, nblk)
+    const int group = (warp - 2) >> 2;
+    const int cb_lo = 0;
+    const int nblk = p.nout >> 4;
     const bool skip = (p.dbg_flags & 4) != 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+    int lt = group;
+    for (int tile = blockIdx.x + group * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, lt += 2) {
       SgPix c;
       c.img = tile / tiles_per_img;
       const int r = tile - c.img * tiles_per_img;
