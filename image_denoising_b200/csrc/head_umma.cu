@@ -170,6 +170,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       bulk_load(wb0, p.wb, p.wb_bytes, w_full);
     }
     __syncwarp();
+    pdl_wait();
     int slot = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img;
@@ -185,6 +186,8 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
     }
   } else if (warp == 1) {
     // ---- MMA issuer: MMA-1 of tile i+1 is issued before MMA-2 of tile i so E1 never starves ----
+    pdl_wait();
+    pdl_release();
     hd_wait(w_full, 0);
     const uint32_t idesc = p.idesc;
     const uint32_t ba16 = (uint32_t)nmid * 2u;              // bytes/16 of one K block of Wa / Wb (nmid rows x 32 B)
@@ -240,6 +243,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
     const int py = m >> 3, px = m & 7;
     const bool is_e1 = warp < 10;
     const int group = ((warp - 2) >> 2) & 1;
+    pdl_wait();
     const int cb_lo = 0, cb_hi = p.mid_blocks;
     int lt = group;
     for (int tile = blockIdx.x + group * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, lt += 2) {
@@ -389,7 +393,7 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = kSMs;
   const int grid = tiles < nsm ? (int)tiles : nsm;
-  head_chain_umma_kernel<<<grid, kHdThreads, smem, st>>>(p);
+  N2N_CUDA(launch_pdl(head_chain_umma_kernel, dim3(grid), dim3(kHdThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }

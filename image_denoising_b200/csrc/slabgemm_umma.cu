@@ -268,6 +268,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       }
     }
     __syncwarp();
+    pdl_wait();                         // activations below are the predecessor's output
     int slot = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img;
@@ -293,6 +294,8 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   } else if (warp == 1) {
     // ---- MMA issuer ----
     int slot = 0; uint32_t phase = 0;
+    pdl_wait();
+    pdl_release();                      // our own dependents may begin their prologue
     sg_wait(wfull_bar, 0);
     const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
     const uint32_t w_lo = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
@@ -352,6 +355,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
     const int group = (warp - 2) >> 2;
+    pdl_wait();                         // mask / addend reads and all stores touch the predecessor's data
     const int cb_lo = 0;
     const int nblk = p.nout >> 4;
     const bool skip = (p.dbg_flags & 4) != 0;
@@ -546,7 +550,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = tiles < sg_num_sms() ? (int)tiles : sg_num_sms();
-  slabgemm_umma_kernel<<<grid, kSgThreads, smem, st>>>(p);
+  N2N_CUDA(launch_pdl(slabgemm_umma_kernel, dim3(grid), dim3(kSgThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }

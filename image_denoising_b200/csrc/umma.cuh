@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace n2n {
 namespace umma {
@@ -111,6 +112,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------
+// A kernel launched with launch_pdl() may start while its stream predecessor is still running: its
+// prologue (barrier init, TMEM allocation, schedule tables, the bulk load of the layer's weights)
+// overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor grid has completed and
+// its memory is visible; it must precede every access to data the predecessor may produce or still
+// read (activations, gradients, partials).  Rule used throughout: a kernel releases its own
+// dependents (pdl_release) only AFTER its own pdl_wait, so when a kernel starts, every kernel before
+// its immediate predecessor has completed — which is what makes the early weight / bias loads safe
+// (they are written by the pack kernels at the start of the pass, never by the immediate predecessor
+// of a PDL launch: non-PDL kernels release their dependents only by completing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- descriptors ---------------------------------------------------------------------------
 constexpr uint32_t kSwizzleNone = 0, kSwizzle128 = 2, kSwizzle64 = 4, kSwizzle32 = 6;
 
@@ -170,6 +184,20 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 // SWIZZLE_32B, zero fill out of bounds (this is what implements the conv's zero padding).
 struct View;
 int encode_c16_tensor_map(CUtensorMap* out, const View& v, int bw, int bh, int cbox);
+
+// Host: launch with the programmatic-stream-serialization attribute (N2N_NO_PDL=1 -> plain launch).
+template <typename P>
+inline cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& params) {
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("N2N_NO_PDL"); use_pdl = (e && atoi(e)) ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
 
 inline uint32_t tmem_cols_for(int ncols) {
   uint32_t c = 32;

@@ -41,6 +41,7 @@ struct WsParams {
   uint32_t a_lbo, a_hi, a_kstep16;       // LBO field (already << 16) of the A descriptor low word; high word; K-step (bytes/16)
   uint32_t b_lbo, b_hi, b_kstep16;
   float* partial;
+  int dbg_flags;                         // N2N_DBG_FLAGS: 2 = skip the MMAs (pipeline / memory rate only)
   uint16_t tap_off16[12];                // start of each tap's view inside its variant box (bytes/16)
   int8_t tap_view[12];                   // tensor map of the tap's variant view
   CUtensorMap tmap_common;
@@ -107,6 +108,8 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                           // everything below reads the predecessor's tensors or writes the partials
+  if (threadIdx.x == 32) pdl_release();
 
   if (warp == 0) {
     // ---- TMA producer ----
@@ -160,7 +163,7 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
             const uint32_t a1 = (acc | (uint32_t)kk) ? 1u : 0u;
 #pragma unroll
             for (int i = 0; i < 10; ++i)
-              if (i < ntap) ws_mma(tmem_base + (uint32_t)(i * ncols), a_lo, a_hi, b_lok + boff[i], b_hi, idesc, a1);
+              if (i < ntap && !(p.dbg_flags & 2)) ws_mma(tmem_base + (uint32_t)(i * ncols), a_lo, a_hi, b_lok + boff[i], b_hi, idesc, a1);
           }
           mma_commit(empty_bar(slot));
         }
@@ -211,6 +214,7 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
 }
 
 int launch_bias_grad(const TapWgrad& g, cudaStream_t st);
+static int g_ring_override = 0;
 
 static int ws_taps_per_cta(int npairs, int variant_blocks, int common_blocks, bool box_per_tap, bool halo) {
   const int bw = halo ? kWsTileW + 2 : kWsTileW, bh = halo ? kWsTileH + 2 : kWsTileH;
@@ -269,6 +273,8 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.npairs = g.npairs; p.m_blocks = m_blocks; p.n_blocks = n_blocks; p.swap = swap ? 1 : 0;
   p.npad = g.n_blocks * 16; p.cpad = g.c_blocks * 16;
   p.partial = g.partial;
+  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
+  { const char* e = getenv("N2N_WS_RING"); if (e && atoi(e) >= 2) g_ring_override = atoi(e); }
   p.halo = halo ? 1 : 0; p.box_per_tap = box_per_tap ? 1 : 0;
   const int bw = halo ? kWsTileW + 2 : kWsTileW, bh = halo ? kWsTileH + 2 : kWsTileH;
   p.a_bytes = (uint32_t)(m_blocks * kWsTileW * kWsTileH * 32);
@@ -283,6 +289,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.slot_bytes = (uint32_t)slot_for(tpc);
   int ring = (int)(budget / p.slot_bytes);
   if (ring > kWsMaxRing) ring = kWsMaxRing;
+  if (g_ring_override && g_ring_override < ring) ring = g_ring_override;
   p.ring = ring;
   p.tiles_x = W / kWsTileW; p.tiles_y = H / kWsTileH;
   p.tiles = (long long)common.N * p.tiles_x * p.tiles_y;
@@ -319,7 +326,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
                                   (int)(kWsSmemMax - kWsStaticSlack)));
     attr_set = true;
   }
-  wgrad_slab_umma_kernel<<<splits * p.tgroups, kWsThreads, smem, st>>>(p);
+  N2N_CUDA(launch_pdl(wgrad_slab_umma_kernel, dim3(splits * p.tgroups), dim3(kWsThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
   if (g.bias_partial) return launch_bias_grad(g, st);
   return 0;

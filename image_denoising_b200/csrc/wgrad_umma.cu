@@ -163,7 +163,20 @@ tapwgrad_umma_kernel(const __grid_constant__ UmmaWgradParams p) {
 
 // Bias gradient: bias_partial[row = split * ndyviews + view][n] = sum over the split's pixel range
 // of dY_view[p, n].  One block per (row, 16-channel block): consecutive threads read consecutive
-// pixels (32 B each -> 1 KB per warp, fully coalesced); HBM-bound single pass over dY.
+// pixels (32 B each -> 1 KB per warp, fully coalesced), four independent 256-bit loads in flight
+// per thread, 32-bit index arithmetic with no division on dense views; HBM-bound single pass over dY.
+__device__ __forceinline__ void bg_accum(const __nv_bfloat16* p, float s[16]) {
+  uint32_t w[8];
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[2 * j] += __uint_as_float(w[j] << 16);
+    s[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, long long pixels, long long per_split,
                  float* __restrict__ bias_partial, int npad) {
@@ -177,15 +190,33 @@ bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, long long
   float s[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) s[q] = 0.f;
-  const long long hw = (long long)dv.W * dv.H;
-  for (long long pp = p0 + threadIdx.x; pp < p1; pp += 256) {
-    const int img = (int)(pp / hw);
-    const long long r = pp - (long long)img * hw;
-    const int y = (int)(r / dv.W), x = (int)(r - (long long)y * dv.W);
-    float v[16];
-    Block16<__nv_bfloat16>::load((const __nv_bfloat16*)dv.ptr + img * dv.sN + cb * dv.sCb + y * dv.sY + x * dv.sX, v);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) s[q] += v[q];
+  const int hw = dv.W * dv.H;
+  const bool dense = dv.sY == (long long)dv.W * dv.sX;
+  // walk the images the split touches; inside an image the pixel index is a 32-bit offset
+  for (long long pbase = p0; pbase < p1;) {
+    const int img = (int)(pbase / hw);
+    const int r0 = (int)(pbase - (long long)img * hw);
+    long long pend = (long long)(img + 1) * hw;
+    if (pend > p1) pend = p1;
+    const int r1 = r0 + (int)(pend - pbase);
+    const __nv_bfloat16* base = (const __nv_bfloat16*)dv.ptr + (long long)img * dv.sN + (long long)cb * dv.sCb;
+    if (dense) {
+      const int sx = (int)dv.sX;
+      int r = r0 + threadIdx.x;
+      for (; r + 768 < r1; r += 1024) {
+        bg_accum(base + (long long)r * sx, s);
+        bg_accum(base + (long long)(r + 256) * sx, s);
+        bg_accum(base + (long long)(r + 512) * sx, s);
+        bg_accum(base + (long long)(r + 768) * sx, s);
+      }
+      for (; r < r1; r += 256) bg_accum(base + (long long)r * sx, s);
+    } else {
+      for (int r = r0 + threadIdx.x; r < r1; r += 256) {
+        const int y = r / dv.W, x = r - y * dv.W;
+        bg_accum(base + (long long)y * dv.sY + (long long)x * dv.sX, s);
+      }
+    }
+    pbase = pend;
   }
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
