@@ -227,7 +227,12 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (image_denoising_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout during the first collective; the contract is ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -258,6 +263,10 @@ def run_b200(args):
     for i in range(args.warmup):
         one_step(i)
     barrier()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

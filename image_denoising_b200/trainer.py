@@ -60,6 +60,9 @@ class N2NTrainer:
         if use_graph is None:
             use_graph = os.environ.get("N2N_NO_GRAPH", "0") != "1"
         self.use_graph = bool(use_graph)
+        # optional: run the two forward passes on two streams (measured: no gain — the persistent
+        # one-CTA-per-SM kernels leave no room to co-schedule — so it is off by default)
+        self.overlap_forwards = os.environ.get("N2N_OVERLAP", "0") == "1"
         self._graph = None
         self._eager_steps = 0
         if self.world > 1:
@@ -92,6 +95,8 @@ class N2NTrainer:
         self.loss_ws = torch.zeros(lib().n2n_loss_workspace_bytes(0), dtype=torch.uint8, device=dev)
         self.param_ptrs = ptr_array(self.params)
         self.grad_ptrs = ptr_array(self.grads)
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self.ev_fork = torch.cuda.Event(); self.ev_join = torch.cuda.Event()
 
     # ------------------------------------------------------------------ one iteration
     def _launch_sequence(self, noisy, rd_idx, lam, lr, dev_scalars):
@@ -102,10 +107,24 @@ class N2NTrainer:
         n, c, h, w = noisy.shape
         check(L.n2n_mask_pair_from_rdidx(ptr(rd_idx), rd_idx.numel(), None, None, ptr(self.packed), st))
         check(L.n2n_subsample_pair(ptr(noisy), None, None, ptr(self.packed), ptr(self.sub1), ptr(self.sub2), n, c, h, w, 4, st))
+        # The no-grad full-resolution pass and the half-resolution training forward are independent
+        # (training_script.md:139-146): run the latter on a side stream so that its launch-bound deep
+        # levels fill the SMs the other pass leaves idle (and vice versa); joined before the loss.
+        side = self.side_stream if self.overlap_forwards else None
+        if side is not None:
+            self.ev_fork.record()
+            side.wait_event(self.ev_fork)
+            with torch.cuda.stream(side):
+                check(L.n2n_unet_forward(self.plan_half, self.param_ptrs, ptr(self.sub1), ptr(self.out), ptr(self.ws_half),
+                                         stream_ptr()))
+                self.ev_join.record()
         check(L.n2n_unet_forward(self.plan_full, self.param_ptrs, ptr(noisy), ptr(self.den), ptr(self.ws_full), st))
         check(L.n2n_subsample_pair(ptr(self.den), None, None, ptr(self.packed), ptr(self.den1), ptr(self.den2),
                                    n, self.net.out_nc, h, w, 4, st))
-        check(L.n2n_unet_forward(self.plan_half, self.param_ptrs, ptr(self.sub1), ptr(self.out), ptr(self.ws_half), st))
+        if side is not None:
+            torch.cuda.current_stream().wait_event(self.ev_join)
+        else:
+            check(L.n2n_unet_forward(self.plan_half, self.param_ptrs, ptr(self.sub1), ptr(self.out), ptr(self.ws_half), st))
         if dev_scalars is None:
             check(L.n2n_loss_n2n_fwdbwd(ptr(self.out), ptr(self.sub2), ptr(self.den1), ptr(self.den2), float(lam), 1.0,
                                         self.out.numel(), ptr(self.loss3), ptr(self.dout), ptr(self.loss_ws), st))
