@@ -105,8 +105,18 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
       if (sc < 0) continue;
       dst = t * J.s_t + sn * J.s_n + sc * J.s_c;
     }
+    // fixed summation order (deterministic); eight independent loads in flight per thread
     float s = 0.f;
-    for (int sp = 0; sp < J.splits; ++sp) s += J.partial[(long long)sp * total + i];
+    const float* src = J.partial + i;
+    int sp = 0;
+    for (; sp + 8 <= J.splits; sp += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (long long)(sp + u) * total);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; sp < J.splits; ++sp) s += __ldg(src + (long long)sp * total);
     J.dst_w[dst] = s;
   }
   if (J.dst_b && J.bias_partial) {
@@ -114,7 +124,15 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
       const int sn = seg_lookup(J.nseg, n);
       if (sn < 0) continue;
       float s = 0.f;
-      for (int sp = 0; sp < J.bias_rows; ++sp) s += J.bias_partial[(long long)sp * J.npad + n];
+      int sp = 0;
+      for (; sp + 8 <= J.bias_rows; sp += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(J.bias_partial + (long long)(sp + u) * J.npad + n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; sp < J.bias_rows; ++sp) s += __ldg(J.bias_partial + (long long)sp * J.npad + n);
       J.dst_b[sn] = s;
     }
   }
@@ -148,7 +166,7 @@ int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st) {
       long long tot = (long long)b.j[i].ntaps * b.j[i].npad * b.j[i].cpad;
       if (tot > maxtotal) maxtotal = tot;
     }
-    dim3 grid(grid_for(maxtotal, 256, 2), b.n);
+    dim3 grid(grid_for(maxtotal, 256, 8), b.n);
     unpack_kernel<<<grid, 256, 0, st>>>(b);
     N2N_LAUNCH_CHECK();
   }

@@ -28,7 +28,7 @@ constexpr int kWsThreads = 192;
 constexpr int kWsMaxRing = 4;
 constexpr int kWsTileW = 8, kWsTileH = 16;
 constexpr size_t kWsSmemMax = 232448;
-constexpr size_t kWsStaticSlack = 2048;
+constexpr size_t kWsStaticSlack = 4096;
 
 struct WsParams {
   int npairs, taps_per_cta, tgroups;
@@ -41,6 +41,7 @@ struct WsParams {
   uint32_t a_lbo, a_hi, a_kstep16;       // LBO field (already << 16) of the A descriptor low word; high word; K-step (bytes/16)
   uint32_t b_lbo, b_hi, b_kstep16;
   float* partial;
+  float* bias_partial;                   // conv only: [splits][npad] fused bias gradient (tap group 0), else null
   int dbg_flags;                         // N2N_DBG_FLAGS: 2 = skip the MMAs (pipeline / memory rate only)
   uint16_t tap_off16[12];                // start of each tap's view inside its variant box (bytes/16)
   int8_t tap_view[12];                   // tensor map of the tap's variant view
@@ -79,6 +80,7 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * kWsMaxRing + 1];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_red[4][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -97,9 +99,12 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
   const int ncols = p.n_blocks * 16;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int nbox = p.box_per_tap ? ntap : 1;
+  // bias gradient = per-channel pixel sum of dY: the four otherwise idle epilogue warps add it up from
+  // the dY tile the pipeline already staged in shared memory (tap group 0 only), so dY is not read twice
+  const bool do_bias = p.bias_partial != nullptr && tg == 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWsMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kWsMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_bias ? 5 : 1); }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
@@ -178,6 +183,53 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
     // ---- epilogue (once): TMEM -> fp32 partial ----
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
+    if (do_bias) {
+      // thread m owns pixel m of every tile; the pixel's 32-byte row of block cb is two 16-byte chunks
+      // whose order is swapped when address bit 7 (= bit 2 of the pixel index) is set
+      float acc[8][16];
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[cb][q] = 0.f;
+      const uint32_t sw = ((uint32_t)m >> 2) & 1u;
+      int slot = 0; uint32_t phase = 0;
+      for (long long tile = tile_begin; tile < tile_end; ++tile) {
+        ws_wait(full_bar(slot), phase);
+        const uint8_t* row = smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)slot * p.slot_bytes + (size_t)m * 32;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+          if (cb < p.m_blocks) {
+            const uint4* c4 = reinterpret_cast<const uint4*>(row + (size_t)cb * (kWsTileW * kWsTileH * 32));
+            const uint4 lo = c4[sw], hi = c4[sw ^ 1u];
+            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[cb][2 * j] += __uint_as_float(w[j] << 16);
+              acc[cb][2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(slot));
+        if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+      }
+      // fixed-order reduction over the 128 pixels: lanes (shuffles), then the four warps
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb) {
+        if (cb < p.m_blocks) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float v = acc[cb][q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[quarter][cb * 16 + q] = v;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (m < p.m_blocks * 16)
+        p.bias_partial[(long long)split * p.npad + m] = s_red[0][m] + s_red[1][m] + s_red[2][m] + s_red[3][m];
+    }
     if (has_work) {
       ws_wait(tfull_bar, 0);
       fence_after_sync();
@@ -273,6 +325,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.npairs = g.npairs; p.m_blocks = m_blocks; p.n_blocks = n_blocks; p.swap = swap ? 1 : 0;
   p.npad = g.n_blocks * 16; p.cpad = g.c_blocks * 16;
   p.partial = g.partial;
+  p.bias_partial = (g.bias_partial && !swap) ? g.bias_partial : nullptr;
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   { const char* e = getenv("N2N_WS_RING"); if (e && atoi(e) >= 2) g_ring_override = atoi(e); }
   p.halo = halo ? 1 : 0; p.box_per_tap = box_per_tap ? 1 : 0;
@@ -328,7 +381,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   }
   N2N_CUDA(launch_pdl(wgrad_slab_umma_kernel, dim3(splits * p.tgroups), dim3(kWsThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
-  if (g.bias_partial) return launch_bias_grad(g, st);
+  if (g.bias_partial && !p.bias_partial) return launch_bias_grad(g, st);   // deconv: dY is the variant operand
   return 0;
 }
 

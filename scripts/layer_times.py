@@ -1,4 +1,5 @@
-"""Per-launch CUDA-event times of the GEMM kernels for one bench-shaped N2N step (diagnostic)."""
+"""Per-launch CUDA-event times of the GEMM-class kernels for one bench-shaped N2N step (diagnostic).
+Labels follow the launch structure of unet_plan.cu for the bf16 engine at 256x256 / 128x128."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,17 +19,32 @@ L.n2n_profile_begin()
 tr.step(x, 0.02)
 buf = (ctypes.c_double * (3 * 400))()
 n = L.n2n_profile_end_list(buf, 400)
-names_fwd = ["enc0", "enc1", "enc2", "enc3", "enc4", "enc5", "enc6"] + ["up5"] * 4 + ["d5a", "d5b"] + ["up4"] * 4 + \
-    ["d4a", "d4b"] + ["up3"] * 4 + ["d3a", "d3b"] + ["up2"] * 4 + ["d2a", "d2b"] + ["up1"] * 4 + ["d1a", "d1b", "nin_a", "nin_b", "nin_c"]
+
+
+def fwd_names(res):
+    """launches of one forward at input resolution `res` (levels res .. res/32)."""
+    def up(name, in_res):
+        return [name] * (2 if in_res % 16 == 0 else 4)          # pair form needs a 16-row tile
+    def dxa(name, r):
+        return [name + ".k0", name + ".k1"] if r % 16 == 0 else [name]
+    r = res
+    out = ["enc0", "enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]
+    out += up("up5", r // 32) + ["d5a", "d5b"]
+    out += up("up4", r // 16) + dxa("d4a", r // 8) + ["d4b"]
+    out += up("up3", r // 8) + dxa("d3a", r // 4) + ["d3b"]
+    out += up("up2", r // 4) + dxa("d2a", r // 2) + ["d2b"]
+    out += up("up1", r // 2) + ["d1a", "d1b", "head"]
+    return out
+
+
+names = ["full:" + s for s in fwd_names(256)] + ["half:" + s for s in fwd_names(128)]
 tot = {0: 0.0, 1: 0.0}
 k = 0
 for i in range(n):
     cls, ms, fl = int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]
     tot[cls] += ms
-    tag = ""
-    if cls == 0 and k < 2 * len(names_fwd):
-        tag = ("full:" if k < len(names_fwd) else "half:") + names_fwd[k % len(names_fwd)]
+    tag = "wgrad" if cls == 1 else ("bwd" if k >= len(names) else names[k])
+    if cls == 0:
         k += 1
-    if ms > 0.0:
-        print(f"{i:3d} cls={cls} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TF/s(exec) {tag}")
+    print(f"{i:3d} cls={cls} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TF/s(exec) {tag}")
 print("totals ms:", tot)
