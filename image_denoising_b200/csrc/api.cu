@@ -24,6 +24,8 @@ struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec>* g_prof = nullptr;
 
+bool profiling_active() { return g_prof_on; }
+
 struct ProfScope {
   ProfRec r; bool on; cudaStream_t st;
   ProfScope(int cls, double flops, cudaStream_t s) : on(g_prof_on), st(s) {

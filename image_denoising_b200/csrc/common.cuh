@@ -17,6 +17,7 @@
 namespace n2n {
 
 void set_error(const char* fmt, ...);
+bool profiling_active();       // per-launch event timing armed (n2n_profile_begin): keep every launch on one stream
 extern thread_local long long g_launch_count;   // kernels launched by this host thread (for gpu_launches)
 
 #define N2N_CHECK_ARG(cond, ...)                       \

@@ -47,8 +47,9 @@ __global__ void c16_to_nchw_kernel(View src, float* __restrict__ dst, int C, lon
   }
 }
 
-template <typename T>
-__global__ void nchw_to_im2col9_kernel(const float* __restrict__ src, int C, View dst, long long items) {
+template <typename T, int CT>
+__global__ void nchw_to_im2col9_kernel(const float* __restrict__ src, int Crt, View dst, long long items) {
+  const int C = CT > 0 ? CT : Crt;        // compile-time channel count (1, 3) keeps the tap decode division-free
   const int H = dst.H, W = dst.W;
   const long long hw = (long long)H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
@@ -78,8 +79,13 @@ int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, 
   N2N_CHECK_ARG(C >= 1 && 9 * C <= 16 * dst.Cb, "nchw_to_im2col9: 9*%d channels do not fit %d blocks", C, dst.Cb);
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
   int grid = grid_for(items, 256);
-  if (dtype == N2N_BF16) nchw_to_im2col9_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, C, dst, items);
-  else nchw_to_im2col9_kernel<float><<<grid, 256, 0, st>>>(src, C, dst, items);
+  if (dtype == N2N_BF16) {
+    if (C == 1) nchw_to_im2col9_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(src, C, dst, items);
+    else if (C == 3) nchw_to_im2col9_kernel<__nv_bfloat16, 3><<<grid, 256, 0, st>>>(src, C, dst, items);
+    else nchw_to_im2col9_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>(src, C, dst, items);
+  } else {
+    nchw_to_im2col9_kernel<float, 0><<<grid, 256, 0, st>>>(src, C, dst, items);
+  }
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -56,6 +56,16 @@ struct n2n_unet_plan {
   size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
   size_t total = 0;
   int fwd_launches = 0, bwd_launches = 0;
+  // backward: weight gradients run on a side stream, forked per layer from the input-gradient chain
+  // (wgrad(i) and dgrad(i) both only READ grad(out_i)); the deep, launch-bound levels of the two
+  // chains then overlap.  Joined before the partial reduction.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  ~n2n_unet_plan() {
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (side) cudaStreamDestroy(side);
+  }
 
   int lh(int lvl) const { return H >> lvl; }
   int lw(int lvl) const { return W >> lvl; }
@@ -192,6 +202,16 @@ extern "C" int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc,
   p->in_nc = in_nc; p->out_nc = out_nc; p->nf = n_feature; p->N = n; p->H = h; p->W = w; p->dtype = dtype;
   p->bwd = with_backward != 0;
   plan_layout(p);
+  { const char* e = getenv("N2N_NO_SIDE");
+    if (p->bwd && dtype == N2N_BF16 && !(e && atoi(e))) {
+      if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        p->side = nullptr;        // no device yet / no resources: stay on one stream
+      }
+    }
+  }
   *plan = p;
   return 0;
 }
@@ -365,7 +385,16 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   N2N_TRY(launch_nchw_to_c16(dy, p->out_nc, p->view(p->grd, ws, B_OUT, 0, cblocks(p->out_nc)), dt, st));
 
   // grad of layer i's OUTPUT lives in grd[out_buf] blocks [out_cb0, +cout_blocks).
+  cudaStream_t main_st = st;
+  const bool use_side = p->side != nullptr && !profiling_active();
   auto wgrad = [&](int i) -> int {
+    cudaStream_t st = main_st;
+    if (use_side) {
+      // fork: everything issued on the main stream so far (in particular grad(out_i)) precedes this wgrad
+      N2N_CUDA(cudaEventRecord(p->ev_ready, main_st));
+      N2N_CUDA(cudaStreamWaitEvent(p->side, p->ev_ready, 0));
+      st = p->side;
+    }
     const LayerIO& io = p->io[i];
     const LayerGeom& L = p->L[i];
     View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
@@ -443,6 +472,10 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   if (want_dx) {
     N2N_TRY(dgrad(0, p->inb, false, true));
     N2N_TRY(launch_c16_to_nchw(p->view(p->grd, ws, B_CAT0, p->c2b, p->inb), dt, dx, p->in_nc, st));
+  }
+  if (use_side) {   // join
+    N2N_CUDA(cudaEventRecord(p->ev_done, p->side));
+    N2N_CUDA(cudaStreamWaitEvent(st, p->ev_done, 0));
   }
   // partials -> PyTorch-layout fp32 gradients
   {
