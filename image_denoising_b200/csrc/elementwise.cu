@@ -9,6 +9,7 @@ namespace n2n {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void nchw_to_c16_kernel(const float* __restrict__ src, int C, View dst, long long items) {
+  pdl_enter();
   const long long hw = (long long)dst.H * dst.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
        i += (long long)gridDim.x * blockDim.x) {
@@ -29,6 +30,7 @@ __global__ void nchw_to_c16_kernel(const float* __restrict__ src, int C, View ds
 
 template <typename T>
 __global__ void c16_to_nchw_kernel(View src, float* __restrict__ dst, int C, long long items) {
+  pdl_enter();
   const long long hw = (long long)src.H * src.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
        i += (long long)gridDim.x * blockDim.x) {
@@ -49,6 +51,7 @@ __global__ void c16_to_nchw_kernel(View src, float* __restrict__ dst, int C, lon
 
 template <typename T, int CT>
 __global__ void nchw_to_im2col9_kernel(const float* __restrict__ src, int Crt, View dst, long long items) {
+  pdl_enter();
   const int C = CT > 0 ? CT : Crt;        // compile-time channel count (1, 3) keeps the tap decode division-free
   const int H = dst.H, W = dst.W;
   const long long hw = (long long)H * W;
@@ -80,11 +83,11 @@ int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, 
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
   int grid = grid_for(items, 256);
   if (dtype == N2N_BF16) {
-    if (C == 1) nchw_to_im2col9_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(src, C, dst, items);
-    else if (C == 3) nchw_to_im2col9_kernel<__nv_bfloat16, 3><<<grid, 256, 0, st>>>(src, C, dst, items);
-    else nchw_to_im2col9_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>(src, C, dst, items);
+    if (C == 1) (void)launch_pdl_v(nchw_to_im2col9_kernel<__nv_bfloat16, 1>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
+    else if (C == 3) (void)launch_pdl_v(nchw_to_im2col9_kernel<__nv_bfloat16, 3>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
+    else (void)launch_pdl_v(nchw_to_im2col9_kernel<__nv_bfloat16, 0>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
   } else {
-    nchw_to_im2col9_kernel<float, 0><<<grid, 256, 0, st>>>(src, C, dst, items);
+    (void)launch_pdl_v(nchw_to_im2col9_kernel<float, 0>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
   }
   N2N_LAUNCH_CHECK();
   return 0;
@@ -94,8 +97,8 @@ int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cuda
   N2N_CHECK_ARG(C >= 1 && C <= 16 * dst.Cb, "nchw_to_c16: C=%d does not fit %d blocks", C, dst.Cb);
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
   int grid = grid_for(items, 256);
-  if (dtype == N2N_BF16) nchw_to_c16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, C, dst, items);
-  else nchw_to_c16_kernel<float><<<grid, 256, 0, st>>>(src, C, dst, items);
+  if (dtype == N2N_BF16) (void)launch_pdl_v(nchw_to_c16_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
+  else (void)launch_pdl_v(nchw_to_c16_kernel<float>, dim3(grid), dim3(256), 0, st, src, C, dst, items);
   N2N_LAUNCH_CHECK();
   return 0;
 }
@@ -104,14 +107,15 @@ int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream
   N2N_CHECK_ARG(C >= 1 && C <= 16 * src.Cb, "c16_to_nchw: C=%d does not fit %d blocks", C, src.Cb);
   long long items = (long long)src.N * src.Cb * src.H * src.W;
   int grid = grid_for(items, 256);
-  if (dtype == N2N_BF16) c16_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, dst, C, items);
-  else c16_to_nchw_kernel<float><<<grid, 256, 0, st>>>(src, dst, C, items);
+  if (dtype == N2N_BF16) (void)launch_pdl_v(c16_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, src, dst, C, items);
+  else (void)launch_pdl_v(c16_to_nchw_kernel<float>, dim3(grid), dim3(256), 0, st, src, dst, C, items);
   N2N_LAUNCH_CHECK();
   return 0;
 }
 
 struct BiasPadBatch { BiasPadJob j[32]; int n; };
 __global__ void bias_pad_kernel(const __grid_constant__ BiasPadBatch b) {
+  pdl_enter();
   const BiasPadJob& J = b.j[blockIdx.x];
   for (int i = threadIdx.x; i < J.npad; i += blockDim.x) J.dst[i] = (i < J.n && J.src) ? J.src[i] : 0.f;
 }
@@ -120,7 +124,7 @@ int launch_bias_pad(const BiasPadJob* jobs, int njobs, cudaStream_t st) {
     BiasPadBatch b;
     b.n = njobs - base < 32 ? njobs - base : 32;
     for (int i = 0; i < b.n; ++i) b.j[i] = jobs[base + i];
-    bias_pad_kernel<<<b.n, 128, 0, st>>>(b);
+    (void)launch_pdl_v(bias_pad_kernel, dim3(b.n), dim3(128), 0, st, b);
     N2N_LAUNCH_CHECK();
   }
   return 0;
@@ -137,6 +141,7 @@ int launch_c16_to_nchw_multi(const View& src, int dtype, float* dst, int C, cuda
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool_kernel(View src, View dst, long long items) {
+  pdl_enter();
   const int Wo = dst.W, Ho = dst.H, Cb = dst.Cb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
        i += (long long)gridDim.x * blockDim.x) {
@@ -162,8 +167,8 @@ int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st)
                 "maxpool: shape mismatch");
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;
   int grid = grid_for(items, 256);
-  if (dtype == N2N_BF16) maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, dst, items);
-  else maxpool_kernel<float><<<grid, 256, 0, st>>>(src, dst, items);
+  if (dtype == N2N_BF16) (void)launch_pdl_v(maxpool_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, src, dst, items);
+  else (void)launch_pdl_v(maxpool_kernel<float>, dim3(grid), dim3(256), 0, st, src, dst, items);
   N2N_LAUNCH_CHECK();
   return 0;
 }
@@ -172,6 +177,7 @@ int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st)
 // Tie rule: ATen keeps the first maximum in row-major window order (update only on >).
 template <typename T>
 __global__ void unpool_lrelu_kernel(View act, View gpool, View gact, float slope, long long items) {
+  pdl_enter();
   const int Wo = gpool.W, Ho = gpool.H, Cb = gpool.Cb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
        i += (long long)gridDim.x * blockDim.x) {
@@ -212,8 +218,8 @@ int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, fl
                 "unpool: shape mismatch");
   long long items = (long long)gpool.N * gpool.Cb * gpool.H * gpool.W;
   int grid = grid_for(items, 128);
-  if (dtype == N2N_BF16) unpool_lrelu_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(act, gpool, gact, slope, items);
-  else unpool_lrelu_kernel<float><<<grid, 128, 0, st>>>(act, gpool, gact, slope, items);
+  if (dtype == N2N_BF16) (void)launch_pdl_v(unpool_lrelu_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, st, act, gpool, gact, slope, items);
+  else (void)launch_pdl_v(unpool_lrelu_kernel<float>, dim3(grid), dim3(128), 0, st, act, gpool, gact, slope, items);
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -53,9 +53,14 @@ __global__ void __launch_bounds__(kRedThreads)
 n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, const float* __restrict__ den1,
                 const float* __restrict__ den2, float lam, float gscale, long long count, float* __restrict__ loss3,
                 float* __restrict__ grad, RedWs* ws, const float* __restrict__ dev_scalars) {
+  pdl_enter();
   __shared__ double red[2 * 8];
   if (dev_scalars) lam = dev_scalars[0];      // graph-replayed steps read Lambda from device memory
+  // per-thread sums stay fp32 over short runs (<= 64 elements between flushes; fp64 throughput on this
+  // part is a small fraction of fp32), then accumulate in double
   double acc[2] = {0.0, 0.0};
+  float a0 = 0.f, a1 = 0.f;
+  int run = 0;
   const float k = gscale * 2.0f / (float)count;
   const long long nvec = count / 4;
   const bool vec_ok = ((((uintptr_t)out | (uintptr_t)sub2 | (uintptr_t)den1 | (uintptr_t)den2 | (uintptr_t)grad) & 15) == 0);
@@ -73,11 +78,12 @@ n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, c
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float r = d[q] - e[q];
-        acc[0] += (double)(d[q] * d[q]);
-        acc[1] += (double)(r * r);
+        a0 += d[q] * d[q];
+        a1 += r * r;
         g[q] = k * (d[q] + lam * r);
       }
       if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(g[0], g[1], g[2], g[3]);
+      if (++run == 16) { acc[0] += (double)a0; acc[1] += (double)a1; a0 = a1 = 0.f; run = 0; }
     }
     start_tail = nvec * 4;
   }
@@ -85,10 +91,11 @@ n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, c
        i += (long long)gridDim.x * blockDim.x) {
     const float d = out[i] - sub2[i];
     const float r = d - (den1[i] - den2[i]);
-    acc[0] += (double)(d * d);
-    acc[1] += (double)(r * r);
+    a0 += d * d;
+    a1 += r * r;
     if (grad) grad[i] = k * (d + lam * r);
   }
+  acc[0] += (double)a0; acc[1] += (double)a1;
   block_reduce<2>(acc, red);
   if (threadIdx.x == 0) { ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; }
   if (last_block_done(ws) && threadIdx.x == 0) {
@@ -109,6 +116,7 @@ __device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 
 __global__ void __launch_bounds__(kRedThreads)
 l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int planes, int h, int w,
                    float lg, float gscale, float* __restrict__ loss3, float* __restrict__ grad, RedWs* ws) {
+  pdl_enter();
   __shared__ double red[3 * 8];
   double acc[3] = {0.0, 0.0, 0.0};
   const long long hw = (long long)h * w, count = (long long)planes * hw;
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(256)
 adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ blocks, float b1, float b2,
                   float eps, float step_size, float inv_sqrt_bc2_recip /* sqrt(bc2) */, float gscale,
                   const float* __restrict__ dev_scalars) {
+  pdl_enter();
   if (dev_scalars) { step_size = dev_scalars[1]; inv_sqrt_bc2_recip = dev_scalars[2]; }
   const int t = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
   const long long* row = table + 5 * (long long)t;
@@ -200,7 +209,7 @@ extern "C" int n2n_loss_n2n_fwdbwd(const float* out, const float* sub2, const fl
   N2N_CHECK_ARG(out && sub2 && den1 && den2 && loss3 && workspace && count > 0, "loss_n2n: bad arguments");
   int grid = grid_for(count / 4 + 1, kRedThreads, 4);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  n2n_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(out, sub2, den1, den2, lam, grad_scale, count,
+  (void)launch_pdl_v(n2n_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, out, sub2, den1, den2, lam, grad_scale, count,
                                                                   loss3, grad, (RedWs*)workspace, nullptr);
   N2N_LAUNCH_CHECK();
   return 0;
@@ -213,7 +222,7 @@ extern "C" int n2n_loss_n2n_fwdbwd_dev(const float* out, const float* sub2, cons
   N2N_CHECK_ARG(out && sub2 && den1 && den2 && loss3 && workspace && dev_scalars && count > 0, "loss_n2n_dev: bad arguments");
   int grid = grid_for(count / 4 + 1, kRedThreads, 4);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  n2n_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(out, sub2, den1, den2, 0.f, grad_scale, count,
+  (void)launch_pdl_v(n2n_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, out, sub2, den1, den2, 0.f, grad_scale, count,
                                                                   loss3, grad, (RedWs*)workspace, dev_scalars);
   N2N_LAUNCH_CHECK();
   return 0;
@@ -226,7 +235,7 @@ extern "C" int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, in
   const long long count = (long long)n * c * h * w;
   int grid = grid_for(count, kRedThreads, 4);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  l1grad_loss_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(pred, target, n * c, h, w, lambda_grad,
+  (void)launch_pdl_v(l1grad_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, n * c, h, w, lambda_grad,
                                                                      grad_scale, loss3, grad, (RedWs*)workspace);
   N2N_LAUNCH_CHECK();
   return 0;
@@ -239,7 +248,7 @@ extern "C" int n2n_adam_multi(const int64_t* table, int ntensors, const int32_t*
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float sqrt_bc2 = (float)sqrt(bc2);
-  adam_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, blocks, beta1, beta2, eps,
+  (void)launch_pdl_v(adam_multi_kernel, dim3(nblocks), dim3(256), 0, (cudaStream_t)stream, (const long long*)table, blocks, beta1, beta2, eps,
                                                               step_size, sqrt_bc2, grad_scale, nullptr);
   N2N_LAUNCH_CHECK();
   return 0;
@@ -250,7 +259,7 @@ extern "C" int n2n_adam_multi_dev(const int64_t* table, int ntensors, const int3
                                   const float* dev_scalars, float beta1, float beta2, float eps, float grad_scale,
                                   void* stream) {
   N2N_CHECK_ARG(table && blocks && dev_scalars && ntensors > 0 && nblocks > 0, "adam_multi_dev: bad arguments");
-  adam_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, blocks, beta1, beta2, eps,
+  (void)launch_pdl_v(adam_multi_kernel, dim3(nblocks), dim3(256), 0, (cudaStream_t)stream, (const long long*)table, blocks, beta1, beta2, eps,
                                                               0.f, 1.f, grad_scale, dev_scalars);
   N2N_LAUNCH_CHECK();
   return 0;

@@ -36,6 +36,7 @@ struct UnpackBatch { UnpackJob j[8]; int n; };
 
 template <bool BF16>
 __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
+  pdl_enter();
   const PackJob& J = b.j[blockIdx.y];
   const int cpad = J.cin_blocks * 16;
   const long long total = (long long)J.ntaps * J.nout_pad * cpad;
@@ -85,6 +86,7 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
 }
 
 __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
+  pdl_enter();
   const UnpackJob& J = b.j[blockIdx.y];
   const long long plane = (long long)J.cpad * J.npad;
   const long long total = (long long)J.ntaps * plane;
@@ -149,8 +151,8 @@ int launch_pack(const PackJob* jobs, int njobs, int dtype, cudaStream_t st) {
       if (tot > maxtotal) maxtotal = tot;
     }
     dim3 grid(grid_for(maxtotal, 256, 2), b.n);
-    if (dtype == N2N_BF16) pack_kernel<true><<<grid, 256, 0, st>>>(b);
-    else pack_kernel<false><<<grid, 256, 0, st>>>(b);
+    if (dtype == N2N_BF16) (void)launch_pdl_v(pack_kernel<true>, grid, dim3(256), 0, st, b);
+    else (void)launch_pdl_v(pack_kernel<false>, grid, dim3(256), 0, st, b);
     N2N_LAUNCH_CHECK();
   }
   return 0;
@@ -167,7 +169,7 @@ int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st) {
       if (tot > maxtotal) maxtotal = tot;
     }
     dim3 grid(grid_for(maxtotal, 256, 8), b.n);
-    unpack_kernel<<<grid, 256, 0, st>>>(b);
+    (void)launch_pdl_v(unpack_kernel, grid, dim3(256), 0, st, b);
     N2N_LAUNCH_CHECK();
   }
   return 0;

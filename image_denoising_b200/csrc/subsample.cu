@@ -21,6 +21,7 @@ __constant__ int8_t c_pair_table[8][2] = {{0, 1}, {0, 2}, {1, 3}, {2, 3}, {1, 0}
 // both masks is written here, so no separate zero-fill pass is needed.
 __global__ void mask_pair_kernel(const int64_t* __restrict__ rd_idx, long long cells, uint32_t* __restrict__ mask1,
                                  uint32_t* __restrict__ mask2, uint8_t* __restrict__ packed) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(rd_idx[i] & 7);
@@ -42,6 +43,7 @@ template <typename E, int MODE>
 __global__ void subsample_vec_kernel(const E* __restrict__ img, const uint8_t* __restrict__ m1,
                                      const uint8_t* __restrict__ m2, E* __restrict__ o1, E* __restrict__ o2,
                                      int n, int c, int h, int w, long long groups) {
+  pdl_enter();
   const int hh = h / 2, ww = w / 2, gw = ww / 4;
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups;
        g += (long long)gridDim.x * blockDim.x) {
@@ -88,6 +90,7 @@ template <typename E, int MODE>
 __global__ void subsample_scalar_kernel(const E* __restrict__ img, const uint8_t* __restrict__ m1,
                                         const uint8_t* __restrict__ m2, E* __restrict__ o1, E* __restrict__ o2,
                                         int n, int c, int h, int w, long long items) {
+  pdl_enter();
   const int hh = h / 2, ww = w / 2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < items;
        t += (long long)gridDim.x * blockDim.x) {
@@ -127,13 +130,13 @@ static int run_subsample(const void* img, const uint8_t* m1, const uint8_t* m2, 
     const long long groups = items / 4;
     const int grid = grid_for(groups, 256);
 #define N2N_SS_LAUNCH(M) \
-    subsample_vec_kernel<E, M><<<grid, 256, 0, st>>>((const E*)img, a, m2, (E*)o1, (E*)o2, n, c, h, w, groups)
+    (void)launch_pdl_v(subsample_vec_kernel<E, M>, dim3(grid), dim3(256), 0, st, (const E*)img, a, m2, (E*)o1, (E*)o2, n, c, h, w, groups)
     if (mode == 0) N2N_SS_LAUNCH(0); else if (mode == 1) N2N_SS_LAUNCH(1); else N2N_SS_LAUNCH(2);
 #undef N2N_SS_LAUNCH
   } else {
     const int grid = grid_for(items, 256);
 #define N2N_SS_LAUNCH(M) \
-    subsample_scalar_kernel<E, M><<<grid, 256, 0, st>>>((const E*)img, a, m2, (E*)o1, (E*)o2, n, c, h, w, items)
+    (void)launch_pdl_v(subsample_scalar_kernel<E, M>, dim3(grid), dim3(256), 0, st, (const E*)img, a, m2, (E*)o1, (E*)o2, n, c, h, w, items)
     if (mode == 0) N2N_SS_LAUNCH(0); else if (mode == 1) N2N_SS_LAUNCH(1); else N2N_SS_LAUNCH(2);
 #undef N2N_SS_LAUNCH
   }
@@ -162,8 +165,8 @@ extern "C" int n2n_mask_pair_from_rdidx(const int64_t* rd_idx, int64_t cells, ui
   N2N_CHECK_ARG(rd_idx != nullptr && cells >= 0, "mask_pair_from_rdidx: bad arguments");
   N2N_CHECK_ARG(((uintptr_t)mask1 % 4) == 0 && ((uintptr_t)mask2 % 4) == 0, "mask_pair_from_rdidx: masks must be 4-byte aligned");
   if (cells == 0) return 0;
-  mask_pair_kernel<<<grid_for(cells, 256), 256, 0, (cudaStream_t)stream>>>(rd_idx, cells, (uint32_t*)mask1,
-                                                                            (uint32_t*)mask2, packed_sel);
+  (void)launch_pdl_v(mask_pair_kernel, dim3(grid_for(cells, 256)), dim3(256), 0, (cudaStream_t)stream, rd_idx, cells,
+                     (uint32_t*)mask1, (uint32_t*)mask2, packed_sel);
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -167,6 +167,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
       }
     }
     __syncwarp();
+    pdl_wait();
     int stage = 0; uint32_t phase = 0;
     long long st_prod = 0;
     const long long k0 = clock64();
@@ -214,6 +215,8 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
   } else if (warp == 1) {
     // ---- MMA issuer: whole warp converged, one elected lane issues tcgen05.mma / commit ----
     int stage = 0; uint32_t phase = 0;
+    pdl_wait();
+    pdl_release();
     if (p.resident_b) mbar_wait(bfull_bar, 0);
     const uint32_t dhi = desc_hi(256, kSwizzle32);
     const uint32_t a_sub16 = p.a_sub >> 4, b_sub16 = b_sub >> 4;
@@ -270,6 +273,7 @@ tapgemm_umma_kernel(const __grid_constant__ UmmaGemmParams p) {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32) ----
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
+    pdl_wait();
     const int py = m / p.bw, px = m - py * p.bw;
     const int nblk = p.nout / 16;
     long long st_tfull = 0;
@@ -484,7 +488,7 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = tiles < num_sms() ? (int)tiles : num_sms();
-  tapgemm_umma_kernel<<<grid, kThreads, smem, st>>>(p);
+  N2N_CUDA(launch_pdl(tapgemm_umma_kernel, dim3(grid), dim3(kThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }

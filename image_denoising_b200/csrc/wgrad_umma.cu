@@ -71,6 +71,8 @@ tapwgrad_umma_kernel(const __grid_constant__ UmmaWgradParams p) {
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   const bool has_work = chunk_end > chunk_begin;
+  pdl_wait();
+  if (threadIdx.x == 32) pdl_release();
 
   if (warp == 0) {
     if (lane == 0 && has_work) {
@@ -180,6 +182,7 @@ __device__ __forceinline__ void bg_accum(const __nv_bfloat16* p, float s[16]) {
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(View dy0, View dy1, View dy2, View dy3, int ndyviews, long long pixels, long long per_split,
                  float* __restrict__ bias_partial, int npad) {
+  pdl_enter();
   __shared__ float red[8][16];
   const int cb = blockIdx.y;
   const int split = blockIdx.x / ndyviews, vi = blockIdx.x - split * ndyviews;
@@ -245,8 +248,8 @@ int launch_bias_grad(const TapWgrad& g, cudaStream_t st) {
   const long long pixels = (long long)g.dy[0].N * g.dy[0].H * g.dy[0].W;
   const long long per_split = (pixels + splits - 1) / splits;
   dim3 bgrid(splits * g.ndyviews, g.n_blocks);
-  bias_grad_kernel<<<bgrid, 256, 0, st>>>(g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, pixels, per_split,
-                                          g.bias_partial, g.n_blocks * 16);
+  (void)launch_pdl_v(bias_grad_kernel, bgrid, dim3(256), 0, st, g.dy[0], g.dy[1], g.dy[2], g.dy[3], g.ndyviews, pixels, per_split,
+                     g.bias_partial, g.n_blocks * 16);
   N2N_LAUNCH_CHECK();
   return 0;
 }
@@ -310,7 +313,7 @@ int launch_tapwgrad_umma(const TapWgrad& g, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(splits, tgroups);
-  tapwgrad_umma_kernel<<<grid, kThreadsW, smem, st>>>(p);
+  N2N_CUDA(launch_pdl(tapwgrad_umma_kernel, grid, dim3(kThreadsW), smem, st, p));
   N2N_LAUNCH_CHECK();
   return launch_bias_grad(g, st);
 }
