@@ -282,6 +282,8 @@ int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cuda
 // dst[p, (ky*3+kx)*C + c] = src[c, y+ky-1, x+kx-1] (zero outside the image): the 3x3 im2col of a
 // C-channel NCHW image as ceil(9C/16) C16 blocks, so that a 3x3 conv over it is ONE K = 16 (32) GEMM step
 int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, cudaStream_t st);
+int launch_input_stage(const float* x, int C, const float* w, const float* bias, int Cout, const View& col,
+                       const View& e0, float slope, cudaStream_t st);
 int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream_t st);
 int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st);
 int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype, cudaStream_t st);

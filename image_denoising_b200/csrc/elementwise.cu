@@ -93,6 +93,86 @@ int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Input stage of the bf16 UNet plan: one pass over the fp32 NCHW input writes BOTH the 3x3 im2col
+// block(s) (dec_conv1a's raw-input operand, enc_conv0's weight-gradient operand) and enc_conv0's
+// activated output (conv3x3 in_nc -> Cout + bias + LeakyReLU, arch_unet.py:114-116 / :201) as C16
+// bf16.  The conv has K = 9*in_nc <= 27: it is HBM-bound (write 32 B per 16 output channels per
+// pixel), so it runs on the CUDA cores in fp32 straight from the fp32 weights instead of going
+// through a K=16-padded tensor-core GEMM and a second pass over the im2col block.
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128)
+input_stage_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                   View col, View e0, float slope, long long pixels) {
+  pdl_enter();
+  constexpr int K = 9 * C;
+  __shared__ __align__(16) float s_w[K * 64];      // [k = tap*C + c][co], co padded to 64
+  __shared__ float s_b[64];
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) {
+    const int k = i >> 6, co = i & 63;
+    const int tap = k / C, c = k - tap * C;
+    s_w[i] = co < Cout ? w[((long long)co * C + c) * 9 + tap] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = i < Cout ? bias[i] : 0.f;
+  __syncthreads();
+  const int H = e0.H, W = e0.W;
+  const long long hw = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(p / hw);
+    const int r = (int)(p - (long long)n * hw);
+    const int y = r / W, xx = r - y * W;
+    float t[K];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = y + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      const bool in = sy >= 0 && sy < H && sx >= 0 && sx < W;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        t[tap * C + c] = in ? x[((long long)n * C + c) * hw + (long long)sy * W + sx] : 0.f;
+    }
+    // im2col block(s)
+#pragma unroll
+    for (int cb = 0; cb < (K + 15) / 16; ++cb) {
+      float v[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = (cb * 16 + q < K) ? t[(cb * 16 + q < K) ? cb * 16 + q : 0] : 0.f;
+      Block16<__nv_bfloat16>::store((__nv_bfloat16*)col.ptr + n * col.sN + cb * col.sCb + y * col.sY + xx * col.sX, v);
+    }
+    // enc_conv0 + bias + LeakyReLU
+    for (int cb = 0; cb < e0.Cb; ++cb) {
+      float acc[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = s_b[cb * 16 + q];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[k * 64 + cb * 16]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = wr[q];
+          acc[4 * q] += t[k] * wv.x; acc[4 * q + 1] += t[k] * wv.y; acc[4 * q + 2] += t[k] * wv.z; acc[4 * q + 3] += t[k] * wv.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = acc[q] > 0.f ? acc[q] : acc[q] * slope;
+      Block16<__nv_bfloat16>::store((__nv_bfloat16*)e0.ptr + n * e0.sN + cb * e0.sCb + y * e0.sY + xx * e0.sX, acc);
+    }
+  }
+}
+
+// Returns kSgNotEligible when the shape is not covered (caller uses im2col + GEMM).
+int launch_input_stage(const float* x, int C, const float* w, const float* bias, int Cout, const View& col,
+                       const View& e0, float slope, cudaStream_t st) {
+  if ((C != 1 && C != 3) || Cout > 64 || e0.Cb * 16 < Cout || col.Cb != (9 * C + 15) / 16) return kSgNotEligible;
+  { const char* e = getenv("N2N_NO_INPUT_STAGE"); if (e && atoi(e)) return kSgNotEligible; }
+  const long long pixels = (long long)e0.N * e0.H * e0.W;
+  const int grid = grid_for(pixels, 128, 16);
+  if (C == 1) (void)launch_pdl_v(input_stage_kernel<1>, dim3(grid), dim3(128), 0, st, x, w, bias, Cout, col, e0, slope, pixels);
+  else (void)launch_pdl_v(input_stage_kernel<3>, dim3(grid), dim3(128), 0, st, x, w, bias, Cout, col, e0, slope, pixels);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_nchw_to_c16(const float* src, int C, const View& dst, int dtype, cudaStream_t st) {
   N2N_CHECK_ARG(C >= 1 && C <= 16 * dst.Cb, "nchw_to_c16: C=%d does not fit %d blocks", C, dst.Cb);
   long long items = (long long)dst.N * dst.Cb * dst.H * dst.W;

@@ -277,8 +277,16 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     N2N_TRY(launch_bias_pad(bj, 25, st));
   }
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
-  if (p->im2col) N2N_TRY(launch_nchw_to_im2col9(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->kb), dt, st));
-  else N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
+  bool enc0_done = false;     // the fused input stage also produced enc_conv0's output
+  if (p->im2col) {
+    const int r = launch_input_stage(x, p->in_nc, params[0], params[1], p->nf, p->view(p->act, ws, B_CAT0, p->c2b, p->kb),
+                                     p->view(p->act, ws, B_E0, 0, p->nfb), 0.2f, st);
+    if (r < 0) return r;
+    enc0_done = r == 0;
+    if (!enc0_done) N2N_TRY(launch_nchw_to_im2col9(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->kb), dt, st));
+  } else {
+    N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
+  }
 
   auto run_layer = [&](int i, int pool_buf = -1, int pool_cb0 = 0) -> int {
     const LayerIO& io = p->io[i];
@@ -344,7 +352,7 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     }
     return launch_tapgemm(g, st);
   };
-  N2N_TRY(run_layer(0));
+  if (!enc0_done) N2N_TRY(run_layer(0));
   N2N_TRY(run_layer(1, B_CAT1, p->c2b));
   N2N_TRY(run_layer(2, B_CAT2, p->c2b));
   N2N_TRY(run_layer(3, B_CAT3, p->c2b));

@@ -28,7 +28,7 @@ def fwd_names(res):
     def dxa(name, r):
         return [name + ".k0", name + ".k1"] if r % 16 == 0 else [name]
     r = res
-    out = ["enc0", "enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]
+    out = ["enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]          # enc0 runs in the fused input stage (not a GEMM launch)
     out += up("up5", r // 32) + ["d5a", "d5b"]
     out += up("up4", r // 16) + dxa("d4a", r // 8) + ["d4b"]
     out += up("up3", r // 8) + dxa("d3a", r // 4) + ["d3b"]
