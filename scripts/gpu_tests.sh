@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv
 rc=0
-for f in test_gpu_umma_probe test_gpu_kernels test_gpu_network test_gpu_entry; do
+for f in test_gpu_umma_probe test_gpu_kernels test_gpu_network test_gpu_entry test_gpu_fullsize; do
   timeout 1200 python -m pytest tests/$f.py -q -s -m gpu --timeout 600 > gpurun_out/$f.log 2>&1
   r=$?; echo "$f rc=$r"; [ $r -ne 0 ] && rc=1
   grep -E "passed|failed" gpurun_out/$f.log | tail -1

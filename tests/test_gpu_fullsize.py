@@ -1,0 +1,101 @@
+"""Full-size checks of the production path (BASELINE.json configs[2..4]) through size-independent
+properties — the oracle cannot run these sizes in test time:
+
+* the CUDA-graph replay of the training step (PDL launches, side-stream weight gradients) is
+  bit-identical to the eager launch sequence, and the step is deterministic run to run
+  (fixed-order split-K / loss reductions);
+* the bf16 tensor-core engine and the fp32 CUDA-core parity engine (itself checked against the
+  oracle at small sizes) agree on a 704x704 whole-image forward within the north-star tolerance
+  (PSNR delta < 0.01 dB), and on the input gradient at RGB width;
+* evaluation metrics are invariant to how images are batched."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import n2n_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _make(dev, precision, in_nc=1, nf=48, seed=3):
+    from image_denoising_b200 import UNet
+    p = O.unet_init(in_nc, in_nc, nf, seed)
+    net = UNet(in_nc=in_nc, out_nc=in_nc, n_feature=nf)
+    net.load_state_dict(p)
+    return net.to(dev).set_precision(precision)
+
+
+def test_graph_replay_equals_eager_at_bench_shape(dev):
+    from image_denoising_b200 import N2NTrainer
+    g = torch.Generator(device=dev).manual_seed(7)
+    batches = []
+    for _ in range(3):
+        clean = torch.rand((64, 1, 256, 256), generator=g, device=dev)
+        batches.append(clean + torch.randn(clean.shape, generator=g, device=dev) * (25 / 255))
+    rds = [torch.randint(0, 8, (64 * 128 * 128,), generator=g, device=dev) for _ in range(3)]
+    results = []
+    for use_graph in (False, True, True):
+        tr = N2NTrainer(_make(dev, "bf16"), lr=3e-4, precision="bf16", use_graph=use_graph)
+        losses = []
+        for i in range(3):
+            losses.append(tr.step(batches[i], 0.5, rd_idx=rds[i]).clone())
+        torch.cuda.synchronize()
+        results.append((torch.stack(losses).cpu(), tr.flat_p.clone().cpu(), tr.flat_g.clone().cpu()))
+        assert use_graph == (tr._graph is not None)
+        del tr
+    (l0, p0, g0), (l1, p1, g1), (l2, p2, g2) = results
+    assert torch.isfinite(l0).all() and torch.isfinite(p0).all()
+    assert torch.equal(l0, l1) and torch.equal(g0, g1) and torch.equal(p0, p1), "graph replay differs from eager launches"
+    assert torch.equal(l1, l2) and torch.equal(p1, p2), "training step is not deterministic"
+    assert l0[2, 0] < l0[0, 0]          # and it trains
+
+
+def test_704_whole_image_bf16_vs_fp32_engine(dev):
+    g = torch.Generator().manual_seed(21)
+    clean = torch.rand(1, 1, 704, 704, generator=g)
+    noisy = (clean + torch.randn(clean.shape, generator=g) * (25 / 255)).to(dev)
+    with torch.no_grad():
+        y32 = _make(dev, "fp32")(noisy).cpu()
+        y16 = _make(dev, "bf16")(noisy).cpu()
+    def psnr(a):
+        return 10 * np.log10(1.0 / float(((a - clean) ** 2).mean()))
+    assert abs(psnr(y16) - psnr(y32)) < 0.01
+    assert float((y16 - y32).abs().max()) < 0.05 * float(y32.abs().max())
+
+
+def test_rgb_input_gradient_bf16_vs_fp32_engine(dev):
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    grads = {}
+    for precision in ("fp32", "bf16"):
+        net = _make(dev, precision, in_nc=3, nf=48, seed=9)
+        xd = x.to(dev).requires_grad_(True)
+        net(xd).square().sum().backward()
+        grads[precision] = (xd.grad.cpu().double(), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu().double())
+    for a, b in zip(grads["bf16"], grads["fp32"]):
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > 0.995, cos
+
+
+def test_eval_metrics_independent_of_batching(dev):
+    from image_denoising_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    clean = (torch.rand(6, 352, 352, generator=g) * 255).to(torch.uint8)
+    noisy = (clean.float() + torch.randn(clean.shape, generator=g) * 25).clamp(0, 255).to(torch.uint8)
+    net = _make(dev, "bf16")
+    def run(bs):
+        out = []
+        for i in range(0, 6, bs):
+            with torch.no_grad():
+                pred = net((noisy[i:i + bs].to(dev).float() / 255).unsqueeze(1))
+            q = ops.quantize_u8(pred, 0.5).squeeze(1)
+            out.append(ops.psnr_ssim_u8(q, clean[i:i + bs].to(dev)).cpu())
+        return torch.cat(out)
+    assert torch.equal(run(6), run(2)) and torch.equal(run(6), run(1))
