@@ -154,6 +154,9 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Producers of data that a successor loads BEFORE its own wait (packed weights, padded biases) must not
+// release their dependents early: they only wait, so that the successor starts after they complete.
+__device__ __forceinline__ void pdl_enter_no_release() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl_v(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   static int use_pdl = -1;

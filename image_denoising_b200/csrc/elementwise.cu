@@ -195,7 +195,7 @@ int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream
 
 struct BiasPadBatch { BiasPadJob j[32]; int n; };
 __global__ void bias_pad_kernel(const __grid_constant__ BiasPadBatch b) {
-  pdl_enter();
+  pdl_enter_no_release();   // its output is prefetched by the next GEMM's prologue
   const BiasPadJob& J = b.j[blockIdx.x];
   for (int i = threadIdx.x; i < J.npad; i += blockDim.x) J.dst[i] = (i < J.n && J.src) ? J.src[i] : 0.f;
 }

@@ -25,7 +25,7 @@ namespace n2n {
 using namespace umma;
 
 constexpr int kHdThreads = 576;            // TMA warp, MMA warp, 8 warps for stage E1, 8 for stage E2
-constexpr int kHdRing = 3;
+constexpr int kHdRing = 5;
 constexpr int kHdMaxOut = 4;
 
 struct HdParams {
@@ -114,7 +114,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   // barriers: x_full[3] x_empty[3] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[2] d2_empty[2] w_full
   __shared__ uint64_t bars[2 * kHdRing + 12 + 1];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_ba[128], s_bb[128], s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
+  __shared__ __align__(16) float s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -122,6 +122,11 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   const uint32_t wa0 = smem0, wb0 = wa0 + p.wa_bytes;
   const uint32_t x0s = wb0 + p.wb_bytes;                     // X ring
   const uint32_t h0s = x0s + kHdRing * p.x_bytes;            // H1 double buffer
+  // Bias through the tensor core: one extra K block whose activation operand is constant (channels 0, 1 = 1)
+  // and whose weight rows carry the bias split into bf16 hi + lo parts — 16 FADD + 4 LDS less per
+  // epilogue block, for one more (cheap) MMA per tile and GEMM.
+  const uint32_t ones0 = h0s + 2 * p.h_bytes;                // [128 rows][32 B]
+  const uint32_t bia0 = ones0 + 4096u, bib0 = bia0 + (uint32_t)p.mid_blocks * 16u * 32u;
   const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](int s) { return bar0 + 8u * s; };
   auto x_empty = [&](int s) { return bar0 + 8u * (kHdRing + s); };
@@ -144,15 +149,28 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 128; i += kHdThreads) {
-    s_ba[i] = i < nmid ? p.bias_a[i] : 0.f;
-    s_bb[i] = i < nmid ? p.bias_b[i] : 0.f;
-  }
   for (int i = threadIdx.x; i < kHdMaxOut * 128; i += kHdThreads) {
     const int oc = i >> 7, c = i & 127;
     s_wc[i] = (oc < p.out_nc && c < nmid) ? p.wc[oc * nmid + c] : 0.f;
   }
   if (threadIdx.x < kHdMaxOut) s_bc[threadIdx.x] = threadIdx.x < p.out_nc ? p.bias_c[threadIdx.x] : 0.f;
+  {
+    uint8_t* base = smem_raw + (smem0 - smem_u32(smem_raw));
+    for (int r = threadIdx.x; r < 128 + 2 * nmid; r += kHdThreads) {
+      // rows 0..127: the ones block; then nmid rows of bias_a, then nmid rows of bias_b
+      const uint32_t addr = r < 128 ? ones0 + r * 32u : (r < 128 + nmid ? bia0 + (r - 128) * 32u : bib0 + (r - 128 - nmid) * 32u);
+      float v = 1.0f;
+      if (r >= 128) v = r < 128 + nmid ? p.bias_a[r - 128] : p.bias_b[r - 128 - nmid];
+      const __nv_bfloat16 hi_part = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo_part = r < 128 ? hi_part : __float2bfloat16_rn(v - __bfloat162float(hi_part));
+      const uint32_t sw = (addr >> 7) & 1u;                  // logical chunk 0 sits in physical chunk sw
+      uint4* row = reinterpret_cast<uint4*>(base + (addr - smem0));
+      __nv_bfloat162 h2 = __halves2bfloat162(hi_part, lo_part);
+      row[sw] = make_uint4(*reinterpret_cast<uint32_t*>(&h2), 0u, 0u, 0u);
+      row[sw ^ 1u] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols); tmem_relinquish(); }
   fence_before_sync();
   __syncthreads();
@@ -201,6 +219,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         const uint32_t b_lo = ((wa0 & 0x3FFFFu) >> 4) | (1u << 16);
         for (int cb = 0; cb < p.in_blocks; ++cb)
           hd_mma(tmem_base + (uint32_t)(b * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+        hd_mma(tmem_base + (uint32_t)(b * nmid), ((ones0 & 0x3FFFFu) >> 4) | (1u << 16), ((bia0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
         mma_commit(x_empty(slot));
         mma_commit(d1_full(b));
       }
@@ -216,6 +235,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         const uint32_t b_lo = ((wb0 & 0x3FFFFu) >> 4) | (1u << 16);
         for (int cb = 0; cb < p.mid_blocks; ++cb)
           hd_mma(tmem_base + (uint32_t)((2 + b) * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+        hd_mma(tmem_base + (uint32_t)((2 + b) * nmid), ((ones0 & 0x3FFFFu) >> 4) | (1u << 16), ((bib0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
         mma_commit(h_empty(b));
         mma_commit(d2_full(b));
       }
@@ -256,38 +276,46 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
       if (is_e1) {
         // ---- E1: D1 -> H1 (shared-memory operand of MMA-2) ----
-        hd_wait(d1_full(b), par);
-        hd_wait(h_empty(b), par ^ 1u);
+        // one warp of the group polls the mbarriers, the other three park on a hardware named barrier
+        // (every mbarrier event wakes every polling warp of the CTA: fewer pollers, fewer wasted issue slots)
+        if (quarter == 0) { hd_wait(d1_full(b), par); hd_wait(h_empty(b), par ^ 1u); }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         fence_after_sync();
         const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
-        uint32_t rr[16];
-        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), rr);
+        // two accumulator-read buffers in ping-pong: the read of block cb+1 is in flight while block cb is processed
+        uint32_t ra[16], rb[16];
+        auto e1_block = [&](int cb, const uint32_t* rv) {
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a0 = __uint_as_float(rv[4 * q]), a1 = __uint_as_float(rv[4 * q + 1]);      // bias already in the accumulator
+              float a2 = __uint_as_float(rv[4 * q + 2]), a3 = __uint_as_float(rv[4 * q + 3]);
+              // LeakyReLU with 0 <= slope <= 1 is max(a, slope * a): two instructions per element
+              a0 = fmaxf(a0, a0 * p.slope); a1 = fmaxf(a1, a1 * p.slope);
+              a2 = fmaxf(a2, a2 * p.slope); a3 = fmaxf(a3, a3 * p.slope);
+              __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+              w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+              w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+            }
+            // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
+            const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
+            const uint32_t sw = ((h0s + off) >> 7) & 1u;
+            uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
+            dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+        };
+        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), ra);
 #pragma unroll 1
-        for (int cb = cb_lo; cb < cb_hi; ++cb) {
-          uint32_t rv[16];
+        for (int cb = cb_lo; cb < cb_hi; cb += 2) {
           hd_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 16; ++q) rv[q] = rr[q];
-          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 1) * 16), rr);   // one block ahead
-          uint32_t w[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(&s_ba[cb * 16 + 4 * q]);
-            float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
-            float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
-            a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
-            a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
-            __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-            w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
-            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 1) * 16), rb);
+          e1_block(cb, ra);
+          if (cb + 1 < cb_hi) {
+            hd_ld_wait();
+            if (cb + 2 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 2) * 16), ra);
+            e1_block(cb + 1, rb);
           }
-          // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
-          const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-          const uint32_t sw = ((h0s + off) >> 7) & 1u;
-          uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
-          dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-          dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
         }
         fence_before_sync();
         fence_proxy_async();                 // generic-proxy writes of H1 -> visible to the tensor core
@@ -295,48 +323,54 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         if (lane == 0) { mbar_arrive(d1_empty(b)); mbar_arrive(h_full(b)); }
       } else {
         // ---- E2: D2 -> nin_c -> fp32 NCHW ----
-        hd_wait(d2_full(b), par);
+        if (quarter == 0) hd_wait(d2_full(b), par);
+        asm volatile("bar.sync %0, 128;" ::"r"(3 + group) : "memory");
         fence_after_sync();
         const long long spix = p.has_save ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
         float o[kHdMaxOut];
 #pragma unroll
         for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
-        uint32_t rr[16];
-        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + cb_lo * 16), rr);
-#pragma unroll 1
-        for (int cb = cb_lo; cb < cb_hi; ++cb) {
-          uint32_t rv[16];
-          hd_ld_wait();
+        uint32_t ra[16], rb[16];
+        auto e2_block = [&](int cb, const uint32_t* rv) {
+            float v[16];
+            uint32_t w[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) rv[q] = rr[q];
-          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 1) * 16), rr);
-          float v[16];
-          uint32_t w[8];
+            for (int q = 0; q < 4; ++q) {
+              float a0 = __uint_as_float(rv[4 * q]), a1 = __uint_as_float(rv[4 * q + 1]);
+              float a2 = __uint_as_float(rv[4 * q + 2]), a3 = __uint_as_float(rv[4 * q + 3]);
+              // LeakyReLU with 0 <= slope <= 1 is max(a, slope * a): two instructions per element
+              a0 = fmaxf(a0, a0 * p.slope); a1 = fmaxf(a1, a1 * p.slope);
+              a2 = fmaxf(a2, a2 * p.slope); a3 = fmaxf(a3, a3 * p.slope);
+              // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
+              __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+              w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
+              w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
+              v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
+              v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
+            }
+            if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(&s_bb[cb * 16 + 4 * q]);
-            float a0 = __uint_as_float(rv[4 * q]) + bb.x, a1 = __uint_as_float(rv[4 * q + 1]) + bb.y;
-            float a2 = __uint_as_float(rv[4 * q + 2]) + bb.z, a3 = __uint_as_float(rv[4 * q + 3]) + bb.w;
-            a0 = a0 > 0.f ? a0 : a0 * p.slope; a1 = a1 > 0.f ? a1 : a1 * p.slope;
-            a2 = a2 > 0.f ? a2 : a2 * p.slope; a3 = a3 > 0.f ? a3 : a3 * p.slope;
-            // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
-            __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-            w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
-            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
-            v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
-            v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
-          }
-          if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+            for (int oc = 0; oc < kHdMaxOut; ++oc) {
+              if (oc < p.out_nc) {
+                const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
 #pragma unroll
-          for (int oc = 0; oc < kHdMaxOut; ++oc) {
-            if (oc < p.out_nc) {
-              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 wv = wr[q];
-                o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
+                for (int q = 0; q < 4; ++q) {
+                  const float4 wv = wr[q];
+                  o[oc] += v[4 * q] * wv.x + v[4 * q + 1] * wv.y + v[4 * q + 2] * wv.z + v[4 * q + 3] * wv.w;
+                }
               }
             }
+        };
+        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + cb_lo * 16), ra);
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; cb += 2) {
+          hd_ld_wait();
+          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 1) * 16), rb);
+          e2_block(cb, ra);
+          if (cb + 1 < cb_hi) {
+            hd_ld_wait();
+            if (cb + 2 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 2) * 16), ra);
+            e2_block(cb + 1, rb);
           }
         }
         fence_before_sync();
@@ -383,7 +417,8 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   p.bias_a = h.bias_a; p.bias_b = h.bias_b; p.wc = h.wc; p.bias_c = h.bias_c;
   p.out_nchw = h.out_nchw; p.x = h.x; p.save_a = h.save_a; p.save_b = h.save_b;
   N2N_TRY(encode_c16_tensor_map(&p.tmap_x, h.x, 8, 16, h.in_blocks));
-  const size_t smem = 1024 + (size_t)p.wa_bytes + p.wb_bytes + (size_t)kHdRing * p.x_bytes + 2 * (size_t)p.h_bytes;
+  const size_t smem = 1024 + (size_t)p.wa_bytes + p.wb_bytes + (size_t)kHdRing * p.x_bytes + 2 * (size_t)p.h_bytes +
+                      4096 + 2 * (size_t)nmid * 32;
   if (smem > 220 * 1024) return kSgNotEligible;
   if (!attr_set) {
     N2N_CUDA(cudaFuncSetAttribute(head_chain_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

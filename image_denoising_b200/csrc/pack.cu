@@ -36,7 +36,7 @@ struct UnpackBatch { UnpackJob j[8]; int n; };
 
 template <bool BF16>
 __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
-  pdl_enter();
+  pdl_enter_no_release();   // its output is prefetched by the next GEMM's prologue
   const PackJob& J = b.j[blockIdx.y];
   const int cpad = J.cin_blocks * 16;
   const long long total = (long long)J.ntaps * J.nout_pad * cpad;

@@ -155,7 +155,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   }
   if (p.act && !(p.dbg_flags & 16)) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+    for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], v[q] * p.slope);     // LeakyReLU / ReLU, 0 <= slope <= 1
   }
   if (p.has_mask) {
     uint32_t aw[8]; float t[16];
@@ -384,7 +384,9 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (cb_lo < nblk) ld_global_32B(ab + cb_lo * as, ax0);
         if (cb_lo + 1 < nblk) ld_global_32B(ab + (cb_lo + 1) * as, ax1);
       }
-      sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      // one warp of the group polls the mbarrier, the other three park on a hardware named barrier
+      if (quarter == 0) sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       fence_after_sync();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
 #pragma unroll 1

@@ -120,8 +120,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 // read (activations, gradients, partials).  Rule used throughout: a kernel releases its own
 // dependents (pdl_release) only AFTER its own pdl_wait, so when a kernel starts, every kernel before
 // its immediate predecessor has completed — which is what makes the early weight / bias loads safe
-// (they are written by the pack kernels at the start of the pass, never by the immediate predecessor
-// of a PDL launch: non-PDL kernels release their dependents only by completing).
+// (they are written by the pack / bias-pad kernels, which wait but never release early —
+// pdl_enter_no_release() in common.cuh — so a kernel launched right behind them starts only after
+// they have completed).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
