@@ -194,7 +194,8 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
       const uint32_t sw = ((uint32_t)m >> 2) & 1u;
       int slot = 0; uint32_t phase = 0;
       for (long long tile = tile_begin; tile < tile_end; ++tile) {
-        ws_wait(full_bar(slot), phase);
+        if (quarter == 0) ws_wait(full_bar(slot), phase);          // one polling warp, three parked on a named barrier
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         const uint8_t* row = smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)slot * p.slot_bytes + (size_t)m * 32;
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb) {
