@@ -599,7 +599,7 @@ probe_mma_rate_kernel(int layout, int N, int iters, int naccum, long long* __res
   __shared__ uint32_t tmem_base_smem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 60 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (smem0 - smem_u32(smem_raw)))[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 100 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (smem0 - smem_u32(smem_raw)))[i] = 0x3c003c00u;
   fence_proxy_async();
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
@@ -607,6 +607,8 @@ probe_mma_rate_kernel(int layout, int N, int iters, int naccum, long long* __res
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  const int distinct = layout >> 3;      // layout + 8: every MMA reads a different A and B tile (8 of each, cycled)
+  layout &= 7;
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N, false, false);
     const uint32_t rowb = layout == 0 ? 32u : (layout == 1 ? 128u : 64u);
@@ -622,8 +624,11 @@ probe_mma_rate_kernel(int layout, int N, int iters, int naccum, long long* __res
     mma_bf16_lo(d1, a_lo, b_lo, hi, idesc, 0);
     for (int it = 0; it < iters; it += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        mma_bf16_lo((u & 1) ? d1 : tmem_base, a_lo + ((u & (ksteps - 1)) << 1), b_lo + ((u & (ksteps - 1)) << 1), hi, idesc, 1);
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t ao = distinct ? (uint32_t)u * (4096u >> 4) : ((u & (ksteps - 1)) << 1);
+        const uint32_t bo = distinct ? (32768u >> 4) + (uint32_t)u * ((uint32_t)N * 32u >> 4) - ((128u * rowb) >> 4) : ((u & (ksteps - 1)) << 1);
+        mma_bf16_lo((u & 1) ? d1 : tmem_base, a_lo + ao, b_lo + bo, hi, idesc, 1);
+      }
     }
     mma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -653,10 +658,10 @@ extern "C" int n2n_probe_umma(int variant, const void* a_bf16, const void* b_bf1
 }
 
 extern "C" int n2n_probe_mma_rate(int layout, int n, int iters, int naccum, long long* cycles_dev, int nblocks, void* stream) {
-  N2N_CHECK_ARG(layout >= 0 && layout <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && naccum >= 1 &&
+  N2N_CHECK_ARG((layout & 7) >= 0 && (layout & 7) <= 2 && layout < 16 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && naccum >= 1 &&
                     naccum * n <= 512 && cycles_dev && nblocks > 0, "probe_mma_rate: bad arguments");
-  N2N_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  probe_mma_rate_kernel<<<nblocks, 128, 62 * 1024, (cudaStream_t)stream>>>(layout, n, iters, naccum, cycles_dev);
+  N2N_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+  probe_mma_rate_kernel<<<nblocks, 128, 102 * 1024, (cudaStream_t)stream>>>(layout, n, iters, naccum, cycles_dev);
   N2N_LAUNCH_CHECK();
   return 0;
 }
