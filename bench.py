@@ -325,7 +325,8 @@ def run_b200(args):
                 "kernel": "slabgemm_umma_kernel (+ head_chain_umma / tapgemm_umma for the shapes it declines): conv/deconv "
                           "forward + input gradient, %d launches/step" % round(tap_n / psteps),
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
-                "traffic": _traffic_note(), "peak_source": pk["src"],
+                "traffic": (_traffic_note() or {}).get("bytes_per_launch"), "traffic_detail": _traffic_note(),
+                "peak_source": pk["src"],
                 "share_of_step": tap_ms / psteps / (ms / args.steps),
                 "executed_tflops_incl_padding": tap_flops_exec / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0,
                 "wgrad_kernel": {"achieved": (GFLOP_WGRAD_PER_PATCH * 1e9 * B * psteps) / (wg_ms / 1e3) / 1e12 if wg_ms > 0 else 0.0,
