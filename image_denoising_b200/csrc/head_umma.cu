@@ -271,6 +271,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       const int r = tile - img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * 16 + py, x = tx * 8 + px;
+      const bool valid = y < p.x.H && x < p.x.W;          // edge tiles
       const int b = lt & 1;
       const uint32_t par = ((uint32_t)lt >> 1) & 1u;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -303,7 +304,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
             uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
             dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
             dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-            if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+            if (p.has_save && valid) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
         };
         if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), ra);
 #pragma unroll 1
@@ -348,7 +349,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
               v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
               v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
             }
-            if (p.has_save) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+            if (p.has_save && valid) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
 #pragma unroll
             for (int oc = 0; oc < kHdMaxOut; ++oc) {
               if (oc < p.out_nc) {
@@ -379,7 +380,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         const long long hw = (long long)p.x.H * p.x.W;
 #pragma unroll
         for (int oc = 0; oc < kHdMaxOut; ++oc)
-          if (oc < p.out_nc) p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc];
+          if (oc < p.out_nc && valid) p.out_nchw[((long long)img * p.out_nc + oc) * hw + (long long)y * p.x.W + x] = o[oc];
       }
     }
   }
@@ -395,11 +396,11 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
   if (h.in_blocks < 1 || h.in_blocks > 8 || h.mid_blocks < 1 || h.mid_blocks > 8 || h.out_nc < 1 || h.out_nc > kHdMaxOut)
     return kSgNotEligible;
-  if (h.x.H % 16 || h.x.W % 8 || h.mid_channels != h.mid_blocks * 16 ) return kSgNotEligible;
+  if (h.x.H < 4 || h.x.W < 4 || h.mid_channels != h.mid_blocks * 16) return kSgNotEligible;
   HdParams p;
   memset(&p, 0, sizeof(p));
   p.in_blocks = h.in_blocks; p.mid_blocks = h.mid_blocks; p.out_nc = h.out_nc;
-  p.tiles_x = h.x.W / 8; p.tiles_y = h.x.H / 16;
+  p.tiles_x = (h.x.W + 7) / 8; p.tiles_y = (h.x.H + 15) / 16;
   const long long tiles = (long long)h.x.N * p.tiles_x * p.tiles_y;
   N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "head_chain: bad tile count");
   p.ntiles = (int)tiles;

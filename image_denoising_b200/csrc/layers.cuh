@@ -184,10 +184,10 @@ inline TapWgrad make_deconv_wgrad(const LayerGeom& L, int dtype, const View& x, 
 // engine wants (splits x tap groups) = one CTA per SM; other geometries keep the old default.
 int wgrad_slab_splits(int npairs, int variant_blocks, int common_blocks, bool box_per_tap, long long tiles);
 inline int layer_wgrad_splits(const LayerGeom& L, int dtype, int n, int h, int w) {
-  if (dtype == N2N_BF16 && h % 16 == 0 && w % 8 == 0) {
+  if (dtype == N2N_BF16 && h >= 4 && w >= 4) {
     const bool dc = L.kind == L_DECONV;
     const int s = wgrad_slab_splits(L.ntaps(), dc ? L.cout_blocks() : L.cin_blocks(), dc ? L.cin_blocks() : L.cout_blocks(), dc,
-                                    (long long)n * (h / 16) * (w / 8));
+                                    (long long)n * ((h + 15) / 16) * ((w + 7) / 8));
     if (s > 0) return s;
   }
   return wgrad_default_splits(dtype, (long long)n * h * w);

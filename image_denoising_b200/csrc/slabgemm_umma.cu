@@ -122,6 +122,7 @@ __device__ __forceinline__ void unpack_bf16x16(const uint32_t w[8], float v[16])
 
 struct SgPix {
   int img, y, x;
+  bool valid;          // pixel inside the image (edge tiles of images that are not multiples of 8 x 16)
   long long ypix, apix, mpix, ppix;
 };
 
@@ -146,8 +147,11 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     if (aux && !p.has_mask) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) aw[q] = aux[q];
-    } else {
+    } else if (c.valid) {
       ld_global_32B((const __nv_bfloat16*)p.addend.ptr + c.apix + cb * p.addend.sCb, aw);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aw[q] = 0u;
     }
     unpack_bf16x16(aw, t);
 #pragma unroll
@@ -162,8 +166,11 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     if (aux) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) aw[q] = aux[q];
-    } else {
+    } else if (c.valid) {
       ld_global_32B((const __nv_bfloat16*)p.mask.ptr + c.mpix + cb * p.mask.sCb, aw);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aw[q] = 0u;
     }
     unpack_bf16x16(aw, t);
 #pragma unroll
@@ -174,7 +181,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int n = cb * 16 + q;
-      if (n < p.out_c) p.out_nchw[((long long)c.img * p.out_c + n) * hw + (long long)c.y * p.y.W + c.x] = v[q];
+      if (n < p.out_c && c.valid) p.out_nchw[((long long)c.img * p.out_c + n) * hw + (long long)c.y * p.y.W + c.x] = v[q];
     }
     return;
   }
@@ -184,7 +191,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     w[j] = *reinterpret_cast<uint32_t*>(&h);
   }
-  if (p.store_y && !(p.dbg_flags & 32)) {
+  if (p.store_y && c.valid && !(p.dbg_flags & 32)) {
     long long o = c.ypix;
     int cbr = cb;
     if (p.n_split && cb >= p.n_split) { cbr = cb - p.n_split; o += p.split_stride; }
@@ -202,7 +209,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
       a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
       w[j] = *reinterpret_cast<uint32_t*>(&a);
     }
-    if ((lane & 9) == 0) st_global_32B((__nv_bfloat16*)p.pool.ptr + c.ppix + cb * p.pool.sCb, w);
+    if ((lane & 9) == 0 && c.valid) st_global_32B((__nv_bfloat16*)p.pool.ptr + c.ppix + cb * p.pool.sCb, w);
   }
 }
 
@@ -366,6 +373,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       const int r = tile - c.img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       c.y = ty * kTileH + py; c.x = tx * kTileW + px;
+      c.valid = c.y < p.y.H && c.x < p.y.W;
       c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
       c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
       c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
@@ -374,7 +382,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       // The epilogue's global operand (activation mask, else skip-gradient addend): warm L2 with the
       // whole tile's worth now, while this tile's MMAs still run, and keep the register loads one
       // block pair ahead of their use, so their latency stays off the critical path.
-      const bool pre = (p.has_mask || p.has_addend) && !skip;
+      const bool pre = (p.has_mask || p.has_addend) && !skip && c.valid;
       const __nv_bfloat16* ab = p.has_mask ? (const __nv_bfloat16*)p.mask.ptr + c.mpix : (const __nv_bfloat16*)p.addend.ptr + c.apix;
       const long long as = p.has_mask ? p.mask.sCb : p.addend.sCb;
       uint32_t ax0[8], ax1[8];
@@ -442,14 +450,14 @@ bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo) {
 }
 bool slab_geometry_ok(int dtype, int h, int w) {
   { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return false; }
-  return dtype == N2N_BF16 && h % kTileH == 0 && w % kTileW == 0 && h >= kTileH && w >= kTileW;
+  return dtype == N2N_BF16 && h >= 4 && w >= 4 && h % 2 == 0 && w % 2 == 0;
 }
 
 // Can ConvTranspose2x2 run as two N = 2*Cout launches on this engine?  (geometry + shared-memory fit)
 bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_blocks) {
   { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return false; }
   { const char* e = getenv("N2N_NO_DECONV_PAIR"); if (e && atoi(e)) return false; }
-  if (dtype != N2N_BF16 || h % kTileH || w % kTileW || h < kTileH || w < kTileW) return false;
+  if (dtype != N2N_BF16 || h < 4 || w < 4) return false;
   const int nout = 2 * cout_blocks * 16;
   if (nout > 256) return false;
   const int ngroups = (cin_blocks + kSgGroup - 1) / kSgGroup;
@@ -464,7 +472,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   static bool attr_set = false;
   if (g.dtype != N2N_BF16 || g.nout < 16 || g.nout > 256 || g.nout % 16) return kSgNotEligible;
   const int H = g.y.H, W = g.y.W;
-  if (H % kTileH || W % kTileW || H < kTileH || W < kTileW) return kSgNotEligible;
+  if (H < 4 || W < 4 || (g.has_pool && ((H | W) & 1))) return kSgNotEligible;     // edge tiles are masked in the epilogue
   { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return kSgNotEligible; }
   const int ngroups = (g.cin_blocks + kSgGroup - 1) / kSgGroup;
   const uint32_t b_sub = (uint32_t)g.nout * 32u;
@@ -537,7 +545,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   p.n_split = g.n_split; p.split_stride = g.split_stride;
   if (g.n_split && (g.has_pool || g.has_mask || g.has_addend || g.out_nchw || 2 * g.n_split * 16 != g.nout)) return kSgNotEligible;
   p.act = g.act; p.slope = g.slope; p.out_nchw = g.out_nchw; p.out_c = g.out_c;
-  p.tiles_x = W / kTileW; p.tiles_y = H / kTileH;
+  p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH;
   const long long tiles = (long long)g.y.N * p.tiles_x * p.tiles_y;
   N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "slabgemm: bad tile count");
   p.ntiles = (int)tiles;

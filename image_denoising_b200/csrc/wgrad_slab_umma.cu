@@ -306,7 +306,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   if (g.dtype != N2N_BF16 || m_blocks < 1 || m_blocks > 8 || n_blocks < 1 || n_blocks > 16) return kSgNotEligible;
   if (g.npairs < 1 || g.npairs > 9) return kSgNotEligible;
   const int H = common.H, W = common.W;
-  if (H % kWsTileH || W % kWsTileW) return kSgNotEligible;
+  if (H < 4 || W < 4) return kSgNotEligible;    // edge tiles: out-of-image pixels are zero-filled by TMA and add nothing
   bool halo = false;
   int nvar = 0;
   for (int t = 0; t < g.npairs; ++t) {
@@ -345,7 +345,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   if (ring > kWsMaxRing) ring = kWsMaxRing;
   if (g_ring_override && g_ring_override < ring) ring = g_ring_override;
   p.ring = ring;
-  p.tiles_x = W / kWsTileW; p.tiles_y = H / kWsTileH;
+  p.tiles_x = (W + kWsTileW - 1) / kWsTileW; p.tiles_y = (H + kWsTileH - 1) / kWsTileH;
   p.tiles = (long long)common.N * p.tiles_x * p.tiles_y;
   const int splits = g.splits;
   p.tiles_per_split = (p.tiles + splits - 1) / splits;

@@ -24,9 +24,9 @@ n = L.n2n_profile_end_list(buf, 400)
 def fwd_names(res):
     """launches of one forward at input resolution `res` (levels res .. res/32)."""
     def up(name, in_res):
-        return [name] * (2 if in_res % 16 == 0 else 4)          # pair form needs a 16-row tile
+        return [name] * (2 if in_res >= 4 else 4)               # pair form (slab engine) from 4x4 inputs up
     def dxa(name, r):
-        return [name + ".k0", name + ".k1"] if r % 16 == 0 else [name]
+        return [name + ".k0", name + ".k1"] if r >= 4 else [name]
     r = res
     out = ["enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]          # enc0 runs in the fused input stage (not a GEMM launch)
     out += up("up5", r // 32) + ["d5a", "d5b"]
