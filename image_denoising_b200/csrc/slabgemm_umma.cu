@@ -35,6 +35,10 @@ constexpr int kSgGroup = 3;               // channel blocks per stage = one pack
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
 constexpr size_t kSgSmemMax = 232448;     // 227 KB per CTA (static + dynamic)
+// CTA-pair (cta_group::2) form: parity-green (N2N_PAIR=3 passes the conv / network suites) and its MMA
+// phase is ~20 % faster (d1b, MMAs only: 248 -> 199 us at 32x256x256), but with the TMA loads coupled
+// across the two SMs the whole kernel is slower today (275 -> 310 us), so it stays opt-in.
+constexpr int kSgPairDefault = 0;
 constexpr size_t kSgStaticSlack = 6144;   // static shared memory of the kernel, rounded up
 
 struct SgStage {
@@ -89,6 +93,44 @@ __device__ __forceinline__ void sg_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       );
+}
+
+// ---- CTA-pair (cta_group::2) primitives: two CTAs of a cluster compute one 256-row tile pair; each
+// holds its own 128 activation rows and HALF of the weight rows, the leader (rank 0) issues the MMAs.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sg_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+// arrive on the same barrier of BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void mma_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t result_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 __device__ __forceinline__ void sg_ld16(uint32_t taddr, uint32_t r[16]) {
@@ -213,10 +255,14 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   }
 }
 
+// CG = 1: one CTA per tile.  CG = 2: clusters of two CTAs, tcgen05 cta_group::2 — rank r of a pair owns
+// tile 2*pair + r (its activations, its accumulator, its epilogue) and rows [r*N/2, (r+1)*N/2) of every
+// weight sub-tile; per MMA each SM then reads 4 KB of A + 16*N B of B instead of 4 KB + 32*N B.
+template <int CG>
 __global__ void __launch_bounds__(kSgThreads, 1)
 slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * kSgMaxRing + 5];
+  __shared__ uint64_t bars[2 * kSgMaxRing + 6];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) uint2 s_tap[kSgMaxStages * 10];  // per (stage, tap): (A offset, B offset) in 16-byte units
   __shared__ int4 s_ld[kSgMaxStages];                 // per stage: view, cb0, ox | oy << 16, tx_bytes
@@ -232,19 +278,23 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   const uint32_t wfull_bar = bar0 + 8u * (2 * kSgMaxRing);
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 1 + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 3 + b); };
-  const uint32_t b_sub16 = (uint32_t)p.nout * 2u;     // nout rows x 32 B, in 16-byte units
+  const uint32_t wready_bar = bar0 + 8u * (2 * kSgMaxRing + 5);   // CG = 2: both CTAs' weight halves have landed
+  const uint32_t b_sub16 = (uint32_t)p.nout * 2u / CG;  // weight rows per CTA x 32 B, in 16-byte units
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // CG = 2: the leader's "slot full" barrier needs its own TMA bytes AND the peer's notification
+    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), (CG == 2 && rank == 0) ? 2 : 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    mbar_init(wready_bar, CG);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
   for (int i = threadIdx.x; i < p.nst * 10; i += kSgThreads) {
     const int s = i / 10, t = i - s * 10;
     const SgStage& S = p.st[s];
-    s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t], S.b_off16[t]) : make_uint2(0u, 0u);
+    s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t], S.b_off16[t] / CG) : make_uint2(0u, 0u);
   }
   for (int i = threadIdx.x; i < p.nout; i += kSgThreads)
     s_bias[i] = p.bias ? p.bias[(p.n_split && i >= p.n_split * 16) ? i - p.n_split * 16 : i] : 0.f;
@@ -255,29 +305,46 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
                                    (uint32_t)S.sbo16 | (1u << 14) | (kSwizzle32 << 29));
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc2(smem_u32(&tmem_base_smem), p.tmem_cols);
+    } else {
+      tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   fence_before_sync();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int first_tile = (int)(blockIdx.x / CG) * CG + (int)rank, tile_step = (int)gridDim.x;   // == blockIdx.x
+  const int npair_iters = (p.ntiles + tile_step - 1 - (int)(blockIdx.x / CG) * CG) / tile_step;   // same trip count for both ranks
 
   if (warp == 0) {
     // ---- TMA producer (whole warp walks the loop, one elected lane issues) ----
     if (elect_one_sync()) {
       for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
-      mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
-      for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
-        const uint32_t n = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
-        bulk_load(smem0 + off, p.w + off, n, wfull_bar);
+      if (CG == 2) {
+        // this CTA's half of the rows of every weight sub-tile ([nout][32 B] each)
+        const uint32_t sub = (uint32_t)p.nout * 32u, half = sub / 2u;
+        mbar_arrive_expect_tx(wfull_bar, p.w_bytes / 2u);
+        for (uint32_t k = 0; k * sub < p.w_bytes; ++k)
+          bulk_load(smem0 + k * half, p.w + (size_t)k * sub + rank * half, half, wfull_bar);
+      } else {
+        mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
+        for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
+          const uint32_t n = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
+          bulk_load(smem0 + off, p.w + off, n, wfull_bar);
+        }
       }
     }
     __syncwarp();
     pdl_wait();                         // activations below are the predecessor's output
     int slot = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int it = 0; it < npair_iters; ++it) {
+      int tile = first_tile + it * tile_step;
+      if (tile >= p.ntiles) tile = p.ntiles - 1;           // odd tile count: the peer reloads the last tile, its epilogue is masked
       const int img = tile / tiles_per_img;
       const int r = tile - img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -288,7 +355,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (elect_one_sync()) {
           if (p.dbg_flags & 1) {
             mbar_arrive(full_bar(slot));
-          } else {
+          } else {   // (CG = 2: each CTA's box completes on its OWN barrier; the peer's MMA warp forwards one arrive per slot)
             mbar_arrive_expect_tx(full_bar(slot), (uint32_t)ld.w);
             tma_load_5d(slots0 + slot * p.slot_bytes, &p.tmap[ld.x], full_bar(slot), 0, x0 + (int)(int16_t)(ld.z & 0xffff),
                         y0 + (int)(int16_t)(ld.z >> 16), ld.y, img);
@@ -304,12 +371,28 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     pdl_wait();
     pdl_release();                      // our own dependents may begin their prologue
     sg_wait(wfull_bar, 0);
+    if (CG == 2) {
+      // tell the leader that this CTA's weight half is in place; only the leader issues MMAs
+      if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
+      __syncwarp();
+      if (rank == 0) sg_wait(wready_bar, 0);
+      if (rank != 0) {
+        // peer: forward "my box of this slot has landed" to the leader's slot barrier — one remote arrive per
+        // stage instead of crediting every TMA packet to a barrier in the other SM
+        for (int lt = 0; lt < npair_iters; ++lt)
+          for (int s = 0; s < p.nst; ++s) {
+            sg_wait(full_bar(slot), phase);
+            if (elect_one_sync()) mbar_arrive_cluster(full_bar(slot) & kPeerMask);
+            __syncwarp();
+            if (++slot == p.ring) { slot = 0; phase ^= 1u; }
+          }
+      }
+    }
     const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
     const uint32_t w_lo = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t idesc = p.idesc;
     const bool skip = (p.dbg_flags & 2) != 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++lt) {
+    for (int lt = 0; lt < ((CG == 2 && rank != 0) ? 0 : npair_iters); ++lt) {
       const int buf = lt & 1;
       sg_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
       fence_after_sync();
@@ -338,20 +421,26 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
             for (int t = 0; t < 9; ++t) {
               if (t < (int)mm.x) {
                 const uint32_t al = a_lo + tp[t].x, bl = w_lo + tp[t].y;
-                sg_mma(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
-                if (mm.y > 1) sg_mma(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
-                if (mm.y > 2) sg_mma(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                if (CG == 2) {
+                  sg_mma2(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma2(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma2(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                } else {
+                  sg_mma(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                }
                 a1 = 1;
               }
             }
           }
-          mma_commit(empty_bar(slot));
+          if (CG == 2) mma_commit2(empty_bar(slot)); else mma_commit(empty_bar(slot));   // frees the slot in both CTAs
         }
         __syncwarp();
         acc = 1;
         if (++slot == p.ring) { slot = 0; phase ^= 1u; }
       }
-      if (elect_one_sync()) mma_commit(tfull_bar(buf));
+      if (elect_one_sync()) { if (CG == 2) mma_commit2(tfull_bar(buf)); else mma_commit(tfull_bar(buf)); }
       __syncwarp();
     }
   } else {
@@ -366,14 +455,16 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const int cb_lo = 0;
     const int nblk = p.nout >> 4;
     const bool skip = (p.dbg_flags & 4) != 0;
-    int lt = group;
-    for (int tile = blockIdx.x + group * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, lt += 2) {
+    for (int lt = group; lt < npair_iters; lt += 2) {
+      int tile = first_tile + lt * tile_step;
+      const bool tile_ok = tile < p.ntiles;                 // odd tile count: the peer's last accumulator is a duplicate
+      if (!tile_ok) tile = p.ntiles - 1;
       SgPix c;
       c.img = tile / tiles_per_img;
       const int r = tile - c.img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       c.y = ty * kTileH + py; c.x = tx * kTileW + px;
-      c.valid = c.y < p.y.H && c.x < p.y.W;
+      c.valid = tile_ok && c.y < p.y.H && c.x < p.y.W;
       c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
       c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
       c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
@@ -416,14 +507,15 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_bar(buf) & kPeerMask); else mbar_arrive(tempty_bar(buf)); }
     }
   }
   fence_before_sync();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // neither CTA may retire its barriers / TMEM while the other still signals them
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (CG == 2) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -530,7 +622,16 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   for (int v = 0; v < 4; ++v)      // unused descriptor slots must still be valid for prefetch.tensormap
     if (v >= nviews) p.tmap[v] = p.tmap[0];
   slot_bytes = align_up(slot_bytes, 1024);
-  const size_t w_region = align_up(w_bytes, 1024);
+  // CTA pairs (cta_group::2): opt-in per shape via N2N_PAIR (bit 0: N <= 64 layers, bit 1: wider layers).
+  // Each CTA of a pair keeps half of the weight rows, which leaves room for a deeper activation ring.
+  int cg = 1;
+  {
+    const long long tiles0 = (long long)g.y.N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+    const char* e = getenv("N2N_PAIR");
+    const int mode = e ? atoi(e) : kSgPairDefault;
+    if (tiles0 >= 2 && g.nout % 16 == 0 && ((g.nout <= 64 && (mode & 1)) || (g.nout > 64 && (mode & 2)))) cg = 2;
+  }
+  const size_t w_region = align_up(w_bytes / cg, 1024);
   const size_t budget = kSgSmemMax - kSgStaticSlack - 1024;
   if (w_region + 2 * slot_bytes > budget) return kSgNotEligible;
   int ring = (int)((budget - w_region) / slot_bytes);
@@ -551,16 +652,25 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   p.ntiles = (int)tiles;
   p.ring = ring; p.slot_bytes = (uint32_t)slot_bytes;
   p.tmem_cols = tmem_cols_for(2 * g.nout);
-  p.idesc = make_idesc_bf16(128, g.nout, false, false);
+  p.idesc = make_idesc_bf16(128 * cg, g.nout, false, false);
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
   if (!attr_set) {
-    N2N_CUDA(cudaFuncSetAttribute(slabgemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    N2N_CUDA(cudaFuncSetAttribute(slabgemm_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kSgSmemMax - kSgStaticSlack)));
+    N2N_CUDA(cudaFuncSetAttribute(slabgemm_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(kSgSmemMax - kSgStaticSlack)));
     attr_set = true;
   }
-  const int grid = tiles < sg_num_sms() ? (int)tiles : sg_num_sms();
-  N2N_CUDA(launch_pdl(slabgemm_umma_kernel, dim3(grid), dim3(kSgThreads), smem, st, p));
+  if (cg == 2) {
+    int grid = (int)((tiles + 1) / 2) * 2;
+    const int cap = sg_num_sms() & ~1;
+    if (grid > cap) grid = cap;
+    N2N_CUDA(launch_pdl_cluster2(slabgemm_umma_kernel<2>, dim3(grid), dim3(kSgThreads), smem, st, p));
+  } else {
+    const int grid = tiles < sg_num_sms() ? (int)tiles : sg_num_sms();
+    N2N_CUDA(launch_pdl(slabgemm_umma_kernel<1>, dim3(grid), dim3(kSgThreads), smem, st, p));
+  }
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -200,6 +200,22 @@ inline cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
+// Same, for kernels that run as clusters of two CTAs (tcgen05 cta_group::2).
+template <typename P>
+inline cudaError_t launch_pdl_cluster2(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& params) {
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("N2N_NO_PDL"); use_pdl = (e && atoi(e)) ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = use_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 inline uint32_t tmem_cols_for(int ncols) {
   uint32_t c = 32;
   while ((int)c < ncols) c <<= 1;
