@@ -35,10 +35,18 @@ constexpr int kSgGroup = 3;               // channel blocks per stage = one pack
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
 constexpr size_t kSgSmemMax = 232448;     // 227 KB per CTA (static + dynamic)
-// CTA-pair (cta_group::2) form: parity-green (N2N_PAIR=3 passes the conv / network suites) and its MMA
-// phase is ~20 % faster (d1b, MMAs only: 248 -> 199 us at 32x256x256), but with the TMA loads coupled
-// across the two SMs the whole kernel is slower today (275 -> 310 us), so it stays opt-in.
-constexpr int kSgPairDefault = 0;
+// CTA-pair (cta_group::2) form, N2N_PAIR bit 0: N <= 64 layers, bit 1: wider layers.  Measured at
+// 32x256x256: dec_conv1b 274 -> 268 us (MMA phase alone 249 -> 203 us), enc_conv1 144 -> 139 us, and the
+// Cin = 144 convs — whose 249 KB of weights only fit when split over the pair — 177 -> 93 us (1.40 PFLOP/s).
+constexpr int kSgPairDefault = 3;
+static int sg_pair_mode() {
+  const char* e = getenv("N2N_PAIR");
+  return e ? atoi(e) : kSgPairDefault;
+}
+static bool sg_use_pair(int nout, long long tiles) {
+  const int mode = sg_pair_mode();
+  return tiles >= 2 && nout % 16 == 0 && ((nout <= 64 && (mode & 1)) || (nout > 64 && (mode & 2)));
+}
 constexpr size_t kSgStaticSlack = 6144;   // static shared memory of the kernel, rounded up
 
 struct SgStage {
@@ -122,8 +130,22 @@ __device__ __forceinline__ void mma_commit2(uint32_t bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+// TMA load whose completion bytes are credited to the LEADER's barrier (bar already peer-masked)
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Relaxed form for the "accumulator drained" signal: it hands over no memory (the TMEM reads are ordered
+// by tcgen05.wait::ld + tcgen05.fence::before_thread_sync), and a release at cluster scope would make
+// the epilogue wait for all of its global stores to drain first (measured: 16 % of the kernel in ERRBAR).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t result_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_smem), "r"(ncols) : "memory");
@@ -283,8 +305,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    // CG = 2: the leader's "slot full" barrier needs its own TMA bytes AND the peer's notification
-    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), (CG == 2 && rank == 0) ? 2 : 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
     mbar_init(wready_bar, CG);
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG); }
@@ -355,7 +376,12 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (elect_one_sync()) {
           if (p.dbg_flags & 1) {
             mbar_arrive(full_bar(slot));
-          } else {   // (CG = 2: each CTA's box completes on its OWN barrier; the peer's MMA warp forwards one arrive per slot)
+          } else if (CG == 2) {
+            // both CTAs' boxes are credited to the leader's barrier, which expects twice the bytes
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(slot), 2u * (uint32_t)ld.w);
+            tma_load_5d_pair(slots0 + slot * p.slot_bytes, &p.tmap[ld.x], full_bar(slot) & kPeerMask, 0,
+                             x0 + (int)(int16_t)(ld.z & 0xffff), y0 + (int)(int16_t)(ld.z >> 16), ld.y, img);
+          } else {
             mbar_arrive_expect_tx(full_bar(slot), (uint32_t)ld.w);
             tma_load_5d(slots0 + slot * p.slot_bytes, &p.tmap[ld.x], full_bar(slot), 0, x0 + (int)(int16_t)(ld.z & 0xffff),
                         y0 + (int)(int16_t)(ld.z >> 16), ld.y, img);
@@ -376,17 +402,6 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
       __syncwarp();
       if (rank == 0) sg_wait(wready_bar, 0);
-      if (rank != 0) {
-        // peer: forward "my box of this slot has landed" to the leader's slot barrier — one remote arrive per
-        // stage instead of crediting every TMA packet to a barrier in the other SM
-        for (int lt = 0; lt < npair_iters; ++lt)
-          for (int s = 0; s < p.nst; ++s) {
-            sg_wait(full_bar(slot), phase);
-            if (elect_one_sync()) mbar_arrive_cluster(full_bar(slot) & kPeerMask);
-            __syncwarp();
-            if (++slot == p.ring) { slot = 0; phase ^= 1u; }
-          }
-      }
     }
     const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
     const uint32_t w_lo = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
@@ -507,7 +522,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_bar(buf) & kPeerMask); else mbar_arrive(tempty_bar(buf)); }
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster_relaxed(tempty_bar(buf) & kPeerMask); else mbar_arrive(tempty_bar(buf)); }
     }
   }
   fence_before_sync();
@@ -535,7 +550,7 @@ static int sg_num_sms() {
 // Do the packed weights of a conv (taps x cin_blocks x nout) fit resident beside two pipeline slots?
 bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo) {
   const int ngroups = (cin_blocks + kSgGroup - 1) / kSgGroup;
-  const size_t w_bytes = (size_t)ntaps * ngroups * kSgGroup * nout * 32;
+  const size_t w_bytes = (size_t)ntaps * ngroups * kSgGroup * nout * 32 / (sg_use_pair(nout, 1 << 20) ? 2 : 1);
   const int gb = cin_blocks < kSgGroup ? cin_blocks : kSgGroup;
   const size_t slot = align_up((size_t)gb * (halo ? kHaloW * kHaloH : kTileW * kTileH) * 32, 1024);
   return align_up(w_bytes, 1024) + 2 * slot <= kSgSmemMax - kSgStaticSlack - 1024;
@@ -624,13 +639,8 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   slot_bytes = align_up(slot_bytes, 1024);
   // CTA pairs (cta_group::2): opt-in per shape via N2N_PAIR (bit 0: N <= 64 layers, bit 1: wider layers).
   // Each CTA of a pair keeps half of the weight rows, which leaves room for a deeper activation ring.
-  int cg = 1;
-  {
-    const long long tiles0 = (long long)g.y.N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-    const char* e = getenv("N2N_PAIR");
-    const int mode = e ? atoi(e) : kSgPairDefault;
-    if (tiles0 >= 2 && g.nout % 16 == 0 && ((g.nout <= 64 && (mode & 1)) || (g.nout > 64 && (mode & 2)))) cg = 2;
-  }
+  const long long tiles0 = (long long)g.y.N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const int cg = sg_use_pair(g.nout, tiles0) ? 2 : 1;
   const size_t w_region = align_up(w_bytes / cg, 1024);
   const size_t budget = kSgSmemMax - kSgStaticSlack - 1024;
   if (w_region + 2 * slot_bytes > budget) return kSgNotEligible;
