@@ -26,7 +26,7 @@ def fwd_names(res):
     def up(name, in_res):
         return [name] * (2 if in_res >= 4 else 4)               # pair form (slab engine) from 4x4 inputs up
     def dxa(name, r):
-        return [name + ".k0", name + ".k1"] if r >= 4 else [name]
+        return [name]                                           # CTA-pair engine: half the weights per SM, no K split
     r = res
     out = ["enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]          # enc0 runs in the fused input stage (not a GEMM launch)
     out += up("up5", r // 32) + ["d5a", "d5b"]
