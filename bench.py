@@ -160,8 +160,10 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "n2n_train_unet48_1x256x256 (bounded sample: batch 4 per step on host CPU)",
-                   "batch_per_step": 4, "patch": PATCH, "n_feature": NF},
+        "config": {"workload": "n2n_train_unet48_b64_1x256x256 (BASELINE configs[2])", "batch_per_gpu": BATCH_PER_GPU,
+                   "global_batch": BATCH_PER_GPU * max(args.gpus, 1), "patch": PATCH, "n_feature": NF,
+                   "parallelism": "host CPU, all torch threads",
+                   "sample": "each timed step = the same N2N iteration on a bounded batch of 4 patches (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
