@@ -10,15 +10,22 @@
 //     Every input pixel crosses L2 -> SMEM 1.4 times per conv (9 in a tap-by-tap implicit GEMM,
 //     3.2 in the row-slab engine).
 //   * the packed weights of the layer stay resident in shared memory for the whole persistent CTA;
-//   * the per-tile MMA schedule (A / B descriptor offsets of every tcgen05.mma) is tabulated in
-//     shared memory once per CTA, so the issuing lane does one LDS + two adds per MMA;
-//   * accumulators are double-buffered in TMEM; the epilogue (4 warps) fuses bias, LeakyReLU /
-//     ReLU, the input-gradient's activation mask and skip-gradient addend, the 2x2 max-pool
-//     (a 2x2 cell is lanes {l, l^1, l^8} of one warp -> two shuffles), the bf16 C16 store and the
-//     fp32 NCHW store of the network head.
+//   * the per-tile MMA schedule (A / B descriptor offsets of every tap) is tabulated in shared
+//     memory once per CTA and pulled into registers per stage, so the issuing lane does two integer
+//     adds per tcgen05.mma;
+//   * default form: clusters of two CTAs and tcgen05 cta_group::2 (see the kernel's comment) — each
+//     SM keeps half of the weight rows, which also makes the Cin = 144 layers fit;
+//   * accumulators are double-buffered in TMEM; two groups of four epilogue warps take alternate
+//     tiles and fuse bias, LeakyReLU / ReLU, the input-gradient's activation mask and skip-gradient
+//     addend (prefetched), the 2x2 max-pool (a 2x2 cell is lanes {l, l^1, l^8} of one warp -> two
+//     shuffles), the 256-bit bf16 C16 store (two adjacent output pixels for the pair-form
+//     ConvTranspose) and the fp32 NCHW store of the network head; one warp per group polls the
+//     mbarrier, the others park on a named barrier;
+//   * images need not be multiples of the tile: out-of-image rows / columns are zero-filled by TMA
+//     on the way in and masked on the way out.
 //
-// Layers whose weights do not fit beside >= 2 pipeline slots (Cin = 144) or whose images are
-// smaller than a tile (the 8x8 / 4x4 levels) return kSgNotEligible and run on the row-slab engine.
+// Only images smaller than 4 x 4 (and N2N_NO_SLAB=1) return kSgNotEligible and run on the
+// first-generation row-slab engine (tapgemm_umma.cu).
 #include <stdlib.h>
 
 #include "common.cuh"

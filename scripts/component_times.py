@@ -9,7 +9,9 @@ dev = torch.device("cuda:0")
 N = int(os.environ.get("B", "32"))
 cases = [("d1b 96->96 3x3 @256^2", N, 96, 96, 256, 256, 3), ("d1a 97->96 3x3 @256^2", N, 97, 96, 256, 256, 3),
          ("nin 96->96 1x1 @256^2", N, 96, 96, 256, 256, 1), ("enc1 48->48 3x3 @256^2", N, 48, 48, 256, 256, 3),
-         ("d2a 144->96 3x3 @128^2", N, 144, 96, 128, 128, 3)]
+         ("d2a 144->96 3x3 @128^2", N, 144, 96, 128, 128, 3),
+         ("d5a 96->96 3x3 @16^2 x64", 64, 96, 96, 16, 16, 3), ("enc5 48->48 3x3 @16^2 x64", 64, 48, 48, 16, 16, 3),
+         ("d4b 96->96 3x3 @32^2 x64", 64, 96, 96, 32, 32, 3)]
 if os.environ.get("CASES"):
     cases = [cases[int(i)] for i in os.environ["CASES"].split(",")]
 for name, n, cin, cout, h, w, k in cases:
