@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libn2n_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "subsample.cu", "loss_adam.cu", "metrics.cu", "pack.cu",
-           "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
+           "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "headbwd_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -66,6 +66,12 @@ int launch_head_chain(const HeadChain& h, cudaStream_t st) {
   ProfScope ps(0, flops, st);
   return launch_head_chain_umma(h, st);
 }
+int launch_head_bwd(const HeadBwd& h, cudaStream_t st) {
+  const double px = (double)h.g_d1b.N * h.g_d1b.H * h.g_d1b.W;
+  const double flops = 2.0 * px * h.channels * (2.0 * h.channels + h.out_nc);
+  ProfScope ps(0, flops, st);
+  return launch_head_bwd_umma(h, st);
+}
 int launch_tapwgrad(const TapWgrad& g, cudaStream_t st) {
   const double flops = 2.0 * g.dy[0].N * g.dy[0].H * g.dy[0].W * 256.0 * g.n_blocks * g.c_blocks * g.npairs;
   ProfScope ps(1, flops, st);

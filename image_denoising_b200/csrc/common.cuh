@@ -225,6 +225,20 @@ struct HeadChain {
 int launch_head_chain(const HeadChain& h, cudaStream_t st);        // api.cu (profiling scope + dispatch)
 int launch_head_chain_umma(const HeadChain& h, cudaStream_t st);   // head_umma.cu
 
+// ---- fused input gradients of the 1x1 head (headbwd_umma.cu) ---------------------------------------
+struct HeadBwd {
+  int blocks = 0, channels = 0, out_nc = 0;
+  float slope = 0.2f;
+  const float* gout = nullptr;       // dL/dout, fp32 NCHW [N][out_nc][H][W]
+  const float* wc = nullptr;         // nin_c weight, torch layout fp32 [out_nc][channels]
+  const void* wb_dgrad = nullptr;    // nin_b / nin_a weights in the input-gradient pack (rows = cin, K = cout)
+  const void* wa_dgrad = nullptr;
+  View act_nb, act_na, act_d1b;      // activated outputs of nin_b, nin_a, dec_conv1b (sign -> lrelu')
+  View g_nb, g_na, g_d1b;            // gradients w.r.t. those outputs (written)
+};
+int launch_head_bwd(const HeadBwd& h, cudaStream_t st);        // api.cu (profiling scope + dispatch)
+int launch_head_bwd_umma(const HeadBwd& h, cudaStream_t st);   // headbwd_umma.cu
+
 // ---- generic weight-gradient GEMM ---------------------------------------------------------
 // P[s][t][c][n] = sum_{p in split s} dY_{a(t)}[p, n] * X_{b(t)}[p + (dy_t, dx_t), c]
 // bias_partial[s][n] = sum_{p in split s} sum_{distinct dY views} dY[p, n]

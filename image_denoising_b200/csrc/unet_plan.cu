@@ -457,7 +457,30 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   };
 
   // head + level-0 decoder
-  for (int i = 24; i >= 21; --i) { N2N_TRY(wgrad(i)); N2N_TRY(dgrad(i, p->L[i].cin_blocks(), true, false)); }
+  int hb = kSgNotEligible;
+  bool w24_done = false;
+  if (dt == N2N_BF16 && p->hb * 16 == 96) {
+    // the three 1x1 input gradients in one kernel (weight gradients still need every intermediate)
+    HeadBwd h;
+    h.blocks = p->hb; h.channels = 96; h.out_nc = p->out_nc; h.slope = 0.2f;
+    h.gout = dy; h.wc = params[2 * 24];
+    h.wb_dgrad = (char*)ws + p->off_wd[23]; h.wa_dgrad = (char*)ws + p->off_wd[22];
+    h.act_nb = p->view(p->act, ws, B_NB, 0, p->hb); h.act_na = p->view(p->act, ws, B_NA, 0, p->hb);
+    h.act_d1b = p->view(p->act, ws, B_D1B, 0, p->hb);
+    h.g_nb = p->view(p->grd, ws, B_NB, 0, p->hb); h.g_na = p->view(p->grd, ws, B_NA, 0, p->hb);
+    h.g_d1b = p->view(p->grd, ws, B_D1B, 0, p->hb);
+    N2N_TRY(wgrad(24));                       // reads grad(out) and nin_b's activation only
+    w24_done = true;
+    hb = launch_head_bwd(h, st);
+    if (hb < 0) return hb;
+    if (hb == 0) { N2N_TRY(wgrad(23)); N2N_TRY(wgrad(22)); }
+  }
+  if (hb == kSgNotEligible)
+    for (int i = 24; i >= 22; --i) {
+      if (!(i == 24 && w24_done)) N2N_TRY(wgrad(i));
+      N2N_TRY(dgrad(i, p->L[i].cin_blocks(), true, false));
+    }
+  N2N_TRY(wgrad(21)); N2N_TRY(dgrad(21, p->L[21].cin_blocks(), true, false));
   N2N_TRY(wgrad(20));
   N2N_TRY(dgrad(20, (want_dx || !p->im2col) ? p->c2b + p->inb : p->c2b, false, false));
   // decoder levels 1..4: up{k} then dec_conv{k+1}b / a
