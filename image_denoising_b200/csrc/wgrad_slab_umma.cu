@@ -41,7 +41,8 @@ struct WsParams {
   uint32_t a_lbo, a_hi, a_kstep16;       // LBO field (already << 16) of the A descriptor low word; high word; K-step (bytes/16)
   uint32_t b_lbo, b_hi, b_kstep16;
   float* partial;
-  float* bias_partial;                   // conv only: [splits][npad] fused bias gradient (tap group 0), else null
+  float* bias_partial;                   // fused bias gradient: conv [splits][npad] (tap group 0 sums the dY tile); deconv
+                                         // [splits * npairs][npad] (every tap group sums its dY parity boxes into its first row)
   int dbg_flags;                         // N2N_DBG_FLAGS: 2 = skip the MMAs (pipeline / memory rate only)
   uint16_t tap_off16[12];                // start of each tap's view inside its variant box (bytes/16)
   int8_t tap_view[12];                   // tensor map of the tap's variant view
@@ -101,7 +102,8 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
   const int nbox = p.box_per_tap ? ntap : 1;
   // bias gradient = per-channel pixel sum of dY: the four otherwise idle epilogue warps add it up from
   // the dY tile the pipeline already staged in shared memory (tap group 0 only), so dY is not read twice
-  const bool do_bias = p.bias_partial != nullptr && tg == 0;
+  const bool do_bias = p.bias_partial != nullptr && (p.swap || tg == 0);
+  const int bias_blocks = p.swap ? p.n_blocks : p.m_blocks;      // channel blocks of dY
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWsMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_bias ? 5 : 1); }
@@ -196,17 +198,22 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
       for (long long tile = tile_begin; tile < tile_end; ++tile) {
         if (quarter == 0) ws_wait(full_bar(slot), phase);          // one polling warp, three parked on a named barrier
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        const uint8_t* row = smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)slot * p.slot_bytes + (size_t)m * 32;
+        // conv: dY is the common tile at the head of the slot; deconv: dY are this group's parity boxes behind it
+        const int nb_boxes = p.swap ? nbox : 1;
+        for (int bx = 0; bx < nb_boxes; ++bx) {
+          const uint8_t* row = smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)slot * p.slot_bytes +
+                               (p.swap ? (size_t)p.a_bytes + (size_t)bx * p.var_box_bytes : (size_t)0) + (size_t)m * 32;
 #pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {
-          if (cb < p.m_blocks) {
-            const uint4* c4 = reinterpret_cast<const uint4*>(row + (size_t)cb * (kWsTileW * kWsTileH * 32));
-            const uint4 lo = c4[sw], hi = c4[sw ^ 1u];
-            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          for (int cb = 0; cb < 8; ++cb) {
+            if (cb < bias_blocks) {
+              const uint4* c4 = reinterpret_cast<const uint4*>(row + (size_t)cb * (kWsTileW * kWsTileH * 32));
+              const uint4 lo = c4[sw], hi = c4[sw ^ 1u];
+              const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc[cb][2 * j] += __uint_as_float(w[j] << 16);
-              acc[cb][2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+              for (int j = 0; j < 8; ++j) {
+                acc[cb][2 * j] += __uint_as_float(w[j] << 16);
+                acc[cb][2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+              }
             }
           }
         }
@@ -217,7 +224,7 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
       // fixed-order reduction over the 128 pixels: lanes (shuffles), then the four warps
 #pragma unroll
       for (int cb = 0; cb < 8; ++cb) {
-        if (cb < p.m_blocks) {
+        if (cb < bias_blocks) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             float v = acc[cb][q];
@@ -228,8 +235,16 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (m < p.m_blocks * 16)
-        p.bias_partial[(long long)split * p.npad + m] = s_red[0][m] + s_red[1][m] + s_red[2][m] + s_red[3][m];
+      if (m < bias_blocks * 16) {
+        const float tot = s_red[0][m] + s_red[1][m] + s_red[2][m] + s_red[3][m];
+        if (p.swap) {
+          // rows [split * npairs + tap0, + ntap): the group's sum goes to its first row, the others are zero
+          for (int i = 0; i < ntap; ++i)
+            p.bias_partial[((long long)split * p.npairs + tap0 + i) * p.npad + m] = i == 0 ? tot : 0.f;
+        } else {
+          p.bias_partial[(long long)split * p.npad + m] = tot;
+        }
+      }
     }
     if (has_work) {
       ws_wait(tfull_bar, 0);
@@ -326,7 +341,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.npairs = g.npairs; p.m_blocks = m_blocks; p.n_blocks = n_blocks; p.swap = swap ? 1 : 0;
   p.npad = g.n_blocks * 16; p.cpad = g.c_blocks * 16;
   p.partial = g.partial;
-  p.bias_partial = (g.bias_partial && !swap) ? g.bias_partial : nullptr;
+  p.bias_partial = (g.bias_partial && (!swap || (box_per_tap && g.ndyviews == g.npairs && n_blocks <= 8))) ? g.bias_partial : nullptr;
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   { const char* e = getenv("N2N_WS_RING"); if (e && atoi(e) >= 2) g_ring_override = atoi(e); }
   p.halo = halo ? 1 : 0; p.box_per_tap = box_per_tap ? 1 : 0;
