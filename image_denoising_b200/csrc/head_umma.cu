@@ -283,6 +283,8 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         fence_after_sync();
         const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
+        uint8_t* const h_row = smem_gen + (h0s - smem0) + (size_t)b * p.h_bytes + (size_t)m * 32u;
+        const uint32_t h_sw = ((h0s + (uint32_t)m * 32u) >> 7) & 1u;
         // two accumulator-read buffers in ping-pong: the read of block cb+1 is in flight while block cb is processed
         uint32_t ra[16], rb[16];
         auto e1_block = [&](int cb, const uint32_t* rv) {
@@ -299,11 +301,10 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
               w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
             }
             // row m of K block cb: 32 bytes at [cb][m]; the two 16-byte chunks swap when address bit 7 is set
-            const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-            const uint32_t sw = ((h0s + off) >> 7) & 1u;
-            uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h0s - smem0) + off);
-            dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-            dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+            // (a per-thread constant: buffers and blocks are multiples of 256 B apart)
+            uint4* dst = reinterpret_cast<uint4*>(h_row + (size_t)cb * 4096u);
+            dst[h_sw] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[h_sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
             if (p.has_save && valid) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
         };
         if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), ra);
