@@ -27,6 +27,9 @@ parser.add_argument('--gpu_devices', default='0', type=str)
 parser.add_argument('--tiled', action='store_true', help='evaluation_704.py semantics')
 parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
 parser.add_argument('--synthetic', type=int, default=0, help='evaluate this many synthetic 704x704 pairs instead of --data_dir')
+# evaluation_adapter.py:17-44: base + output adapter loaded from an epoch_adapter_XXX.pth checkpoint
+parser.add_argument('--adapter_ckpt', type=str, default=None, help='epoch_adapter_XXX.pth (base.* + adapter.* keys)')
+parser.add_argument('--adapter_hidden', type=int, default=16)
 
 
 def main():
@@ -40,6 +43,20 @@ def main():
         state = torch.load(opt.checkpoint, map_location="cpu")
         network.load_state_dict(state)                      # strict, as evaluation.py:52-53
     network = network.to(f"cuda:{local}").set_precision(opt.precision).eval()
+    if opt.adapter_ckpt:
+        # evaluation_adapter.py:59-69, :100-112: strict=False load, "module." prefixes stripped
+        from image_denoising_b200 import DenoiserWithAdapter
+        state = torch.load(opt.adapter_ckpt, map_location="cpu")
+        if any(k.startswith("module.") for k in state.keys()):
+            state = {k.replace("module.", "", 1): v for k, v in state.items()}
+        model = DenoiserWithAdapter(network, in_channels=opt.n_channel, hidden_channels=opt.adapter_hidden,
+                                    freeze_base=True, use_no_grad_for_base=True)
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        if missing:
+            print(f"[Warning] Missing keys when loading adapter model: {missing}")
+        if unexpected:
+            print(f"[Warning] Unexpected keys when loading adapter model: {unexpected}")
+        network = model.to(f"cuda:{local}").eval()
     if opt.synthetic:
         clean, noisy = _data.synthetic_images(opt.synthetic, 704, 704, opt.n_channel)
         names = [f"synthetic_{i:03d}.png" for i in range(opt.synthetic)]

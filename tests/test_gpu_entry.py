@@ -39,3 +39,8 @@ def test_train_finetune_eval_roundtrip(tmp_path):
     txt = open(os.path.join(ev, "metrics.txt")).read()
     assert txt.count("PSNR=") == 3 and "AVG" in txt
     _run([os.path.join(ROOT, "entry", "evaluation.py"), "--synthetic", "1", "--checkpoint", ckpts[-1], "--save_dir", ev, "--tiled"], ROOT)
+    # evaluation_adapter.py: base + adapter from the finetune checkpoint
+    ev2 = os.path.join(out, "eval_adapter")
+    _run([os.path.join(ROOT, "entry", "evaluation.py"), "--synthetic", "1", "--adapter_ckpt", os.path.join(out, "ft", "epoch_adapter_001.pth"),
+          "--save_dir", ev2], ROOT)
+    assert "PSNR=" in open(os.path.join(ev2, "metrics.txt")).read()
