@@ -225,7 +225,7 @@ struct HeadChain {
 int launch_head_chain(const HeadChain& h, cudaStream_t st);        // api.cu (profiling scope + dispatch)
 int launch_head_chain_umma(const HeadChain& h, cudaStream_t st);   // head_umma.cu
 
-// ---- fused input gradients of the 1x1 head (headbwd_umma.cu) ---------------------------------------
+// ---- fused backward of the 1x1 head (headbwd_umma.cu) -----------------------------------------------
 struct HeadBwd {
   int blocks = 0, channels = 0, out_nc = 0;
   float slope = 0.2f;
@@ -233,9 +233,15 @@ struct HeadBwd {
   const float* wc = nullptr;         // nin_c weight, torch layout fp32 [out_nc][channels]
   const void* wb_dgrad = nullptr;    // nin_b / nin_a weights in the input-gradient pack (rows = cin, K = cout)
   const void* wa_dgrad = nullptr;
-  View act_nb, act_na, act_d1b;      // activated outputs of nin_b, nin_a, dec_conv1b (sign -> lrelu')
-  View g_nb, g_na, g_d1b;            // gradients w.r.t. those outputs (written)
+  View act_nb, act_na, act_d1b;      // activated outputs of nin_b, nin_a, dec_conv1b (sign -> lrelu'; wgrad operands)
+  View g_d1b;                        // gradient w.r.t. dec_conv1b's output (written; the other two stay on chip)
+  int splits = 0;                    // = head_bwd_splits(...): CTAs of the kernel = rows of the partials below
+  float* partial_b = nullptr;        // nin_b weight-gradient partial [splits][channels(c)][channels(n)]
+  float* bpartial_b = nullptr;       // nin_b bias-gradient partial   [splits][channels]
+  float* partial_a = nullptr;        // same for nin_a
+  float* bpartial_a = nullptr;
 };
+int head_bwd_splits(int dtype, int blocks, int out_nc, int n, int h, int w);   // 0 = geometry not covered
 int launch_head_bwd(const HeadBwd& h, cudaStream_t st);        // api.cu (profiling scope + dispatch)
 int launch_head_bwd_umma(const HeadBwd& h, cudaStream_t st);   // headbwd_umma.cu
 

@@ -1,18 +1,28 @@
-// headbwd_umma.cu — input gradients of the 1x1 head (nin_c -> nin_b -> nin_a, arch_unet.py:186-190 /
-// :257-259) as ONE persistent tcgen05 kernel, the mirror image of head_umma.cu:
+// headbwd_umma.cu — the whole backward of the 1x1 head (nin_c -> nin_b -> nin_a, arch_unet.py:186-190 /
+// :257-259) below nin_c's own weight gradient, as ONE persistent tcgen05 kernel, the mirror image of
+// head_umma.cu:
 //
 //   g_nb  = (Wc^T  g_out) * lrelu'(NB)        rank-out_nc outer product per pixel, CUDA cores (stage S0)
 //   g_na  = (Wb^T  g_nb ) * lrelu'(NA)        GEMM-1 on the tensor core, masked in stage S1
 //   g_d1b = (Wa^T  g_na ) * lrelu'(D1B)       GEMM-2, masked in stage S2
+//   dWb   = g_nb^T  NA ,  dbb = sum g_nb      weight-gradient GEMMs over the pixel axis, accumulated in
+//   dWa   = g_na^T  D1B,  dba = sum g_na      TMEM across all tiles of the CTA (bias = a column of ones)
 //
-// Unfused these are three HBM-bound launches that each read a gradient tensor back that the previous
-// one just wrote; fused, every gradient is written once (the weight-gradient kernels need all three)
-// and never re-read, and the 96-channel intermediates feed the next GEMM straight from shared memory
-// in the swizzled K-major operand layout.  LeakyReLU is in-place in the reference (arch_unet.py:113),
-// so lrelu'(.) is taken from the sign of the saved activated outputs (slope > 0).
+// Unfused these are three HBM-bound input-gradient launches plus two weight-gradient launches that
+// each read back a gradient tensor the previous one just wrote; fused, g_nb and g_na never leave the
+// SM: they are written once into shared memory in the swizzled 32-byte-row tile layout, where the
+// SAME bytes serve as the K-major A operand of the next input-gradient GEMM and as the MN-major A
+// operand (K = pixels) of the weight-gradient GEMM.  The saved activations NA / D1B arrive by TMA in
+// that layout too: they are the B operand of the weight-gradient GEMM and, read back by the stage
+// threads, the sign that gives lrelu'(.) (LeakyReLU is in-place in the reference, arch_unet.py:113,
+// slope > 0).  Stage S1 overwrites the NA tile in place with g_na once GEMM-1 / dWb have consumed it.
 //
-// Per 8 x 16-pixel tile: warp 1 issues the MMAs; warps 2-5 run S0, 6-9 S1, 10-13 S2 (thread = pixel =
-// TMEM lane); H0 / H1 / D1 / D2 are double-buffered so the three stages work on consecutive tiles.
+// Per 8 x 16-pixel tile: warp 0 is the TMA producer, warp 1 issues the MMAs; warps 2-5 run S0, 6-9
+// S1, 10-13 S2 (thread = pixel = TMEM lane).  The tiles are double-buffered so the three stages work
+// on consecutive tiles; the two input-gradient accumulators are single TMEM buffers that a stage
+// drains into registers and hands back before it starts its arithmetic.  Each CTA stores its fp32
+// weight-gradient partial once at the end ([grid][c][n]; pack.cu's unpack kernel reduces the CTAs in
+// a fixed order -> deterministic).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,16 +35,27 @@ using namespace umma;
 constexpr int kHbThreads = 448;
 constexpr int kHbMaxOut = 4;
 constexpr int kHbBlocks = 6;              // the head is literally 96 channels wide (arch_unet.py:177-190)
+constexpr int kHbCh = kHbBlocks * 16;
+constexpr uint32_t kHbBlk = 4096;         // one 16-channel block of a 128-pixel tile (32-byte rows)
+constexpr uint32_t kHbHBuf = kHbBlocks * kHbBlk;          // g_nb tile
+constexpr uint32_t kHbXBuf = (kHbBlocks + 1) * kHbBlk;    // activation tile + the block of ones behind it
+constexpr uint32_t kHbWBytes = kHbBlocks * kHbCh * 32;    // one packed 96 x 96 input-gradient weight
+constexpr int kHbWN = kHbCh + 16;         // weight-gradient accumulator width: 96 input channels + bias block
+// TMEM columns: D1 | D2 | dWb | dWa
+constexpr uint32_t kHbColD1 = 0, kHbColD2 = kHbCh, kHbColWb = 2 * kHbCh, kHbColWa = 2 * kHbCh + kHbWN;
+constexpr uint32_t kHbTmemCols = 512;
+static_assert(kHbColWa + kHbWN <= kHbTmemCols, "TMEM budget");
+constexpr size_t kHbSmem = 1024 + 2 * (size_t)kHbWBytes + 2 * (size_t)kHbHBuf + 4 * (size_t)kHbXBuf;
 
 struct HbParams {
-  int blocks, out_nc;
+  int out_nc;
   int tiles_x, tiles_y, ntiles, H, W;
   float slope;
-  uint32_t wb_bytes, wa_bytes, h_bytes, tmem_cols, idesc;
   const uint8_t *wb, *wa;
   const float *wc, *gout;
-  View act_nb, act_na, act_d1b;
-  View g_nb, g_na, g_d1b;
+  View act_nb, g_d1b;
+  float *partial_b, *bpartial_b, *partial_a, *bpartial_a;
+  CUtensorMap tmap_na, tmap_d1b;
 };
 
 __device__ __forceinline__ void hb_wait(uint32_t bar, uint32_t parity) {
@@ -61,15 +82,15 @@ __device__ __forceinline__ void hb_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate));
 }
-__device__ __forceinline__ void hb_ld16(uint32_t taddr, uint32_t r[16]) {
+__device__ __forceinline__ void hb_ld16_nowait(uint32_t taddr, uint32_t r[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void hb_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void hb_ld_global_32B(const void* ptr, uint32_t w[8]) {
   asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
@@ -96,110 +117,170 @@ __device__ __forceinline__ void hb_mask_pack(const float v[16], const uint32_t m
 __global__ void __launch_bounds__(kHbThreads, 1)
 head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // h0_full[2] h0_empty[2] d1_full[2] d1_empty[2] h1_full[2] h1_empty[2] d2_full[2] d2_empty[2] w_full
-  __shared__ uint64_t bars[17];
+  // double-buffered: h0_full h0_empty na_full na_empty db_full db_empty h1_full; single: d1_full d1_empty d2_full
+  // d2_empty w_full acc_full
+  __shared__ uint64_t bars[20];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_wc[kHbMaxOut * 128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  const uint32_t wb0 = smem0, wa0 = wb0 + p.wb_bytes;
-  const uint32_t h00 = wa0 + p.wa_bytes, h10 = h00 + 2 * p.h_bytes;
+  const uint32_t wb0 = smem0, wa0 = wb0 + kHbWBytes;
+  const uint32_t h00 = wa0 + kHbWBytes;                  // g_nb tiles (written by S0)
+  const uint32_t na0 = h00 + 2 * kHbHBuf;                // NA tiles (TMA), overwritten in place with g_na by S1
+  const uint32_t db0 = na0 + 2 * kHbXBuf;                // D1B tiles (TMA)
   const uint32_t bar0 = smem_u32(bars);
+  enum { H0F = 0, H0E, NAF, NAE, DBF, DBE, H1F };
   auto bar = [&](int kind, int b) { return bar0 + 8u * (2 * kind + b); };
-  enum { H0F = 0, H0E, D1F, D1E, H1F, H1E, D2F, D2E };
-  const uint32_t w_full = bar0 + 8u * 16;
-  const int nch = p.blocks * 16;
+  const uint32_t d1_full = bar0 + 8u * 14, d1_empty = bar0 + 8u * 15, d2_full = bar0 + 8u * 16, d2_empty = bar0 + 8u * 17;
+  const uint32_t w_full = bar0 + 8u * 18;
+  const uint32_t acc_full = bar0 + 8u * 19;
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(H0F, b), 4); mbar_init(bar(H0E, b), 1);
-      mbar_init(bar(D1F, b), 1); mbar_init(bar(D1E, b), 4);
-      mbar_init(bar(H1F, b), 4); mbar_init(bar(H1E, b), 1);
-      mbar_init(bar(D2F, b), 1); mbar_init(bar(D2E, b), 4);
+      mbar_init(bar(NAF, b), 1); mbar_init(bar(NAE, b), 1);
+      mbar_init(bar(DBF, b), 1); mbar_init(bar(DBE, b), 4);
+      mbar_init(bar(H1F, b), 4);
     }
-    mbar_init(w_full, 1);
+    mbar_init(d1_full, 1); mbar_init(d1_empty, 4);
+    mbar_init(d2_full, 1); mbar_init(d2_empty, 4);
+    mbar_init(w_full, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < kHbMaxOut * 128; i += kHbThreads) {
     const int oc = i >> 7, c = i & 127;
-    s_wc[i] = (oc < p.out_nc && c < nch) ? p.wc[oc * nch + c] : 0.f;
+    s_wc[i] = (oc < p.out_nc && c < kHbCh) ? p.wc[oc * kHbCh + c] : 0.f;
   }
-  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols); tmem_relinquish(); }
+  // the block of ones behind every activation tile: column 96 of the weight-gradient GEMM = bias gradient
+  for (int i = threadIdx.x; i < 4 * (int)(kHbBlk / 4); i += kHbThreads) {
+    const int buf = i / (int)(kHbBlk / 4), wd = i - buf * (int)(kHbBlk / 4);
+    const uint32_t base = (buf < 2 ? na0 + buf * kHbXBuf : db0 + (buf - 2) * kHbXBuf) + kHbBlocks * kHbBlk;
+    reinterpret_cast<uint32_t*>(smem_gen + (base - smem0))[wd] = 0x3F803F80u;
+  }
+  fence_proxy_async();
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), kHbTmemCols); tmem_relinquish(); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const uint32_t hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
   const int niter = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
+    // ---- TMA producer: weights once, then the NA / D1B activation tiles ----
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(w_full, p.wb_bytes + p.wa_bytes);
-      bulk_load(wb0, p.wb, p.wb_bytes, w_full);
-      bulk_load(wa0, p.wa, p.wa_bytes, w_full);
+      prefetch_tensormap(&p.tmap_na);
+      prefetch_tensormap(&p.tmap_d1b);
+      mbar_arrive_expect_tx(w_full, 2 * kHbWBytes);
+      bulk_load(wb0, p.wb, kHbWBytes, w_full);
+      bulk_load(wa0, p.wa, kHbWBytes, w_full);
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---- MMA issuer: GEMM-1 of tile i, then GEMM-2 of tile i-1 ----
-    pdl_wait();
-    pdl_release();
-    hb_wait(w_full, 0);
-    const uint32_t idesc = p.idesc;
-    const uint32_t bsub16 = (uint32_t)nch * 2u;
-    auto gemm = [&](int lt, uint32_t h_base, uint32_t w_base, int d_slot, int kind_hfull, int kind_dempty, int kind_hempty,
-                    int kind_dfull) {
-      const int b = lt & 1;
-      const uint32_t par = ((uint32_t)lt >> 1) & 1u;
-      hb_wait(bar(kind_dempty, b), par ^ 1u);
-      hb_wait(bar(kind_hfull, b), par);
-      fence_after_sync();
-      if (elect_one_sync()) {
-        const uint32_t a_lo = (((h_base + b * p.h_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t b_lo = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int cb = 0; cb < p.blocks; ++cb)
-          hb_mma(tmem_base + (uint32_t)((d_slot + b) * nch), a_lo + cb * 256u, b_lo + cb * bsub16, hi, idesc, cb ? 1u : 0u);
-        mma_commit(bar(kind_hempty, b));
-        mma_commit(bar(kind_dfull, b));
-      }
-      __syncwarp();
-    };
-    for (int lt = 0; lt <= niter; ++lt) {
-      if (lt < niter) gemm(lt, h00, wb0, 0, H0F, D1E, H0E, D1F);
-      if (lt >= 1) gemm(lt - 1, h10, wa0, 2, H1F, D2E, H1E, D2F);
-    }
-  } else if (warp < 14) {
-    const int stage = (warp - 2) >> 2;                 // 0: S0, 1: S1, 2: S2
-    const int quarter = warp & 3;
-    const int m = quarter * 32 + lane;
-    const int py = m >> 3, px = m & 7;
-    const View& act = stage == 0 ? p.act_nb : (stage == 1 ? p.act_na : p.act_d1b);
-    const View& gdst = stage == 0 ? p.g_nb : (stage == 1 ? p.g_na : p.g_d1b);
     pdl_wait();
     for (int lt = 0; lt < niter; ++lt) {
       const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
       const int img = tile / tiles_per_img;
       const int r = tile - img * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int y = ty * 16 + py, x = tx * 8 + px;
-      const bool valid = y < p.H && x < p.W;
       const int b = lt & 1;
       const uint32_t par = ((uint32_t)lt >> 1) & 1u;
-      const long long apix = (long long)img * act.sN + (long long)y * act.sY + (long long)x * act.sX;
-      const long long gpix = (long long)img * gdst.sN + (long long)y * gdst.sY + (long long)x * gdst.sX;
-      // the activation words that give lrelu' for this pixel: issue all loads before waiting on the pipeline
-      uint32_t mk[kHbBlocks][8];
-#pragma unroll
-      for (int cb = 0; cb < kHbBlocks; ++cb) {
-        if (valid) hb_ld_global_32B((const __nv_bfloat16*)act.ptr + apix + cb * act.sCb, mk[cb]);
-        else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) mk[cb][q] = 0u;
-        }
+      hb_wait(bar(NAE, b), par ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar(NAF, b), kHbHBuf);
+        tma_load_5d(na0 + b * kHbXBuf, &p.tmap_na, bar(NAF, b), 0, tx * 8, ty * 16, 0, img);
       }
-      if (stage == 0) {
+      __syncwarp();
+      hb_wait(bar(DBE, b), par ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar(DBF, b), kHbHBuf);
+        tma_load_5d(db0 + b * kHbXBuf, &p.tmap_d1b, bar(DBF, b), 0, tx * 8, ty * 16, 0, img);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: dWb + GEMM-1 of tile i, then dWa + GEMM-2 of tile i-1 ----
+    pdl_wait();
+    pdl_release();
+    hb_wait(w_full, 0);
+    const uint32_t hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);   // SBO = one 8-pixel image row, both majors
+    const uint32_t idesc_g = make_idesc_bf16(128, kHbCh, false, false);
+    const uint32_t idesc_w = make_idesc_bf16(128, kHbWN, true, true);
+    const uint32_t lbo_k = 1u << 16, lbo_mn = (kHbBlk >> 4) << 16;
+    auto lo = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
+    // weight gradient: K = pixels, two image rows (512 B) per MMA; input gradient: K = channels, one block per MMA
+    auto issue = [&](uint32_t g_buf, uint32_t x_buf, uint32_t w_buf, uint32_t col_w, uint32_t col_d, uint32_t first) {
+      const uint32_t ga = lo(g_buf), xa = lo(x_buf), wa = lo(w_buf);
+#pragma unroll 1
+      for (int kk = 0; kk < 8; ++kk)
+        hb_mma(tmem_base + col_w, (ga + kk * 32u) | lbo_mn, (xa + kk * 32u) | lbo_mn, hi, idesc_w, (first | (uint32_t)kk) ? 1u : 0u);
+#pragma unroll 1
+      for (int cb = 0; cb < kHbBlocks; ++cb)
+        hb_mma(tmem_base + col_d, (ga + cb * (kHbBlk >> 4)) | lbo_k, (wa + cb * (uint32_t)(kHbCh * 2)) | lbo_k, hi, idesc_g,
+               cb ? 1u : 0u);
+    };
+    for (int lt = 0; lt <= niter; ++lt) {
+      if (lt < niter) {
+        const int b = lt & 1;
+        const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+        hb_wait(d1_empty, ((uint32_t)lt & 1u) ^ 1u);
+        hb_wait(bar(NAF, b), par);
+        hb_wait(bar(H0F, b), par);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          issue(h00 + b * kHbHBuf, na0 + b * kHbXBuf, wb0, kHbColWb, kHbColD1, (uint32_t)lt);
+          mma_commit(bar(H0E, b));
+          mma_commit(d1_full);
+        }
+        __syncwarp();
+      }
+      if (lt >= 1) {
+        const int t = lt - 1;
+        const int b = t & 1;
+        const uint32_t par = ((uint32_t)t >> 1) & 1u;
+        hb_wait(d2_empty, ((uint32_t)t & 1u) ^ 1u);
+        hb_wait(bar(DBF, b), par);
+        hb_wait(bar(H1F, b), par);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          issue(na0 + b * kHbXBuf, db0 + b * kHbXBuf, wa0, kHbColWa, kHbColD2, (uint32_t)t);
+          mma_commit(bar(NAE, b));
+          mma_commit(d2_full);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one_sync()) mma_commit(acc_full);
+    __syncwarp();
+  } else if (warp < 14) {
+    const int stage = (warp - 2) >> 2;                 // 0: S0, 1: S1, 2: S2
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    const uint32_t sw = ((uint32_t)m >> 2) & 1u;       // 16-byte chunk swap of this pixel's rows (address bit 7)
+    pdl_wait();
+    if (stage == 0) {
+      for (int lt = 0; lt < niter; ++lt) {
+        const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int img = tile / tiles_per_img;
+        const int r = tile - img * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int y = ty * 16 + py, x = tx * 8 + px;
+        const bool valid = y < p.H && x < p.W;
+        const int b = lt & 1;
+        const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+        const long long apix = (long long)img * p.act_nb.sN + (long long)y * p.act_nb.sY + (long long)x * p.act_nb.sX;
+        // the activation words that give lrelu' for this pixel: issue all loads before waiting on the pipeline
+        uint32_t mk[kHbBlocks][8];
+#pragma unroll
+        for (int cb = 0; cb < kHbBlocks; ++cb) {
+          if (valid) hb_ld_global_32B((const __nv_bfloat16*)p.act_nb.ptr + apix + cb * p.act_nb.sCb, mk[cb]);
+          else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mk[cb][q] = 0u;
+          }
+        }
         float go[kHbMaxOut];
         const long long hw = (long long)p.H * p.W;
 #pragma unroll
@@ -207,115 +288,144 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
           go[oc] = (oc < p.out_nc && valid) ? p.gout[((long long)img * p.out_nc + oc) * hw + (long long)y * p.W + x] : 0.f;
         if (quarter == 0) hb_wait(bar(H0E, b), par ^ 1u);
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* row = smem_gen + (h00 - smem0) + (uint32_t)b * kHbHBuf + (uint32_t)m * 32u;
 #pragma unroll
         for (int cb = 0; cb < kHbBlocks; ++cb) {
-          {
-            float v[16];
+          float v[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = 0.f;
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
 #pragma unroll
-            for (int oc = 0; oc < kHbMaxOut; ++oc) {
-              if (oc < p.out_nc) {
-                const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
+          for (int oc = 0; oc < kHbMaxOut; ++oc) {
+            if (oc < p.out_nc) {
+              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 wv = wr[q];
-                  v[4 * q] += wv.x * go[oc]; v[4 * q + 1] += wv.y * go[oc]; v[4 * q + 2] += wv.z * go[oc]; v[4 * q + 3] += wv.w * go[oc];
-                }
+              for (int q = 0; q < 4; ++q) {
+                const float4 wv = wr[q];
+                v[4 * q] += wv.x * go[oc]; v[4 * q + 1] += wv.y * go[oc]; v[4 * q + 2] += wv.z * go[oc]; v[4 * q + 3] += wv.w * go[oc];
               }
             }
-            uint32_t w[8];
-            hb_mask_pack(v, mk[cb], p.slope, w);
-            const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-            const uint32_t sw = ((h00 + off) >> 7) & 1u;
-            uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h00 - smem0) + off);
-            dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-            dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-            if (valid) hb_st_global_32B((__nv_bfloat16*)gdst.ptr + gpix + cb * gdst.sCb, w);
           }
+          uint32_t w[8];
+          hb_mask_pack(v, mk[cb], p.slope, w);
+          uint4* dst = reinterpret_cast<uint4*>(row + (uint32_t)cb * kHbBlk);
+          dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(H0F, b));
-      } else {
-        const int dfull = stage == 1 ? D1F : D2F, dempty = stage == 1 ? D1E : D2E;
+      }
+    } else {
+      const bool s1 = stage == 1;
+      const uint32_t dfull = s1 ? d1_full : d2_full, dempty = s1 ? d1_empty : d2_empty;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t dcol = s1 ? kHbColD1 : kHbColD2;
+      for (int lt = 0; lt < niter; ++lt) {
+        const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int img = tile / tiles_per_img;
+        const int r = tile - img * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int y = ty * 16 + py, x = tx * 8 + px;
+        const bool valid = y < p.H && x < p.W;
+        const int b = lt & 1;
+        const uint32_t par = ((uint32_t)lt >> 1) & 1u;
         if (quarter == 0) {
-          hb_wait(bar(dfull, b), par);
-          if (stage == 1) hb_wait(bar(H1E, b), par ^ 1u);
+          hb_wait(bar(s1 ? NAF : DBF, b), par);       // the TMA'd activation tile is visible to this warp group
+          hb_wait(dfull, (uint32_t)lt & 1u);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + stage) : "memory");
         fence_after_sync();
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((stage == 1 ? 0 : 2) + b) * nch);
+        // drain the accumulator into registers and hand it back before any arithmetic
+        uint32_t rr[kHbBlocks][16];
+#pragma unroll
+        for (int cb = 0; cb < kHbBlocks; ++cb) hb_ld16_nowait(lane_addr + dcol + cb * 16, rr[cb]);
+        hb_ld_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dempty);
+        uint8_t* row = smem_gen + ((s1 ? na0 : db0) - smem0) + (uint32_t)b * kHbXBuf + (uint32_t)m * 32u;
+        const long long gpix = (long long)img * p.g_d1b.sN + (long long)y * p.g_d1b.sY + (long long)x * p.g_d1b.sX;
 #pragma unroll
         for (int cb = 0; cb < kHbBlocks; ++cb) {
-          {
-            uint32_t rr[16];
-            hb_ld16(lane_addr + cb * 16, rr);
-            float v[16];
+          uint4* rowb = reinterpret_cast<uint4*>(row + (uint32_t)cb * kHbBlk);
+          const uint4 m0 = rowb[sw], m1 = rowb[sw ^ 1u];
+          const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          float v[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rr[q]);
-            uint32_t w[8];
-            hb_mask_pack(v, mk[cb], p.slope, w);
-            if (stage == 1) {
-              const uint32_t off = (uint32_t)b * p.h_bytes + (uint32_t)cb * 4096u + (uint32_t)m * 32u;
-              const uint32_t sw = ((h10 + off) >> 7) & 1u;
-              uint4* dst = reinterpret_cast<uint4*>(smem_gen + (h10 - smem0) + off);
-              dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
-              dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-            if (valid) hb_st_global_32B((__nv_bfloat16*)gdst.ptr + gpix + cb * gdst.sCb, w);
+          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rr[cb][q]);
+          uint32_t w[8];
+          hb_mask_pack(v, mk, p.slope, w);
+          if (s1) {
+            rowb[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+            rowb[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+          } else if (valid) {
+            hb_st_global_32B((__nv_bfloat16*)p.g_d1b.ptr + gpix + cb * p.g_d1b.sCb, w);
           }
         }
-        fence_before_sync();
-        if (stage == 1) fence_proxy_async();
+        if (s1) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(dempty, b));
-          if (stage == 1) mbar_arrive(bar(H1F, b));
+        if (lane == 0) mbar_arrive(bar(s1 ? H1F : DBE, b));
+      }
+      // ---- this CTA's weight-gradient partial: TMEM lane = output channel n, column = input channel c ----
+      if (quarter == 0) hb_wait(acc_full, 0);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + stage) : "memory");
+      fence_after_sync();
+      float* P = (s1 ? p.partial_b : p.partial_a) + (size_t)blockIdx.x * kHbCh * kHbCh;
+      float* Bp = (s1 ? p.bpartial_b : p.bpartial_a) + (size_t)blockIdx.x * kHbCh;
+      const uint32_t wcol = s1 ? kHbColWb : kHbColWa;
+      for (int cb = 0; cb <= kHbBlocks; ++cb) {
+        float v[16];
+        tmem_ld16(lane_addr + wcol + cb * 16, v);
+        if (m < kHbCh) {
+          if (cb < kHbBlocks) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) P[(cb * 16 + q) * kHbCh + m] = v[q];
+          } else {
+            Bp[m] = v[0];
+          }
         }
       }
+      fence_before_sync();
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, kHbTmemCols); }
+}
+
+// Geometry the fused kernel covers, and how many CTAs (= weight-gradient partial rows) it runs: the
+// plan sizes the nin_a / nin_b partial buffers and the unpack reduction from this.
+int head_bwd_splits(int dtype, int blocks, int out_nc, int n, int h, int w) {
+  { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return 0; }
+  if (dtype != N2N_BF16 || blocks != kHbBlocks || out_nc < 1 || out_nc > kHbMaxOut || h < 4 || w < 4) return 0;
+  const long long tiles = (long long)n * ((w + 7) / 8) * ((h + 15) / 16);
+  if (tiles < 1 || tiles >= (1LL << 31)) return 0;
+  return tiles < kSMs ? (int)tiles : kSMs;
 }
 
 // Returns 0 when launched, kSgNotEligible when the geometry is not covered (caller runs the three
-// input-gradient launches one by one).
+// input-gradient and two weight-gradient launches one by one).
 int launch_head_bwd_umma(const HeadBwd& h, cudaStream_t st) {
   static bool attr_set = false;
-  { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
-  if (h.blocks != kHbBlocks || h.channels != h.blocks * 16 || h.out_nc < 1 || h.out_nc > kHbMaxOut) return kSgNotEligible;
-  if (h.g_d1b.H < 4 || h.g_d1b.W < 4) return kSgNotEligible;
+  const int grid = head_bwd_splits(N2N_BF16, h.blocks, h.out_nc, h.g_d1b.N, h.g_d1b.H, h.g_d1b.W);
+  if (grid < 1 || h.channels != kHbCh || h.splits != grid) return kSgNotEligible;
+  N2N_CHECK_ARG(h.partial_a && h.partial_b && h.bpartial_a && h.bpartial_b, "head_bwd: null partial buffer");
   HbParams p;
   memset(&p, 0, sizeof(p));
-  p.blocks = h.blocks; p.out_nc = h.out_nc; p.H = h.g_d1b.H; p.W = h.g_d1b.W;
+  p.out_nc = h.out_nc; p.H = h.g_d1b.H; p.W = h.g_d1b.W;
   p.tiles_x = (p.W + 7) / 8; p.tiles_y = (p.H + 15) / 16;
-  const long long tiles = (long long)h.g_d1b.N * p.tiles_x * p.tiles_y;
-  N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "head_bwd: bad tile count");
-  p.ntiles = (int)tiles;
+  p.ntiles = h.g_d1b.N * p.tiles_x * p.tiles_y;
   p.slope = h.slope;
-  const int nch = h.blocks * 16;
-  if (4 * nch > 512) return kSgNotEligible;
-  p.wb_bytes = p.wa_bytes = (uint32_t)(((h.blocks + 2) / 3) * 3 * nch * 32);
-  p.h_bytes = (uint32_t)(h.blocks * 4096);
-  p.tmem_cols = tmem_cols_for(4 * nch);
-  p.idesc = make_idesc_bf16(128, nch, false, false);
   p.wb = (const uint8_t*)h.wb_dgrad; p.wa = (const uint8_t*)h.wa_dgrad; p.wc = h.wc; p.gout = h.gout;
-  p.act_nb = h.act_nb; p.act_na = h.act_na; p.act_d1b = h.act_d1b;
-  p.g_nb = h.g_nb; p.g_na = h.g_na; p.g_d1b = h.g_d1b;
-  const size_t smem = 1024 + (size_t)p.wb_bytes + p.wa_bytes + 4 * (size_t)p.h_bytes;
-  if (smem > 200 * 1024) return kSgNotEligible;
+  p.act_nb = h.act_nb; p.g_d1b = h.g_d1b;
+  p.partial_b = h.partial_b; p.bpartial_b = h.bpartial_b; p.partial_a = h.partial_a; p.bpartial_a = h.bpartial_a;
+  N2N_TRY(encode_c16_tensor_map(&p.tmap_na, h.act_na, 8, 16, kHbBlocks));
+  N2N_TRY(encode_c16_tensor_map(&p.tmap_d1b, h.act_d1b, 8, 16, kHbBlocks));
   if (!attr_set) {
-    N2N_CUDA(cudaFuncSetAttribute(head_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    N2N_CUDA(cudaFuncSetAttribute(head_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem));
     attr_set = true;
   }
-  int nsm = 0, dev = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = kSMs;
-  const int grid = tiles < nsm ? (int)tiles : nsm;
-  N2N_CUDA(launch_pdl(head_bwd_umma_kernel, dim3(grid), dim3(kHbThreads), smem, st, p));
+  N2N_CUDA(launch_pdl(head_bwd_umma_kernel, dim3(grid), dim3(kHbThreads), kHbSmem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -47,6 +47,7 @@ struct n2n_unet_plan {
   LayerIO io[25];
   int dgrad_blocks[25];   // how many input blocks the layer's dgrad produces (0 = none)
   int splits[25];
+  int head_splits = 0;                   // > 0: fused head backward (headbwd_umma.cu) with that many CTAs
   // 3x3 convs over a two-segment concat whose packed weights exceed shared memory (Cin = 2nf + nf):
   // forward = two launches over the K segments (the second adds the first's bf16 partial), input
   // gradient = two launches over the N segments; each half keeps its weights resident on the slab engine.
@@ -162,6 +163,7 @@ static void plan_layout(n2n_unet_plan* p) {
     p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
   }
   if (p->bwd) {
+    p->head_splits = head_bwd_splits(p->dtype, p->hb, p->out_nc, p->N, p->H, p->W);
     for (int b = 0; b < B_COUNT; ++b)
       p->grd[b].off = take((size_t)p->N * p->grd[b].Cb * p->lh(p->grd[b].lvl) * p->lw(p->grd[b].lvl) * 16 * es);
     for (int i = 0; i < 25; ++i) {
@@ -183,6 +185,8 @@ static void plan_layout(n2n_unet_plan* p) {
           p->off_wd20_full = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));   // only used when dL/dx is wanted
         }
       }
+      // nin_a / nin_b: their weight gradients come out of the fused head backward, one partial per CTA of it
+      if ((i == 22 || i == 23) && p->head_splits > 0) p->splits[i] = p->head_splits;
       p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
       p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
     }
@@ -457,29 +461,28 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   };
 
   // head + level-0 decoder
-  int hb = kSgNotEligible;
-  bool w24_done = false;
-  if (dt == N2N_BF16 && p->hb * 16 == 96) {
-    // the three 1x1 input gradients in one kernel (weight gradients still need every intermediate)
+  if (p->head_splits > 0) {
+    // input gradients of the three 1x1 layers and the weight gradients of nin_a / nin_b in one kernel
     HeadBwd h;
     h.blocks = p->hb; h.channels = 96; h.out_nc = p->out_nc; h.slope = 0.2f;
     h.gout = dy; h.wc = params[2 * 24];
     h.wb_dgrad = (char*)ws + p->off_wd[23]; h.wa_dgrad = (char*)ws + p->off_wd[22];
     h.act_nb = p->view(p->act, ws, B_NB, 0, p->hb); h.act_na = p->view(p->act, ws, B_NA, 0, p->hb);
     h.act_d1b = p->view(p->act, ws, B_D1B, 0, p->hb);
-    h.g_nb = p->view(p->grd, ws, B_NB, 0, p->hb); h.g_na = p->view(p->grd, ws, B_NA, 0, p->hb);
     h.g_d1b = p->view(p->grd, ws, B_D1B, 0, p->hb);
+    h.splits = p->head_splits;
+    h.partial_b = (float*)((char*)ws + p->off_partial[23]); h.bpartial_b = (float*)((char*)ws + p->off_bpartial[23]);
+    h.partial_a = (float*)((char*)ws + p->off_partial[22]); h.bpartial_a = (float*)((char*)ws + p->off_bpartial[22]);
     N2N_TRY(wgrad(24));                       // reads grad(out) and nin_b's activation only
-    w24_done = true;
-    hb = launch_head_bwd(h, st);
+    const int hb = launch_head_bwd(h, st);
     if (hb < 0) return hb;
-    if (hb == 0) { N2N_TRY(wgrad(23)); N2N_TRY(wgrad(22)); }
-  }
-  if (hb == kSgNotEligible)
+    N2N_CHECK_ARG(hb == 0, "unet_backward: fused head backward declined a geometry the plan was built for");
+  } else {
     for (int i = 24; i >= 22; --i) {
-      if (!(i == 24 && w24_done)) N2N_TRY(wgrad(i));
+      N2N_TRY(wgrad(i));
       N2N_TRY(dgrad(i, p->L[i].cin_blocks(), true, false));
     }
+  }
   N2N_TRY(wgrad(21)); N2N_TRY(dgrad(21, p->L[21].cin_blocks(), true, false));
   N2N_TRY(wgrad(20));
   N2N_TRY(dgrad(20, (want_dx || !p->im2col) ? p->c2b + p->inb : p->c2b, false, false));
