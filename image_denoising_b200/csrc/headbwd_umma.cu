@@ -32,7 +32,8 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kHbThreads = 448;
+constexpr int kHbThreads = 480;
+constexpr int kHbNaBufs = 3;             // NA tiles live longest (TMA -> GEMM-1 -> S1 in place -> GEMM-2)
 constexpr int kHbMaxOut = 4;
 constexpr int kHbBlocks = 6;              // the head is literally 96 channels wide (arch_unet.py:177-190)
 constexpr int kHbCh = kHbBlocks * 16;
@@ -45,7 +46,7 @@ constexpr int kHbWN = kHbCh + 16;         // weight-gradient accumulator width: 
 constexpr uint32_t kHbColD1 = 0, kHbColD2 = kHbCh, kHbColWb = 2 * kHbCh, kHbColWa = 2 * kHbCh + kHbWN;
 constexpr uint32_t kHbTmemCols = 512;
 static_assert(kHbColWa + kHbWN <= kHbTmemCols, "TMEM budget");
-constexpr size_t kHbSmem = 1024 + 2 * (size_t)kHbWBytes + 2 * (size_t)kHbHBuf + 4 * (size_t)kHbXBuf;
+constexpr size_t kHbSmem = 1024 + 2 * (size_t)kHbWBytes + 2 * (size_t)kHbHBuf + (2 + kHbNaBufs) * (size_t)kHbXBuf;
 
 struct HbParams {
   int out_nc;
@@ -61,13 +62,13 @@ struct HbParams {
 __device__ __forceinline__ void hb_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
   }
@@ -103,25 +104,29 @@ __device__ __forceinline__ void hb_st_global_32B(void* ptr, const uint32_t w[8])
                : "memory");
 }
 
-// v[16] (fp32 gradient of one channel block of one pixel) * lrelu'(activation words) -> packed bf16
+// v[16] (fp32 gradient of one channel block of one pixel) * lrelu'(activation words) -> packed bf16.
+// lrelu' = 1 where the bf16 activation is > 0 (sign clear and non-zero, tested on the raw bits), else slope:
+// one compare and one predicated multiply per element.
 __device__ __forceinline__ void hb_mask_pack(const float v[16], const uint32_t mk[8], float slope, uint32_t w[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float a0 = __uint_as_float(mk[j] << 16), a1 = __uint_as_float(mk[j] & 0xffff0000u);
-    const float g0 = v[2 * j] * (a0 > 0.f ? 1.f : slope), g1 = v[2 * j + 1] * (a1 > 0.f ? 1.f : slope);
+    float g0 = v[2 * j], g1 = v[2 * j + 1];
+    if ((int)(mk[j] << 16) <= 0) g0 *= slope;
+    if ((int)mk[j] <= 0xFFFF) g1 *= slope;
     __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
     w[j] = *reinterpret_cast<uint32_t*>(&h);
   }
 }
 
+template <int OUT_NC>
 __global__ void __launch_bounds__(kHbThreads, 1)
 head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // double-buffered: h0_full h0_empty na_full na_empty db_full db_empty h1_full; single: d1_full d1_empty d2_full
+  // h0_full[2] h0_empty[2] db_full[2] db_empty[2] | na_full[3] na_empty[3] h1_full[3] | d1_full d1_empty d2_full
   // d2_empty w_full acc_full
-  __shared__ uint64_t bars[20];
+  __shared__ uint64_t bars[23];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_wc[kHbMaxOut * 128];
+  __shared__ __align__(16) float s_wc[OUT_NC * kHbCh];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -129,34 +134,34 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
   const uint32_t wb0 = smem0, wa0 = wb0 + kHbWBytes;
   const uint32_t h00 = wa0 + kHbWBytes;                  // g_nb tiles (written by S0)
   const uint32_t na0 = h00 + 2 * kHbHBuf;                // NA tiles (TMA), overwritten in place with g_na by S1
-  const uint32_t db0 = na0 + 2 * kHbXBuf;                // D1B tiles (TMA)
+  const uint32_t db0 = na0 + kHbNaBufs * kHbXBuf;        // D1B tiles (TMA)
   const uint32_t bar0 = smem_u32(bars);
-  enum { H0F = 0, H0E, NAF, NAE, DBF, DBE, H1F };
+  enum { H0F = 0, H0E, DBF, DBE };
+  enum { NAF = 0, NAE, H1F };
   auto bar = [&](int kind, int b) { return bar0 + 8u * (2 * kind + b); };
-  const uint32_t d1_full = bar0 + 8u * 14, d1_empty = bar0 + 8u * 15, d2_full = bar0 + 8u * 16, d2_empty = bar0 + 8u * 17;
-  const uint32_t w_full = bar0 + 8u * 18;
-  const uint32_t acc_full = bar0 + 8u * 19;
+  auto bar3 = [&](int kind, int b) { return bar0 + 8u * (8 + 3 * kind + b); };
+  const uint32_t d1_full = bar0 + 8u * 17, d1_empty = bar0 + 8u * 18, d2_full = bar0 + 8u * 19, d2_empty = bar0 + 8u * 20;
+  const uint32_t w_full = bar0 + 8u * 21;
+  const uint32_t acc_full = bar0 + 8u * 22;
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(H0F, b), 4); mbar_init(bar(H0E, b), 1);
-      mbar_init(bar(NAF, b), 1); mbar_init(bar(NAE, b), 1);
       mbar_init(bar(DBF, b), 1); mbar_init(bar(DBE, b), 4);
-      mbar_init(bar(H1F, b), 4);
+    }
+    for (int b = 0; b < kHbNaBufs; ++b) {
+      mbar_init(bar3(NAF, b), 1); mbar_init(bar3(NAE, b), 1); mbar_init(bar3(H1F, b), 4);
     }
     mbar_init(d1_full, 1); mbar_init(d1_empty, 4);
     mbar_init(d2_full, 1); mbar_init(d2_empty, 4);
-    mbar_init(w_full, 1); mbar_init(acc_full, 1);
+    mbar_init(w_full, 1); mbar_init(acc_full, 2);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < kHbMaxOut * 128; i += kHbThreads) {
-    const int oc = i >> 7, c = i & 127;
-    s_wc[i] = (oc < p.out_nc && c < kHbCh) ? p.wc[oc * kHbCh + c] : 0.f;
-  }
+  for (int i = threadIdx.x; i < OUT_NC * kHbCh; i += kHbThreads) s_wc[i] = p.wc[i];
   // the block of ones behind every activation tile: column 96 of the weight-gradient GEMM = bias gradient
-  for (int i = threadIdx.x; i < 4 * (int)(kHbBlk / 4); i += kHbThreads) {
+  for (int i = threadIdx.x; i < (2 + kHbNaBufs) * (int)(kHbBlk / 4); i += kHbThreads) {
     const int buf = i / (int)(kHbBlk / 4), wd = i - buf * (int)(kHbBlk / 4);
-    const uint32_t base = (buf < 2 ? na0 + buf * kHbXBuf : db0 + (buf - 2) * kHbXBuf) + kHbBlocks * kHbBlk;
+    const uint32_t base = na0 + buf * kHbXBuf + kHbBlocks * kHbBlk;      // the D1B buffers follow the NA buffers
     reinterpret_cast<uint32_t*>(smem_gen + (base - smem0))[wd] = 0x3F803F80u;
   }
   fence_proxy_async();
@@ -179,6 +184,22 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
     }
     __syncwarp();
     pdl_wait();
+    // A tile's buffer is held from the TMA issue until the GEMMs and the stage that read it are done, so
+    // with two buffers the DRAM latency would sit inside the per-tile cycle: pull the boxes into L2 a few
+    // tiles ahead and let the shared-memory load pay only the L2 latency.
+    constexpr int kAhead = 3;
+    auto prefetch = [&](int lt) {
+      if (lt < niter && elect_one_sync()) {
+        const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int img = tile / tiles_per_img;
+        const int r = tile - img * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        tma_prefetch_l2_5d(&p.tmap_na, 0, tx * 8, ty * 16, 0, img);
+        tma_prefetch_l2_5d(&p.tmap_d1b, 0, tx * 8, ty * 16, 0, img);
+      }
+      __syncwarp();
+    };
+    for (int lt = 0; lt < kAhead; ++lt) prefetch(lt);
     for (int lt = 0; lt < niter; ++lt) {
       const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
       const int img = tile / tiles_per_img;
@@ -186,10 +207,13 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int b = lt & 1;
       const uint32_t par = ((uint32_t)lt >> 1) & 1u;
-      hb_wait(bar(NAE, b), par ^ 1u);
+      const int b3 = lt % kHbNaBufs;
+      const uint32_t par3 = (uint32_t)(lt / kHbNaBufs) & 1u;
+      prefetch(lt + kAhead);
+      hb_wait(bar3(NAE, b3), par3 ^ 1u);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar(NAF, b), kHbHBuf);
-        tma_load_5d(na0 + b * kHbXBuf, &p.tmap_na, bar(NAF, b), 0, tx * 8, ty * 16, 0, img);
+        mbar_arrive_expect_tx(bar3(NAF, b3), kHbHBuf);
+        tma_load_5d(na0 + b3 * kHbXBuf, &p.tmap_na, bar3(NAF, b3), 0, tx * 8, ty * 16, 0, img);
       }
       __syncwarp();
       hb_wait(bar(DBE, b), par ^ 1u);
@@ -199,10 +223,13 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer: dWb + GEMM-1 of tile i, then dWa + GEMM-2 of tile i-1 ----
+  } else if (warp == 1 || warp == 14) {
+    // ---- MMA issuers.  Warp 1: dWb + GEMM-1 per tile; warp 14: dWa + GEMM-2.  Two issuers, because one
+    // in-order issuer would hold GEMM-2 of tile i-1 (which frees an NA buffer for the next TMA load) behind
+    // GEMM-1 of tile i (which waits for a TMA load): the loads would run strictly one at a time.
+    const bool second = warp == 14;
     pdl_wait();
-    pdl_release();
+    if (!second) pdl_release();
     hb_wait(w_full, 0);
     const uint32_t hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);   // SBO = one 8-pixel image row, both majors
     const uint32_t idesc_g = make_idesc_bf16(128, kHbCh, false, false);
@@ -220,36 +247,33 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
         hb_mma(tmem_base + col_d, (ga + cb * (kHbBlk >> 4)) | lbo_k, (wa + cb * (uint32_t)(kHbCh * 2)) | lbo_k, hi, idesc_g,
                cb ? 1u : 0u);
     };
-    for (int lt = 0; lt <= niter; ++lt) {
-      if (lt < niter) {
-        const int b = lt & 1;
-        const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+    for (int lt = 0; lt < niter; ++lt) {
+      const int b = lt & 1;
+      const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+      const int b3 = lt % kHbNaBufs;
+      const uint32_t par3 = (uint32_t)(lt / kHbNaBufs) & 1u;
+      if (!second) {
         hb_wait(d1_empty, ((uint32_t)lt & 1u) ^ 1u);
-        hb_wait(bar(NAF, b), par);
+        hb_wait(bar3(NAF, b3), par3);
         hb_wait(bar(H0F, b), par);
         fence_after_sync();
         if (elect_one_sync()) {
-          issue(h00 + b * kHbHBuf, na0 + b * kHbXBuf, wb0, kHbColWb, kHbColD1, (uint32_t)lt);
+          issue(h00 + b * kHbHBuf, na0 + b3 * kHbXBuf, wb0, kHbColWb, kHbColD1, (uint32_t)lt);
           mma_commit(bar(H0E, b));
           mma_commit(d1_full);
         }
-        __syncwarp();
-      }
-      if (lt >= 1) {
-        const int t = lt - 1;
-        const int b = t & 1;
-        const uint32_t par = ((uint32_t)t >> 1) & 1u;
-        hb_wait(d2_empty, ((uint32_t)t & 1u) ^ 1u);
+      } else {
+        hb_wait(d2_empty, ((uint32_t)lt & 1u) ^ 1u);
         hb_wait(bar(DBF, b), par);
-        hb_wait(bar(H1F, b), par);
+        hb_wait(bar3(H1F, b3), par3);
         fence_after_sync();
         if (elect_one_sync()) {
-          issue(na0 + b * kHbXBuf, db0 + b * kHbXBuf, wa0, kHbColWa, kHbColD2, (uint32_t)t);
-          mma_commit(bar(NAE, b));
+          issue(na0 + b3 * kHbXBuf, db0 + b * kHbXBuf, wa0, kHbColWa, kHbColD2, (uint32_t)lt);
+          mma_commit(bar3(NAE, b3));
           mma_commit(d2_full);
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
     if (elect_one_sync()) mma_commit(acc_full);
     __syncwarp();
@@ -261,31 +285,50 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
     const uint32_t sw = ((uint32_t)m >> 2) & 1u;       // 16-byte chunk swap of this pixel's rows (address bit 7)
     pdl_wait();
     if (stage == 0) {
-      for (int lt = 0; lt < niter; ++lt) {
+      // Software pipeline over tiles: the global loads of tile i+1 (activation words that give lrelu', the
+      // output gradient) are issued while tile i is processed, each into the registers its block just freed.
+      const long long hw = (long long)p.H * p.W;
+      uint32_t mk[kHbBlocks][8];
+      float go_next[OUT_NC];
+      long long apix = 0;
+      bool valid = false;
+      auto locate = [&](int lt, long long& gidx) {
         const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
         const int img = tile / tiles_per_img;
         const int r = tile - img * tiles_per_img;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int y = ty * 16 + py, x = tx * 8 + px;
-        const bool valid = y < p.H && x < p.W;
+        valid = lt < niter && y < p.H && x < p.W;
+        apix = (long long)img * p.act_nb.sN + (long long)y * p.act_nb.sY + (long long)x * p.act_nb.sX;
+        gidx = (long long)img * OUT_NC * hw + (long long)y * p.W + x;
+      };
+      auto load_block = [&](int cb) {
+        if (valid) hb_ld_global_32B((const __nv_bfloat16*)p.act_nb.ptr + apix + cb * p.act_nb.sCb, mk[cb]);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) mk[cb][q] = 0u;
+        }
+      };
+      auto load_gout = [&](long long gidx) {
+#pragma unroll
+        for (int oc = 0; oc < OUT_NC; ++oc) go_next[oc] = valid ? p.gout[gidx + oc * hw] : 0.f;
+      };
+      {
+        long long gidx;
+        locate(0, gidx);
+#pragma unroll
+        for (int cb = 0; cb < kHbBlocks; ++cb) load_block(cb);
+        load_gout(gidx);
+      }
+      for (int lt = 0; lt < niter; ++lt) {
         const int b = lt & 1;
         const uint32_t par = ((uint32_t)lt >> 1) & 1u;
-        const long long apix = (long long)img * p.act_nb.sN + (long long)y * p.act_nb.sY + (long long)x * p.act_nb.sX;
-        // the activation words that give lrelu' for this pixel: issue all loads before waiting on the pipeline
-        uint32_t mk[kHbBlocks][8];
+        float go[OUT_NC];
 #pragma unroll
-        for (int cb = 0; cb < kHbBlocks; ++cb) {
-          if (valid) hb_ld_global_32B((const __nv_bfloat16*)p.act_nb.ptr + apix + cb * p.act_nb.sCb, mk[cb]);
-          else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) mk[cb][q] = 0u;
-          }
-        }
-        float go[kHbMaxOut];
-        const long long hw = (long long)p.H * p.W;
-#pragma unroll
-        for (int oc = 0; oc < kHbMaxOut; ++oc)
-          go[oc] = (oc < p.out_nc && valid) ? p.gout[((long long)img * p.out_nc + oc) * hw + (long long)y * p.W + x] : 0.f;
+        for (int oc = 0; oc < OUT_NC; ++oc) go[oc] = go_next[oc];
+        long long gidx;
+        locate(lt + 1, gidx);                       // from here on `valid` / `apix` describe the NEXT tile
+        load_gout(gidx);
         if (quarter == 0) hb_wait(bar(H0E, b), par ^ 1u);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint8_t* row = smem_gen + (h00 - smem0) + (uint32_t)b * kHbHBuf + (uint32_t)m * 32u;
@@ -293,20 +336,21 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
         for (int cb = 0; cb < kHbBlocks; ++cb) {
           float v[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+          for (int oc = 0; oc < OUT_NC; ++oc) {
+            const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * kHbCh + cb * 16]);
 #pragma unroll
-          for (int oc = 0; oc < kHbMaxOut; ++oc) {
-            if (oc < p.out_nc) {
-              const float4* wr = reinterpret_cast<const float4*>(&s_wc[oc * 128 + cb * 16]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 wv = wr[q];
+            for (int q = 0; q < 4; ++q) {
+              const float4 wv = wr[q];
+              if (oc == 0) {
+                v[4 * q] = wv.x * go[0]; v[4 * q + 1] = wv.y * go[0]; v[4 * q + 2] = wv.z * go[0]; v[4 * q + 3] = wv.w * go[0];
+              } else {
                 v[4 * q] += wv.x * go[oc]; v[4 * q + 1] += wv.y * go[oc]; v[4 * q + 2] += wv.z * go[oc]; v[4 * q + 3] += wv.w * go[oc];
               }
             }
           }
           uint32_t w[8];
           hb_mask_pack(v, mk[cb], p.slope, w);
+          load_block(cb);
           uint4* dst = reinterpret_cast<uint4*>(row + (uint32_t)cb * kHbBlk);
           dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
           dst[sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -329,8 +373,10 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
         const bool valid = y < p.H && x < p.W;
         const int b = lt & 1;
         const uint32_t par = ((uint32_t)lt >> 1) & 1u;
+        const int b3 = lt % kHbNaBufs;
+        const uint32_t par3 = (uint32_t)(lt / kHbNaBufs) & 1u;
         if (quarter == 0) {
-          hb_wait(bar(s1 ? NAF : DBF, b), par);       // the TMA'd activation tile is visible to this warp group
+          hb_wait(s1 ? bar3(NAF, b3) : bar(DBF, b), s1 ? par3 : par);   // the TMA'd activation tile is visible to this group
           hb_wait(dfull, (uint32_t)lt & 1u);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + stage) : "memory");
@@ -343,7 +389,7 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(dempty);
-        uint8_t* row = smem_gen + ((s1 ? na0 : db0) - smem0) + (uint32_t)b * kHbXBuf + (uint32_t)m * 32u;
+        uint8_t* row = smem_gen + ((s1 ? na0 + (uint32_t)b3 * kHbXBuf : db0 + (uint32_t)b * kHbXBuf) - smem0) + (uint32_t)m * 32u;
         const long long gpix = (long long)img * p.g_d1b.sN + (long long)y * p.g_d1b.sY + (long long)x * p.g_d1b.sX;
 #pragma unroll
         for (int cb = 0; cb < kHbBlocks; ++cb) {
@@ -364,7 +410,7 @@ head_bwd_umma_kernel(const __grid_constant__ HbParams p) {
         }
         if (s1) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(s1 ? H1F : DBE, b));
+        if (lane == 0) mbar_arrive(s1 ? bar3(H1F, b3) : bar(DBE, b));
       }
       // ---- this CTA's weight-gradient partial: TMEM lane = output channel n, column = input channel c ----
       if (quarter == 0) hb_wait(acc_full, 0);
@@ -406,7 +452,7 @@ int head_bwd_splits(int dtype, int blocks, int out_nc, int n, int h, int w) {
 // Returns 0 when launched, kSgNotEligible when the geometry is not covered (caller runs the three
 // input-gradient and two weight-gradient launches one by one).
 int launch_head_bwd_umma(const HeadBwd& h, cudaStream_t st) {
-  static bool attr_set = false;
+  static int attr_set = 0;
   const int grid = head_bwd_splits(N2N_BF16, h.blocks, h.out_nc, h.g_d1b.N, h.g_d1b.H, h.g_d1b.W);
   if (grid < 1 || h.channels != kHbCh || h.splits != grid) return kSgNotEligible;
   N2N_CHECK_ARG(h.partial_a && h.partial_b && h.bpartial_a && h.bpartial_b, "head_bwd: null partial buffer");
@@ -421,11 +467,13 @@ int launch_head_bwd_umma(const HeadBwd& h, cudaStream_t st) {
   p.partial_b = h.partial_b; p.bpartial_b = h.bpartial_b; p.partial_a = h.partial_a; p.bpartial_a = h.bpartial_a;
   N2N_TRY(encode_c16_tensor_map(&p.tmap_na, h.act_na, 8, 16, kHbBlocks));
   N2N_TRY(encode_c16_tensor_map(&p.tmap_d1b, h.act_d1b, 8, 16, kHbBlocks));
-  if (!attr_set) {
-    N2N_CUDA(cudaFuncSetAttribute(head_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem));
-    attr_set = true;
+  void (*kernel)(HbParams) = h.out_nc == 1 ? head_bwd_umma_kernel<1> : h.out_nc == 2 ? head_bwd_umma_kernel<2>
+                             : h.out_nc == 3 ? head_bwd_umma_kernel<3> : head_bwd_umma_kernel<4>;
+  if (!(attr_set & (1 << h.out_nc))) {
+    N2N_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem));
+    attr_set |= 1 << h.out_nc;
   }
-  N2N_CUDA(launch_pdl(head_bwd_umma_kernel, dim3(grid), dim3(kHbThreads), kHbSmem, st, p));
+  N2N_CUDA(launch_pdl(kernel, dim3(grid), dim3(kHbThreads), kHbSmem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }
