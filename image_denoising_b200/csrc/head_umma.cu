@@ -24,7 +24,8 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kHdThreads = 576;            // TMA warp, MMA warp, 8 warps for stage E1, 8 for stage E2
+constexpr int kHdThreads = 608;            // TMA warp, MMA-1 warp, 8 warps for stage E1, 8 for stage E2, MMA-2 warp
+constexpr int kHdD2Bufs = 3;               // E2 is the longest stage: a third accumulator keeps MMA-2 ahead of it
 constexpr int kHdRing = 5;
 constexpr int kHdMaxOut = 4;
 
@@ -44,13 +45,13 @@ struct HdParams {
 __device__ __forceinline__ void hd_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of spinning
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
   }
@@ -108,11 +109,12 @@ __device__ __forceinline__ void hd_st_global_32B(void* ptr, const uint32_t w[8])
                : "memory");
 }
 
+template <bool SAVE>
 __global__ void __launch_bounds__(kHdThreads, 1)
 head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // barriers: x_full[3] x_empty[3] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[2] d2_empty[2] w_full
-  __shared__ uint64_t bars[2 * kHdRing + 12 + 1];
+  // barriers: x_full[ring] x_empty[ring] d1_full[2] d1_empty[2] h_full[2] h_empty[2] d2_full[3] d2_empty[3] w_full
+  __shared__ uint64_t bars[2 * kHdRing + 8 + 2 * kHdD2Bufs + 1];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_wc[kHdMaxOut * 128], s_bc[kHdMaxOut];
 
@@ -135,8 +137,8 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
   auto h_full = [&](int b) { return bar0 + 8u * (2 * kHdRing + 4 + b); };
   auto h_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 6 + b); };
   auto d2_full = [&](int b) { return bar0 + 8u * (2 * kHdRing + 8 + b); };
-  auto d2_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 10 + b); };
-  const uint32_t w_full = bar0 + 8u * (2 * kHdRing + 12);
+  auto d2_empty = [&](int b) { return bar0 + 8u * (2 * kHdRing + 8 + kHdD2Bufs + b); };
+  const uint32_t w_full = bar0 + 8u * (2 * kHdRing + 8 + 2 * kHdD2Bufs);
   const int nmid = p.mid_blocks * 16;
 
   if (threadIdx.x == 0) {
@@ -144,8 +146,8 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4);
       mbar_init(h_full(b), 4);  mbar_init(h_empty(b), 1);
-      mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
     }
+    for (int b = 0; b < kHdD2Bufs; ++b) { mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -202,58 +204,52 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
       __syncwarp();
       if (++slot == kHdRing) { slot = 0; phase ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer: MMA-1 of tile i+1 is issued before MMA-2 of tile i so E1 never starves ----
+  } else if (warp == 1 || warp == 18) {
+    // ---- MMA issuers: warp 1 runs MMA-1 (needs an X tile and a free D1), warp 18 MMA-2 (needs E1's H1 tile and a
+    // free D2).  Two warps so that neither GEMM queues behind the other one's wait.
     pdl_wait();
-    pdl_release();
+    if (warp == 1) pdl_release();
     hd_wait(w_full, 0);
     const uint32_t idesc = p.idesc;
     const uint32_t ba16 = (uint32_t)nmid * 2u;              // bytes/16 of one K block of Wa / Wb (nmid rows x 32 B)
-    auto mma1 = [&](int lt, int slot, uint32_t xph) {
-      const int b = lt & 1;
-      hd_wait(d1_empty(b), (((uint32_t)lt >> 1) & 1u) ^ 1u);
-      hd_wait(x_full(slot), xph);
-      fence_after_sync();
-      if (elect_one_sync()) {
-        const uint32_t a_lo = (((x0s + slot * p.x_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t b_lo = ((wa0 & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int cb = 0; cb < p.in_blocks; ++cb)
-          hd_mma(tmem_base + (uint32_t)(b * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
-        hd_mma(tmem_base + (uint32_t)(b * nmid), ((ones0 & 0x3FFFFu) >> 4) | (1u << 16), ((bia0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
-        mma_commit(x_empty(slot));
-        mma_commit(d1_full(b));
-      }
-      __syncwarp();
-    };
-    auto mma2 = [&](int lt) {
-      const int b = lt & 1;
-      hd_wait(d2_empty(b), (((uint32_t)lt >> 1) & 1u) ^ 1u);
-      hd_wait(h_full(b), ((uint32_t)lt >> 1) & 1u);
-      fence_after_sync();
-      if (elect_one_sync()) {
-        const uint32_t a_lo = (((h0s + b * p.h_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t b_lo = ((wb0 & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int cb = 0; cb < p.mid_blocks; ++cb)
-          hd_mma(tmem_base + (uint32_t)((2 + b) * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
-        hd_mma(tmem_base + (uint32_t)((2 + b) * nmid), ((ones0 & 0x3FFFFu) >> 4) | (1u << 16), ((bib0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
-        mma_commit(h_empty(b));
-        mma_commit(d2_full(b));
-      }
-      __syncwarp();
-    };
-    int slot = 0; uint32_t xph = 0;
-    int lt = 0;
-    const int first = blockIdx.x;
-    if (first < p.ntiles) {
-      mma1(0, slot, xph);
-      if (++slot == kHdRing) { slot = 0; xph ^= 1u; }
-    }
-    for (int tile = first; tile < p.ntiles; tile += gridDim.x, ++lt) {
-      if (tile + (int)gridDim.x < p.ntiles) {
-        mma1(lt + 1, slot, xph);
+    const uint32_t ones_lo = ((ones0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const int niter = p.ntiles > (int)blockIdx.x ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 1) {
+      int slot = 0; uint32_t xph = 0;
+      for (int lt = 0; lt < niter; ++lt) {
+        const int b = lt & 1;
+        hd_wait(d1_empty(b), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        hd_wait(x_full(slot), xph);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = (((x0s + slot * p.x_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t b_lo = ((wa0 & 0x3FFFFu) >> 4) | (1u << 16);
+          for (int cb = 0; cb < p.in_blocks; ++cb)
+            hd_mma(tmem_base + (uint32_t)(b * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+          hd_mma(tmem_base + (uint32_t)(b * nmid), ones_lo, ((bia0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
+          mma_commit(x_empty(slot));
+          mma_commit(d1_full(b));
+        }
+        __syncwarp();
         if (++slot == kHdRing) { slot = 0; xph ^= 1u; }
       }
-      mma2(lt);
+    } else {
+      for (int lt = 0; lt < niter; ++lt) {
+        const int b = lt & 1, b2 = lt % kHdD2Bufs;
+        hd_wait(d2_empty(b2), ((uint32_t)(lt / kHdD2Bufs) & 1u) ^ 1u);
+        hd_wait(h_full(b), ((uint32_t)lt >> 1) & 1u);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = (((h0s + b * p.h_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t b_lo = ((wb0 & 0x3FFFFu) >> 4) | (1u << 16);
+          for (int cb = 0; cb < p.mid_blocks; ++cb)
+            hd_mma(tmem_base + (uint32_t)((2 + b2) * nmid), a_lo + cb * 256u, b_lo + cb * ba16, hi, idesc, cb ? 1u : 0u);
+          hd_mma(tmem_base + (uint32_t)((2 + b2) * nmid), ones_lo, ((bib0 & 0x3FFFFu) >> 4) | (1u << 16), hi, idesc, 1u);
+          mma_commit(h_empty(b));
+          mma_commit(d2_full(b2));
+        }
+        __syncwarp();
+      }
     }
   } else {
     // warps 2-9: stage E1, warps 10-17: stage E2; each stage has two groups of four warps that take
@@ -282,7 +278,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
         if (quarter == 0) { hd_wait(d1_full(b), par); hd_wait(h_empty(b), par ^ 1u); }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         fence_after_sync();
-        const long long spix = p.has_save ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
+        const long long spix = SAVE ? (long long)img * p.save_a.sN + (long long)y * p.save_a.sY + (long long)x * p.save_a.sX : 0;
         uint8_t* const h_row = smem_gen + (h0s - smem0) + (size_t)b * p.h_bytes + (size_t)m * 32u;
         const uint32_t h_sw = ((h0s + (uint32_t)m * 32u) >> 7) & 1u;
         // two accumulator-read buffers in ping-pong: the read of block cb+1 is in flight while block cb is processed
@@ -305,52 +301,63 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
             uint4* dst = reinterpret_cast<uint4*>(h_row + (size_t)cb * 4096u);
             dst[h_sw] = make_uint4(w[0], w[1], w[2], w[3]);
             dst[h_sw ^ 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-            if (p.has_save && valid) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+            if (SAVE && valid) hd_st_global_32B((__nv_bfloat16*)p.save_a.ptr + spix + cb * p.save_a.sCb, w);
+        };
+        // D1 goes back to the MMA-1 warp as soon as its last block is in registers, before that block is processed
+        auto release_d1 = [&]() {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d1_empty(b));
         };
         if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + cb_lo * 16), ra);
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; cb += 2) {
           hd_ld_wait();
           if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 1) * 16), rb);
+          else release_d1();
           e1_block(cb, ra);
           if (cb + 1 < cb_hi) {
             hd_ld_wait();
             if (cb + 2 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)(b * nmid + (cb + 2) * 16), ra);
+            else release_d1();
             e1_block(cb + 1, rb);
           }
         }
-        fence_before_sync();
         fence_proxy_async();                 // generic-proxy writes of H1 -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { mbar_arrive(d1_empty(b)); mbar_arrive(h_full(b)); }
+        if (lane == 0) mbar_arrive(h_full(b));
       } else {
         // ---- E2: D2 -> nin_c -> fp32 NCHW ----
-        if (quarter == 0) hd_wait(d2_full(b), par);
+        const int b2 = lt % kHdD2Bufs;
+        if (quarter == 0) hd_wait(d2_full(b2), (uint32_t)(lt / kHdD2Bufs) & 1u);
         asm volatile("bar.sync %0, 128;" ::"r"(3 + group) : "memory");
         fence_after_sync();
-        const long long spix = p.has_save ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
+        const long long spix = SAVE ? (long long)img * p.save_b.sN + (long long)y * p.save_b.sY + (long long)x * p.save_b.sX : 0;
         float o[kHdMaxOut];
 #pragma unroll
         for (int oc = 0; oc < kHdMaxOut; ++oc) o[oc] = s_bc[oc];
         uint32_t ra[16], rb[16];
         auto e2_block = [&](int cb, const uint32_t* rv) {
             float v[16];
-            uint32_t w[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float a0 = __uint_as_float(rv[4 * q]), a1 = __uint_as_float(rv[4 * q + 1]);
               float a2 = __uint_as_float(rv[4 * q + 2]), a3 = __uint_as_float(rv[4 * q + 3]);
               // LeakyReLU with 0 <= slope <= 1 is max(a, slope * a): two instructions per element
-              a0 = fmaxf(a0, a0 * p.slope); a1 = fmaxf(a1, a1 * p.slope);
-              a2 = fmaxf(a2, a2 * p.slope); a3 = fmaxf(a3, a3 * p.slope);
-              // nin_c (and the backward) see the bf16-rounded activation, as in the unfused path
-              __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-              w[2 * q] = *reinterpret_cast<uint32_t*>(&h01);
-              w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h23);
-              v[4 * q] = __uint_as_float(w[2 * q] << 16); v[4 * q + 1] = __uint_as_float(w[2 * q] & 0xffff0000u);
-              v[4 * q + 2] = __uint_as_float(w[2 * q + 1] << 16); v[4 * q + 3] = __uint_as_float(w[2 * q + 1] & 0xffff0000u);
+              v[4 * q] = fmaxf(a0, a0 * p.slope); v[4 * q + 1] = fmaxf(a1, a1 * p.slope);
+              v[4 * q + 2] = fmaxf(a2, a2 * p.slope); v[4 * q + 3] = fmaxf(a3, a3 * p.slope);
             }
-            if (p.has_save && valid) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+            if (SAVE) {
+              // training pass: nin_c sees the bf16-rounded activation that is saved for the backward
+              uint32_t w[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                w[q] = *reinterpret_cast<uint32_t*>(&h);
+                v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+              }
+              if (valid) hd_st_global_32B((__nv_bfloat16*)p.save_b.ptr + spix + cb * p.save_b.sCb, w);
+            }
 #pragma unroll
             for (int oc = 0; oc < kHdMaxOut; ++oc) {
               if (oc < p.out_nc) {
@@ -363,21 +370,21 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
               }
             }
         };
-        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + cb_lo * 16), ra);
+        if (cb_lo < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b2) * nmid + cb_lo * 16), ra);
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; cb += 2) {
           hd_ld_wait();
-          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 1) * 16), rb);
+          if (cb + 1 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b2) * nmid + (cb + 1) * 16), rb);
           e2_block(cb, ra);
           if (cb + 1 < cb_hi) {
             hd_ld_wait();
-            if (cb + 2 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b) * nmid + (cb + 2) * 16), ra);
+            if (cb + 2 < cb_hi) hd_ld16_issue(lane_base + (uint32_t)((2 + b2) * nmid + (cb + 2) * 16), ra);
             e2_block(cb + 1, rb);
           }
         }
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d2_empty(b));
+        if (lane == 0) mbar_arrive(d2_empty(b2));
         const long long hw = (long long)p.x.H * p.x.W;
 #pragma unroll
         for (int oc = 0; oc < kHdMaxOut; ++oc)
@@ -393,7 +400,7 @@ head_chain_umma_kernel(const __grid_constant__ HdParams p) {
 // Returns 0 when launched, kSgNotEligible when the geometry is not covered (caller runs the three
 // layers one by one).
 int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
-  static bool attr_set = false;
+  static int attr_set = 0;
   { const char* e = getenv("N2N_NO_HEAD_FUSION"); if (e && atoi(e)) return kSgNotEligible; }
   if (h.in_blocks < 1 || h.in_blocks > 8 || h.mid_blocks < 1 || h.mid_blocks > 8 || h.out_nc < 1 || h.out_nc > kHdMaxOut)
     return kSgNotEligible;
@@ -412,8 +419,8 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   p.wb_bytes = (uint32_t)(((h.mid_blocks + 2) / 3) * 3 * nmid * 32);
   p.x_bytes = (uint32_t)(h.in_blocks * 4096);
   p.h_bytes = (uint32_t)(h.mid_blocks * 4096);
-  p.tmem_cols = tmem_cols_for(4 * nmid);
-  if (4 * nmid > 512) return kSgNotEligible;
+  p.tmem_cols = tmem_cols_for((2 + kHdD2Bufs) * nmid);
+  if ((2 + kHdD2Bufs) * nmid > 512) return kSgNotEligible;
   p.idesc = make_idesc_bf16(128, nmid, false, false);
   p.wa = (const uint8_t*)h.wa; p.wb = (const uint8_t*)h.wb;
   p.bias_a = h.bias_a; p.bias_b = h.bias_b; p.wc = h.wc; p.bias_c = h.bias_c;
@@ -422,15 +429,16 @@ int launch_head_chain_umma(const HeadChain& h, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)p.wa_bytes + p.wb_bytes + (size_t)kHdRing * p.x_bytes + 2 * (size_t)p.h_bytes +
                       4096 + 2 * (size_t)nmid * 32;
   if (smem > 220 * 1024) return kSgNotEligible;
-  if (!attr_set) {
-    N2N_CUDA(cudaFuncSetAttribute(head_chain_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+  void (*kernel)(HdParams) = h.has_save ? head_chain_umma_kernel<true> : head_chain_umma_kernel<false>;
+  if (!(attr_set & (h.has_save ? 2 : 1))) {
+    N2N_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set |= h.has_save ? 2 : 1;
   }
   int nsm = 0, dev = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = kSMs;
   const int grid = tiles < nsm ? (int)tiles : nsm;
-  N2N_CUDA(launch_pdl(head_chain_umma_kernel, dim3(grid), dim3(kHdThreads), smem, st, p));
+  N2N_CUDA(launch_pdl(kernel, dim3(grid), dim3(kHdThreads), smem, st, p));
   N2N_LAUNCH_CHECK();
   return 0;
 }

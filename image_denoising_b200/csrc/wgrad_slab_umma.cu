@@ -25,7 +25,7 @@ namespace n2n {
 using namespace umma;
 
 constexpr int kWsThreads = 192;
-constexpr int kWsMaxRing = 4;
+constexpr int kWsMaxRing = 8;
 constexpr int kWsTileW = 8, kWsTileH = 16;
 constexpr size_t kWsSmemMax = 232448;
 constexpr size_t kWsStaticSlack = 4096;
