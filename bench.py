@@ -34,9 +34,12 @@ PATCH = 256
 NF = 48
 # algorithmic FLOPs per 256^2 patch: no-grad fwd 38.573 + fwd@128^2 9.643 + bwd 2*9.643 - 0.014
 GFLOP_PER_PATCH = 67.49
-# of which the tap-GEMM kernel (conv/deconv forward + input gradients) and the weight-gradient kernel:
-GFLOP_TAPGEMM_PER_PATCH = 38.573 + 9.643 + (9.643 - 0.014)
-GFLOP_WGRAD_PER_PATCH = 9.643
+# of which the tap-GEMM kernels (conv/deconv forward + input gradients) and the weight-gradient kernel; the
+# fused head backward (class "tap-GEMM") also produces the nin_a / nin_b weight gradients:
+# 2 layers x 2 x 128^2 px x 96 x 96 = 0.604 GFLOP per patch move from the second line to the first
+GFLOP_HEAD_WGRAD_PER_PATCH = 2 * 2 * 128 * 128 * 96 * 96 / 1e9
+GFLOP_TAPGEMM_PER_PATCH = 38.573 + 9.643 + (9.643 - 0.014) + GFLOP_HEAD_WGRAD_PER_PATCH
+GFLOP_WGRAD_PER_PATCH = 9.643 - GFLOP_HEAD_WGRAD_PER_PATCH
 
 
 def _peaks():
@@ -324,8 +327,8 @@ def run_b200(args):
         alg_flops = GFLOP_TAPGEMM_PER_PATCH * 1e9 * B * psteps
         achieved = alg_flops / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0
         roof = {"bound": "tensor",
-                "kernel": "slabgemm_umma_kernel (+ head_chain_umma / tapgemm_umma for the shapes it declines): conv/deconv "
-                          "forward + input gradient, %d launches/step" % round(tap_n / psteps),
+                "kernel": "slabgemm_umma_kernel (+ head_chain_umma / head_bwd_umma, tapgemm_umma for the shapes the slab engine "
+                          "declines): conv/deconv forward + input gradient, %d launches/step" % round(tap_n / psteps),
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
                 "traffic": (_traffic_note() or {}).get("bytes_per_launch"), "traffic_detail": _traffic_note(),
                 "peak_source": pk["src"],
