@@ -15,7 +15,7 @@
 //     adds per tcgen05.mma;
 //   * default form: clusters of two CTAs and tcgen05 cta_group::2 (see the kernel's comment) — each
 //     SM keeps half of the weight rows, which also makes the Cin = 144 layers fit;
-//   * accumulators are double-buffered in TMEM; two groups of four epilogue warps take alternate
+//   * accumulators are triple-buffered in TMEM when 3 * N <= 512 columns (else double); two groups of four epilogue warps take alternate
 //     tiles and fuse bias, LeakyReLU / ReLU, the input-gradient's activation mask and skip-gradient
 //     addend (prefetched), the 2x2 max-pool (a 2x2 cell is lanes {l, l^1, l^8} of one warp -> two
 //     shuffles), the 256-bit bf16 C16 store (two adjacent output pixels for the pair-form
@@ -68,7 +68,7 @@ struct SgStage {
 
 struct SgParams {
   // hot (epilogue / loop) fields first: they stay in the first constant-cache lines
-  int nst, nout, ring, dbg_flags;
+  int nst, nout, ring, dbg_flags, nbuf;
   int tiles_x, tiles_y, ntiles;
   int act; float slope;
   int store_y, has_addend, has_mask, has_pool, out_c, n_split;
@@ -291,7 +291,7 @@ template <int CG>
 __global__ void __launch_bounds__(kSgThreads, 1)
 slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * kSgMaxRing + 6];
+  __shared__ uint64_t bars[2 * kSgMaxRing + 8];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) uint2 s_tap[kSgMaxStages * 10];  // per (stage, tap): (A offset, B offset) in 16-byte units
   __shared__ int4 s_ld[kSgMaxStages];                 // per stage: view, cb0, ox | oy << 16, tx_bytes
@@ -305,9 +305,9 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kSgMaxRing + s); };
   const uint32_t wfull_bar = bar0 + 8u * (2 * kSgMaxRing);
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 1 + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 3 + b); };
-  const uint32_t wready_bar = bar0 + 8u * (2 * kSgMaxRing + 5);   // CG = 2: both CTAs' weight halves have landed
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 1 + b); };      // up to three accumulators
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 4 + b); };
+  const uint32_t wready_bar = bar0 + 8u * (2 * kSgMaxRing + 7);   // CG = 2: both CTAs' weight halves have landed
   const uint32_t b_sub16 = (uint32_t)p.nout * 2u / CG;  // weight rows per CTA x 32 B, in 16-byte units
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
@@ -315,7 +315,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
     mbar_init(wready_bar, CG);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG); }
+    for (int b = 0; b < 3; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
@@ -415,8 +415,8 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const uint32_t idesc = p.idesc;
     const bool skip = (p.dbg_flags & 2) != 0;
     for (int lt = 0; lt < ((CG == 2 && rank != 0) ? 0 : npair_iters); ++lt) {
-      const int buf = lt & 1;
-      sg_wait(tempty_bar(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      const int buf = lt % p.nbuf;
+      sg_wait(tempty_bar(buf), ((uint32_t)(lt / p.nbuf) & 1u) ^ 1u);
       fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
       uint32_t acc = 0;
@@ -491,7 +491,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
       c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
       c.ppix = (long long)c.img * p.pool.sN + (long long)(c.y >> 1) * p.pool.sY + (long long)(c.x >> 1) * p.pool.sX;
-      const int buf = lt & 1;
+      const int buf = lt % p.nbuf;
       // The epilogue's global operand (activation mask, else skip-gradient addend): warm L2 with the
       // whole tile's worth now, while this tile's MMAs still run, and keep the register loads one
       // block pair ahead of their use, so their latency stays off the critical path.
@@ -506,7 +506,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (cb_lo + 1 < nblk) ld_global_32B(ab + (cb_lo + 1) * as, ax1);
       }
       // one warp of the group polls the mbarrier, the other three park on a hardware named barrier
-      if (quarter == 0) sg_wait(tfull_bar(buf), ((uint32_t)lt >> 1) & 1u);
+      if (quarter == 0) sg_wait(tfull_bar(buf), (uint32_t)(lt / p.nbuf) & 1u);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       fence_after_sync();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.nout);
@@ -668,7 +668,11 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(tiles > 0 && tiles < (1LL << 31), "slabgemm: bad tile count");
   p.ntiles = (int)tiles;
   p.ring = ring; p.slot_bytes = (uint32_t)slot_bytes;
-  p.tmem_cols = tmem_cols_for(2 * g.nout);
+  // accumulators: three when they fit in TMEM, so the MMAs of tile i+2 need not wait for the epilogue group
+  // that is still draining tile i (two groups on alternate tiles); else two
+  p.nbuf = 3 * g.nout <= 512 ? 3 : 2;
+  { const char* e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
+  p.tmem_cols = tmem_cols_for(p.nbuf * g.nout);
   p.idesc = make_idesc_bf16(128 * cg, g.nout, false, false);
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
