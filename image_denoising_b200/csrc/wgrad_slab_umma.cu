@@ -11,7 +11,7 @@
 // (256 B for a tile, 320 B for a halo'd window) walks the image rows; one tcgen05.mma covers
 // K = 16 pixels = two image rows, so a tile is 8 K-steps per tap.
 //
-// Grid = (pixel splits) x (tap groups): a CTA owns a contiguous range of tiles and as many taps as
+// Grid = (pixel splits) x (tap groups): a CTA owns every splits-th tile and as many taps as
 // fit in TMEM (512 / (16 * variant blocks) accumulators of [128 x N] fp32); it accumulates over its
 // whole tile range in TMEM and stores its fp32 partial once at the end (pack.cu's unpack kernel
 // reduces the splits in a fixed order -> deterministic).
@@ -35,7 +35,7 @@ struct WsParams {
   int m_blocks, n_blocks, swap;
   int npad, cpad;
   int tiles_x, tiles_y;
-  long long tiles, tiles_per_split;
+  long long tiles; int nsplits;
   int ring, halo, box_per_tap;           // box_per_tap: 1 = every tap has its own variant box (deconv), 0 = one shared box
   uint32_t slot_bytes, a_bytes, var_box_bytes, tmem_cols, idesc;
   uint32_t a_lbo, a_hi, a_kstep16;       // LBO field (already << 16) of the A descriptor low word; high word; K-step (bytes/16)
@@ -43,7 +43,7 @@ struct WsParams {
   float* partial;
   float* bias_partial;                   // fused bias gradient: conv [splits][npad] (tap group 0 sums the dY tile); deconv
                                          // [splits * npairs][npad] (every tap group sums its dY parity boxes into its first row)
-  int dbg_flags;                         // N2N_DBG_FLAGS: 2 = skip the MMAs (pipeline / memory rate only)
+  int dbg_flags;                         // N2N_DBG_FLAGS: 1 = skip the loads, 2 = skip the MMAs, 4 = skip the bias sums
   uint16_t tap_off16[12];                // start of each tap's view inside its variant box (bytes/16)
   int8_t tap_view[12];                   // tensor map of the tap's variant view
   CUtensorMap tmap_common;
@@ -53,13 +53,13 @@ struct WsParams {
 __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of spinning
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
   }
@@ -74,6 +74,21 @@ __device__ __forceinline__ void ws_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "setp.ne.b32 p, %6, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+// All MMAs of one tile for NT taps: 8 K-steps (two image rows each) x NT accumulators.
+template <int NT>
+__device__ __forceinline__ void ws_issue(uint32_t d_tmem, uint32_t ncols, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_kstep16,
+                                         uint32_t b_kstep16, uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc,
+                                         const uint32_t (&boff)[10]) {
+#pragma unroll 1
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint32_t a_lo = a_lo0 + kk * a_kstep16;
+    const uint32_t b_lok = b_lo0 + kk * b_kstep16;
+    const uint32_t a1 = (acc | (uint32_t)kk) ? 1u : 0u;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) ws_mma(d_tmem + (uint32_t)i * ncols, a_lo, a_hi, b_lok + boff[i], b_hi, idesc, a1);
+  }
 }
 
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -93,16 +108,16 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
   const int tap0 = tg * p.taps_per_cta;
   int ntap = p.npairs - tap0;
   if (ntap > p.taps_per_cta) ntap = p.taps_per_cta;
-  const long long tile_begin = (long long)split * p.tiles_per_split;
-  long long tile_end = tile_begin + p.tiles_per_split;
-  if (tile_end > p.tiles) tile_end = p.tiles;
+  // split s owns tiles s, s + splits, s + 2*splits, ...: at any moment the CTAs read neighbouring tiles (adjacent
+  // 256-byte row segments of the same DRAM pages), not 148 far-apart streams
+  const int tile_begin = split, tile_end = (int)p.tiles, tile_step = p.nsplits;
   const bool has_work = tile_end > tile_begin;
   const int ncols = p.n_blocks * 16;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int nbox = p.box_per_tap ? ntap : 1;
   // bias gradient = per-channel pixel sum of dY: the four otherwise idle epilogue warps add it up from
   // the dY tile the pipeline already staged in shared memory (tap group 0 only), so dY is not read twice
-  const bool do_bias = p.bias_partial != nullptr && (p.swap || tg == 0);
+  const bool do_bias = p.bias_partial != nullptr && (p.swap || tg == 0) && !(p.dbg_flags & 32);
   const int bias_blocks = p.swap ? p.n_blocks : p.m_blocks;      // channel blocks of dY
 
   if (threadIdx.x == 0) {
@@ -128,13 +143,19 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
     const uint32_t tx = p.a_bytes + (uint32_t)nbox * p.var_box_bytes;
     const int org = p.halo ? -1 : 0;
     int slot = 0; uint32_t phase = 0;
-    for (long long tile = tile_begin; tile < tile_end; ++tile) {
-      const int img = (int)(tile / tiles_per_img);
-      const int r = (int)(tile - (long long)img * tiles_per_img);
-      const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      int img, r, ty, txi;
+      if (p.dbg_flags & 8) { img = 0; r = 0; ty = 0; txi = 0; }
+      else {
+        img = tile / tiles_per_img;
+        r = tile - img * tiles_per_img;
+        ty = r / p.tiles_x; txi = r - ty * p.tiles_x;
+      }
       const int x0 = txi * kWsTileW, y0 = ty * kWsTileH;
       ws_wait(empty_bar(slot), phase ^ 1u);
-      if (elect_one_sync()) {
+      if (p.dbg_flags & 1) {            // diagnostic: no loads, the pipeline runs on stale shared memory
+        if (elect_one_sync()) mbar_arrive(full_bar(slot));
+      } else if (elect_one_sync()) {
         const uint32_t dst = smem0 + slot * p.slot_bytes;
         mbar_arrive_expect_tx(full_bar(slot), tx);
         tma_load_5d(dst, &p.tmap_common, full_bar(slot), 0, x0, y0, 0, img);
@@ -156,23 +177,30 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
       const uint32_t a_hi = p.a_hi, b_hi = p.b_hi, idesc = p.idesc;
       int slot = 0; uint32_t phase = 0;
       uint32_t acc = 0;
-      for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const uint32_t s0 = smem0 + slot * p.slot_bytes;
         const uint32_t a_lo0 = ((s0 & 0x3FFFFu) >> 4) | p.a_lbo;
         const uint32_t b_lo0 = (((s0 + p.a_bytes) & 0x3FFFFu) >> 4) | p.b_lbo;
         ws_wait(full_bar(slot), phase);
         fence_after_sync();
         if (elect_one_sync()) {
-#pragma unroll 1
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t a_lo = a_lo0 + kk * p.a_kstep16;
-            const uint32_t b_lok = b_lo0 + kk * p.b_kstep16;
-            const uint32_t a1 = (acc | (uint32_t)kk) ? 1u : 0u;
-#pragma unroll
-            for (int i = 0; i < 10; ++i)
-              if (i < ntap && !(p.dbg_flags & 2)) ws_mma(tmem_base + (uint32_t)(i * ncols), a_lo, a_hi, b_lok + boff[i], b_hi, idesc, a1);
+          if (!(p.dbg_flags & 2)) {
+            const uint32_t d0 = tmem_base, nc = (uint32_t)ncols;
+            // compile-time tap count: the issuing lane runs exactly 8 * ntap MMAs and nothing else
+            switch (ntap) {
+              case 1: ws_issue<1>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 2: ws_issue<2>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 3: ws_issue<3>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 4: ws_issue<4>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 5: ws_issue<5>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 6: ws_issue<6>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 7: ws_issue<7>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 8: ws_issue<8>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              case 9: ws_issue<9>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+              default: ws_issue<10>(d0, nc, a_lo0, b_lo0, p.a_kstep16, p.b_kstep16, a_hi, b_hi, idesc, acc, boff); break;
+            }
           }
-          mma_commit(empty_bar(slot));
+          if (p.dbg_flags & 16) mbar_arrive(empty_bar(slot)); else mma_commit(empty_bar(slot));
         }
         __syncwarp();
         acc = 1;
@@ -195,11 +223,11 @@ wgrad_slab_umma_kernel(const __grid_constant__ WsParams p) {
         for (int q = 0; q < 16; ++q) acc[cb][q] = 0.f;
       const uint32_t sw = ((uint32_t)m >> 2) & 1u;
       int slot = 0; uint32_t phase = 0;
-      for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         if (quarter == 0) ws_wait(full_bar(slot), phase);          // one polling warp, three parked on a named barrier
         asm volatile("bar.sync 2, 128;" ::: "memory");
         // conv: dY is the common tile at the head of the slot; deconv: dY are this group's parity boxes behind it
-        const int nb_boxes = p.swap ? nbox : 1;
+        const int nb_boxes = (p.dbg_flags & 4) ? 0 : (p.swap ? nbox : 1);
         for (int bx = 0; bx < nb_boxes; ++bx) {
           const uint8_t* row = smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)slot * p.slot_bytes +
                                (p.swap ? (size_t)p.a_bytes + (size_t)bx * p.var_box_bytes : (size_t)0) + (size_t)m * 32;
@@ -363,7 +391,8 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.tiles_x = (W + kWsTileW - 1) / kWsTileW; p.tiles_y = (H + kWsTileH - 1) / kWsTileH;
   p.tiles = (long long)common.N * p.tiles_x * p.tiles_y;
   const int splits = g.splits;
-  p.tiles_per_split = (p.tiles + splits - 1) / splits;
+  p.nsplits = splits;
+  if (p.tiles >= (1LL << 31)) return kSgNotEligible;
   p.tmem_cols = tmem_cols_for(tpc * n_blocks * 16);
   p.idesc = make_idesc_bf16(128, n_blocks * 16, true, true);
   // MN-major descriptors: LBO = bytes between 16-channel blocks of a box, SBO = bytes between image rows
