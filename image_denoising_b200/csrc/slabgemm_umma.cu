@@ -35,7 +35,8 @@ namespace n2n {
 
 using namespace umma;
 
-constexpr int kSgThreads = 320;           // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kSgEpiGroups = 3;           // groups of four epilogue warps, each takes every third tile
+constexpr int kSgThreads = 64 + 128 * kSgEpiGroups;   // TMA warp, MMA warp, epilogue warps
 constexpr int kSgMaxStages = 12;          // pipeline stages (TMA boxes) per tile
 constexpr int kSgMaxRing = 8;
 constexpr int kSgGroup = 3;               // channel blocks per stage = one packed-weight group
@@ -467,8 +468,8 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     }
   } else {
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile;
-    //      two groups of four warps take alternate tiles (group g <-> accumulator buffer g), so the
-    //      per-tile bookkeeping is paid once per group and both accumulators drain concurrently ----
+    //      groups of four warps take tiles round-robin (group g <-> accumulator buffer g), so the
+    //      per-tile bookkeeping is paid once per group and all accumulators drain concurrently ----
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int py = m >> 3, px = m & 7;
@@ -477,7 +478,9 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const int cb_lo = 0;
     const int nblk = p.nout >> 4;
     const bool skip = (p.dbg_flags & 4) != 0;
-    for (int lt = group; lt < npair_iters; lt += 2) {
+    // group g <-> accumulator g: a group only ever waits on consecutive phases of its own barriers (with more
+    // groups than accumulators a group could run two phases ahead, which a parity wait cannot tell apart)
+    for (int lt = group < p.nbuf ? group : npair_iters; lt < npair_iters; lt += p.nbuf) {
       int tile = first_tile + lt * tile_step;
       const bool tile_ok = tile < p.ntiles;                 // odd tile count: the peer's last accumulator is a duplicate
       if (!tile_ok) tile = p.ntiles - 1;
@@ -488,9 +491,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       c.y = ty * kTileH + py; c.x = tx * kTileW + px;
       c.valid = tile_ok && c.y < p.y.H && c.x < p.y.W;
       c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
-      c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
-      c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
-      c.ppix = (long long)c.img * p.pool.sN + (long long)(c.y >> 1) * p.pool.sY + (long long)(c.x >> 1) * p.pool.sX;
+      c.apix = c.mpix = c.ppix = 0;                        // only the operands this launch has (uniform branches)
+      if (p.has_addend) c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
+      if (p.has_mask) c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
+      if (p.has_pool) c.ppix = (long long)c.img * p.pool.sN + (long long)(c.y >> 1) * p.pool.sY + (long long)(c.x >> 1) * p.pool.sX;
       const int buf = lt % p.nbuf;
       // The epilogue's global operand (activation mask, else skip-gradient addend): warm L2 with the
       // whole tile's worth now, while this tile's MMAs still run, and keep the register loads one
@@ -524,8 +528,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (skip) continue;
         sg_epilogue_block(p, c, cb, r0, lane, s_bias, pre ? ax0 : nullptr);
         if (two) sg_epilogue_block(p, c, cb + 1, r1, lane, s_bias, pre ? ax1 : nullptr);
+        if (pre) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { ax0[q] = nx0[q]; ax1[q] = nx1[q]; }
+          for (int q = 0; q < 8; ++q) { ax0[q] = nx0[q]; ax1[q] = nx1[q]; }
+        }
       }
       fence_before_sync();
       __syncwarp();

@@ -56,7 +56,7 @@ __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)

@@ -13,7 +13,7 @@ cases = [("nin 96->96 1x1 @128^2", N, 96, 96, 128, 128, 1), ("d1b 96->96 3x3 @12
 for name, n, cin, cout, h, w, k in cases:
     x = torch.randn(n, cin, h, w, device=dev); dy = torch.randn(n, cout, h, w, device=dev)
     row = []
-    for flags, ring in ((0, 0), (2, 0), (7, 0)):
+    for flags, ring in [(int(f), 0) for f in os.environ.get('FLAGS', '0,2,7').split(',')]:
         os.environ["N2N_DBG_FLAGS"] = str(flags); os.environ["N2N_WS_RING"] = str(ring) if ring else "9"
         for _ in range(2):
             ops.conv2d_wgrad(x, dy, k, "bf16")
