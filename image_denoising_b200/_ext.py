@@ -109,6 +109,7 @@ _SIGS = {
     "n2n_unet_workspace_bytes": (c_size_t, [c_void_p]),
     "n2n_unet_launches": (c_int, [c_void_p, c_int]),
     "n2n_unet_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_unet_share_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "n2n_unet_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p), c_void_p,
                                   c_void_p, c_void_p]),
     "n2n_adapter_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

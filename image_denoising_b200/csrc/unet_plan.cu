@@ -57,6 +57,11 @@ struct n2n_unet_plan {
   size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
   size_t total = 0;
   int fwd_launches = 0, bwd_launches = 0;
+  // forward weights / padded biases may be borrowed from another plan of the same network that has already
+  // packed them for this step (n2n_unet_share_weights): the pack is a function of the parameters only
+  const n2n_unet_plan* donor = nullptr;
+  const void* donor_ws = nullptr;
+  bool share[25] = {false};              // per layer: the donor packs this layer exactly as this plan would
   // backward: weight gradients run on a side stream, forked per layer from the input-gradient chain
   // (wgrad(i) and dgrad(i) both only READ grad(out_i)); the deep, launch-bound levels of the two
   // chains then overlap.  Joined before the partial reduction.
@@ -225,6 +230,28 @@ extern "C" int n2n_unet_launches(const n2n_unet_plan* plan, int backward) {
   return plan ? (backward ? plan->bwd_launches : plan->fwd_launches) : 0;
 }
 
+// Let `plan` read its forward weights and padded biases from `donor`'s workspace instead of packing its own copy:
+// valid when donor's n2n_unet_forward on the SAME parameters precedes plan's on the same stream (one training step
+// runs the no-grad full-resolution pass and the half-resolution pass on the same weights).  Returns 0 when
+// shared (layer by layer: a layer the two plans lay out differently is still packed locally), 1 when the plans
+// are not the same network (nothing changed), donor = NULL to stop.
+extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* donor, const void* donor_ws) {
+  N2N_CHECK_ARG(plan != nullptr, "unet_share_weights: plan is NULL");
+  plan->donor = nullptr; plan->donor_ws = nullptr;
+  if (!donor) return 0;
+  N2N_CHECK_ARG(donor_ws != nullptr && donor != plan, "unet_share_weights: bad donor");
+  const bool same = donor->in_nc == plan->in_nc && donor->out_nc == plan->out_nc && donor->nf == plan->nf &&
+                    donor->dtype == plan->dtype && donor->im2col == plan->im2col && donor->kb == plan->kb;
+  if (!same) return 1;
+  // per layer: the deepest levels of the two plans can pick different launch forms (pair-form ConvTranspose
+  // needs H, W >= 4), which changes that layer's packed layout only
+  for (int i = 0; i < 25; ++i)
+    plan->share[i] = donor->ksplit[i] == plan->ksplit[i] && donor->deconv_pair[i] == plan->deconv_pair[i] &&
+                     donor->L[i].fwd_pack_bytes(donor->dtype) == plan->L[i].fwd_pack_bytes(plan->dtype);
+  plan->donor = donor; plan->donor_ws = donor_ws;
+  return 0;
+}
+
 extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y,
                                 void* ws, void* stream) {
   N2N_CHECK_ARG(p && params && x && y && ws, "unet_forward: null argument");
@@ -236,7 +263,9 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     std::vector<PackJob> jobs;
     BiasPadJob bj[25];
     for (int i = 0; i < 25; ++i) {
-      if (p->im2col && i == 0) {
+      if (p->donor && p->share[i]) {
+        // forward pack borrowed
+      } else if (p->im2col && i == 0) {
         PackJob j = make_fwd_pack(p->L[0], params[0], (char*)ws + p->off_wp[0]);
         j.ntaps = 1; j.cin_blocks = p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = 0;
         jobs.push_back(j);
@@ -277,8 +306,8 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
                                        (p->im2col && i == 20) ? p->c2b : p->L[i].cin_blocks()));
       bj[i] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), p->L[i].cout, p->L[i].cout_blocks() * 16};
     }
-    N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
-    N2N_TRY(launch_bias_pad(bj, 25, st));
+    if (!jobs.empty()) N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
+    if (!p->donor) N2N_TRY(launch_bias_pad(bj, 25, st));
   }
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
   bool enc0_done = false;     // the fused input stage also produced enc_conv0's output
@@ -292,12 +321,18 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
   }
 
+  auto fw = [&](int i) -> const void* {
+    return (p->donor && p->share[i]) ? (const char*)p->donor_ws + p->donor->off_wp[i] : (const char*)ws + p->off_wp[i];
+  };
+  auto fb = [&](int i) -> const float* {
+    return (const float*)(p->donor ? (const char*)p->donor_ws + p->donor->off_bias[i] : (const char*)ws + p->off_bias[i]);
+  };
   auto run_layer = [&](int i, int pool_buf = -1, int pool_cb0 = 0) -> int {
     const LayerIO& io = p->io[i];
     const LayerGeom& L = p->L[i];
     View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
-    const void* wp = (char*)ws + p->off_wp[i];
-    const float* bias = (const float*)((char*)ws + p->off_bias[i]);
+    const void* wp = fw(i);
+    const float* bias = fb(i);
     if (p->im2col && (i == 0 || i == 20)) {
       TapGemm g;
       g.dtype = dt; g.nout = L.cout_blocks() * 16; g.w = wp; g.bias = bias;
@@ -370,8 +405,8 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     HeadChain h;
     h.x = p->view(p->act, ws, B_D1B, 0, p->hb);
     h.in_blocks = p->hb; h.mid_blocks = p->hb; h.mid_channels = 96; h.out_nc = p->out_nc;
-    h.wa = (char*)ws + p->off_wp[22]; h.wb = (char*)ws + p->off_wp[23];
-    h.bias_a = (const float*)((char*)ws + p->off_bias[22]); h.bias_b = (const float*)((char*)ws + p->off_bias[23]);
+    h.wa = fw(22); h.wb = fw(23);
+    h.bias_a = fb(22); h.bias_b = fb(23);
     h.wc = params[2 * 24]; h.bias_c = params[2 * 24 + 1];
     h.slope = 0.2f; h.has_save = p->bwd;
     h.save_a = p->view(p->act, ws, B_NA, 0, p->hb); h.save_b = p->view(p->act, ws, B_NB, 0, p->hb);

@@ -83,6 +83,14 @@ class N2NTrainer:
                                          h // 2, w // 2, dt, 1))
         self.ws_full = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_full), dtype=torch.uint8, device=dev)
         self.ws_half = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_half), dtype=torch.uint8, device=dev)
+        # the half-resolution pass runs right behind the full-resolution one on the same weights: borrow its packed
+        # forward weights instead of repacking them (not when the two passes run on different streams)
+        self.shared_weights = False
+        if not self.overlap_forwards and os.environ.get("N2N_NO_SHARE", "0") != "1":
+            rc = lib().n2n_unet_share_weights(self.plan_half, self.plan_full, ptr(self.ws_full))
+            if rc < 0:
+                check(rc)
+            self.shared_weights = rc == 0
         f32 = dict(dtype=torch.float32, device=dev)
         self.den = torch.empty((n, net.out_nc, h, w), **f32)
         half = (n, c, h // 2, w // 2)

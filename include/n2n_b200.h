@@ -145,6 +145,15 @@ int n2n_unet_launches(const n2n_unet_plan* plan, int backward);
  * workspace until the next forward on the same workspace. */
 int n2n_unet_forward(n2n_unet_plan* plan, const float* const* params, const float* x, float* y,
                      void* workspace, void* stream);
+/* One N2N step runs the network twice on the same weights (the no-grad denoise of the
+ * full image and the training forward on the sub-image, training_script.md:139-146).
+ * After this call `plan` reads its forward weights / padded biases from `donor`'s
+ * workspace instead of repacking them: the caller guarantees that donor's
+ * n2n_unet_forward with the same `params` precedes plan's on the same stream.
+ * Sharing is per layer: a layer whose launch form differs between the two plans
+ * (deepest levels of small inputs) is still packed locally.  Returns 0 when shared,
+ * 1 when the plans are not the same network (nothing changed); donor = NULL ends it. */
+int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* donor, const void* donor_workspace);
 /* grads[i] (fp32, same shapes as params) are OVERWRITTEN with dL/dparam for the
  * last forward; dy is dL/dy [N,out_nc,H,W].  dx (may be NULL) receives dL/dx. */
 int n2n_unet_backward(n2n_unet_plan* plan, const float* const* params, const float* dy,

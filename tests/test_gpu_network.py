@@ -254,3 +254,24 @@ def test_no_cpu_fallback(dev):
         UNet(1, 1, 4, blindspot=True)
     with pytest.raises(ValueError):
         net.to(dev)(torch.zeros(1, 1, 40, 32, device=dev))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shared_forward_weights_bit_identical(dev, precision, monkeypatch):
+    """n2n_unet_share_weights: the half-resolution plan borrowing the full-resolution plan's packed forward
+    weights must give exactly the step it gives when it packs its own copy."""
+    from image_denoising_b200 import N2NTrainer
+    p = _weights(1, 48, 5, 6)
+    g = torch.Generator().manual_seed(13)
+    noisy = torch.rand(2, 1, 64, 64, generator=g).to(dev)
+    rd = torch.randint(0, 8, (2 * 32 * 32,), generator=g).to(dev)
+    res = {}
+    for share in (True, False):
+        monkeypatch.setenv("N2N_NO_SHARE", "0" if share else "1")
+        tr = N2NTrainer(_net(dev, 1, 48, p, precision), lr=1e-3, precision=precision, use_graph=False)
+        losses = [tr.step(noisy, 1.0, rd_idx=rd).clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        assert tr.shared_weights == share
+        res[share] = (torch.stack(losses).cpu(), tr.flat_g.clone().cpu(), tr.flat_p.clone().cpu())
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
