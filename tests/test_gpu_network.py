@@ -275,3 +275,21 @@ def test_shared_forward_weights_bit_identical(dev, precision, monkeypatch):
         res[share] = (torch.stack(losses).cpu(), tr.flat_g.clone().cpu(), tr.flat_p.clone().cpu())
     for a, b in zip(res[True], res[False]):
         assert torch.equal(a, b)
+
+
+def test_device_prefetcher_order_and_reuse(dev):
+    """DevicePrefetcher: batches come out in the order they were put, buffers are reused only after release."""
+    from image_denoising_b200.prefetch import DevicePrefetcher
+    host = [torch.full((4, 1, 64, 64), float(i)).pin_memory() for i in range(7)]
+    pf = DevicePrefetcher(torch.empty((4, 1, 64, 64), device=dev))
+    sums = []
+    pf.put(host[0])
+    for i in range(7):
+        x = pf.get()
+        if i + 1 < 7:
+            pf.put(host[i + 1])
+        sums.append(x.double().mean())          # consumer enqueued on the current stream
+        pf.release()
+    torch.cuda.synchronize()
+    assert [float(s) for s in sums] == [float(i) for i in range(7)]
+    assert pf.bytes_copied == 7 * 4 * 64 * 64 * 4
