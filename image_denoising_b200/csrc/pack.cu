@@ -85,15 +85,24 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
   }
 }
 
+// Four consecutive lanes share one group of four output channels: each sums a fixed quarter of the splits, the
+// quarters are combined by shuffles in a fixed order (deterministic).  One thread per output made the kernel a
+// chain of splits / 8 dependent load batches (19 DRAM round trips at 148 splits) whatever the data volume.
+constexpr int kUnpackLanes = 4;
+
 __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
   pdl_enter();
   const UnpackJob& J = b.j[blockIdx.y];
-  // four consecutive output channels (same tap, same input channel) per thread: 16-byte loads of the
-  // split partials, 32-bit index arithmetic, eight independent loads in flight, fixed summation order
   const int plane = J.cpad * J.npad;
   const int total = J.ntaps * plane;
   const int npad4 = J.npad >> 2;
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < (total >> 2); i4 += gridDim.x * blockDim.x) {
+  const int sub = threadIdx.x & (kUnpackLanes - 1);
+  const unsigned gmask = ((1u << kUnpackLanes) - 1u) << (threadIdx.x & (32 - kUnpackLanes) & 31);   // this group's lanes within the warp
+  const int per = (J.splits + kUnpackLanes - 1) / kUnpackLanes;
+  const int s0 = sub * per < J.splits ? sub * per : J.splits;
+  const int s1 = s0 + per < J.splits ? s0 + per : J.splits;
+  const int groups = (gridDim.x * blockDim.x) / kUnpackLanes;
+  for (int i4 = (blockIdx.x * blockDim.x + threadIdx.x) / kUnpackLanes; i4 < (total >> 2); i4 += groups) {
     const int n0 = (i4 % npad4) << 2;
     const int ct = i4 / npad4;
     const int c = ct % J.cpad;
@@ -111,40 +120,55 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* src = reinterpret_cast<const float4*>(J.partial) + i4;
     const long long stride4 = total >> 2;
-    int sp = 0;
-    for (; sp + 8 <= J.splits; sp += 8) {
+    int sp = s0;
+    for (; sp + 8 <= s1; sp += 8) {
       float4 v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (long long)(sp + u) * stride4);
 #pragma unroll
       for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
-    for (; sp < J.splits; ++sp) {
+    for (; sp < s1; ++sp) {
       const float4 v = __ldg(src + (long long)sp * stride4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    const float r[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int sn = seg_lookup(J.nseg, n0 + q);
-      if (sn >= 0) J.dst_w[cdst + sn * J.s_n] = r[q];
+    for (int o = kUnpackLanes / 2; o > 0; o >>= 1) {
+      s.x += __shfl_down_sync(gmask, s.x, o, kUnpackLanes); s.y += __shfl_down_sync(gmask, s.y, o, kUnpackLanes);
+      s.z += __shfl_down_sync(gmask, s.z, o, kUnpackLanes); s.w += __shfl_down_sync(gmask, s.w, o, kUnpackLanes);
+    }
+    if (sub == 0) {
+      const float r[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int sn = seg_lookup(J.nseg, n0 + q);
+        if (sn >= 0) J.dst_w[cdst + sn * J.s_n] = r[q];
+      }
     }
   }
   if (J.dst_b && J.bias_partial) {
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < J.npad; n += gridDim.x * blockDim.x) {
-      const int sn = seg_lookup(J.nseg, n);
-      if (sn < 0) continue;
+    // one warp per channel: lane l sums rows l, l + 32, ... (up to splits x taps = 592 rows for the deconvs; one
+    // thread per channel made that a 74-deep chain of dependent load batches, the longest thing in the launch),
+    // then a fixed-order shuffle tree
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < J.npad; n += nwarps) {
       float s = 0.f;
-      int sp = 0;
-      for (; sp + 8 <= J.bias_rows; sp += 8) {
-        float v[8];
+      int r = lane;
+      for (; r + 96 < J.bias_rows; r += 128) {
+        float v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(J.bias_partial + (long long)(sp + u) * J.npad + n);
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(J.bias_partial + (long long)(r + 32 * u) * J.npad + n);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
+        for (int u = 0; u < 4; ++u) s += v[u];
       }
-      for (; sp < J.bias_rows; ++sp) s += __ldg(J.bias_partial + (long long)sp * J.npad + n);
-      J.dst_b[sn] = s;
+      for (; r < J.bias_rows; r += 32) s += __ldg(J.bias_partial + (long long)r * J.npad + n);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        const int sn = seg_lookup(J.nseg, n);
+        if (sn >= 0) J.dst_b[sn] = s;
+      }
     }
   }
 }
@@ -174,7 +198,7 @@ int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st) {
     long long maxtotal = 1;
     for (int i = 0; i < b.n; ++i) {
       b.j[i] = jobs[base + i];
-      long long tot = (long long)b.j[i].ntaps * b.j[i].npad * b.j[i].cpad / 4;
+      long long tot = (long long)b.j[i].ntaps * b.j[i].npad * b.j[i].cpad / 4 * kUnpackLanes;
       if (tot > maxtotal) maxtotal = tot;
     }
     dim3 grid(grid_for(maxtotal, 256, 8), b.n);
