@@ -48,6 +48,20 @@ __device__ __forceinline__ bool last_block_done(RedWs* ws) {
   return last;
 }
 
+// Second stage, run by every thread of the last block: thread t adds partials t, t + 256, ... and the block tree
+// finishes (fixed order -> deterministic).  One thread walking up to 592 partials was a chain of dependent L2
+// loads several times longer than the streaming pass itself.
+template <int NQ>
+__device__ __forceinline__ void final_reduce(const RedWs* ws, double (&v)[NQ], double* smem) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) v[q] = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kRedThreads) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] += __ldcg(&ws->partial[b][q]);
+  }
+  block_reduce<NQ>(v, smem);
+}
+
 // ---- N2N loss --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRedThreads)
 n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, const float* __restrict__ den1,
@@ -98,9 +112,10 @@ n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, c
   acc[0] += (double)a0; acc[1] += (double)a1;
   block_reduce<2>(acc, red);
   if (threadIdx.x == 0) { ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; }
-  if (last_block_done(ws) && threadIdx.x == 0) {
-    double s0 = 0, s1 = 0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) { s0 += ws->partial[b][0]; s1 += ws->partial[b][1]; }
+  if (!last_block_done(ws)) return;
+  final_reduce<2>(ws, acc, red);
+  if (threadIdx.x == 0) {
+    const double s0 = acc[0], s1 = acc[1];
     const float l1 = (float)(s0 / (double)count);
     const float l2 = lam * (float)(s1 / (double)count);
     loss3[0] = l1 + l2; loss3[1] = l1; loss3[2] = l2;
@@ -155,9 +170,10 @@ l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
   if (threadIdx.x == 0) {
     ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; ws->partial[blockIdx.x][2] = acc[2];
   }
-  if (last_block_done(ws) && threadIdx.x == 0) {
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) { s0 += ws->partial[b][0]; s1 += ws->partial[b][1]; s2 += ws->partial[b][2]; }
+  if (!last_block_done(ws)) return;
+  final_reduce<3>(ws, acc, red);
+  if (threadIdx.x == 0) {
+    const double s0 = acc[0], s1 = acc[1], s2 = acc[2];
     const float l1 = (float)(s0 / (double)count);
     const float gx = cx > 0 ? (float)(s1 / (double)cx) : 0.f;
     const float gy = cy > 0 ? (float)(s2 / (double)cy) : 0.f;
