@@ -135,3 +135,21 @@ def test_fused_head_backward_equals_layerwise_path(dev, monkeypatch):
         worst = max(worst, rel)
         assert rel <= 2e-2 and cos >= 0.9999, (k, rel, cos)
     print(f"fused vs layer-wise head backward: worst relative gradient difference {worst:.3e}")
+
+
+def test_rgb_head_gradients_many_tiles_bf16_vs_fp32_engine(dev):
+    """RGB width (out_nc = 3 instance of the fused head backward) with ~17 tiles per CTA: the head's weight / bias
+    gradients accumulated in TMEM over many tiles against the fp32 CUDA-core engine, parameter by parameter."""
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(20, 3, 128, 128, generator=g)
+    tgt = torch.rand(20, 3, 128, 128, generator=g)
+    grads = {}
+    for precision in ("fp32", "bf16"):
+        net = _make(dev, precision, in_nc=3, nf=48, seed=4)
+        (net(x.to(dev)) - tgt.to(dev)).square().mean().backward()
+        grads[precision] = {k: p.grad.detach().cpu().double() for k, p in net.named_parameters()}
+    for k in grads["fp32"]:
+        a, b = grads["bf16"][k].flatten(), grads["fp32"][k].flatten()
+        assert torch.isfinite(a).all(), k
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > (0.995 if k.startswith("nin_") else 0.98), (k, cos)
