@@ -75,6 +75,7 @@ struct SgParams {
   int store_y, has_addend, has_mask, has_pool, out_c, n_split;
   long long split_stride;
   uint32_t slot_bytes, tmem_cols, idesc, w_bytes, w_region;
+  uint32_t bias_off;         // > 0: bias rides in the GEMM (ones block at smem0 + bias_off, bias rows 4 KB behind it)
   const uint8_t* w;
   const float* bias;
   float* out_nchw;
@@ -206,7 +207,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   float v[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
-  if (!(p.dbg_flags & 8)) {
+  if (!(p.dbg_flags & 8) && !p.bias_off) {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb * 16);   // shared-memory broadcast
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -327,6 +328,29 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   }
   for (int i = threadIdx.x; i < p.nout; i += kSgThreads)
     s_bias[i] = p.bias ? p.bias[(p.n_split && i >= p.n_split * 16) ? i - p.n_split * 16 : i] : 0.f;
+  if (p.bias_off) {
+    // Bias through the tensor core: one extra K block per tile whose A operand is constant (elements 0, 1 of every
+    // row = 1) and whose B rows carry the bias split into bf16 hi + lo parts (relative error 2^-17) — the epilogue
+    // saves 4 LDS + 16 FADD per channel block, which is what bounds the narrow layers.
+    uint8_t* base = smem_raw + (smem0 - smem_u32(smem_raw));
+    const int nrows = p.nout / CG;                         // this CTA's half of the B rows in pair form
+    for (int r = threadIdx.x; r < 128 + nrows; r += kSgThreads) {
+      const uint32_t off = r < 128 ? p.bias_off + (uint32_t)r * 32u : p.bias_off + 4096u + (uint32_t)(r - 128) * 32u;
+      float v = 1.0f;
+      if (r >= 128) {
+        const int n = (int)rank * nrows + (r - 128);
+        v = p.bias[(p.n_split && n >= p.n_split * 16) ? n - p.n_split * 16 : n];
+      }
+      const __nv_bfloat16 hi_part = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo_part = r < 128 ? hi_part : __float2bfloat16_rn(v - __bfloat162float(hi_part));
+      const uint32_t sw = ((smem0 + off) >> 7) & 1u;       // logical 16-byte chunk 0 sits in physical chunk sw
+      uint4* row = reinterpret_cast<uint4*>(base + off);
+      __nv_bfloat162 h2 = __halves2bfloat162(hi_part, lo_part);
+      row[sw] = make_uint4(*reinterpret_cast<uint32_t*>(&h2), 0u, 0u, 0u);
+      row[sw ^ 1u] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   if (threadIdx.x < p.nst) {
     const SgStage& S = p.st[threadIdx.x];
     s_ld[threadIdx.x] = make_int4(S.view, S.cb0, (int)(uint16_t)S.ox | ((int)(uint16_t)S.oy << 16), (int)S.tx_bytes);
@@ -463,7 +487,14 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         acc = 1;
         if (++slot == p.ring) { slot = 0; phase ^= 1u; }
       }
-      if (elect_one_sync()) { if (CG == 2) mma_commit2(tfull_bar(buf)); else mma_commit(tfull_bar(buf)); }
+      if (elect_one_sync()) {
+        if (p.bias_off && !skip) {
+          const uint32_t one_lo = (((smem0 + p.bias_off) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t bia_lo = (((smem0 + p.bias_off + 4096u) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (CG == 2) sg_mma2(d_tmem, one_lo, b_hi, bia_lo, b_hi, idesc, 1); else sg_mma(d_tmem, one_lo, b_hi, bia_lo, b_hi, idesc, 1);
+        }
+        if (CG == 2) mma_commit2(tfull_bar(buf)); else mma_commit(tfull_bar(buf));
+      }
       __syncwarp();
     }
   } else {
@@ -673,15 +704,22 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   // Each CTA of a pair keeps half of the weight rows, which leaves room for a deeper activation ring.
   const long long tiles0 = (long long)g.y.N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   const int cg = sg_use_pair(g.nout, tiles0) ? 2 : 1;
-  const size_t w_region = align_up(w_bytes / cg, 1024);
+  size_t w_region = align_up(w_bytes / cg, 1024);
   const size_t budget = kSgSmemMax - kSgStaticSlack - 1024;
   if (w_region + 2 * slot_bytes > budget) return kSgNotEligible;
+  // bias through the GEMM when the ones block + bias rows still leave a ring of at least four slots
+  uint32_t bias_off = 0;
+  {
+    const size_t extra = 4096 + align_up((size_t)g.nout / cg * 32, 1024);
+    const char* e = getenv("N2N_NO_BIAS_MMA");
+    if (g.bias && !(e && atoi(e)) && w_region + extra + 4 * slot_bytes <= budget) { bias_off = (uint32_t)w_region; w_region += extra; }
+  }
   int ring = (int)((budget - w_region) / slot_bytes);
   if (ring > kSgMaxRing) ring = kSgMaxRing;
   { const char* e = getenv("N2N_SG_RING"); if (e && atoi(e) >= 2 && atoi(e) < ring) ring = atoi(e); }
 
   p.nst = nst; p.nout = g.nout;
-  p.w = (const uint8_t*)g.w; p.w_bytes = (uint32_t)w_bytes; p.w_region = (uint32_t)w_region;
+  p.w = (const uint8_t*)g.w; p.w_bytes = (uint32_t)w_bytes; p.w_region = (uint32_t)w_region; p.bias_off = bias_off;
   p.bias = g.bias; p.y = g.y; p.store_y = g.store_y ? 1 : 0;
   p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
   p.has_pool = g.has_pool; p.pool = g.pool;
