@@ -6,13 +6,14 @@
 //
 // Per 8 x 16-pixel tile (M = 128):
 //   warp 0     TMA: the X tile [in_blocks][128 px][16 ch] (K-major SWIZZLE_32B operand) -> ring slot
-//   warp 1     MMA-1: D1 = X * Wa^T            (TMEM, double buffered)
-//              MMA-2: D2 = H1 * Wb^T           (H1 = shared-memory operand written by stage E1)
-//   warps 2-9  E1: D1 -> +bias_a -> LeakyReLU -> bf16 -> H1 tile in shared memory, in exactly the
-//              swizzled K-major layout MMA-2 wants (16-byte chunk XOR address bit 7), then
-//              fence.proxy.async so the tensor core sees it
-//   warps 10-17 E2: D2 -> +bias_b -> LeakyReLU -> dot with nin_c's rows (fp32, registers) -> +bias_c ->
-//              fp32 NCHW store
+//   warp 1     MMA-1: D1 = X * Wa^T + bias_a   (TMEM, double buffered; the bias is one more K block)
+//   warp 18    MMA-2: D2 = H1 * Wb^T + bias_b  (H1 = shared-memory operand written by stage E1; triple buffered —
+//              E2 is the longest stage; its own issuer so that neither GEMM queues behind the other one's wait)
+//   warps 2-9  E1: D1 -> LeakyReLU -> bf16 -> H1 tile in shared memory, in exactly the swizzled K-major
+//              layout MMA-2 wants (16-byte chunk XOR address bit 7), then fence.proxy.async so the tensor
+//              core sees it; D1 goes back to MMA-1 as soon as its last block is in registers
+//   warps 10-17 E2: D2 -> LeakyReLU -> dot with nin_c's rows (fp32, registers) -> +bias_c -> fp32 NCHW
+//              store (training pass: the bf16-rounded activation is what is saved and what nin_c sees)
 // E1 and E2 work on different tiles at the same time; both weight matrices stay resident in
 // shared memory; nin_c's weights are broadcast reads of a small shared-memory table.
 #include <stdlib.h>

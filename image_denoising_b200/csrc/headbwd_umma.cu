@@ -17,10 +17,13 @@
 // threads, the sign that gives lrelu'(.) (LeakyReLU is in-place in the reference, arch_unet.py:113,
 // slope > 0).  Stage S1 overwrites the NA tile in place with g_na once GEMM-1 / dWb have consumed it.
 //
-// Per 8 x 16-pixel tile: warp 0 is the TMA producer, warp 1 issues the MMAs; warps 2-5 run S0, 6-9
-// S1, 10-13 S2 (thread = pixel = TMEM lane).  The tiles are double-buffered so the three stages work
-// on consecutive tiles; the two input-gradient accumulators are single TMEM buffers that a stage
-// drains into registers and hands back before it starts its arithmetic.  Each CTA stores its fp32
+// Per 8 x 16-pixel tile: warp 0 is the TMA producer (activation tiles, prefetched into L2 three tiles ahead),
+// warp 1 issues dWb + GEMM-1 and warp 14 dWa + GEMM-2 (two issuers: one in-order issuer would queue the GEMM
+// that frees a tile buffer behind the GEMM that waits for a TMA load); warps 2-5 run S0, 6-9 S1, 10-13 S2
+// (thread = pixel = TMEM lane).  The g_nb and D1B tiles are double-buffered, the NA tile (which lives from its
+// TMA load through S1's in-place rewrite to GEMM-2) triple-buffered, so the three stages work on consecutive
+// tiles; the two input-gradient accumulators are single TMEM buffers that a stage drains into registers and
+// hands back before it starts its arithmetic.  Each CTA stores its fp32
 // weight-gradient partial once at the end ([grid][c][n]; pack.cu's unpack kernel reduces the CTAs in
 // a fixed order -> deterministic).
 #include <stdlib.h>
