@@ -15,8 +15,10 @@
 //     adds per tcgen05.mma;
 //   * default form: clusters of two CTAs and tcgen05 cta_group::2 (see the kernel's comment) — each
 //     SM keeps half of the weight rows, which also makes the Cin = 144 layers fit;
-//   * accumulators are triple-buffered in TMEM when 3 * N <= 512 columns (else double); two groups of four epilogue warps take alternate
-//     tiles and fuse bias, LeakyReLU / ReLU, the input-gradient's activation mask and skip-gradient
+//   * accumulators are triple-buffered in TMEM when 3 * N <= 512 columns (else double); one group of
+//     four epilogue warps per accumulator takes every nbuf-th tile; the bias rides in the GEMM as one
+//     more K block (a constant ones block x bias rows split into bf16 hi + lo) when shared memory
+//     allows, else it is added here; the groups fuse LeakyReLU / ReLU, the input-gradient's activation mask and skip-gradient
 //     addend (prefetched), the 2x2 max-pool (a 2x2 cell is lanes {l, l^1, l^8} of one warp -> two
 //     shuffles), the 256-bit bf16 C16 store (two adjacent output pixels for the pair-form
 //     ConvTranspose) and the fp32 NCHW store of the network head; one warp per group polls the
