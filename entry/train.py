@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from entry import _data  # noqa: E402
 from image_denoising_b200 import AugmentNoise, N2NTrainer, UNet, checkpoint, dp  # noqa: E402
+from image_denoising_b200.prefetch import DevicePrefetcher  # noqa: E402
 
 parser = argparse.ArgumentParser()
 parser.add_argument("--noisetype", type=str, default="gauss25")
@@ -88,6 +89,8 @@ def main():
     trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)
     if rank == 0:
         checkpoint(network, 0, "model", opt.save_model_path, opt.log_name, systime)      # train.py:343
+    staged = DevicePrefetcher(torch.empty((per_rank, opt.n_channel, opt.patch, opt.patch), dtype=torch.float32, device=dev))
+    staged.put(next_batch())
     steps_per_epoch = max(len(images) * 16 // (per_rank * world), 1)
     print(f"rank {rank}/{world}: {len(images)} images, {steps_per_epoch} steps/epoch, batch {per_rank}/GPU")
     for epoch in range(1, opt.n_epoch + 1):
@@ -95,7 +98,10 @@ def main():
         Lambda = epoch / opt.n_epoch * opt.increase_ratio                                   # training_script.md:148
         st = time.time()
         for it in range(steps_per_epoch):
-            clean = next_batch().to(dev, non_blocking=True) / 255.0
+            # batch i+1 is cropped on the host and copied H2D (copy stream) while step i runs
+            clean = staged.get() / 255.0
+            staged.release()
+            staged.put(next_batch())
             noisy = noise_adder.add_train_noise(clean)
             loss3 = trainer.step(noisy, Lambda, lr=lr)
             if it % 50 == 0 and rank == 0:
