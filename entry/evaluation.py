@@ -56,7 +56,7 @@ def main():
             print(f"[Warning] Missing keys when loading adapter model: {missing}")
         if unexpected:
             print(f"[Warning] Unexpected keys when loading adapter model: {unexpected}")
-        network = model.to(f"cuda:{local}").eval()
+        network = model.to(f"cuda:{local}").set_precision(opt.precision).eval()
     if opt.synthetic:
         clean, noisy = _data.synthetic_images(opt.synthetic, 704, 704, opt.n_channel)
         names = [f"synthetic_{i:03d}.png" for i in range(opt.synthetic)]

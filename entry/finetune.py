@@ -60,7 +60,7 @@ def main():
         base.load_state_dict(state, strict=False)
     model = DenoiserWithAdapter(base, in_channels=args.n_channel, hidden_channels=args.adapter_hidden,
                                 freeze_base=True, use_no_grad_for_base=True).to(dev)
-    model.base.set_precision(args.precision)
+    model.set_precision(args.precision)
     opt = FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=args.lr)
     out_dir = os.path.join(args.save_model_path, args.log_name)
     os.makedirs(out_dir, exist_ok=True)

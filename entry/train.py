@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from entry import _data  # noqa: E402
 from image_denoising_b200 import AugmentNoise, N2NTrainer, UNet, checkpoint, dp  # noqa: E402
+from image_denoising_b200.optim import multistep_lr  # noqa: E402
 from image_denoising_b200.prefetch import DevicePrefetcher  # noqa: E402
 
 parser = argparse.ArgumentParser()
@@ -43,13 +44,6 @@ parser.add_argument("--increase_ratio", type=float, default=2.0)
 parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
 parser.add_argument("--patch", type=int, default=256, help="random-crop size of the training patches")
 parser.add_argument("--synthetic", type=int, default=0, help="train on this many synthetic clean images instead of --data_dir")
-
-
-def multistep_lr(base_lr, epoch, n_epoch, gamma):
-    """train.py:333-340: milestones int(20r)-1, int(40r)-1, int(60r)-1, int(80r)-1 with r = n_epoch/100."""
-    ratio = n_epoch / 100
-    milestones = [int(20 * ratio) - 1, int(40 * ratio) - 1, int(60 * ratio) - 1, int(80 * ratio) - 1]
-    return base_lr * gamma ** sum(1 for m in milestones if epoch > m)
 
 
 def main():
@@ -85,7 +79,7 @@ def main():
 
     torch.manual_seed(0)
     network = UNet(in_nc=opt.n_channel, out_nc=opt.n_channel, n_feature=opt.n_feature).to(dev).set_precision(opt.precision)
-    noise_adder = AugmentNoise(style=opt.noisetype)
+    noise_adder = AugmentNoise(style=opt.noisetype, rank=rank, world=world)      # global-batch noise, this rank's slice
     trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)
     if rank == 0:
         checkpoint(network, 0, "model", opt.save_model_path, opt.log_name, systime)      # train.py:343
@@ -94,7 +88,7 @@ def main():
     steps_per_epoch = max(len(images) * 16 // (per_rank * world), 1)
     print(f"rank {rank}/{world}: {len(images)} images, {steps_per_epoch} steps/epoch, batch {per_rank}/GPU")
     for epoch in range(1, opt.n_epoch + 1):
-        lr = multistep_lr(opt.lr, epoch - 1, opt.n_epoch, opt.gamma)
+        lr = multistep_lr(opt.lr, epoch, opt.n_epoch, opt.gamma)      # train.py:333-340, :375
         Lambda = epoch / opt.n_epoch * opt.increase_ratio                                   # training_script.md:148
         st = time.time()
         for it in range(steps_per_epoch):

@@ -86,6 +86,7 @@ _SIGS = {
     "n2n_subsample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "n2n_subsample_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "n2n_space_to_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "n2n_conv2d_workspace_bytes": (c_size_t, [c_int] * 7),
     "n2n_conv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_float, c_int, c_void_p, c_void_p]),

@@ -16,12 +16,15 @@ from ._ext import check, lib, ptr, ptr_array, require_cuda, stream_ptr
 
 
 class _AdapterFunction(torch.autograd.Function):
+    """The workspace (cat buffer + hidden activations) is checked out of the module's pool until backward has
+    run, so two forwards before one backward (gradient accumulation) keep separate activations."""
+
     @staticmethod
     def forward(ctx, mod, noisy, base_out, *params):
-        plan, ws = mod._plan(noisy, True)
+        key, plan, ws = mod._checkout(noisy, True)
         out = torch.empty_like(base_out)
         check(lib().n2n_adapter_forward(plan, ptr_array(params), ptr(noisy), ptr(base_out), ptr(out), ptr(ws), stream_ptr()))
-        ctx.plan, ctx.ws, ctx.params = plan, ws, params
+        ctx.mod, ctx.key, ctx.plan, ctx.ws, ctx.params = mod, key, plan, ws, params
         return out
 
     @staticmethod
@@ -29,6 +32,8 @@ class _AdapterFunction(torch.autograd.Function):
         dout = dout.contiguous().float()
         grads = [torch.empty_like(p) for p in ctx.params]
         check(lib().n2n_adapter_backward(ctx.plan, ptr_array(ctx.params), ptr(dout), ptr_array(grads), ptr(ctx.ws), stream_ptr()))
+        ctx.mod._give_back(ctx.key, ctx.ws)
+        ctx.ws = None
         return (None, None, None) + tuple(grads)
 
 
@@ -43,29 +48,57 @@ class OutputAdapter(nn.Module):
             nn.Conv2d(hidden_channels, in_channels, kernel_size=3, padding=1, bias=True),
         )
         self.precision = _ext.default_precision()
-        self._plans = {}
+        self._plans = {}       # key -> plan handle
+        self._free_ws = {}     # key -> workspaces not held by an autograd graph
 
-    def _plan(self, x, bwd):
+    def _checkout(self, x, bwd):
         n, c, h, w = x.shape
-        key = (n, h, w, _ext.dtype_tag(self.precision), bool(bwd))
+        key = (n, h, w, _ext.dtype_tag(self.precision), bool(bwd), x.device.index)
         if key not in self._plans:
             handle = ctypes.c_void_p()
             check(lib().n2n_adapter_plan_create(ctypes.byref(handle), self.in_channels, self.hidden_channels,
                                                 n, h, w, key[3], int(bwd)))
-            ws = torch.empty(lib().n2n_adapter_workspace_bytes(handle), dtype=torch.uint8, device=x.device)
-            self._plans[key] = (handle, ws)
-        return self._plans[key]
+            self._plans[key] = handle
+        pool = self._free_ws.setdefault(key, [])
+        ws = pool.pop() if pool else torch.empty(lib().n2n_adapter_workspace_bytes(self._plans[key]),
+                                                 dtype=torch.uint8, device=x.device)
+        return key, self._plans[key], ws
+
+    def _give_back(self, key, ws):
+        pool = self._free_ws.setdefault(key, [])
+        if len(pool) < 2:
+            pool.append(ws)
+
+    def clear_plans(self):
+        for h in self._plans.values():
+            lib().n2n_adapter_plan_destroy(h)
+        self._plans.clear()
+        self._free_ws.clear()
+
+    def __del__(self):
+        try:
+            self.clear_plans()
+        except Exception:
+            pass
 
     def forward(self, noisy: torch.Tensor, base_out: torch.Tensor) -> torch.Tensor:
         require_cuda(noisy, "OutputAdapter.forward")
         noisy = noisy.contiguous().float()
         base_out = base_out.contiguous().float()
         params = [self.net[0].weight, self.net[0].bias, self.net[2].weight, self.net[2].bias]
+        if torch.is_grad_enabled() and (base_out.requires_grad or noisy.requires_grad):
+            # adapter.py:22-26 lets gradients flow into base_out (d out / d base_out = I + the conv path); the
+            # B200 path implements the frozen-base finetune of finetune.py:238-263 only: fail loudly instead
+            # of silently detaching the base network.
+            raise NotImplementedError(
+                "OutputAdapter: gradients with respect to noisy / base_out are not implemented on the B200 path "
+                "(use freeze_base=True, use_no_grad_for_base=True as finetune.py:238-246 does)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _AdapterFunction.apply(self, noisy, base_out, *params)
-        plan, ws = self._plan(noisy, False)
+        key, plan, ws = self._checkout(noisy, False)
         out = torch.empty_like(base_out)
         check(lib().n2n_adapter_forward(plan, ptr_array(params), ptr(noisy), ptr(base_out), ptr(out), ptr(ws), stream_ptr()))
+        self._give_back(key, ws)
         return out
 
 

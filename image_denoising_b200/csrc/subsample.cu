@@ -114,6 +114,36 @@ __global__ void subsample_scalar_kernel(const E* __restrict__ img, const uint8_t
   }
 }
 
+// train.py:134-138: F.unfold(x, bs, stride=bs).view(n, c*bs*bs, h/bs, w/bs):
+// y[n, c*bs*bs + ky*bs + kx, i, j] = x[n, c, i*bs + ky, j*bs + kx].  One thread per output element; a warp's
+// 32 consecutive j read a 32*bs-element span of one input row (every byte of it is used by the bs kx-planes
+// scheduled back to back, so it stays in L1/L2) and write 32 consecutive elements.
+template <typename E>
+__global__ void space_to_depth_kernel(const E* __restrict__ x, E* __restrict__ y, int c, int h, int w, int bs,
+                                      long long items) {
+  pdl_enter();
+  const int hh = h / bs, ww = w / bs, b2 = bs * bs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < items;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int j = (int)(r % ww); r /= ww;
+    const int i = (int)(r % hh); r /= hh;
+    const int k = (int)(r % b2); r /= b2;
+    const int ch = (int)(r % c);
+    const long long b = r / c;
+    y[t] = x[((b * c + ch) * h + (long long)i * bs + k / bs) * w + (long long)j * bs + k % bs];
+  }
+}
+
+template <typename E>
+static int run_space_to_depth(const void* x, void* y, int n, int c, int h, int w, int bs, cudaStream_t st) {
+  const long long items = (long long)n * c * bs * bs * (h / bs) * (w / bs);
+  if (items == 0) return 0;
+  (void)launch_pdl_v(space_to_depth_kernel<E>, dim3(grid_for(items, 256)), dim3(256), 0, st, (const E*)x, (E*)y, c, h, w, bs, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename E>
 static int run_subsample(const void* img, const uint8_t* m1, const uint8_t* m2, const uint8_t* packed, void* o1,
                          void* o2, int n, int c, int h, int w, cudaStream_t st) {
@@ -187,4 +217,21 @@ extern "C" int n2n_subsample_pair(const void* img, const uint8_t* mask1, const u
   N2N_CHECK_ARG(img && out1 && out2, "subsample_pair: null pointer");
   N2N_CHECK_ARG(packed_sel || (mask1 && mask2), "subsample_pair: need both masks or the packed selector");
   return dispatch_subsample(img, mask1, mask2, packed_sel, out1, out2, n, c, h, w, elem_size, (cudaStream_t)stream);
+}
+
+extern "C" int n2n_space_to_depth(const void* x, void* y, int n, int c, int h, int w, int block_size, int elem_size,
+                                  void* stream) {
+  N2N_CHECK_ARG(n >= 0 && c >= 0 && h >= 0 && w >= 0 && block_size >= 1, "space_to_depth: bad dimensions");
+  N2N_CHECK_ARG(h % block_size == 0 && w % block_size == 0, "space_to_depth: H and W must be multiples of block_size (%d)", block_size);
+  if ((long long)n * c * h * w == 0) return 0;
+  N2N_CHECK_ARG(x && y, "space_to_depth: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (elem_size) {
+    case 1: return run_space_to_depth<uint8_t>(x, y, n, c, h, w, block_size, st);
+    case 2: return run_space_to_depth<uint16_t>(x, y, n, c, h, w, block_size, st);
+    case 4: return run_space_to_depth<uint32_t>(x, y, n, c, h, w, block_size, st);
+    case 8: return run_space_to_depth<uint64_t>(x, y, n, c, h, w, block_size, st);
+  }
+  set_error("space_to_depth: unsupported element size %d", elem_size);
+  return N2N_ERR_ARG;
 }

@@ -29,10 +29,25 @@ def get_generator(device="cuda"):
     return g
 
 
+def _normal_out(shape, std, generator, device):
+    """``torch.normal(mean=0.0, std=std[B,1,1,1], generator=g, out=noise[B,C,H,W])`` as the reference's pinned
+    PyTorch 1.3 (README.md:6-9) executes it: fill ``noise`` with N(0,1) at ITS OWN shape, then ``mul_(std)``
+    (per-pixel noise, per-sample sigma).  torch >= 2 instead resizes ``out`` to std's shape [B,1,1,1] (with a
+    deprecation warning), which would turn train.py:84-94 into one constant offset per sample; the intended
+    per-pixel semantics are kept here."""
+    noise = torch.empty(shape, dtype=torch.float32, device=device)
+    noise.normal_(mean=0.0, std=1.0, generator=generator)
+    return noise.mul_(std)
+
+
 class AugmentNoise(object):
     """train.py:64-131 — synthetic noise for training (torch RNG; data generation only)."""
 
-    def __init__(self, style):
+    def __init__(self, style, rank: int = 0, world: int = 1):
+        """``rank`` / ``world`` (not in the reference): data-parallel ranks draw the noise of the GLOBAL batch from the
+        same counter-seeded generator and keep their own slice, so that W processes see exactly the noise one
+        process would have added to the concatenated batch (and never W copies of one realisation)."""
+        self.rank, self.world = int(rank), int(world)
         if style.startswith('gauss'):
             self.params = [float(p) / 255.0 for p in style.replace('gauss', '', 1).split('_')]
             self.style = "gauss_fix" if len(self.params) == 1 else "gauss_range"
@@ -42,20 +57,24 @@ class AugmentNoise(object):
         else:
             raise ValueError(f"unknown noise style {style!r}")
 
+    def _mine(self, t):
+        n = t.shape[0] // self.world
+        return t[self.rank * n:(self.rank + 1) * n]
+
     def add_train_noise(self, x):
-        shape = x.shape
         dev = x.device
+        shape = (x.shape[0] * self.world,) + tuple(x.shape[1:])        # the global batch
         if self.style == "gauss_fix":
             std = self.params[0] * torch.ones((shape[0], 1, 1, 1), device=dev)
-            noise = torch.empty(shape, dtype=torch.float32, device=dev)
-            torch.normal(mean=0.0, std=std, generator=get_generator(dev), out=noise)
-            return x + noise
+            noise = _normal_out(shape, std, get_generator(dev), dev)
+            return x + self._mine(noise)
         if self.style == "gauss_range":
             min_std, max_std = self.params
             std = torch.rand(size=(shape[0], 1, 1, 1), device=dev) * (max_std - min_std) + min_std
-            noise = torch.empty(shape, dtype=torch.float32, device=dev)
-            torch.normal(mean=0, std=std, generator=get_generator(dev), out=noise)
-            return x + noise
+            noise = _normal_out(shape, std, get_generator(dev), dev)
+            return x + self._mine(noise)
+        if self.world > 1:
+            raise NotImplementedError("Poisson training noise depends on the data; draw it per rank (world=1)")
         if self.style == "poisson_fix":
             lam = self.params[0] * torch.ones((shape[0], 1, 1, 1), device=dev)
             return torch.poisson(lam * x, generator=get_generator(dev)) / lam
@@ -77,9 +96,14 @@ class AugmentNoise(object):
         return np.array(np.random.poisson(lam * x) / lam, dtype=np.float32)
 
 
-def draw_rd_idx(img: torch.Tensor) -> torch.Tensor:
-    """train.py:155-162: one randint(0, 8) per 2x2 cell from a fresh counter-seeded generator."""
+def draw_rd_idx(img: torch.Tensor, batch: int = None) -> torch.Tensor:
+    """train.py:155-162: one randint(0, 8) per 2x2 cell from a fresh counter-seeded generator.
+    ``batch`` overrides the batch dimension: data-parallel ranks draw the selector of the GLOBAL batch
+    (same counter seed on every rank) and keep their slice, so that W ranks use exactly the masks one
+    process would use on the concatenated batch."""
     n, c, h, w = img.shape
+    if batch is not None:
+        n = int(batch)
     cells = n * h // 2 * w // 2
     rd_idx = torch.zeros(size=(cells,), dtype=torch.int64, device=img.device)
     torch.randint(low=0, high=8, size=(cells,), generator=get_generator(img.device), out=rd_idx)
@@ -109,9 +133,9 @@ def generate_subimage_pair(img, mask1=None, mask2=None, packed=None):
 
 
 def space_to_depth(x, block_size):
-    """train.py:134-138 — kept for API parity; only block_size == 2 is on the hot path and the
-    kernels never materialise it."""
-    raise NotImplementedError("space_to_depth is fused into generate_subimages; it is never materialised")
+    """train.py:134-138: F.unfold(x, block_size, stride=block_size).view(n, c*bs**2, h//bs, w//bs) as one gather
+    kernel (generate_subimages itself never materialises it)."""
+    return ops.space_to_depth(x, block_size)
 
 
 def checkpoint(net, epoch, name, save_model_path, log_name, systime=None):

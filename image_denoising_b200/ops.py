@@ -74,6 +74,19 @@ def subsample_pair(img: torch.Tensor, mask1: Optional[torch.Tensor] = None, mask
     return o1, o2
 
 
+def space_to_depth(x: torch.Tensor, block_size: int) -> torch.Tensor:
+    """train.py:134-138: [n,c,h,w] -> [n, c*bs*bs, h//bs, w//bs], channel = c*bs*bs + ky*bs + kx."""
+    require_cuda(x, "space_to_depth")
+    n, c, h, w = x.shape
+    bs = int(block_size)
+    if bs < 1 or h % bs or w % bs:
+        raise ValueError(f"space_to_depth: H, W = {h}, {w} must be multiples of block_size {block_size}")
+    x = x.contiguous()
+    y = torch.empty((n, c * bs * bs, h // bs, w // bs), dtype=x.dtype, device=x.device)
+    check(lib().n2n_space_to_depth(ptr(x), ptr(y), n, c, h, w, bs, _ELEM[x.dtype], stream_ptr()))
+    return y
+
+
 # ----------------------------------------------------------------------------- single layers
 def conv2d_fwd(x, w, b=None, act_slope: float = -1.0, precision: str = "fp32"):
     require_cuda(x, "conv2d_fwd")

@@ -11,6 +11,19 @@ from . import _ext
 from ._ext import check, lib, ptr, stream_ptr
 
 
+def multistep_milestones(n_epoch: int):
+    """train.py:333-340: MultiStepLR milestones int(20r)-1, int(40r)-1, int(60r)-1, int(80r)-1, r = n_epoch/100."""
+    ratio = n_epoch / 100
+    return [int(20 * ratio) - 1, int(40 * ratio) - 1, int(60 * ratio) - 1, int(80 * ratio) - 1]
+
+
+def multistep_lr(base_lr: float, epoch: int, n_epoch: int, gamma: float) -> float:
+    """Learning rate in force during the 1-based ``epoch`` of the reference's loop (train.py:333-340, :346,
+    :375): ``scheduler.step()`` runs at the END of every epoch, so epoch e trains with last_epoch = e - 1 and
+    torch's MultiStepLR has decayed once for every milestone m <= e - 1."""
+    return base_lr * gamma ** sum(1 for m in multistep_milestones(n_epoch) if (epoch - 1) >= m)
+
+
 def build_adam_tables(params, grads, exp_avg, exp_avg_sq, device):
     """Device tables for n2n_adam_multi: int64 [ntensors,5] and int32 [nblocks,2]."""
     rows, blocks = [], []

@@ -20,16 +20,18 @@ from .optim import build_adam_tables
 
 class N2NTrainer:
     def __init__(self, network, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, precision=None, process_group=None,
-                 buckets=2, use_graph=None):
+                 buckets=2, use_graph=None, data_parallel=True):
         self.net = network
         self.precision = precision or network.precision
         network.set_precision(self.precision)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
         self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        self.world, self.rank = 1, 0
+        if data_parallel and (process_group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
         params = list(network.parameters())
         dev = params[0].device
         _ext.require_cuda(params[0], "N2NTrainer")
@@ -167,8 +169,11 @@ class N2NTrainer:
 
     def step(self, noisy, Lambda, rd_idx=None, lr=None):
         """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
-        device tensor [loss_all, loss1, loss2] (no host sync).  ``rd_idx`` may carry this rank's
-        slice of a globally drawn selector (mask parity with a 1-GPU run)."""
+        device tensor [loss_all, loss1, loss2] (no host sync; the SAME buffer every step — clone it to keep a
+        value across steps).  Without ``rd_idx`` the selector is drawn as train.py:155-162 does; with W > 1 ranks
+        it is drawn for the GLOBAL batch (identical counter seed on every rank) and this rank keeps its slice, so
+        a W-rank run uses the masks a 1-GPU run on the concatenated batch would.  ``rd_idx`` may
+        also be passed explicitly (this rank's slice)."""
         noisy = noisy.contiguous()
         shapes_before = self._shapes
         self._prepare(noisy)
@@ -178,9 +183,13 @@ class N2NTrainer:
         L = lib()
         launches0 = L.n2n_launch_count()
         if rd_idx is None:
-            rd_idx = n2n.draw_rd_idx(noisy)
+            if self.world > 1:
+                n = noisy.shape[0]
+                rd_idx = dp.shard_selector(n2n.draw_rd_idx(noisy, batch=n * self.world), self.rank, self.world, n * self.world)
+            else:
+                rd_idx = n2n.draw_rd_idx(noisy)
         self.step_count += 1
-        lr = float(lr or self.lr)
+        lr = float(self.lr if lr is None else lr)
         profiling = L.n2n_profile_active() == 1
         if self.use_graph and not profiling and self._eager_steps >= 1:
             if self._graph is None:

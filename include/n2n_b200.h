@@ -83,6 +83,12 @@ int n2n_subsample_pair(const void* img, const uint8_t* mask1, const uint8_t* mas
                        const uint8_t* packed_sel, void* out1, void* out2,
                        int n, int c, int h, int w, int elem_size, void* stream);
 
+/* train.py:134-138 (space_to_depth): F.unfold(x, bs, stride=bs) viewed as [n, c*bs*bs, h/bs, w/bs]:
+ * y[n, c*bs*bs + ky*bs + kx, i, j] = x[n, c, i*bs+ky, j*bs+kx].  Pure copy, elem_size in {1,2,4,8}.
+ * (generate_subimages never materialises it; kept because it is a public name of the reference.) */
+int n2n_space_to_depth(const void* x, void* y, int n, int c, int h, int w, int block_size,
+                       int elem_size, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Single layers (NCHW fp32 at the boundary; compute in `dtype`) —
  * arch_unet.py:113-190 (nn.Conv2d 3x3 s1 p1 / 1x1, LeakyReLU(0.2) in place),

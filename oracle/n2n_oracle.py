@@ -57,6 +57,29 @@ def draw_rd_idx(n: int, h: int, w: int, seed: int) -> np.ndarray:
     return torch.randint(0, 8, (cells,), generator=g, dtype=torch.int64).numpy()
 
 
+def add_train_noise_gauss(x: torch.Tensor, sigma255: float, seed: int) -> torch.Tensor:
+    """train.py:84-94 (gauss_fix) with the generator of training_script.md:4-10 seeded with the operation
+    counter value ``seed``: x + N(0, (sigma/255)^2), per-sample std tensor, no clamp.
+    PARITY NOTE: ``torch.normal(mean, std[B,1,1,1], out=noise[B,C,H,W])`` fills ``noise`` at its own shape under the
+    reference's pinned PyTorch 1.3 (normal_(0,1) then mul_(std)); torch >= 2 resizes ``out`` to [B,1,1,1] (one offset
+    per sample).  The intended per-pixel form is restated; it cannot be pinned by running the reference under torch 2.x
+    ("parity unpinned" for this data-generation helper only)."""
+    g = torch.Generator(device=x.device)
+    g.manual_seed(int(seed))
+    std = (sigma255 / 255.0) * torch.ones((x.shape[0], 1, 1, 1), device=x.device)
+    noise = torch.zeros(x.shape, dtype=torch.float32, device=x.device)
+    noise.normal_(0.0, 1.0, generator=g)
+    return x + noise * std
+
+
+def space_to_depth(x: np.ndarray, bs: int) -> np.ndarray:
+    """train.py:134-138: F.unfold(x, bs, stride=bs).view(n, c*bs*bs, h//bs, w//bs);
+    channel = c*bs*bs + ky*bs + kx."""
+    n, c, h, w = x.shape
+    t = x.reshape(n, c, h // bs, bs, w // bs, bs)           # n c i ky j kx
+    return np.ascontiguousarray(t.transpose(0, 1, 3, 5, 2, 4)).reshape(n, c * bs * bs, h // bs, w // bs)
+
+
 def subimage_from_mask(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
     """train.py:175-190 — out[n,c,i,j] = img[n,c,2i+k//2,2j+k%2], k = the True slot
     of cell (n,i,j) in ``mask``; the same mask serves every channel."""
