@@ -43,11 +43,15 @@ GFLOP_WGRAD_PER_PATCH = 9.643 - GFLOP_HEAD_WGRAD_PER_PATCH
 
 
 def _peaks():
+    """bf16 tensor peak: the SUSTAINED figure is the denominator of `frac` (the timed region follows >= 3 s of
+    soak steps, so the kernels run at steady-state clocks inside a long step); the burst figure is printed
+    beside it.  Fallbacks are the ones /opt/skills/guides/B200_PROFILING.md states."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(bf16=p.get("bf16_tflops_sustained", 1400.0), hbm=p.get("hbm_gbs", 6650.0), src="measured (sustained)")
-    return dict(bf16=1400.0, hbm=6650.0, src="fallback")
+        return dict(bf16=p.get("bf16_tflops_sustained", 1400.0), bf16_burst=p.get("bf16_tflops", 1650.0),
+                    hbm=p.get("hbm_gbs", 6650.0), src="MEASURED_PEAKS.json (sustained)")
+    return dict(bf16=1400.0, bf16_burst=1650.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
 def _traffic_note():
@@ -127,28 +131,70 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def _ref_dir():
+    """oracle/_ref: the reference's own importable modules, vendored by oracle/build_ref.py in the build container
+    (git-ignored, ships with the gpurun snapshot).  None when absent (then the oracle port is timed)."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return d if os.path.exists(os.path.join(d, "arch_unet.py")) and os.path.exists(os.path.join(d, "train_functions.py")) else None
+
+
 def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
-    """The reference algorithm on the host CPU (oracle port, fp32, all torch threads):
-    one N2N step + Adam on `batch` 1x256x256 patches (BASELINE.json configs[0])."""
+    """The reference algorithm on the host CPU, fp32, all host threads: one N2N step + Adam on `batch`
+    1x256x256 patches (BASELINE.json configs[0]).  kind "reference": the reference's own arch_unet.UNet,
+    generate_mask_pair / generate_subimages (oracle/_ref) in the loop of training_script.md:128-156 with
+    torch.optim.Adam; kind "port": the oracle restatement.  Returns (patches/s, threads, s/step, kind)."""
     import torch
-    from oracle import n2n_oracle as O
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use all host cores
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
-    p = O.unet_init(1, 1, NF, 0)
-    m = {k: torch.zeros_like(v).numpy() for k, v in p.items()}
-    v = {k: torch.zeros_like(v).numpy() for k, v in p.items()}
     clean = torch.rand(batch, 1, PATCH, PATCH)
     noisy = clean + torch.randn(clean.shape) * (25.0 / 255.0)
     times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        rd = O.draw_rd_idx(batch, PATCH, PATCH, it + 1)
-        m1, m2 = O.masks_from_rd_idx(rd)
-        _, _, _, grads, _, _ = O.n2n_step_grads(p, noisy, m1, m2, 0.02)
-        for k in p:
-            O.adam_update(p[k].numpy(), grads[k].numpy(), m[k], v[k], it + 1, 3e-4)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    return batch / (sum(times) / len(times)), torch.get_num_threads(), sum(times) / len(times)
+    ref = _ref_dir()
+    if ref is not None:
+        sys.path.insert(0, ref)
+        try:
+            import arch_unet as ref_arch
+            import train_functions as tf
+        finally:
+            sys.path.remove(ref)
+        network = ref_arch.UNet(in_nc=1, out_nc=1, n_feature=NF)
+        optimizer = torch.optim.Adam(network.parameters(), lr=3e-4)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            optimizer.zero_grad()
+            mask1, mask2 = tf.generate_mask_pair(noisy)
+            noisy_sub1 = tf.generate_subimages(noisy, mask1)
+            noisy_sub2 = tf.generate_subimages(noisy, mask2)
+            with torch.no_grad():
+                noisy_denoised = network(noisy)
+            noisy_sub1_denoised = tf.generate_subimages(noisy_denoised, mask1)
+            noisy_sub2_denoised = tf.generate_subimages(noisy_denoised, mask2)
+            noisy_output = network(noisy_sub1)
+            diff = noisy_output - noisy_sub2
+            exp_diff = noisy_sub1_denoised - noisy_sub2_denoised
+            loss_all = torch.mean(diff ** 2) + 0.02 * torch.mean((diff - exp_diff) ** 2)
+            loss_all.backward()
+            optimizer.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "reference"
+    else:
+        from oracle import n2n_oracle as O
+        p = O.unet_init(1, 1, NF, 0)
+        m = {k: torch.zeros_like(v).numpy() for k, v in p.items()}
+        v = {k: torch.zeros_like(v).numpy() for k, v in p.items()}
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            rd = O.draw_rd_idx(batch, PATCH, PATCH, it + 1)
+            m1, m2 = O.masks_from_rd_idx(rd)
+            _, _, _, grads, _, _ = O.n2n_step_grads(p, noisy, m1, m2, 0.02)
+            for k in p:
+                O.adam_update(p[k].numpy(), grads[k].numpy(), m[k], v[k], it + 1, 3e-4)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
+    return batch / (sum(times) / len(times)), torch.get_num_threads(), sum(times) / len(times), kind
 
 
 def run_reference(args):
@@ -157,21 +203,32 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 5))
     warmup = max(1, min(args.warmup, 2))
-    value, cores, sec = cpu_reference_steps(steps, warmup, batch=4)
-    sample = f"{steps} timed N2N steps (+{warmup} warm-up) on batch 4x1x256x256 fp32, oracle port on torch CPU"
+    value, cores, sec, kind = cpu_reference_steps(steps, warmup, batch=4)
+    what = ("the reference's own arch_unet.UNet + generate_mask_pair/generate_subimages (oracle/_ref) + torch.optim.Adam"
+            if kind == "reference" else "oracle port")
+    sample = f"{steps} timed N2N steps (+{warmup} warm-up) on batch 4x1x256x256 fp32, {what}, torch CPU"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "n2n_train_unet48_b64_1x256x256 (BASELINE configs[2])", "batch_per_gpu": BATCH_PER_GPU,
                    "global_batch": BATCH_PER_GPU * max(args.gpus, 1), "patch": PATCH, "n_feature": NF,
-                   "parallelism": "host CPU, all torch threads",
+                   "parallelism": "host CPU, all host threads",
                    "sample": "each timed step = the same N2N iteration on a bounded batch of 4 patches (rank 0 only)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _max_over_ranks(ms, world, dev, dist):
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def inference_704(dev, precision, world, rank, dist, total_images=128, per_launch=8, reps=2):
@@ -208,22 +265,252 @@ def inference_704(dev, precision, world, rank, dist, total_images=128, per_launc
         one_pass()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev, dist)
     ips = world * mine * reps / (ms / 1e3)
+    pk = _peaks()
     return {"metric": "inference_images_per_s_704x704_whole_image", "value": ips, "unit": "images/s",
             "images": world * mine, "per_launch": per_launch, "psnr_first": float(res_h[0, 0]),
             "gflop_per_image": 291.71, "tflops": ips * 291.71 / 1e3,
+            "frac_of_bf16_sustained_per_gpu": ips / world * 291.71 / 1e3 / pk["bf16"],
             "note": "e2e: pinned uint8 H2D + forward + quantise + PSNR/SSIM kernel + D2H of metrics; random-init weights"}
+
+
+def inference_704_tiled(dev, precision, world, rank, dist, total_images=128, per_launch=8):
+    """BASELINE configs[3] with evaluation_704.py semantics (9 reflect-padded 352x352 tiles per image, triangular
+    blend, truncating quantiser) through the public `evaluate.denoise_tiled` + `psnr_ssim_batch` calls: host uint8
+    images in, uint8 predictions and metrics out (host tiling, H2D, forward on 72 tiles, blend kernels, D2H)."""
+    import numpy as np
+    import torch
+    from image_denoising_b200 import UNet, evaluate, utils_eval
+    torch.manual_seed(4321)
+    net = UNet(in_nc=1, out_nc=1, n_feature=NF).to(dev).set_precision(precision)
+    rng = np.random.default_rng(7 + rank)
+    clean = [rng.integers(0, 256, (704, 704), dtype=np.uint8) for _ in range(per_launch)]
+    noisy = [np.clip(c.astype(np.float32) + rng.normal(0, 25.0, c.shape), 0, 255).astype(np.uint8) for c in clean]
+    mine = max(per_launch, total_images // world // 2)          # bounded sample: half of this rank's shard
+
+    def one_pass():
+        res = None
+        for _ in range(0, mine, per_launch):
+            preds, _l1 = evaluate.denoise_tiled(net, noisy, device=dev, images_per_batch=per_launch)
+            res = utils_eval.psnr_ssim_batch(preds, clean, device=dev)
+        return res
+
+    one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = one_pass()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev, dist)
+    ips = world * mine / (ms / 1e3)
+    pk = _peaks()
+    return {"metric": "inference_images_per_s_704x704_tiled_9x352", "value": ips, "unit": "images/s", "images": world * mine,
+            "gflop_per_image": 656.3, "tflops": ips * 656.3 / 1e3,
+            "frac_of_bf16_sustained_per_gpu": ips / world * 656.3 / 1e3 / pk["bf16"], "psnr_first": float(res[0, 0]),
+            "note": "e2e through evaluate.denoise_tiled + psnr_ssim_batch with host uint8 images (wall clock incl. host tiling)"}
+
+
+def adapter_finetune_c5(dev, precision, steps=10, batch=32):
+    """BASELINE configs[4]: adapter.py finetune on a frozen UNet(3,3,48), batch 32 x 3x256x256: frozen base forward
+    under no_grad -> OutputAdapter forward -> L1 + 0.1 * gradient loss -> adapter backward -> Adam (1 315 params)."""
+    import torch
+    from image_denoising_b200 import DenoiserWithAdapter, FusedAdam, UNet, l1_grad_loss
+    torch.manual_seed(77)
+    model = DenoiserWithAdapter(UNet(in_nc=3, out_nc=3, n_feature=NF), in_channels=3, hidden_channels=16).to(dev)
+    model.set_precision(precision)
+    opt = FusedAdam(filter(lambda q: q.requires_grad, model.parameters()), lr=1e-4)
+    g = torch.Generator(device=dev).manual_seed(7)
+    data = []
+    for _ in range(4):
+        clean = torch.rand((batch, 3, PATCH, PATCH), generator=g, device=dev)
+        data.append((clean + torch.randn(clean.shape, generator=g, device=dev) * (25.0 / 255.0), clean))
+
+    def step(i):
+        noisy, clean = data[i % len(data)]
+        opt.zero_grad(set_to_none=True)
+        loss, _l3 = l1_grad_loss(model(noisy), clean, 0.1)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pps = batch / (ms / 1e3)
+    pk = _peaks()
+    gflop = 39.45
+    return {"metric": "adapter_finetune_patches_per_s_3x256x256", "value": pps, "unit": "patches/s", "batch": batch,
+            "ms_per_step": ms, "gflop_per_patch": gflop, "tflops": pps * gflop / 1e3,
+            "frac_of_bf16_sustained": pps * gflop / 1e3 / pk["bf16"], "loss": float(loss),
+            "inputs": "4 device-resident batches (151 MB each side) rotated; activations >> L2"}
+
+
+def hbm_kernels(dev):
+    """HBM-bound rows: achieved GB/s = ALGORITHMIC bytes per launch / average launch duration
+    (CUDA events around R back-to-back launches on the launching stream, rotating over buffer sets whose total
+    exceeds 2x the 126 MB L2 so that no launch finds its inputs cached)."""
+    import torch
+    from image_denoising_b200 import _ext, ops
+    from image_denoising_b200.optim import build_adam_tables
+    from image_denoising_b200._ext import check, lib, ptr, stream_ptr
+    L = lib()
+    pk = _peaks()
+    out = {}
+
+    def timed(fn, nsets, reps):
+        for i in range(nsets):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i % nsets)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps          # us per launch
+
+    def row(name, nbytes, us, note):
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out[name] = {"bytes_per_launch": nbytes, "us_per_launch": us, "achieved_gbs": gbs, "peak_gbs": pk["hbm"],
+                     "frac": gbs / pk["hbm"], "note": note}
+
+    # ---- C2: sub-sampler pair on 32 x 1 x 512 x 512 fp32 (BASELINE configs[1])
+    n, c, h, w = 32, 1, 512, 512
+    g = torch.Generator(device=dev).manual_seed(1)
+    nsets = 6
+    imgs = [torch.rand((n, c, h, w), generator=g, device=dev) for _ in range(nsets)]
+    rds = [torch.randint(0, 8, (n * h // 2 * w // 2,), generator=g, device=dev) for _ in range(nsets)]
+    trip = [ops.mask_pair_from_rdidx(r, want_masks=True, want_packed=True) for r in rds]
+    o1 = [torch.empty((n, c, h // 2, w // 2), device=dev) for _ in range(nsets)]
+    o2 = [torch.empty_like(t) for t in o1]
+    st = stream_ptr()
+    img_b, sub_b, cells = n * c * h * w * 4, n * c * (h // 2) * (w // 2) * 4, n * (h // 2) * (w // 2)
+    us = timed(lambda i: check(L.n2n_subsample_pair(ptr(imgs[i]), ptr(trip[i][0]), ptr(trip[i][1]), None, ptr(o1[i]), ptr(o2[i]),
+                                                    n, c, h, w, 4, st)), nsets, 60)
+    row("subsample_pair_masks_32x1x512x512_f32", img_b + 2 * 4 * cells + 2 * sub_b, us,
+        "reference call form: img + two bool masks (4 B/cell each) -> two sub-images; 67.1 MB")
+    us = timed(lambda i: check(L.n2n_subsample_pair(ptr(imgs[i]), None, None, ptr(trip[i][2]), ptr(o1[i]), ptr(o2[i]),
+                                                    n, c, h, w, 4, st)), nsets, 60)
+    row("subsample_pair_packed_32x1x512x512_f32", img_b + cells + 2 * sub_b, us,
+        "trainer form: img + packed 1 B/cell selector -> two sub-images; 52.4 MB")
+    us = timed(lambda i: check(L.n2n_mask_pair_from_rdidx(ptr(rds[i]), cells, ptr(trip[i][0]), ptr(trip[i][1]), ptr(trip[i][2]), st)),
+               nsets, 60)
+    row("mask_pair_from_rdidx_32x512x512", cells * (8 + 4 + 4 + 1), us, "int64 rd_idx -> two bool masks + packed selector")
+    del imgs, rds, trip, o1, o2
+
+    # ---- N2N loss fwd+bwd at the C3 shape (64 x 1 x 128 x 128 fp32): 4 reads + 1 write = 21.0 MB
+    m = 64 * 128 * 128
+    nsets = 14
+    bufs = [[torch.rand(m, generator=g, device=dev) for _ in range(5)] for _ in range(nsets)]
+    loss3 = torch.zeros(3, device=dev)
+    lws = torch.zeros(L.n2n_loss_workspace_bytes(0), dtype=torch.uint8, device=dev)
+    us = timed(lambda i: check(L.n2n_loss_n2n_fwdbwd(ptr(bufs[i][0]), ptr(bufs[i][1]), ptr(bufs[i][2]), ptr(bufs[i][3]), 0.5, 1.0, m,
+                                                     ptr(loss3), ptr(bufs[i][4]), ptr(lws), st)), nsets, 140)
+    row("n2n_loss_fwdbwd_64x128x128", 5 * m * 4, us, "out, sub2, den1, den2 read + dL/dout written, fp64 two-stage reduction")
+    del bufs
+
+    # ---- Adam over the UNet's 1 256 689 parameters: read p,g,m,v + write p,m,v = 35.2 MB
+    npar = 1256689
+    nsets = 16
+    sets = []
+    for _ in range(nsets):
+        p_, g_ = torch.randn(npar, generator=g, device=dev) * 0.01, torch.randn(npar, generator=g, device=dev) * 1e-3
+        m_, v_ = torch.zeros(npar, device=dev), torch.zeros(npar, device=dev)
+        sets.append((p_, g_, m_, v_) + build_adam_tables([p_], [g_], [m_], [v_], dev))
+    us = timed(lambda i: check(L.n2n_adam_multi(ptr(sets[i][4]), 1, ptr(sets[i][5]), sets[i][5].shape[0], 3e-4, 0.9, 0.999, 1e-8, 1, 1.0, st)),
+               nsets, 160)
+    row("adam_multi_1256689_params", 7 * npar * 4, us, "one launch; p,g,m,v read, p,m,v written")
+    del sets
+
+    # ---- PSNR + SSIM on 704x704 uint8 pairs, 16 pairs per launch (0.99 MB / image)
+    nb = 16
+    nsets = 20
+    a = [(torch.rand((nb, 704, 704), generator=g, device=dev) * 255).to(torch.uint8) for _ in range(nsets)]
+    b = [(torch.rand((nb, 704, 704), generator=g, device=dev) * 255).to(torch.uint8) for _ in range(nsets)]
+    res = torch.empty((nb, 2), dtype=torch.float64, device=dev)
+    ws = torch.empty(max(16, L.n2n_psnr_ssim_workspace_bytes(nb, 704, 704, 1)), dtype=torch.uint8, device=dev)
+    us = timed(lambda i: check(L.n2n_psnr_ssim_u8(ptr(a[i]), ptr(b[i]), nb, 704, 704, 1, ptr(res), ptr(ws), st)), nsets, 60)
+    row("psnr_ssim_u8_16x704x704", 2 * nb * 704 * 704, us, "16 image pairs per launch; compute-bound on the fp64 11-tap separable filter, not HBM")
+    out["psnr_ssim_u8_16x704x704"]["images_per_s"] = nb / (us * 1e-6)
+    torch.cuda.empty_cache()
+    return out
+
+
+def torch_gpu_baseline(dev, batch, steps=3):
+    """Stock PyTorch on the same B200: the same N2N iteration expressed with
+    ATen/cuDNN ops (F.conv2d / conv_transpose2d / max_pool2d / leaky_relu through the oracle's functional UNet,
+    an index-gather sub-sampler, torch.optim.Adam), fp32 (TF32 off, as the reference runs) and bf16 autocast +
+    channels_last.  Baseline only: the library path this repo's kernels replace."""
+    import torch
+    from oracle import n2n_oracle as O
+    table = torch.tensor(O.PAIR_TABLE, device=dev)
+    res = {}
+
+    def sub(img, k):                                              # out[n,c,i,j] = img[n,c,2i+k//2,2j+k%2]
+        n, c, h, w = img.shape
+        t = img.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(n, c, h // 2, w // 2, 4)
+        return torch.gather(t, 4, k[:, None, :, :, None].expand(n, c, h // 2, w // 2, 1)).squeeze(-1)
+
+    for mode in ("fp32", "bf16_autocast_channels_last"):
+        torch.manual_seed(1234)
+        p = {k: v.to(dev).requires_grad_(True) for k, v in O.unet_init(1, 1, NF, 0).items()}
+        if mode != "fp32":
+            for k, v in p.items():
+                if v.dim() == 4:
+                    p[k] = v.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        opt = torch.optim.Adam(list(p.values()), lr=3e-4)
+        g = torch.Generator(device=dev).manual_seed(5)
+        clean = torch.rand((batch, 1, PATCH, PATCH), generator=g, device=dev)
+        noisy = clean + torch.randn(clean.shape, generator=g, device=dev) * (25.0 / 255.0)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            rd = torch.randint(0, 8, (batch, PATCH // 2, PATCH // 2), generator=g, device=dev)
+            k1, k2 = table[rd, 0], table[rd, 1]
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode != "fp32"):
+                x = noisy if mode == "fp32" else noisy.contiguous(memory_format=torch.channels_last)
+                with torch.no_grad():
+                    den = O.unet_forward(p, x).float()
+                out = O.unet_forward(p, sub(x, k1)).float()
+            loss, _, _ = O.n2n_loss(out, sub(noisy, k2), sub(den, k1), sub(den, k2), 0.02)
+            loss.backward()
+            opt.step()
+            return loss
+
+        try:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[mode] = {"value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": batch, "loss": float(loss)}
+        except Exception as e:                                     # e.g. out of memory on a shared device
+            res[mode] = {"error": repr(e)[:200]}
+        del p, opt
+        torch.cuda.empty_cache()
+    res["note"] = ("stock PyTorch %s / cuDNN on this GPU, same N2N iteration and batch; fp32 with TF32 disabled (reference default), "
+                   "bf16 = torch.autocast + channels_last" % torch.__version__)
+    return res
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from image_denoising_b200 import N2NTrainer, UNet, _ext, n2n
+    from image_denoising_b200 import N2NTrainer, UNet, _ext, n2n, selfcheck
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,8 +552,29 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(k):
+            l3 = one_step(i)
+        e1.record()
+        barrier()
+        return _max_over_ranks(e0.elapsed_time(e1), world, dev, dist), l3
+
     for i in range(args.warmup):
         one_step(i)
+    barrier()
+    # burst number (what round 1 reported): K steps right after the warm-up, clocks still at boost
+    burst_ms, _ = timed_steps(args.steps)
+    # soak: keep stepping for >= soak_seconds so that the timed region below runs at steady-state clocks / power
+    soak_steps = 0
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < args.soak_seconds:
+        for i in range(25):
+            one_step(i)
+        soak_steps += 25
+        torch.cuda.synchronize()
     barrier()
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -275,19 +583,9 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss3 = one_step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, loss3 = timed_steps(args.steps)
     if rank == 0:
         sampler.stop_flag = True
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     launches = int(trainer.last_launches) * args.steps
     final_loss = float(loss3[0].item())
     value = world * B * args.steps / (ms / 1e3)
@@ -312,12 +610,16 @@ def run_b200(args):
         loss_host.copy_(l3, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss every step (train.py:364)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, world, dev, dist)
     e2e_value = world * B * args.steps / e2e_s
+
+    # ---- data-parallel self-checks on this hardware (N > 1): replicas bit-identical after all the steps above,
+    # W ranks x 8 patches reproduce the 1-process 8W-patch gradient (global-batch masks) ----
+    dp_parity = None
+    if world > 1:
+        same = selfcheck.replicas_identical(trainer.flat_p)
+        gp = selfcheck.dp_gradient_parity(dev, per_rank=8, patch=PATCH, nf=NF, precision=args.precision)
+        dp_parity = {"ok": bool(same and gp["ok"]), "replicas_identical_after_steps": bool(same), "gradient": gp}
 
     # ---- roofline leg: per-launch CUDA events around the GEMM kernels, same steps, same stream ----
     # every rank runs the same eager steps (they contain the gradient all-reduce); rank 0 reports
@@ -334,29 +636,58 @@ def run_b200(args):
         tap_ms, tap_flops_exec, tap_n, wg_ms, wg_flops_exec, wg_n = [float(x) for x in out]
         alg_flops = GFLOP_TAPGEMM_PER_PATCH * 1e9 * B * psteps
         achieved = alg_flops / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0
+        step_tflops = GFLOP_PER_PATCH * B * 1e9 / (ms / args.steps / 1e3) / 1e12
         roof = {"bound": "tensor",
                 "kernel": "slabgemm_umma_kernel (+ head_chain_umma / head_bwd_umma, tapgemm_umma for the shapes the slab engine "
                           "declines): conv/deconv forward + input gradient, %d launches/step" % round(tap_n / psteps),
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+                "frac_sustained": achieved / pk["bf16"], "frac_burst": achieved / pk["bf16_burst"],
+                "peak_burst": pk["bf16_burst"],
                 "traffic": (_traffic_note() or {}).get("bytes_per_launch"), "traffic_detail": _traffic_note(),
                 "peak_source": pk["src"],
                 "share_of_step": tap_ms / psteps / (ms / args.steps),
                 "executed_tflops_incl_padding": tap_flops_exec / (tap_ms / 1e3) / 1e12 if tap_ms > 0 else 0.0,
                 "wgrad_kernel": {"achieved": (GFLOP_WGRAD_PER_PATCH * 1e9 * B * psteps) / (wg_ms / 1e3) / 1e12 if wg_ms > 0 else 0.0,
                                  "unit": "TFLOP/s", "ms_per_step": wg_ms / psteps, "launches_per_step": round(wg_n / psteps)},
+                "whole_step": {"achieved": step_tflops, "frac_sustained": step_tflops / pk["bf16"],
+                               "frac_burst": step_tflops / pk["bf16_burst"]},
                 "ms_per_step": tap_ms / psteps}
 
-    infer = None
-    if not args.no_inference:
-        del trainer
-        torch.cuda.empty_cache()
-        infer = inference_704(dev, args.precision, world, rank, dist)
+    # ---- strong scaling: the SAME global batch of 64 split over the N ranks ----
+    strong = None
+    if world > 1 and BATCH_PER_GPU % world == 0:
+        bs = BATCH_PER_GPU // world
+        small = [b[:bs].contiguous() for b in batches]
+        for i in range(4):
+            trainer.step(small[i % nbuf], lam)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            trainer.step(small[i % nbuf], lam)
+        e1.record()
+        barrier()
+        sms = _max_over_ranks(e0.elapsed_time(e1), world, dev, dist)
+        strong = {"global_batch": BATCH_PER_GPU, "batch_per_gpu": bs, "value": BATCH_PER_GPU * args.steps / (sms / 1e3),
+                  "unit": UNIT, "ms_per_step": sms / args.steps}
 
-    cpu = None
+    del trainer
+    torch.cuda.empty_cache()
+    infer = infer_tiled = None
+    if not args.no_inference:
+        infer = inference_704(dev, args.precision, world, rank, dist)
+        infer_tiled = inference_704_tiled(dev, args.precision, world, rank, dist)
+
+    cpu = adapter = hbm = torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        adapter = adapter_finetune_c5(dev, args.precision)
+        hbm = hbm_kernels(dev)
+        torch_gpu = torch_gpu_baseline(dev, B)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sec = cpu_reference_steps(2, 1, batch=4)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "2 timed N2N steps (+1 warm-up) on batch 4x1x256x256 fp32 (BASELINE configs[0]), oracle port on torch CPU"}
+        v, cores, sec, kind = cpu_reference_steps(2, 1, batch=4)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "2 timed N2N steps (+1 warm-up) on batch 4x1x256x256 fp32 (BASELINE configs[0]), %s on torch CPU"
+                         % ("reference modules from oracle/_ref" if kind == "reference" else "oracle port")}
 
     if rank == 0:
         line = {
@@ -366,14 +697,25 @@ def run_b200(args):
             "config": {"workload": "n2n_train_unet48_b64_1x256x256 (BASELINE configs[2])", "batch_per_gpu": B,
                        "global_batch": B * world, "patch": PATCH, "n_feature": NF, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; inputs rotate over 8 batches (134 MB)",
+                       "soak": "%d untimed steps (%.1f s) between the warm-up and the timed region: timed at steady-state clocks"
+                               % (soak_steps, args.soak_seconds),
                        "tflops_per_step_algorithmic": GFLOP_PER_PATCH * B / 1e3},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * PATCH * PATCH * 4, "d2h_bytes_per_step": 12},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "burst": {"value": world * B * args.steps / (burst_ms / 1e3), "unit": UNIT, "ms_per_step": burst_ms / args.steps,
+                      "note": "same K steps timed right after the warm-up, before the soak (boost clocks)"},
             "step_tflops": GFLOP_PER_PATCH * B * 1e9 / (ms / args.steps / 1e3) / 1e12,
+            "dp_parity": dp_parity["ok"] if dp_parity else None,
+            "dp_parity_detail": dp_parity,
+            "strong_scaling": strong,
             "inference_704": infer,
+            "inference_704_tiled": infer_tiled,
+            "adapter_finetune": adapter,
+            "hbm_kernels": hbm,
+            "torch_gpu_baseline": torch_gpu,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -389,8 +731,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--soak-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the adapter / HBM-kernel / stock-PyTorch legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -120,3 +120,32 @@ def test_tiled_and_whole_eval_match_reference(golden):
     with torch.no_grad():
         w = O.quantize_round(O.unet_forward(p, x)[0, 0].numpy())
     assert np.array_equal(w, z["whole255"])
+
+
+def test_oracle_ref_modules_agree_with_the_restatement():
+    """oracle/_ref (the reference's own modules staged by oracle/build_ref.py; present in the build container and on
+    the GPU box, absent from a bare checkout) against the restatement: UNet forward and the sub-sampler."""
+    import os
+    import sys
+    import pytest
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "train_functions.py")):
+        pytest.skip("oracle/_ref not staged")
+    sys.path.insert(0, ref)
+    try:
+        import arch_unet as ref_arch
+        import train_functions as tf
+    finally:
+        sys.path.remove(ref)
+    p = O.unet_init(1, 1, 8, 3)
+    net = ref_arch.UNet(in_nc=1, out_nc=1, n_feature=8)
+    net.load_state_dict(p)
+    x = torch.rand(1, 1, 32, 64, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.allclose(net(x), O.unet_forward(p, x), atol=1e-6)
+    tf.operation_seed_counter = 6
+    m1, m2 = tf.generate_mask_pair(x)
+    o1, o2 = O.masks_from_rd_idx(O.draw_rd_idx(1, 32, 64, 7))
+    assert np.array_equal(m1.numpy(), o1) and np.array_equal(m2.numpy(), o2)
+    assert np.array_equal(tf.generate_subimages(x, m1).numpy(), O.subimage_from_mask(x.numpy(), o1))
+    assert np.array_equal(tf.space_to_depth(x, 2).numpy(), O.space_to_depth(x.numpy(), 2))
