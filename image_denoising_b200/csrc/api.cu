@@ -42,17 +42,18 @@ struct ProfScope {
 };
 
 int launch_tapgemm(const TapGemm& g, cudaStream_t st) {
-  N2N_CHECK_ARG(g.ntaps >= 1 && g.ntaps <= 12 && g.cin_blocks >= 1 && g.nout >= 16 && g.nout % 16 == 0,
+  N2N_CHECK_ARG(g.ntaps >= 1 && g.ntaps <= kTapMax && g.cin_blocks >= 1 && g.nout >= 16 && g.nout % 16 == 0,
                 "tapgemm: bad geometry (taps=%d cin_blocks=%d nout=%d)", g.ntaps, g.cin_blocks, g.nout);
   // executed (padded) FLOPs of this launch: 2 * pixels * nout * taps * 16*cin_blocks
   double kblocks = 0;
   for (int t = 0; t < g.ntaps; ++t) kblocks += g.view_blocks[g.tap_view[t]] ? g.view_blocks[g.tap_view[t]] : g.cin_blocks;
-  const double flops = 2.0 * g.y.N * g.y.H * g.y.W * (double)g.nout * 16.0 * kblocks;
+  const double flops = 2.0 * g.y.N * g.y.H * g.y.W * (double)(g.mma_n ? g.mma_n : g.nout) * 16.0 * kblocks;
   ProfScope ps(0, flops, st);
   if (g.dtype == N2N_BF16) {
     const int r = launch_slabgemm_umma(g, st);
     if (r != kSgNotEligible) return r;
-    N2N_CHECK_ARG(g.n_split == 0 && g.view_blocks[1] == 0, "tapgemm: this launch form needs the slab engine (geometry not eligible)");
+    N2N_CHECK_ARG(g.n_split == 0 && g.view_blocks[1] == 0 && g.mma_n == 0 && g.ntaps <= 12,
+                  "tapgemm: this launch form needs the slab engine (geometry not eligible)");
     N2N_TRY(launch_tapgemm_umma(g, st));
   } else {
     N2N_TRY(launch_tapgemm_simt(g, st));

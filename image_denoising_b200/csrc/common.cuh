@@ -178,18 +178,32 @@ inline int grid_for(long long items, int threads, int max_waves = 8) {
   return (int)blocks;
 }
 
+constexpr int kTapMax = 32, kTapViews = 6;
 // ---- generic "tap GEMM" (conv3x3 / conv1x1 / deconv2x2 fwd+dgrad) ------------------------
 // D[p, n] = sum_t sum_c X_{view(t)}[p + (dy_t, dx_t), c] * Wp[t][n][c]
 // out = epilogue(D): v = D + bias[n] (+ addend[p,n]); act; (* (mask[p,n] > 0 ? 1 : slope)).
 struct TapGemm {
   int dtype = N2N_F32;
-  View x[4];
+  View x[kTapViews];
   int ntaps = 0;
-  int tap_dy[12] = {0}, tap_dx[12] = {0}, tap_view[12] = {0};
-  int tap_slab[12] = {0};         // which packed-weight slab each tap uses
+  int tap_dy[kTapMax] = {0}, tap_dx[kTapMax] = {0}, tap_view[kTapMax] = {0};
+  int tap_slab[kTapMax] = {0};    // which packed-weight slab each tap uses
   int cin_blocks = 0;             // K per tap = 16 * cin_blocks
-  int view_blocks[4] = {0, 0, 0, 0};   // per-view override of cin_blocks (0 = cin_blocks); slab engine only
+  int view_blocks[kTapViews] = {0};    // per-view override of cin_blocks (0 = cin_blocks); slab engine only
   int nout = 0;                   // padded to a multiple of 16
+  // Column-range form (slab engine only; mma_n > 0): every tap is an N = mma_n GEMM into accumulator columns
+  // [tap_col, tap_col + mma_n) of the nout-wide tile accumulator, reading the weight slab that starts tap_woff bytes
+  // into `w` (its channel-block groups follow each other, 3 * mma_n * 32 B apart).  Used by the fused
+  // ConvTranspose2x2 -> conv3x3 launch (layers.cuh: make_upconv_fwd), where the two column halves are the two
+  // horizontally adjacent output pixels and each has its own set of source-pixel taps.
+  int mma_n = 0;
+  int tap_col[kTapMax] = {0};
+  long long tap_woff[kTapMax] = {0};
+  // Fused up-conv only: the 3x3 conv zero-pads the UPSAMPLED image, so output pixels on the image border miss the
+  // ConvTranspose bias of their out-of-image taps: border_corr[cls][mma_n] (cls = 3*ycls + xcls, 1 = first row/col,
+  // 2 = last) is subtracted in the epilogue; up_py = output-row parity of this launch (y is the parity view).
+  const float* border_corr = nullptr;
+  int up_py = 0;
   const void* w = nullptr;        // packed weights (engine layout, see pack.cu)
   const float* bias = nullptr;    // [nout] fp32 (padded) or null
   View y;                         // output view (C16, dtype); ignored when out_nchw set
@@ -290,6 +304,20 @@ struct UnpackJob {
   long long s_t = 0, s_n = 0, s_c = 0;
   Segs nseg, cseg;
 };
+
+// Fused ConvTranspose2x2 -> conv3x3 weights (pack.cu: upfuse_pack_kernel), bf16 engine only.
+struct UpFuseJob {
+  const float* w3 = nullptr;      // dec_conv a weight  [Co][Cu + Cs][3][3]
+  const float* b3 = nullptr;      // dec_conv a bias    [Co]
+  const float* wd = nullptr;      // ConvTranspose2d weight [Ci][Cu][2][2]
+  const float* bd = nullptr;      // ConvTranspose2d bias   [Cu]
+  int Ci = 0, Cu = 0, Cs = 0, Co = 0;
+  int ngroups = 1, co_pad = 16;   // channel-block groups of Ci (3 blocks each); Co padded to 16
+  void* dst[2] = {nullptr, nullptr};   // per output-row parity: 8 composite slabs [(px, sy, sx)][group][3][co_pad][32 B]
+  float* bias_full = nullptr;     // [co_pad]
+  float* corr = nullptr;          // [9][co_pad]
+};
+int launch_upfuse_pack(const UpFuseJob* jobs, int njobs, cudaStream_t st);
 
 size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks);
 

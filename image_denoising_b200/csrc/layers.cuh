@@ -139,6 +139,66 @@ inline TapGemm make_deconv_fwd_pair(const LayerGeom& L, int dtype, const View& x
   g.n_split = L.cout_blocks(); g.split_stride = y_full.sX;       // column parity 1 = the next output pixel
   return g;
 }
+// ---- fused ConvTranspose2x2 -> conv3x3 (no-grad passes, slab engine, see pack.cu: upfuse_pack_kernel) ----------
+// Packed weights of ONE output-row parity: 8 composite slabs over the deconv's input channels, then the conv's
+// skip-channel slabs (nine 3x3 taps over `skip_blocks`, or the single im2col tap of the raw network input).
+struct UpConvGeom {
+  int ci_blocks = 0, skip_blocks = 0, co_blocks = 0;
+  bool skip_im2col = false;       // level 1 on the bf16 engine: the skip is the 9-tap im2col block of the input
+  int gu() const { return (ci_blocks + 2) / 3; }
+  int gs() const { return (skip_blocks + 2) / 3; }
+  size_t slab_bytes() const { return (size_t)3 * co_blocks * 16 * 32; }
+  size_t skip_base() const { return (size_t)8 * gu() * slab_bytes(); }
+  int skip_slabs() const { return skip_im2col ? 1 : 9; }
+  size_t region_bytes() const { return skip_base() + (size_t)skip_slabs() * gs() * slab_bytes(); }
+};
+bool slab_upconv_ok(int dtype, int n, int h, int w, int ci_blocks, int skip_blocks, int co_blocks, size_t w_bytes);
+
+// x: the ConvTranspose's input (source resolution); skip_hi: the skip channels of the concat buffer (2x resolution);
+// y_full: the conv's output (2x resolution); py: output-row parity of this launch; wreg: this parity's weight region.
+inline TapGemm make_upconv_fwd(const UpConvGeom& U, int dtype, const View& x, const View& skip_hi, const View& y_full,
+                               int py, const void* wreg, const float* bias_full, const float* corr) {
+  TapGemm g;
+  g.dtype = dtype;
+  const int cop = U.co_blocks * 16;
+  g.nout = 2 * cop; g.mma_n = cop; g.cin_blocks = U.ci_blocks; g.w = wreg; g.bias = bias_full;
+  g.border_corr = corr; g.up_py = py;
+  g.y = parity_view(y_full, dtype, py, 0);
+  g.n_split = U.co_blocks; g.split_stride = y_full.sX;
+  g.x[0] = x;
+  int t = 0;
+  for (int px = 0; px < 2; ++px)
+    for (int syi = 0; syi < 2; ++syi)
+      for (int sxi = 0; sxi < 2; ++sxi) {
+        g.tap_view[t] = 0; g.tap_dy[t] = syi + py - 1; g.tap_dx[t] = sxi + px - 1;
+        g.tap_col[t] = px * cop;
+        g.tap_woff[t] = (long long)(((px * 2 + syi) * 2 + sxi) * U.gu()) * (long long)U.slab_bytes();
+        ++t;
+      }
+  if (U.skip_im2col) {
+    for (int px = 0; px < 2; ++px) {
+      g.x[1 + px] = parity_view(skip_hi, dtype, py, px); g.view_blocks[1 + px] = U.skip_blocks;
+      g.tap_view[t] = 1 + px; g.tap_dy[t] = 0; g.tap_dx[t] = 0; g.tap_col[t] = px * cop;
+      g.tap_woff[t] = (long long)U.skip_base();
+      ++t;
+    }
+  } else {
+    for (int q = 0; q < 4; ++q) { g.x[1 + q] = parity_view(skip_hi, dtype, q >> 1, q & 1); g.view_blocks[1 + q] = U.skip_blocks; }
+    for (int px = 0; px < 2; ++px)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yo = py + ky - 1, xo = px + kx - 1;          // offset on the 2x grid relative to (2i, 2j)
+          g.tap_view[t] = 1 + (yo & 1) * 2 + (xo & 1);
+          g.tap_dy[t] = yo >= 0 ? yo >> 1 : -1; g.tap_dx[t] = xo >= 0 ? xo >> 1 : -1;
+          g.tap_col[t] = px * cop;
+          g.tap_woff[t] = (long long)U.skip_base() + (long long)((ky * 3 + kx) * U.gs()) * (long long)U.slab_bytes();
+          ++t;
+        }
+  }
+  g.ntaps = t;
+  return g;
+}
+
 bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_blocks);
 bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo);
 bool slab_geometry_ok(int dtype, int h, int w);

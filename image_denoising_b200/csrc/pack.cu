@@ -173,6 +173,97 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused ConvTranspose2x2(s2) -> conv3x3 (arch_unet.py:57-62 followed by dec_conv{k}a, :230-242), no-grad passes.
+// conv3x3(cat[deconv(x), skip]) is linear in x: for the output pixel (2i+py, 2j+px) the nine taps of the 3x3 conv
+// land on a 2x2 neighbourhood of SOURCE pixels (i+sy, j+sx), sy in {py-1, py}, sx in {px-1, px}, so
+//   y[:, 2i+py, 2j+px] = sum_{sy,sx} Wc[py][px][sy][sx] x[:, i+sy, j+sx] + (skip part) + bias,
+//   Wc[py][px][sy][sx][co][ci] = sum_{ky: floor((py+ky-1)/2) = sy} sum_{kx: ...} sum_c
+//                                 W3[co][c][ky][kx] * Wd[ci][c][(py+ky-1)&1][(px+kx-1)&1]
+// — 4 source taps of K = Ci instead of 9 taps of K = Cu on the upsampled image, and the upsampled tensor is never
+// written.  This kernel builds the 16 composite matrices per layer (bf16, engine layout, one region per py), the
+// full bias b3 + sum_taps W3[tap] bd, and the border table: the 3x3 conv zero-pads the UPSAMPLED image, so a
+// border pixel's out-of-image taps contribute no ConvTranspose bias: corr[3*ycls + xcls][co] (1 = first row / column
+// -> ky / kx = 0 outside, 2 = last -> ky / kx = 2 outside) is what the epilogue subtracts there.
+struct UpFuseBatch { UpFuseJob j[5]; int n; };
+
+__global__ void upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
+  pdl_enter_no_release();   // its output is prefetched by the next GEMM's prologue
+  const UpFuseJob& J = b.j[blockIdx.y];
+  const int ci_pad = J.ngroups * kGroupBlocks * 16;        // whole groups (the bulk copy reads the padding too)
+  const long long total = 16LL * J.co_pad * ci_pad;
+  const int cin3 = J.Cu + J.Cs;                            // dec_conv a's input channels
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % ci_pad);
+    const int co = (int)((i / ci_pad) % J.co_pad);
+    const int u = (int)((i / ((long long)ci_pad * J.co_pad)) % 8);     // (px, syi, sxi)
+    const int py = (int)(i / (8LL * ci_pad * J.co_pad));
+    const int px = u >> 2, sy = ((u >> 1) & 1) + py - 1, sx = (u & 1) + px - 1;
+    float v = 0.f;
+    if (co < J.Co && ci < J.Ci) {
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yo = py + ky - 1;
+        if ((yo >= 0 ? yo >> 1 : -1) != sy) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xo = px + kx - 1;
+          if ((xo >= 0 ? xo >> 1 : -1) != sx) continue;
+          const float* w3 = J.w3 + ((long long)co * cin3 * 3 + ky) * 3 + kx;                  // + c * 9
+          const float* wd = J.wd + ((long long)ci * J.Cu * 2 + (yo & 1)) * 2 + (xo & 1);      // + c * 4
+          float acc = 0.f;
+          for (int c = 0; c < J.Cu; ++c) acc = fmaf(__ldg(w3 + c * 9), __ldg(wd + c * 4), acc);
+          v += acc;
+        }
+      }
+    }
+    const int cb = ci >> 4, e = ci & 15;
+    const int g = cb / kGroupBlocks, jj = cb - g * kGroupBlocks;
+    const size_t byte = ((size_t)((u * J.ngroups + g) * kGroupBlocks + jj) * J.co_pad + co) * 32 +
+                        ((((e >> 3) ^ ((co >> 2) & 1))) << 4) + (e & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>((char*)J.dst[py] + byte) = __float2bfloat16_rn(v);
+  }
+  if (blockIdx.x == 0) {
+    for (int co = threadIdx.x; co < J.co_pad; co += blockDim.x) {
+      float tap[9];
+      float full = 0.f;
+      for (int t = 0; t < 9; ++t) {
+        float acc = 0.f;
+        if (co < J.Co)
+          for (int c = 0; c < J.Cu; ++c) acc = fmaf(J.w3[((long long)co * cin3 + c) * 9 + t], J.bd[c], acc);
+        tap[t] = acc; full += acc;
+      }
+      J.bias_full[co] = co < J.Co ? J.b3[co] + full : 0.f;
+      for (int cls = 0; cls < 9; ++cls) {
+        const int yc = cls / 3, xc = cls % 3;
+        float s = 0.f;
+        for (int t = 0; t < 9; ++t) {
+          const int ky = t / 3, kx = t % 3;
+          const bool out = (yc == 1 && ky == 0) || (yc == 2 && ky == 2) || (xc == 1 && kx == 0) || (xc == 2 && kx == 2);
+          if (out) s += tap[t];
+        }
+        J.corr[cls * J.co_pad + co] = s;
+      }
+    }
+  }
+}
+
+int launch_upfuse_pack(const UpFuseJob* jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  N2N_CHECK_ARG(njobs <= 5, "upfuse_pack: too many jobs");
+  UpFuseBatch b;
+  b.n = njobs;
+  long long maxtotal = 1;
+  for (int i = 0; i < njobs; ++i) {
+    b.j[i] = jobs[i];
+    const long long tot = 16LL * jobs[i].co_pad * jobs[i].ngroups * kGroupBlocks * 16;
+    if (tot > maxtotal) maxtotal = tot;
+  }
+  dim3 grid(grid_for(maxtotal, 256, 4), njobs);
+  (void)launch_pdl_v(upfuse_pack_kernel, grid, dim3(256), 0, st, b);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_pack(const PackJob* jobs, int njobs, int dtype, cudaStream_t st) {
   for (int base = 0; base < njobs; base += 8) {
     PackBatch b;

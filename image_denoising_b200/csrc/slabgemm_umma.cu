@@ -64,7 +64,9 @@ struct SgStage {
   uint16_t cb_bytes16;       // bytes/16 between channel blocks inside the staged box
   uint16_t sbo16;            // bytes/16 between image rows of the box (A descriptor stride-byte-offset)
   uint16_t a_off16[9];       // start of each tap's operand view inside the box (bytes/16)
-  uint16_t pad;
+  uint16_t first;            // bit t: tap t is the first MMA into its accumulator columns (stage 0 only)
+  uint8_t col16[9];          // accumulator column (/16) each tap's MMA starts at (column-range form, else 0)
+  uint8_t pad8[3];
   uint32_t b_off16[9];       // start of each tap's weight slab inside the resident weights (bytes/16)
   uint32_t tx_bytes;         // bytes the TMA box delivers
 };
@@ -72,6 +74,8 @@ struct SgStage {
 struct SgParams {
   // hot (epilogue / loop) fields first: they stay in the first constant-cache lines
   int nst, nout, ring, dbg_flags, nbuf;
+  int mma_n, up_py;          // MMA width (= nout unless the launch is in column-range form); fused up-conv: output-row parity
+  const float* corr;         // fused up-conv: border bias correction [9][mma_n] (see TapGemm::border_corr)
   int tiles_x, tiles_y, ntiles;
   int act; float slope;
   int store_y, has_addend, has_mask, has_pool, out_c, n_split;
@@ -82,7 +86,7 @@ struct SgParams {
   const float* bias;
   float* out_nchw;
   View y, addend, mask, pool;
-  CUtensorMap tmap[4];
+  CUtensorMap tmap[kTapViews];
   SgStage st[kSgMaxStages];
 };
 
@@ -198,6 +202,7 @@ __device__ __forceinline__ void unpack_bf16x16(const uint32_t w[8], float v[16])
 struct SgPix {
   int img, y, x;
   bool valid;          // pixel inside the image (edge tiles of images that are not multiples of 8 x 16)
+  int cls0, cls1;      // fused up-conv: border class of the two output pixels of the column halves (0 = interior)
   long long ypix, apix, mpix, ppix;
 };
 
@@ -215,6 +220,18 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     for (int q = 0; q < 4; ++q) {
       const float4 b = b4[q];
       v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+  }
+  if (p.corr) {
+    const bool hi = p.n_split && cb >= p.n_split;
+    const int cls = hi ? c.cls1 : c.cls0;
+    if (cls) {                                             // image-border pixel: drop the out-of-image taps' ConvTranspose bias
+      const float4* c4 = reinterpret_cast<const float4*>(p.corr + cls * p.mma_n + (hi ? cb - p.n_split : cb) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(c4 + q);
+        v[4 * q] -= b.x; v[4 * q + 1] -= b.y; v[4 * q + 2] -= b.z; v[4 * q + 3] -= b.w;
+      }
     }
   }
   if (p.has_addend) {
@@ -312,7 +329,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 1 + b); };      // up to three accumulators
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kSgMaxRing + 4 + b); };
   const uint32_t wready_bar = bar0 + 8u * (2 * kSgMaxRing + 7);   // CG = 2: both CTAs' weight halves have landed
-  const uint32_t b_sub16 = (uint32_t)p.nout * 2u / CG;  // weight rows per CTA x 32 B, in 16-byte units
+  const uint32_t b_sub16 = (uint32_t)p.mma_n * 2u / CG;  // weight rows per CTA x 32 B, in 16-byte units
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
@@ -326,7 +343,9 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   for (int i = threadIdx.x; i < p.nst * 10; i += kSgThreads) {
     const int s = i / 10, t = i - s * 10;
     const SgStage& S = p.st[s];
-    s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t], S.b_off16[t] / CG) : make_uint2(0u, 0u);
+    s_tap[i] = t < S.ntaps ? make_uint2((uint32_t)S.a_off16[t] | ((uint32_t)S.col16[t] << 20),
+                                        (S.b_off16[t] / CG) | (((uint32_t)(S.first >> t) & 1u) << 31))
+                           : make_uint2(0u, 0u);
   }
   for (int i = threadIdx.x; i < p.nout; i += kSgThreads)
     s_bias[i] = p.bias ? p.bias[(p.n_split && i >= p.n_split * 16) ? i - p.n_split * 16 : i] : 0.f;
@@ -335,7 +354,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     // row = 1) and whose B rows carry the bias split into bf16 hi + lo parts (relative error 2^-17) — the epilogue
     // saves 4 LDS + 16 FADD per channel block, which is what bounds the narrow layers.
     uint8_t* base = smem_raw + (smem0 - smem_u32(smem_raw));
-    const int nrows = p.nout / CG;                         // this CTA's half of the B rows in pair form
+    const int nrows = p.mma_n / CG;                        // this CTA's half of the B rows in pair form
     for (int r = threadIdx.x; r < 128 + nrows; r += kSgThreads) {
       const uint32_t off = r < 128 ? p.bias_off + (uint32_t)r * 32u : p.bias_off + 4096u + (uint32_t)(r - 128) * 32u;
       float v = 1.0f;
@@ -379,10 +398,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   if (warp == 0) {
     // ---- TMA producer (whole warp walks the loop, one elected lane issues) ----
     if (elect_one_sync()) {
-      for (int v = 0; v < 4; ++v) prefetch_tensormap(&p.tmap[v]);
+      for (int v = 0; v < kTapViews; ++v) prefetch_tensormap(&p.tmap[v]);
       if (CG == 2) {
         // this CTA's half of the rows of every weight sub-tile ([nout][32 B] each)
-        const uint32_t sub = (uint32_t)p.nout * 32u, half = sub / 2u;
+        const uint32_t sub = (uint32_t)p.mma_n * 32u, half = sub / 2u;
         mbar_arrive_expect_tx(wfull_bar, p.w_bytes / 2u);
         for (uint32_t k = 0; k * sub < p.w_bytes; ++k)
           bulk_load(smem0 + k * half, p.w + (size_t)k * sub + rank * half, half, wfull_bar);
@@ -465,21 +484,22 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         fence_after_sync();
         if (elect_one_sync()) {
           if (!skip) {
-            uint32_t a1 = acc;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               if (t < (int)mm.x) {
-                const uint32_t al = a_lo + tp[t].x, bl = w_lo + tp[t].y;
+                // x: A offset (bits 0..19) | accumulator column (bits 20..); y: B offset | "first MMA into these columns"
+                const uint32_t al = a_lo + (tp[t].x & 0xFFFFFu), bl = w_lo + (tp[t].y & 0x7FFFFFFFu);
+                const uint32_t dt = d_tmem + (tp[t].x >> 20) * 16u;
+                const uint32_t a1 = acc | ((tp[t].y >> 31) ^ 1u);
                 if (CG == 2) {
-                  sg_mma2(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
-                  if (mm.y > 1) sg_mma2(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
-                  if (mm.y > 2) sg_mma2(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                  sg_mma2(dt, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma2(dt, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma2(dt, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
                 } else {
-                  sg_mma(d_tmem, al, mm.w, bl, b_hi, idesc, a1);
-                  if (mm.y > 1) sg_mma(d_tmem, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
-                  if (mm.y > 2) sg_mma(d_tmem, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                  sg_mma(dt, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma(dt, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma(dt, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
                 }
-                a1 = 1;
               }
             }
           }
@@ -493,7 +513,9 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (p.bias_off && !skip) {
           const uint32_t one_lo = (((smem0 + p.bias_off) & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t bia_lo = (((smem0 + p.bias_off + 4096u) & 0x3FFFFu) >> 4) | (1u << 16);
-          if (CG == 2) sg_mma2(d_tmem, one_lo, b_hi, bia_lo, b_hi, idesc, 1); else sg_mma(d_tmem, one_lo, b_hi, bia_lo, b_hi, idesc, 1);
+          for (int col = 0; col < p.nout; col += p.mma_n) {      // column-range form: the same bias rows serve every column range
+            if (CG == 2) sg_mma2(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1); else sg_mma(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1);
+          }
         }
         if (CG == 2) mma_commit2(tfull_bar(buf)); else mma_commit(tfull_bar(buf));
       }
@@ -543,6 +565,14 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       c.y = ty * kTileH + py; c.x = tx * kTileW + px;
       c.valid = tile_ok && c.y < p.y.H && c.x < p.y.W;
       c.ypix = (long long)c.img * p.y.sN + (long long)c.y * p.y.sY + (long long)c.x * p.y.sX;
+      c.cls0 = c.cls1 = 0;
+      if (p.corr) {
+        // output pixels (2y + up_py, 2x) and (2y + up_py, 2x + 1) of the upsampled image (2H x 2W)
+        const int Y = 2 * c.y + p.up_py;
+        const int ycls = Y == 0 ? 3 : (Y == 2 * p.y.H - 1 ? 6 : 0);
+        c.cls0 = ycls + (c.x == 0 ? 1 : 0);
+        c.cls1 = ycls + (c.x == p.y.W - 1 ? 2 : 0);
+      }
       c.apix = c.mpix = c.ppix = 0;                        // only the operands this launch has (uniform branches)
       if (p.has_addend) c.apix = (long long)c.img * p.addend.sN + (long long)c.y * p.addend.sY + (long long)c.x * p.addend.sX;
       if (p.has_mask) c.mpix = (long long)c.img * p.mask.sN + (long long)c.y * p.mask.sY + (long long)c.x * p.mask.sX;
@@ -639,6 +669,22 @@ bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_block
   return align_up(w_bytes, 1024) + 2 * slot <= kSgSmemMax - kSgStaticSlack - 1024;
 }
 
+// Can ConvTranspose2x2 -> conv3x3 run as the fused column-range launch (layers.cuh: make_upconv_fwd)?  h, w = SOURCE
+// (pre-upsampling) image size; w_bytes = packed weights of one output-row parity.  Needs the CTA-pair form (each SM
+// keeps half of the weight rows).
+bool slab_upconv_ok(int dtype, int n, int h, int w, int ci_blocks, int skip_blocks, int co_blocks, size_t w_bytes) {
+  { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return false; }
+  { const char* e = getenv("N2N_NO_UPFUSE"); if (e && atoi(e)) return false; }
+  if (dtype != N2N_BF16 || h < 4 || w < 4) return false;
+  const int mma_n = co_blocks * 16;
+  if (2 * mma_n > 256) return false;
+  const long long tiles = (long long)n * ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
+  if (!sg_use_pair(mma_n, tiles)) return false;
+  const int gb = ci_blocks < kSgGroup ? ci_blocks : kSgGroup, gs = skip_blocks < kSgGroup ? skip_blocks : kSgGroup;
+  const size_t slot = align_up((size_t)(gb > gs ? gb : gs) * kHaloW * kHaloH * 32, 1024);
+  return align_up(w_bytes / 2, 1024) + 2 * slot <= kSgSmemMax - kSgStaticSlack - 1024;
+}
+
 // Returns 0 when launched, kSgNotEligible when this geometry belongs to the row-slab engine, < 0 on error.
 int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   static bool attr_set = false;
@@ -647,7 +693,9 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   if (H < 4 || W < 4 || (g.has_pool && ((H | W) & 1))) return kSgNotEligible;     // edge tiles are masked in the epilogue
   { const char* e = getenv("N2N_NO_SLAB"); if (e && atoi(e)) return kSgNotEligible; }
   const int ngroups = (g.cin_blocks + kSgGroup - 1) / kSgGroup;
-  const uint32_t b_sub = (uint32_t)g.nout * 32u;
+  const int mma_n = g.mma_n ? g.mma_n : g.nout;
+  if (mma_n % 16 || g.nout % mma_n) return kSgNotEligible;
+  const uint32_t b_sub = (uint32_t)mma_n * 32u;
   const size_t slab_bytes = (size_t)kSgGroup * b_sub;
   int max_slab = 0, nviews = 0;
   for (int t = 0; t < g.ntaps; ++t) {
@@ -655,7 +703,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
     if (g.tap_view[t] + 1 > nviews) nviews = g.tap_view[t] + 1;
     if (g.tap_dy[t] < -1 || g.tap_dy[t] > 1 || g.tap_dx[t] < -1 || g.tap_dx[t] > 1) return kSgNotEligible;
   }
-  if (nviews > 4) return kSgNotEligible;
+  if (nviews > kTapViews) return kSgNotEligible;
   size_t w_bytes = 0;   // = end of the last weight byte any tap reads (set below)
 
   SgParams p;
@@ -688,10 +736,15 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
       int k = 0;
       for (int t = 0; t < g.ntaps; ++t) {
         if (g.tap_view[t] != v) continue;
+        if (k >= 9) return kSgNotEligible;
         const int oy = halo ? g.tap_dy[t] + 1 : 0, ox = halo ? g.tap_dx[t] + 1 : 0;
         S.a_off16[k] = (uint16_t)(((oy * bw + ox) * 32) >> 4);
-        const size_t boff = ((size_t)g.tap_slab[t] * ngroups + grp) * slab_bytes;
+        const size_t boff = g.mma_n ? (size_t)g.tap_woff[t] + (size_t)grp * slab_bytes
+                                    : ((size_t)g.tap_slab[t] * ngroups + grp) * slab_bytes;
         S.b_off16[k] = (uint32_t)(boff >> 4);
+        const int col = g.mma_n ? g.tap_col[t] : 0;
+        if (col % 16 || col + mma_n > g.nout) return kSgNotEligible;
+        S.col16[k] = (uint8_t)(col >> 4);
         if (boff + (size_t)S.nb * b_sub > w_bytes) w_bytes = boff + (size_t)S.nb * b_sub;
         ++k;
       }
@@ -699,20 +752,31 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
       if ((size_t)gb * cb_bytes > slot_bytes) slot_bytes = (size_t)gb * cb_bytes;
     }
   }
-  for (int v = 0; v < 4; ++v)      // unused descriptor slots must still be valid for prefetch.tensormap
+  for (int v = 0; v < kTapViews; ++v)      // unused descriptor slots must still be valid for prefetch.tensormap
     if (v >= nviews) p.tmap[v] = p.tmap[0];
+  // "first MMA into these accumulator columns" flags: every column range must be opened by a tap of stage 0
+  // (the only stage whose MMAs may overwrite instead of accumulate)
+  {
+    uint32_t opened = 0;       // bit c: columns [16c, ...) of a range starting at 16c already written
+    for (int k = 0; k < p.st[0].ntaps; ++k) {
+      const uint32_t bit = 1u << p.st[0].col16[k];
+      if (!(opened & bit)) { p.st[0].first |= (uint16_t)(1u << k); opened |= bit; }
+    }
+    for (int col = 0; col < g.nout; col += mma_n)
+      if (!(opened & (1u << (col >> 4)))) return kSgNotEligible;
+  }
   slot_bytes = align_up(slot_bytes, 1024);
   // CTA pairs (cta_group::2): opt-in per shape via N2N_PAIR (bit 0: N <= 64 layers, bit 1: wider layers).
   // Each CTA of a pair keeps half of the weight rows, which leaves room for a deeper activation ring.
   const long long tiles0 = (long long)g.y.N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-  const int cg = sg_use_pair(g.nout, tiles0) ? 2 : 1;
+  const int cg = sg_use_pair(mma_n, tiles0) ? 2 : 1;
   size_t w_region = align_up(w_bytes / cg, 1024);
   const size_t budget = kSgSmemMax - kSgStaticSlack - 1024;
   if (w_region + 2 * slot_bytes > budget) return kSgNotEligible;
   // bias through the GEMM when the ones block + bias rows still leave a ring of at least four slots
   uint32_t bias_off = 0;
   {
-    const size_t extra = 4096 + align_up((size_t)g.nout / cg * 32, 1024);
+    const size_t extra = 4096 + align_up((size_t)mma_n / cg * 32, 1024);
     const char* e = getenv("N2N_NO_BIAS_MMA");
     if (g.bias && !(e && atoi(e)) && w_region + extra + 4 * slot_bytes <= budget) { bias_off = (uint32_t)w_region; w_region += extra; }
   }
@@ -720,7 +784,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   if (ring > kSgMaxRing) ring = kSgMaxRing;
   { const char* e = getenv("N2N_SG_RING"); if (e && atoi(e) >= 2 && atoi(e) < ring) ring = atoi(e); }
 
-  p.nst = nst; p.nout = g.nout;
+  p.nst = nst; p.nout = g.nout; p.mma_n = mma_n; p.corr = g.border_corr; p.up_py = g.up_py;
   p.w = (const uint8_t*)g.w; p.w_bytes = (uint32_t)w_bytes; p.w_region = (uint32_t)w_region; p.bias_off = bias_off;
   p.bias = g.bias; p.y = g.y; p.store_y = g.store_y ? 1 : 0;
   p.has_addend = g.has_addend; p.addend = g.addend; p.has_mask = g.has_mask; p.mask = g.mask;
@@ -738,7 +802,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   p.nbuf = 3 * g.nout <= 512 ? 3 : 2;
   { const char* e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
   p.tmem_cols = tmem_cols_for(p.nbuf * g.nout);
-  p.idesc = make_idesc_bf16(128 * cg, g.nout, false, false);
+  p.idesc = make_idesc_bf16(128 * cg, mma_n, false, false);
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
   if (!attr_set) {

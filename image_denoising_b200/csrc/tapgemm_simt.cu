@@ -99,6 +99,7 @@ template <typename T>
 static int run_tapgemm(const TapGemm& g, cudaStream_t st) {
   TapGemmDev d;
   memset(&d, 0, sizeof(d));
+  N2N_CHECK_ARG(g.ntaps <= 9 && g.mma_n == 0, "tapgemm_simt: launch form not supported by the fp32 engine");
   for (int i = 0; i < 4; ++i) d.x[i] = g.x[i];
   d.ntaps = g.ntaps;
   for (int t = 0; t < g.ntaps; ++t) {

@@ -53,6 +53,13 @@ struct n2n_unet_plan {
   // gradient = two launches over the N segments; each half keeps its weights resident on the slab engine.
   bool ksplit[25];
   bool deconv_pair[25];   // ConvTranspose layers that run as two N = 2*Cout launches on the slab engine
+  // No-grad plans on the bf16 engine: ConvTranspose layer dc and the 3x3 conv dc + 1 behind it run as ONE fused
+  // layer (two launches, one per output-row parity) on composite weights — the upsampled tensor is never written
+  // and the conv's nine taps over it collapse to four source-pixel taps (pack.cu: upfuse_pack_kernel).
+  bool upfuse[25] = {false};
+  UpConvGeom ug[25];
+  size_t off_upw[25][2] = {{0}}, off_upbias[25] = {0}, off_upcorr[25] = {0};
+  bool fused_layer(int i) const { return (L[i].kind == L_DECONV && upfuse[i]) || (i > 0 && L[i - 1].kind == L_DECONV && upfuse[i - 1]); }
   Buf act[B_COUNT], grd[B_COUNT];
   size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
   size_t total = 0;
@@ -155,6 +162,15 @@ static void plan_layout(n2n_unet_plan* p) {
       p->deconv_pair[i] = slab_deconv_pair_ok(p->dtype, p->lh(lvl), p->lw(lvl), p->L[i].cin_blocks(), p->L[i].cout_blocks());
     }
   }
+  for (int dc = 7; dc <= 19; dc += 3) {
+    const int lv = p->act[p->io[dc].in_buf].lvl;                 // source (pre-upsampling) level
+    UpConvGeom& U = p->ug[dc];
+    U.ci_blocks = p->L[dc].cin_blocks(); U.co_blocks = p->L[dc + 1].cout_blocks();
+    U.skip_im2col = dc == 19 && p->im2col;
+    U.skip_blocks = dc == 19 ? p->skipb : nfb;
+    p->upfuse[dc] = !p->bwd && p->dtype == N2N_BF16 && !p->ksplit[dc + 1] &&
+                    slab_upconv_ok(p->dtype, p->N, p->lh(lv), p->lw(lv), U.ci_blocks, U.skip_blocks, U.co_blocks, U.region_bytes());
+  }
   // ---- workspace layout ----
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
@@ -166,6 +182,12 @@ static void plan_layout(n2n_unet_plan* p) {
   for (int i = 0; i < 25; ++i) {
     p->off_wp[i] = take(p->L[i].fwd_pack_bytes(p->dtype));
     p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
+  }
+  for (int dc = 7; dc <= 19; dc += 3) {
+    if (!p->upfuse[dc]) continue;
+    for (int py = 0; py < 2; ++py) p->off_upw[dc][py] = take(p->ug[dc].region_bytes());
+    p->off_upbias[dc] = take(p->ug[dc].co_blocks * 16 * sizeof(float));
+    p->off_upcorr[dc] = take(9 * p->ug[dc].co_blocks * 16 * sizeof(float));
   }
   if (p->bwd) {
     p->head_splits = head_bwd_splits(p->dtype, p->hb, p->out_nc, p->N, p->H, p->W);
@@ -246,7 +268,8 @@ extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* 
   // per layer: the deepest levels of the two plans can pick different launch forms (pair-form ConvTranspose
   // needs H, W >= 4), which changes that layer's packed layout only
   for (int i = 0; i < 25; ++i)
-    plan->share[i] = donor->ksplit[i] == plan->ksplit[i] && donor->deconv_pair[i] == plan->deconv_pair[i] &&
+    plan->share[i] = !donor->fused_layer(i) && !plan->fused_layer(i) &&
+                     donor->ksplit[i] == plan->ksplit[i] && donor->deconv_pair[i] == plan->deconv_pair[i] &&
                      donor->L[i].fwd_pack_bytes(donor->dtype) == plan->L[i].fwd_pack_bytes(plan->dtype);
   plan->donor = donor; plan->donor_ws = donor_ws;
   return 0;
@@ -262,9 +285,32 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
   {
     std::vector<PackJob> jobs;
     BiasPadJob bj[25];
+    UpFuseJob uj[5];
+    int nuj = 0;
+    for (int dc = 7; dc <= 19; dc += 3) {
+      if (!p->upfuse[dc]) continue;
+      const UpConvGeom& U = p->ug[dc];
+      const LayerGeom& D = p->L[dc]; const LayerGeom& A = p->L[dc + 1];
+      UpFuseJob& j = uj[nuj++];
+      j.w3 = params[2 * (dc + 1)]; j.b3 = params[2 * (dc + 1) + 1]; j.wd = params[2 * dc]; j.bd = params[2 * dc + 1];
+      j.Ci = D.cin.real(); j.Cu = D.cout; j.Cs = A.cin.real() - D.cout; j.Co = A.cout;
+      j.ngroups = U.gu(); j.co_pad = U.co_blocks * 16;
+      j.bias_full = (float*)((char*)ws + p->off_upbias[dc]); j.corr = (float*)((char*)ws + p->off_upcorr[dc]);
+      for (int py = 0; py < 2; ++py) {
+        j.dst[py] = (char*)ws + p->off_upw[dc][py];
+        // the conv's skip-channel slabs behind the composite slabs of each parity's region
+        PackJob k = make_fwd_pack(A, params[2 * (dc + 1)], (char*)ws + p->off_upw[dc][py] + U.skip_base());
+        k.cin_blocks = U.skip_blocks;
+        if (U.skip_im2col) { k.ntaps = 1; k.im2col_nc = p->in_nc; k.im2col_c0 = D.cout; }
+        else { k.cseg.n = 1; k.cseg.src0[0] = D.cout; k.cseg.cnt[0] = j.Cs; k.cseg.dst0[0] = 0; }
+        jobs.push_back(k);
+      }
+    }
     for (int i = 0; i < 25; ++i) {
       if (p->donor && p->share[i]) {
         // forward pack borrowed
+      } else if (p->fused_layer(i)) {
+        // packed above in fused form
       } else if (p->im2col && i == 0) {
         PackJob j = make_fwd_pack(p->L[0], params[0], (char*)ws + p->off_wp[0]);
         j.ntaps = 1; j.cin_blocks = p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = 0;
@@ -307,6 +353,7 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
       bj[i] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), p->L[i].cout, p->L[i].cout_blocks() * 16};
     }
     if (!jobs.empty()) N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
+    N2N_TRY(launch_upfuse_pack(uj, nuj, st));
     if (!p->donor) N2N_TRY(launch_bias_pad(bj, 25, st));
   }
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
@@ -333,6 +380,24 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
     const void* wp = fw(i);
     const float* bias = fb(i);
+    if (L.kind == L_DECONV && p->upfuse[i]) return 0;            // runs inside the next layer's fused launches
+    if (i > 0 && p->L[i - 1].kind == L_DECONV && p->upfuse[i - 1]) {
+      const int dc = i - 1;
+      const LayerIO& dio = p->io[dc];
+      const UpConvGeom& U = p->ug[dc];
+      View xsrc = p->view(p->act, ws, dio.in_buf, dio.in_cb0, dio.in_cb);
+      View skip = p->view(p->act, ws, io.in_buf, p->L[dc].cout_blocks(), U.skip_blocks);
+      View yfull = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      for (int py = 0; py < 2; ++py) {
+        TapGemm g = make_upconv_fwd(U, dt, xsrc, skip, yfull, py, (const char*)ws + p->off_upw[dc][py],
+                                    (const float*)((const char*)ws + p->off_upbias[dc]),
+                                    (const float*)((const char*)ws + p->off_upcorr[dc]));
+        if (io.act) { g.act = 1; g.slope = 0.2f; }
+        const int r = launch_tapgemm(g, st);
+        if (r != 0) return r;
+      }
+      return 0;
+    }
     if (p->im2col && (i == 0 || i == 20)) {
       TapGemm g;
       g.dtype = dt; g.nout = L.cout_blocks() * 16; g.w = wp; g.bias = bias;

@@ -42,7 +42,16 @@ def main():
     if rank == 0:
         sys.stderr.flush()
         print("DP_PARITY " + json.dumps(res), flush=True)
+    # the captured step graph holds NCCL work: drop it before the communicator goes away, and never let a stuck
+    # teardown outlive the result that has already been printed
+    del tr
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    import threading
+    threading.Timer(30.0, lambda: os._exit(0)).start()
+    dist.barrier()
     dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":

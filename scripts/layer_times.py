@@ -21,11 +21,16 @@ buf = (ctypes.c_double * (3 * 400))()
 n = L.n2n_profile_end_list(buf, 400)
 
 
-def fwd_names(res):
-    """launches of one forward at input resolution `res` (levels res .. res/32)."""
+def fwd_names(res, fused=False):
+    """launches of one forward at input resolution `res` (levels res .. res/32).  fused: the no-grad pass, where
+    ConvTranspose + dec_conv a run as two fused launches (one per output-row parity) and no deconv launch exists."""
     def up(name, in_res):
+        if fused and in_res >= 4 and os.environ.get("N2N_NO_UPFUSE", "0") != "1":
+            return []
         return [name] * (2 if in_res >= 4 else 4)               # pair form (slab engine) from 4x4 inputs up
     def dxa(name, r):
+        if fused and r // 2 >= 4 and os.environ.get("N2N_NO_UPFUSE", "0") != "1":
+            return [name + "+up"] * 2
         return [name]                                           # CTA-pair engine: half the weights per SM, no K split
     r = res
     out = ["enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]          # enc0 runs in the fused input stage (not a GEMM launch)
@@ -33,11 +38,11 @@ def fwd_names(res):
     out += up("up4", r // 16) + dxa("d4a", r // 8) + ["d4b"]
     out += up("up3", r // 8) + dxa("d3a", r // 4) + ["d3b"]
     out += up("up2", r // 4) + dxa("d2a", r // 2) + ["d2b"]
-    out += up("up1", r // 2) + ["d1a", "d1b", "head"]
+    out += up("up1", r // 2) + dxa("d1a", r) + ["d1b", "head"]
     return out
 
 
-names = ["full:" + s for s in fwd_names(256)] + ["half:" + s for s in fwd_names(128)]
+names = ["full:" + s for s in fwd_names(256, True)] + ["half:" + s for s in fwd_names(128)]
 tot = {0: 0.0, 1: 0.0}
 k = 0
 for i in range(n):

@@ -1,0 +1,88 @@
+"""Fused ConvTranspose2x2 -> conv3x3 (no-grad bf16 passes: the full-resolution pass of the N2N step, evaluation,
+the adapter's frozen base): composite weights + border bias correction against (a) the layer-by-layer launches it
+replaces (N2N_NO_UPFUSE=1) and (b) the fp32 oracle, with NON-ZERO ConvTranspose biases so that the image-border
+correction (the 3x3 conv zero-pads the UPSAMPLED tensor) is exercised, on shapes whose levels are not multiples of
+the 8x16 tile."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import n2n_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _weights(in_nc, nf, seed, bias_scale=0.05):
+    p = O.unet_init(in_nc, in_nc, nf, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in p:
+        if k.endswith(".bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * bias_scale
+        else:
+            p[k] = p[k] * 6.0          # larger activations deep in the net: border effects are not lost in the noise
+    return p
+
+
+def _net(dev, in_nc, nf, params):
+    from image_denoising_b200 import UNet
+    net = UNet(in_nc=in_nc, out_nc=in_nc, n_feature=nf)
+    net.load_state_dict(params)
+    return net.to(dev).set_precision("bf16")
+
+
+@pytest.mark.parametrize("in_nc,nf,shape", [(1, 48, (2, 64, 96)), (3, 48, (1, 96, 160)), (1, 48, (1, 352, 352)), (1, 16, (3, 32, 64))])
+def test_fused_upconv_matches_layerwise_and_oracle(dev, monkeypatch, in_nc, nf, shape):
+    p = _weights(in_nc, nf, 11)
+    n, h, w = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(n, in_nc, h, w, generator=g)
+    with torch.no_grad():
+        ref = O.unet_forward(p, x)
+    outs = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("N2N_NO_UPFUSE", raising=False)
+        else:
+            monkeypatch.setenv("N2N_NO_UPFUSE", "1")
+        net = _net(dev, in_nc, nf, p)
+        with torch.no_grad():
+            outs[fused] = net(x.to(dev)).cpu()
+        launches = net.last_launches
+        outs[(fused, "launches")] = launches
+    assert outs[(True, "launches")] < outs[(False, "launches")], "the fused path did not engage"
+    scale = float(ref.abs().max())
+    e_f = (outs[True] - ref).abs()
+    e_u = (outs[False] - ref).abs()
+    # same accuracy class as the layer-by-layer bf16 path, everywhere ...
+    assert float(e_f.max()) <= max(2.0 * float(e_u.max()), 0.02 * scale), (float(e_f.max()), float(e_u.max()), scale)
+    assert float(e_f.mean()) <= 1.5 * float(e_u.mean()) + 1e-6
+    # ... and in particular on the image border (first / last two rows and columns), where the correction acts
+    border = torch.zeros_like(ref, dtype=torch.bool)
+    border[..., :2, :] = True; border[..., -2:, :] = True; border[..., :, :2] = True; border[..., :, -2:] = True
+    assert float(e_f[border].mean()) <= 1.5 * float(e_u[border].mean()) + 1e-6, (float(e_f[border].mean()), float(e_u[border].mean()))
+    mse = lambda a: float(((a - ref) ** 2).mean())
+    assert mse(outs[True]) <= 2.0 * mse(outs[False]) + 1e-12
+
+
+def test_fused_upconv_border_correction_is_needed(dev):
+    """Sanity of the test itself: with a large ConvTranspose bias the border correction changes the output by far more
+    than the bf16 tolerance, so a missing / wrong correction cannot pass the test above."""
+    p = _weights(1, 48, 3, bias_scale=0.0)
+    for k in p:
+        if "deconv.bias" in k:
+            p[k] = torch.full(p[k].shape, 0.5)
+    x = torch.rand(1, 1, 64, 64, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = O.unet_forward(p, x)
+        y = _net(dev, 1, 48, p)(x.to(dev)).cpu()
+    interior_err = float((y - ref)[..., 4:-4, 4:-4].abs().mean())
+    border_err = float(torch.cat([(y - ref)[..., 0, :].flatten(), (y - ref)[..., -1, :].flatten(),
+                                  (y - ref)[..., :, 0].flatten(), (y - ref)[..., :, -1].flatten()]).abs().mean())
+    assert border_err <= 3.0 * interior_err + 1e-4, (border_err, interior_err)
