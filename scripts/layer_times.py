@@ -34,7 +34,7 @@ def fwd_names(res, fused=False):
         return [name]                                           # CTA-pair engine: half the weights per SM, no K split
     r = res
     out = ["enc1", "enc2", "enc3", "enc4", "enc5", "enc6"]          # enc0 runs in the fused input stage (not a GEMM launch)
-    out += up("up5", r // 32) + ["d5a", "d5b"]
+    out += up("up5", r // 32) + dxa("d5a", r // 16) + ["d5b"]
     out += up("up4", r // 16) + dxa("d4a", r // 8) + ["d4b"]
     out += up("up3", r // 8) + dxa("d3a", r // 4) + ["d3b"]
     out += up("up2", r // 4) + dxa("d2a", r // 2) + ["d2b"]
