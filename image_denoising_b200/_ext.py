@@ -106,6 +106,7 @@ _SIGS = {
     "n2n_maxpool2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                  c_void_p, c_void_p]),
     "n2n_unet_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "n2n_resnet_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "n2n_unet_plan_destroy": (None, [c_void_p]),
     "n2n_unet_workspace_bytes": (c_size_t, [c_void_p]),
     "n2n_unet_launches": (c_int, [c_void_p, c_int]),
@@ -123,6 +124,8 @@ _SIGS = {
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_loss_l1grad_fwdbwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_loss_structure_fwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                          c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_adam_multi": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_float, c_float, c_int,
                                c_float, c_void_p]),
     "n2n_set_step_scalars": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p]),

@@ -58,9 +58,10 @@ class _PlanCache:
 
     def plan(self, key):
         if key not in self.plans:
-            in_nc, out_nc, nf, n, h, w, dt, bwd = key
+            arch, in_nc, out_nc, nf, n, h, w, dt, bwd = key
             handle = _ext.c_void_p()
-            check(lib().n2n_unet_plan_create(_ext.ctypes.byref(handle), in_nc, out_nc, nf, n, h, w, dt, int(bwd)))
+            create = lib().n2n_resnet_plan_create if arch == "resnet" else lib().n2n_unet_plan_create
+            check(create(_ext.ctypes.byref(handle), in_nc, out_nc, nf, n, h, w, dt, int(bwd)))
             self.plans[key] = handle
         return self.plans[key]
 
@@ -109,7 +110,8 @@ class _UNetFunction(torch.autograd.Function):
                                       ptr(ctx.ws), stream_ptr()))
         net._cache.give_back(ctx.key, dy.device, ctx.ws)
         ctx.ws = None
-        return (None, dx) + tuple(grads)
+        unused = getattr(net, "_unused_params", ())
+        return (None, dx) + tuple(None if i in unused else g for i, g in enumerate(grads))
 
 
 class UNet(nn.Module):
@@ -170,22 +172,26 @@ class UNet(nn.Module):
 
     def _plan_key(self, x, bwd: bool):
         n, c, h, w = x.shape
-        return (self.in_nc, self.out_nc, self.n_feature, n, h, w, _ext.dtype_tag(self.precision), bool(bwd))
+        return (self._arch, self.in_nc, self.out_nc, self.n_feature, n, h, w, _ext.dtype_tag(self.precision), bool(bwd))
+
+    _arch = "unet"
+    _num_params = 50
+    _size_multiple = 32       # five 2x2 poolings (arch_unet.py:203-219)
 
     def _param_list(self):
         ps = list(self.parameters())
-        if len(ps) != 50:
-            raise RuntimeError(f"expected 50 parameters, found {len(ps)}")
+        if len(ps) != self._num_params:
+            raise RuntimeError(f"expected {self._num_params} parameters, found {len(ps)}")
         for p in ps:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("UNet parameters must be contiguous float32 tensors")
         return ps
 
     def forward(self, x):
-        require_cuda(x, "UNet.forward")
+        require_cuda(x, type(self).__name__ + ".forward")
         if x.dim() != 4 or x.shape[1] != self.in_nc:
             raise ValueError(f"expected input [N,{self.in_nc},H,W], got {tuple(x.shape)}")
-        if x.shape[2] % 32 or x.shape[3] % 32:
+        if x.shape[2] % self._size_multiple or x.shape[3] % self._size_multiple:
             raise ValueError("H and W must be multiples of 32 (five 2x2 poolings, arch_unet.py:203-219)")
         x = x.contiguous().float()
         params = self._param_list()
@@ -203,8 +209,65 @@ class UNet(nn.Module):
         return y
 
 
-def RESNET(*a, **k):  # arch_unet.py:263-409 — "next" row N3, not on the north-star path
-    raise NotImplementedError("RESNET is outside the B200 hot-path scope (SURVEY.md §8f N3)")
+class RESNET(UNet):
+    """Drop-in ``arch_unet.RESNET`` (reference arch_unet.py:263-409, non-blindspot): the UNet's 3x3 / 1x1 convolutions at
+    full resolution (no pooling, no up-sampling), ``torch.cat([x, pool_k])`` skips and a global residual ``+ in_`` (:409).
+    Same 42 parameters / names / registration and initialisation order as the reference — including ``up5.deconv.*``,
+    which the reference constructs (:303) but never uses: it stays in the state_dict and receives no gradient.  Runs on
+    the same native executor (n2n_resnet_plan_create + n2n_unet_forward / n2n_unet_backward)."""
+
+    _arch = "resnet"
+    _num_params = 42
+    _size_multiple = 1
+    _unused_params = (14, 15)          # up5.deconv.weight / .bias in parameter order
+
+    def __init__(self, in_nc=3, out_nc=3, n_feature=48, blindspot=False, zero_last=False):
+        nn.Module.__init__(self)
+        if blindspot:
+            raise NotImplementedError("blindspot=True is not part of the B200 hot path")
+        if in_nc != out_nc:
+            raise ValueError("RESNET adds its input to its output (arch_unet.py:409): in_nc must equal out_nc")
+        self.in_nc = in_nc
+        self.out_nc = out_nc
+        self.n_feature = n_feature
+        self.blindspot = blindspot
+        self.zero_last = zero_last
+        nf = n_feature
+        # same construction / initialisation order as arch_unet.py:279-347
+        self.enc_conv0 = nn.Conv2d(in_nc, nf, 3, 1, 1)
+        self.enc_conv1 = nn.Conv2d(nf, nf, 3, 1, 1)
+        initialize_weights(self.enc_conv0, 0.1)
+        initialize_weights(self.enc_conv1, 0.1)
+        for i in range(2, 7):
+            conv = nn.Conv2d(nf, nf, 3, 1, 1)
+            setattr(self, f"enc_conv{i}", conv)
+            initialize_weights(conv, 0.1)
+        self.up5 = UpsampleCat(nf, nf)
+        self.dec_conv5a = nn.Conv2d(nf * 2, nf * 2, 3, 1, 1)
+        self.dec_conv5b = nn.Conv2d(nf * 2, nf * 2, 3, 1, 1)
+        initialize_weights(self.dec_conv5a, 0.1)
+        initialize_weights(self.dec_conv5b, 0.1)
+        for lvl in (4, 3, 2):
+            a = nn.Conv2d(nf * 3, nf * 2, 3, 1, 1)
+            b = nn.Conv2d(nf * 2, nf * 2, 3, 1, 1)
+            setattr(self, f"dec_conv{lvl}a", a)
+            setattr(self, f"dec_conv{lvl}b", b)
+            initialize_weights(a, 0.1)
+            initialize_weights(b, 0.1)
+        self.dec_conv1a = nn.Conv2d(nf * 2 + in_nc, 96, 3, 1, 1)
+        initialize_weights(self.dec_conv1a, 0.1)
+        self.dec_conv1b = nn.Conv2d(96, 96, 3, 1, 1)
+        initialize_weights(self.dec_conv1b, 0.1)
+        self.nin_a = nn.Conv2d(96, 96, 1, 1, 0)
+        self.nin_b = nn.Conv2d(96, 96, 1, 1, 0)
+        initialize_weights(self.nin_a, 0.1)
+        initialize_weights(self.nin_b, 0.1)
+        self.nin_c = nn.Conv2d(96, out_nc, 1, 1, 0)
+        if not self.zero_last:
+            initialize_weights(self.nin_c, 0.1)
+        self.precision = _ext.default_precision()
+        self._cache = _PlanCache()
+        self.last_launches = 0
 
 
 def ImprovedUNet(*a, **k):  # arch_unet.py:475-531 — "next" row N2

@@ -339,6 +339,7 @@ int launch_c16_to_nchw(const View& src, int dtype, float* dst, int C, cudaStream
 int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st);
 int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype, cudaStream_t st);
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t st);
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
 
 // bf16 tensor-core engine (tapgemm_umma.cu / wgrad_umma.cu)
 int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st);

@@ -304,6 +304,18 @@ int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, fl
   return 0;
 }
 
+// y[i] += x[i] (fp32): the global residual of arch_unet.RESNET (arch_unet.py:409) and its input gradient
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  pdl_enter();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  (void)launch_pdl_v(add_inplace_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, y, x, n);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t st) {
   N2N_CUDA(cudaMemsetAsync(p, 0, bytes, st));
   return 0;

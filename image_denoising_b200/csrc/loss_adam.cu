@@ -183,6 +183,54 @@ l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
   }
 }
 
+// ---- Structure loss (util.py:41-70) ---------------------------------------------------------
+// loss = alpha * mean|p - t| + beta * (mean_y|p2[y+1]-p2[y]| + mean_x|p2[x+1]-p2[x]|) / 2 + gamma * mean|p2 - t|
+// with p = network(noisy), p2 = network(clean), t = clean (train.py:361-363).  One pass: both gradients and the four
+// sums.  d/dp = alpha sgn(p-t)/M;  d/dp2 = gamma sgn(p2-t)/M + beta/2 ((sgn(dy[y-1]) - sgn(dy[y]))/My + (sgn(dx[x-1]) - sgn(dx[x]))/Mx).
+__global__ void __launch_bounds__(kRedThreads)
+structure_loss_kernel(const float* __restrict__ pred, const float* __restrict__ pred2, const float* __restrict__ tgt,
+                      int planes, int h, int w, float alpha, float beta, float gamma, float gscale,
+                      float* __restrict__ loss4, float* __restrict__ grad1, float* __restrict__ grad2, RedWs* ws) {
+  pdl_enter();
+  __shared__ double red[4 * 8];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};        // |p-t|, |dy p2|, |dx p2|, |p2-t|
+  const long long hw = (long long)h * w, count = (long long)planes * hw;
+  const long long cy = (long long)planes * (h - 1) * w, cx = (long long)planes * h * (w - 1);
+  const float k1 = gscale * alpha / (float)count, k3 = gscale * gamma / (float)count;
+  const float ky = cy > 0 ? gscale * beta * 0.5f / (float)cy : 0.f;
+  const float kx = cx > 0 ? gscale * beta * 0.5f / (float)cx : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % hw;
+    const int y = (int)(r / w), x = (int)(r - (long long)y * w);
+    const float t = tgt[i], q = pred2[i];
+    const float e1 = pred[i] - t, e2 = q - t;
+    acc[0] += (double)fabsf(e1);
+    acc[3] += (double)fabsf(e2);
+    float g2 = k3 * sgnf(e2);
+    if (y + 1 < h) { const float d = pred2[i + w] - q; acc[1] += (double)fabsf(d); g2 -= ky * sgnf(d); }
+    if (y > 0) g2 += ky * sgnf(q - pred2[i - w]);
+    if (x + 1 < w) { const float d = pred2[i + 1] - q; acc[2] += (double)fabsf(d); g2 -= kx * sgnf(d); }
+    if (x > 0) g2 += kx * sgnf(q - pred2[i - 1]);
+    if (grad1) grad1[i] = k1 * sgnf(e1);
+    if (grad2) grad2[i] = g2;
+  }
+  block_reduce<4>(acc, red);
+  if (threadIdx.x == 0)
+    for (int q = 0; q < 4; ++q) ws->partial[blockIdx.x][q] = acc[q];
+  if (!last_block_done(ws)) return;
+  final_reduce<4>(ws, acc, red);
+  if (threadIdx.x == 0) {
+    const float pixel = (float)(acc[0] / (double)count);
+    const float tv1 = cy > 0 ? (float)(acc[1] / (double)cy) : 0.f;
+    const float tv2 = cx > 0 ? (float)(acc[2] / (double)cx) : 0.f;
+    const float tv = (tv1 + tv2) / 2.f;
+    const float cst = (float)(acc[3] / (double)count);
+    loss4[0] = alpha * pixel + beta * tv + gamma * cst; loss4[1] = pixel; loss4[2] = tv; loss4[3] = cst;
+    ws->counter = 0;
+  }
+}
+
 // ---- multi-tensor Adam ---------------------------------------------------------------------
 // torch.optim.Adam (defaults, no amsgrad / weight decay), same operation order as
 // torch/optim/adam.py: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
@@ -253,6 +301,19 @@ extern "C" int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, in
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   (void)launch_pdl_v(l1grad_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, n * c, h, w, lambda_grad,
                                                                      grad_scale, loss3, grad, (RedWs*)workspace);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_loss_structure_fwdbwd(const float* pred, const float* pred2, const float* target, int n, int c, int h,
+                                         int w, float alpha, float beta, float gamma, float grad_scale, float* loss4,
+                                         float* grad_pred, float* grad_pred2, void* workspace, void* stream) {
+  N2N_CHECK_ARG(pred && pred2 && target && loss4 && workspace && n > 0 && c > 0 && h > 0 && w > 0, "loss_structure: bad arguments");
+  const long long count = (long long)n * c * h * w;
+  int grid = grid_for(count, kRedThreads, 4);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  (void)launch_pdl_v(structure_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, pred2, target, n * c, h, w,
+                     alpha, beta, gamma, grad_scale, loss4, grad_pred, grad_pred2, (RedWs*)workspace);
   N2N_LAUNCH_CHECK();
   return 0;
 }

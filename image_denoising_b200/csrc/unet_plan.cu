@@ -34,9 +34,13 @@ struct LayerIO {
 
 using namespace n2n;
 
+enum { ARCH_UNET = 0, ARCH_RESNET = 1 };
+
 struct n2n_unet_plan {
   int in_nc, out_nc, nf, N, H, W, dtype;
   bool bwd;
+  int arch = ARCH_UNET;
+  int nlayers = 25;                      // RESNET: 21 (state_dict order, arch_unet.py:279-347; layer 7 = the unused up5)
   // bf16 engine: the network input is kept as its 3x3 im2col (kb = ceil(9*in_nc/16) blocks), so
   // enc_conv0 and the raw-input part of dec_conv1a's concat are ONE K = 16*kb GEMM step each
   // instead of nine taps over a 16-channel block with in_nc real channels.
@@ -221,6 +225,30 @@ static void plan_layout(n2n_unet_plan* p) {
   p->total = off;
 }
 
+static void resnet_layout(n2n_unet_plan* p);
+static int resnet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y, void* ws, cudaStream_t st);
+static int resnet_backward(n2n_unet_plan* p, const float* const* params, const float* dy, float* const* grads, float* dx,
+                           void* ws, cudaStream_t st);
+
+// arch_unet.RESNET (arch_unet.py:263-409): same plan type and the same forward / backward / workspace entry points as the
+// UNet; params / grads are the 42 tensors in state_dict order (up5.deconv.* are registered by the reference but never
+// used by forward: they are ignored, and their gradient slots are left untouched).  Needs out_nc == in_nc (global
+// residual, :409); H and W are unconstrained (no pooling).
+extern "C" int n2n_resnet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature, int n, int h, int w,
+                                      int dtype, int with_backward) {
+  N2N_CHECK_ARG(plan != nullptr, "resnet_plan_create: plan is NULL");
+  N2N_CHECK_ARG(in_nc >= 1 && in_nc <= 16 && out_nc == in_nc, "resnet_plan_create: need 1 <= in_nc == out_nc <= 16 (x + in_, arch_unet.py:409)");
+  N2N_CHECK_ARG(n_feature >= 1 && n_feature <= 256 && n >= 1 && h >= 1 && w >= 1, "resnet_plan_create: bad geometry");
+  N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, "resnet_plan_create: bad dtype %d", dtype);
+  n2n_unet_plan* p = new n2n_unet_plan();
+  p->in_nc = in_nc; p->out_nc = out_nc; p->nf = n_feature; p->N = n; p->H = h; p->W = w; p->dtype = dtype;
+  p->bwd = with_backward != 0;
+  p->arch = ARCH_RESNET; p->nlayers = 21;
+  resnet_layout(p);
+  *plan = p;
+  return 0;
+}
+
 extern "C" int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature, int n, int h, int w,
                                     int dtype, int with_backward) {
   N2N_CHECK_ARG(plan != nullptr, "unet_plan_create: plan is NULL");
@@ -261,6 +289,7 @@ extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* 
   N2N_CHECK_ARG(plan != nullptr, "unet_share_weights: plan is NULL");
   plan->donor = nullptr; plan->donor_ws = nullptr;
   if (!donor) return 0;
+  if (plan->arch != ARCH_UNET || donor->arch != ARCH_UNET) return 1;
   N2N_CHECK_ARG(donor_ws != nullptr && donor != plan, "unet_share_weights: bad donor");
   const bool same = donor->in_nc == plan->in_nc && donor->out_nc == plan->out_nc && donor->nf == plan->nf &&
                     donor->dtype == plan->dtype && donor->im2col == plan->im2col && donor->kb == plan->kb;
@@ -280,6 +309,11 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
   N2N_CHECK_ARG(p && params && x && y && ws, "unet_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const long long launches0 = g_launch_count;
+  if (p->arch == ARCH_RESNET) {
+    N2N_TRY(resnet_forward(p, params, x, y, ws, st));
+    p->fwd_launches = (int)(g_launch_count - launches0);
+    return 0;
+  }
   const int dt = p->dtype;
   // weights -> engine layout (fwd; dgrad copies too when a backward will follow)
   {
@@ -491,6 +525,11 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   N2N_CHECK_ARG(p->bwd, "unet_backward: plan was created without with_backward");
   cudaStream_t st = (cudaStream_t)stream;
   const long long launches0 = g_launch_count;
+  if (p->arch == ARCH_RESNET) {
+    N2N_TRY(resnet_backward(p, params, dy, grads, dx, ws, st));
+    p->bwd_launches = (int)(g_launch_count - launches0);
+    return 0;
+  }
   const int dt = p->dtype;
   const bool want_dx = dx != nullptr;
 
@@ -633,6 +672,233 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   }
   p->bwd_launches = (int)(g_launch_count - launches0);
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// RESNET (arch_unet.py:263-409, non-blindspot): the UNet's convolutions with no pooling and no up-sampling — every
+// tensor at full resolution, torch.cat([x, pool_k]) skips, global residual.  Buffers ("CAT_k" = [decoder output |
+// encoder skip], both written in place by their producers, so no concat is materialised):
+//   enc1 -> CAT1[c2b:], enc2 -> CAT2[c2b:], enc3 -> CAT3[c2b:], enc4 -> CAT4[nfb:], enc5 -> E5, enc6 -> CAT4[0:nfb]
+//   dec5a: CAT4 -> D5A, dec5b -> CAT3[0:c2b]; dec4a: CAT3 -> D4A, dec4b -> CAT2[0:]; dec3a: CAT2 -> D3A, dec3b -> CAT1[0:];
+//   dec2a: CAT1 -> D2A, dec2b -> CAT0[0:c2b]; dec1a: CAT0 = [dec2b | input] -> D1A; dec1b -> D1B; nin_a/b/c; + input.
+// ------------------------------------------------------------------------------------------
+static void resnet_layout(n2n_unet_plan* p) {
+  const int nf = p->nf, in_nc = p->in_nc, out_nc = p->out_nc;
+  p->nfb = cblocks(nf); p->c2b = cblocks(2 * nf); p->inb = cblocks(in_nc); p->hb = cblocks(96);
+  p->im2col = false; p->kb = 0; p->skipb = p->inb;
+  const int nfb = p->nfb, c2b = p->c2b, inb = p->inb, hb = p->hb;
+  auto setbuf = [&](int b, int Cb) { p->act[b].Cb = Cb; p->act[b].lvl = 0; p->grd[b].Cb = Cb; p->grd[b].lvl = 0; };
+  for (int b = 0; b < B_COUNT; ++b) setbuf(b, 0);
+  setbuf(B_CAT0, c2b + inb); setbuf(B_CAT1, c2b + nfb); setbuf(B_CAT2, c2b + nfb); setbuf(B_CAT3, c2b + nfb);
+  setbuf(B_CAT4, nfb + nfb); setbuf(B_E0, nfb); setbuf(B_E5, nfb);
+  setbuf(B_D5A, c2b); setbuf(B_D4A, c2b); setbuf(B_D3A, c2b); setbuf(B_D2A, c2b);
+  setbuf(B_D1A, hb); setbuf(B_D1B, hb); setbuf(B_NA, hb); setbuf(B_NB, hb); setbuf(B_OUT, cblocks(out_nc));
+  auto conv3 = [&](int i, ChanSegs cin, int cout) { p->L[i].kind = L_CONV3; p->L[i].cin = cin; p->L[i].cout = cout; };
+  auto conv1 = [&](int i, ChanSegs cin, int cout) { p->L[i].kind = L_CONV1; p->L[i].cin = cin; p->L[i].cout = cout; };
+  auto setio = [&](int i, int ib, int icb0, int icb, int ob, int ocb0) { p->io[i] = LayerIO{ib, icb0, icb, ob, ocb0, true}; p->dgrad_blocks[i] = icb; };
+  conv3(0, chan1(in_nc), nf);  setio(0, B_CAT0, c2b, inb, B_E0, 0);
+  conv3(1, chan1(nf), nf);     setio(1, B_E0, 0, nfb, B_CAT1, c2b);
+  conv3(2, chan1(nf), nf);     setio(2, B_CAT1, c2b, nfb, B_CAT2, c2b);
+  conv3(3, chan1(nf), nf);     setio(3, B_CAT2, c2b, nfb, B_CAT3, c2b);
+  conv3(4, chan1(nf), nf);     setio(4, B_CAT3, c2b, nfb, B_CAT4, nfb);
+  conv3(5, chan1(nf), nf);     setio(5, B_CAT4, nfb, nfb, B_E5, 0);
+  conv3(6, chan1(nf), nf);     setio(6, B_E5, 0, nfb, B_CAT4, 0);
+  p->L[7].kind = L_DECONV; p->L[7].cin = chan1(nf); p->L[7].cout = nf; p->io[7] = LayerIO{B_E5, 0, 0, B_E5, 0, false};   // up5: unused
+  conv3(8, chan2(nf, nf), 2 * nf);        setio(8, B_CAT4, 0, 2 * nfb, B_D5A, 0);
+  conv3(9, chan1(2 * nf), 2 * nf);        setio(9, B_D5A, 0, c2b, B_CAT3, 0);
+  conv3(10, chan2(2 * nf, nf), 2 * nf);   setio(10, B_CAT3, 0, c2b + nfb, B_D4A, 0);
+  conv3(11, chan1(2 * nf), 2 * nf);       setio(11, B_D4A, 0, c2b, B_CAT2, 0);
+  conv3(12, chan2(2 * nf, nf), 2 * nf);   setio(12, B_CAT2, 0, c2b + nfb, B_D3A, 0);
+  conv3(13, chan1(2 * nf), 2 * nf);       setio(13, B_D3A, 0, c2b, B_CAT1, 0);
+  conv3(14, chan2(2 * nf, nf), 2 * nf);   setio(14, B_CAT1, 0, c2b + nfb, B_D2A, 0);
+  conv3(15, chan1(2 * nf), 2 * nf);       setio(15, B_D2A, 0, c2b, B_CAT0, 0);
+  conv3(16, chan2(2 * nf, in_nc), 96);    setio(16, B_CAT0, 0, c2b + inb, B_D1A, 0);
+  conv3(17, chan1(96), 96);               setio(17, B_D1A, 0, hb, B_D1B, 0);
+  conv1(18, chan1(96), 96);               setio(18, B_D1B, 0, hb, B_NA, 0);
+  conv1(19, chan1(96), 96);               setio(19, B_NA, 0, hb, B_NB, 0);
+  conv1(20, chan1(96), out_nc);           setio(20, B_NB, 0, hb, B_OUT, 0);
+  p->io[20].act = false;
+  for (int i = 0; i < 25; ++i) { p->ksplit[i] = false; p->deconv_pair[i] = false; p->upfuse[i] = false; }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t es = dtype_size(p->dtype);
+  const size_t px = (size_t)p->N * p->H * p->W * 16 * es;
+  for (int b = 0; b < B_COUNT; ++b) {
+    if (b == B_OUT || p->act[b].Cb == 0) continue;
+    p->act[b].off = take((size_t)p->act[b].Cb * px);
+  }
+  for (int i = 0; i < 21; ++i) {
+    if (i == 7) continue;
+    p->off_wp[i] = take(p->L[i].fwd_pack_bytes(p->dtype));
+    p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
+  }
+  if (p->bwd) {
+    // the fused head backward covers the UNet's head geometry (same three layers here); tiles of 8 x 16 need H, W >= 4
+    p->head_splits = (p->H >= 4 && p->W >= 4) ? head_bwd_splits(p->dtype, p->hb, p->out_nc, p->N, p->H, p->W) : 0;
+    for (int b = 0; b < B_COUNT; ++b)
+      if (p->grd[b].Cb) p->grd[b].off = take((size_t)p->grd[b].Cb * px);
+    for (int i = 0; i < 21; ++i) {
+      if (i == 7) continue;
+      p->splits[i] = layer_wgrad_splits(p->L[i], p->dtype, p->N, p->H, p->W);
+      p->off_wd[i] = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));
+      if ((i == 18 || i == 19) && p->head_splits > 0) p->splits[i] = p->head_splits;
+      p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
+      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
+    }
+  }
+  p->total = off;
+}
+
+static int resnet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y, void* ws, cudaStream_t st) {
+  const int dt = p->dtype;
+  {
+    std::vector<PackJob> jobs;
+    BiasPadJob bj[21];
+    int nb = 0;
+    for (int i = 0; i < 21; ++i) {
+      if (i == 7) continue;
+      const LayerGeom& G = p->L[i];
+      jobs.push_back(make_fwd_pack(G, params[2 * i], (char*)ws + p->off_wp[i]));
+      if (p->bwd) {
+        if (G.cin.n == 2) {
+          // input gradient of a concat consumer = two launches over its two channel segments (the first is masked by the
+          // decoder activation it feeds back into, the skip segment is not — see resnet_backward)
+          const int b0 = cblocks(G.cin.cnt[0]), b1 = cblocks(G.cin.cnt[1]);
+          PackJob j = make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i], b0);
+          j.nseg = chan1(G.cin.cnt[0]).to_segs();
+          jobs.push_back(j);
+          PackJob k = make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i] + packed_weight_bytes(dt, 9, b0 * 16, G.cout_blocks()), b1);
+          k.nseg.n = 1; k.nseg.src0[0] = G.cin.cnt[0]; k.nseg.cnt[0] = G.cin.cnt[1]; k.nseg.dst0[0] = 0;
+          jobs.push_back(k);
+        } else {
+          jobs.push_back(make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i], G.cin_blocks()));
+        }
+      }
+      bj[nb++] = BiasPadJob{params[2 * i + 1], (float*)((char*)ws + p->off_bias[i]), G.cout, G.cout_blocks() * 16};
+    }
+    N2N_TRY(launch_pack(jobs.data(), (int)jobs.size(), dt, st));
+    N2N_TRY(launch_bias_pad(bj, nb, st));
+  }
+  N2N_TRY(launch_nchw_to_c16(x, p->in_nc, p->view(p->act, ws, B_CAT0, p->c2b, p->inb), dt, st));
+  auto run_layer = [&](int i) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    View xin = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb);
+    TapGemm g;
+    const void* wp = (const char*)ws + p->off_wp[i];
+    const float* bias = (const float*)((const char*)ws + p->off_bias[i]);
+    if (io.out_buf == B_OUT) {
+      View dummy = p->view(p->act, ws, B_NB, 0, L.cout_blocks());
+      g = make_conv_fwd(L, dt, xin, dummy, wp, bias);
+      g.out_nchw = y; g.out_c = p->out_nc;
+    } else {
+      g = make_conv_fwd(L, dt, xin, p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks()), wp, bias);
+    }
+    if (io.act) { g.act = 1; g.slope = 0.2f; }
+    return launch_tapgemm(g, st);
+  };
+  for (int i = 0; i < 18; ++i)
+    if (i != 7) N2N_TRY(run_layer(i));
+  int head = kSgNotEligible;
+  if (dt == N2N_BF16 && p->H >= 4 && p->W >= 4) {
+    HeadChain h;
+    h.x = p->view(p->act, ws, B_D1B, 0, p->hb);
+    h.in_blocks = p->hb; h.mid_blocks = p->hb; h.mid_channels = 96; h.out_nc = p->out_nc;
+    h.wa = (const char*)ws + p->off_wp[18]; h.wb = (const char*)ws + p->off_wp[19];
+    h.bias_a = (const float*)((const char*)ws + p->off_bias[18]); h.bias_b = (const float*)((const char*)ws + p->off_bias[19]);
+    h.wc = params[2 * 20]; h.bias_c = params[2 * 20 + 1];
+    h.slope = 0.2f; h.has_save = p->bwd;
+    h.save_a = p->view(p->act, ws, B_NA, 0, p->hb); h.save_b = p->view(p->act, ws, B_NB, 0, p->hb);
+    h.out_nchw = y;
+    head = launch_head_chain(h, st);
+    if (head < 0) return head;
+  }
+  if (head == kSgNotEligible)
+    for (int i = 18; i < 21; ++i) N2N_TRY(run_layer(i));
+  // global residual (arch_unet.py:409)
+  return launch_add_inplace(y, x, (long long)p->N * p->out_nc * p->H * p->W, st);
+}
+
+static int resnet_backward(n2n_unet_plan* p, const float* const* params, const float* dy, float* const* grads, float* dx,
+                           void* ws, cudaStream_t st) {
+  const int dt = p->dtype;
+  const bool want_dx = dx != nullptr;
+  N2N_TRY(launch_nchw_to_c16(dy, p->out_nc, p->view(p->grd, ws, B_OUT, 0, cblocks(p->out_nc)), dt, st));
+  auto wgrad = [&](int i) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    return launch_tapwgrad(make_conv_wgrad(L, dt, p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb),
+                                           p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks()),
+                                           (float*)((char*)ws + p->off_partial[i]), (float*)((char*)ws + p->off_bpartial[i]), p->splits[i]), st);
+  };
+  // grd[buf] always holds the gradient w.r.t. the producer's PRE-activation output: a dgrad multiplies by
+  // lrelu'(its input) (= the in-place activated output of the producer, arch_unet.py:276) on the way out.
+  auto dgrad = [&](int i, bool mask, bool add_existing) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+    View gx = p->view(p->grd, ws, io.in_buf, io.in_cb0, io.in_cb);
+    TapGemm g = make_conv_dgrad(L, dt, gy, gx, (char*)ws + p->off_wd[i], L.cin_blocks());
+    if (mask) { g.has_mask = true; g.mask = p->view(p->act, ws, io.in_buf, io.in_cb0, io.in_cb); g.slope = 0.2f; }
+    if (add_existing) { g.has_addend = true; g.addend = gx; }
+    return launch_tapgemm(g, st);
+  };
+  // concat consumer: decoder segment (masked by the decoder activation) and skip segment (NOT masked here: the skip
+  // tensor also feeds the next encoder conv, whose dgrad adds its share and applies the mask once to the sum)
+  auto dgrad_cat = [&](int i, bool want_skip) -> int {
+    const LayerIO& io = p->io[i];
+    const LayerGeom& L = p->L[i];
+    const int b0 = cblocks(L.cin.cnt[0]), b1 = cblocks(L.cin.cnt[1]);
+    View gy = p->view(p->grd, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+    TapGemm g0 = make_conv_dgrad(L, dt, gy, p->view(p->grd, ws, io.in_buf, io.in_cb0, b0), (char*)ws + p->off_wd[i], b0);
+    g0.has_mask = true; g0.mask = p->view(p->act, ws, io.in_buf, io.in_cb0, b0); g0.slope = 0.2f;
+    N2N_TRY(launch_tapgemm(g0, st));
+    if (!want_skip) return 0;
+    TapGemm g1 = make_conv_dgrad(L, dt, gy, p->view(p->grd, ws, io.in_buf, io.in_cb0 + b0, b1),
+                                 (const char*)ws + p->off_wd[i] + packed_weight_bytes(dt, 9, b0 * 16, L.cout_blocks()), b1);
+    return launch_tapgemm(g1, st);
+  };
+  if (p->head_splits > 0) {
+    HeadBwd h;
+    h.blocks = p->hb; h.channels = 96; h.out_nc = p->out_nc; h.slope = 0.2f;
+    h.gout = dy; h.wc = params[2 * 20];
+    h.wb_dgrad = (char*)ws + p->off_wd[19]; h.wa_dgrad = (char*)ws + p->off_wd[18];
+    h.act_nb = p->view(p->act, ws, B_NB, 0, p->hb); h.act_na = p->view(p->act, ws, B_NA, 0, p->hb);
+    h.act_d1b = p->view(p->act, ws, B_D1B, 0, p->hb);
+    h.g_d1b = p->view(p->grd, ws, B_D1B, 0, p->hb);
+    h.splits = p->head_splits;
+    h.partial_b = (float*)((char*)ws + p->off_partial[19]); h.bpartial_b = (float*)((char*)ws + p->off_bpartial[19]);
+    h.partial_a = (float*)((char*)ws + p->off_partial[18]); h.bpartial_a = (float*)((char*)ws + p->off_bpartial[18]);
+    N2N_TRY(wgrad(20));
+    const int hb = launch_head_bwd(h, st);
+    if (hb < 0) return hb;
+    N2N_CHECK_ARG(hb == 0, "resnet_backward: fused head backward declined a geometry the plan was built for");
+  } else {
+    for (int i = 20; i >= 18; --i) { N2N_TRY(wgrad(i)); N2N_TRY(dgrad(i, true, false)); }
+  }
+  N2N_TRY(wgrad(17)); N2N_TRY(dgrad(17, true, false));
+  N2N_TRY(wgrad(16)); N2N_TRY(dgrad_cat(16, want_dx));
+  for (int a = 14; a >= 8; a -= 2) {         // (dec_conv{k}b, dec_conv{k}a) for k = 2, 3, 4, 5
+    N2N_TRY(wgrad(a + 1)); N2N_TRY(dgrad(a + 1, true, false));
+    N2N_TRY(wgrad(a)); N2N_TRY(dgrad_cat(a, true));
+  }
+  N2N_TRY(wgrad(6)); N2N_TRY(dgrad(6, true, false));
+  for (int i = 5; i >= 2; --i) { N2N_TRY(wgrad(i)); N2N_TRY(dgrad(i, true, true)); }
+  N2N_TRY(wgrad(1)); N2N_TRY(dgrad(1, true, false));
+  N2N_TRY(wgrad(0));
+  if (want_dx) {
+    N2N_TRY(dgrad(0, false, true));
+    N2N_TRY(launch_c16_to_nchw(p->view(p->grd, ws, B_CAT0, p->c2b, p->inb), dt, dx, p->in_nc, st));
+    N2N_TRY(launch_add_inplace(dx, dy, (long long)p->N * p->in_nc * p->H * p->W, st));      // d(x + in_)/d in_
+  }
+  UnpackJob jobs[21];
+  int nj = 0;
+  for (int i = 0; i < 21; ++i) {
+    if (i == 7) continue;
+    jobs[nj++] = make_unpack(p->L[i], (const float*)((char*)ws + p->off_partial[i]), (const float*)((char*)ws + p->off_bpartial[i]),
+                             p->splits[i], grads[2 * i], grads[2 * i + 1]);
+  }
+  return launch_unpack(jobs, nj, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -45,3 +45,37 @@ def l1_grad_loss(pred, clean, lambda_grad):
     """finetune.py:283-285: L1(pred, clean) + lambda_grad * gradient_loss(pred, clean) ->
     (loss, [loss, loss_l1, loss_grad])."""
     return _L1GradLoss.apply(pred, clean.detach(), float(lambda_grad))
+
+
+class _StructureLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, pred2, target, alpha, beta, gamma):
+        loss4, g1, g2 = ops.structure_loss_fwdbwd(pred, pred2, target, alpha, beta, gamma, 1.0, want_grad=True)
+        ctx.save_for_backward(g1, g2)
+        ctx.mark_non_differentiable(loss4)
+        return loss4[0].clone(), loss4
+
+    @staticmethod
+    def backward(ctx, g, _g4):
+        g1, g2 = ctx.saved_tensors
+        return g1 * g, g2 * g, None, None, None, None
+
+
+class Structure_loss(torch.nn.Module):
+    """Drop-in ``util.Structure_loss`` (util.py:41-70), the criterion of the fork's live training loop
+    (train.py:322, :361-363): ``criterion(network(noisy), network(clean), clean)`` =
+    alpha*L1(pred, target) + beta*TV(pred2) + gamma*L1(pred2, target), forward and both gradients in ONE kernel.
+    ``last_terms`` holds the device tensor [loss, pixel, TV, consistency] of the most recent call (pixel is the
+    ``F.l1_loss(noisy_output, clean)`` the reference logs separately, train.py:365)."""
+
+    def __init__(self, alpha: float = 1.0, beta: float = .5, gamma: float = .5, reduction: str = 'mean'):
+        super().__init__()
+        if reduction != 'mean':
+            raise NotImplementedError("Structure_loss: only reduction='mean' (the reference's default and only use) is implemented")
+        self.alpha, self.beta, self.gamma, self.reduction = alpha, beta, gamma, reduction
+        self.last_terms = None
+
+    def forward(self, pred, pred2, target):
+        loss, self.last_terms = _StructureLoss.apply(pred, pred2, target.detach(), float(self.alpha), float(self.beta),
+                                                      float(self.gamma))
+        return loss

@@ -223,6 +223,23 @@ def l1grad_loss_fwdbwd(pred, target, lambda_grad: float, grad_scale: float = 1.0
     return loss3, grad
 
 
+def structure_loss_fwdbwd(pred, pred2, target, alpha: float, beta: float, gamma: float, grad_scale: float = 1.0,
+                          want_grad: bool = True):
+    """util.py:41-70 -> (loss4 [loss, pixel, TV, consistency], dloss/dpred or None, dloss/dpred2 or None)."""
+    require_cuda(pred, "structure_loss")
+    pred = _f32c(pred); pred2 = _f32c(pred2); target = _f32c(target)
+    if not (pred.shape == pred2.shape == target.shape) or pred.dim() != 4:
+        raise ValueError("structure_loss: need three [N,C,H,W] tensors of equal shape")
+    n, c, h, w = pred.shape
+    loss4 = torch.empty(4, dtype=torch.float32, device=pred.device)
+    g1 = torch.empty_like(pred) if want_grad else None
+    g2 = torch.empty_like(pred2) if want_grad else None
+    check(lib().n2n_loss_structure_fwdbwd(ptr(pred), ptr(pred2), ptr(target), n, c, h, w, float(alpha), float(beta),
+                                          float(gamma), float(grad_scale), ptr(loss4), ptr(g1), ptr(g2),
+                                          ptr(_loss_workspace(pred.device)), stream_ptr()))
+    return loss4, g1, g2
+
+
 # ----------------------------------------------------------------------------- evaluation
 def quantize_u8(pred: torch.Tensor, bias: float) -> torch.Tensor:
     require_cuda(pred, "quantize_u8")

@@ -142,6 +142,13 @@ typedef struct n2n_unet_plan n2n_unet_plan;
 
 int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature,
                          int n, int h, int w, int dtype, int with_backward);
+/* arch_unet.RESNET (arch_unet.py:263-409): the same convolutions at full resolution, no pooling / up-sampling, global
+ * residual out = net(x) + x (:409).  Returns the same plan type: n2n_unet_forward / _backward / _workspace_bytes /
+ * _plan_destroy apply, with params / grads = the 42 tensors in state_dict order (:279-347; up5.deconv.* are registered by
+ * the reference but unused: ignored here, their gradient slots are not written).  Needs out_nc == in_nc. */
+#define N2N_RESNET_NUM_PARAMS 42
+int n2n_resnet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_feature,
+                           int n, int h, int w, int dtype, int with_backward);
 void n2n_unet_plan_destroy(n2n_unet_plan* plan);
 size_t n2n_unet_workspace_bytes(const n2n_unet_plan* plan);
 /* number of kernel launches one forward / backward issues (for gpu_launches). */
@@ -196,6 +203,14 @@ int n2n_loss_n2n_fwdbwd(const float* out, const float* sub2, const float* den1, 
 int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, int n, int c, int h, int w,
                            float lambda_grad, float grad_scale, float* loss3, float* grad,
                            void* workspace, void* stream);
+
+/* util.py:41-70 (Structure_loss, the criterion of the fork's live loop train.py:322, :361-363):
+ * loss = alpha*L1(pred, target) + beta*(L1(dy pred2) + L1(dx pred2))/2 + gamma*L1(pred2, target), pred = network(noisy),
+ * pred2 = network(clean).  loss4 = {loss, pixel, TV, consistency}; grad_pred / grad_pred2 (may be NULL) receive
+ * grad_scale * dloss/dpred and dloss/dpred2. */
+int n2n_loss_structure_fwdbwd(const float* pred, const float* pred2, const float* target, int n, int c, int h, int w,
+                              float alpha, float beta, float gamma, float grad_scale, float* loss4,
+                              float* grad_pred, float* grad_pred2, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Adam — train.py:332 (torch.optim.Adam defaults), finetune.py:260-263.

@@ -342,3 +342,81 @@ def tiled_denoise(forward, noisy_u8: np.ndarray, ps: int = 352, overlap: int = 6
             cnt[r0:r1, c0:c1] += wv
     cnt[cnt == 0] = 1
     return np.clip(acc / cnt * 255.0, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# N1: Structure_loss (util.py:41-70) — the criterion of the fork's live loop (train.py:322, :361-363)
+# ----------------------------------------------------------------------------
+def structure_loss(pred, pred2, target, alpha: float = 1.0, beta: float = 0.5, gamma: float = 0.5):
+    """util.py:56-70: alpha*L1(pred,target) + beta*(L1(dy pred2)+L1(dx pred2))/2 + gamma*L1(pred2,target).
+    Returns (loss, pixel, TV, consistency)."""
+    pixel = torch.mean(torch.abs(pred - target))
+    tv1 = torch.mean(torch.abs(pred2[:, :, 1:, :] - pred2[:, :, :-1, :]))
+    tv2 = torch.mean(torch.abs(pred2[:, :, :, 1:] - pred2[:, :, :, :-1]))
+    tv = (tv1 + tv2) / 2
+    cst = torch.mean(torch.abs(pred2 - target))
+    return alpha * pixel + beta * tv + gamma * cst, pixel, tv, cst
+
+
+# ----------------------------------------------------------------------------
+# N3: RESNET (arch_unet.py:263-409, non-blindspot): the UNet's convolutions without pooling / up-sampling, all at
+# full resolution, global residual (:409).  up5 is constructed (:303) but never used by forward.
+# ----------------------------------------------------------------------------
+def resnet_param_shapes(in_nc: int, out_nc: int, nf: int) -> "OrderedDict[str, tuple]":
+    """arch_unet.py:279-347 — registration order of the 42 tensors (21 layers)."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k)
+        s[name + ".bias"] = (co,)
+
+    conv("enc_conv0", nf, in_nc, 3)
+    for i in range(1, 7):
+        conv(f"enc_conv{i}", nf, nf, 3)
+    s["up5.deconv.weight"] = (nf, nf, 2, 2)
+    s["up5.deconv.bias"] = (nf,)
+    conv("dec_conv5a", 2 * nf, 2 * nf, 3)
+    conv("dec_conv5b", 2 * nf, 2 * nf, 3)
+    for lvl in (4, 3, 2):
+        conv(f"dec_conv{lvl}a", 2 * nf, 3 * nf, 3)
+        conv(f"dec_conv{lvl}b", 2 * nf, 2 * nf, 3)
+    conv("dec_conv1a", 96, 2 * nf + in_nc, 3)
+    conv("dec_conv1b", 96, 96, 3)
+    conv("nin_a", 96, 96, 1)
+    conv("nin_b", 96, 96, 1)
+    conv("nin_c", out_nc, 96, 1)
+    return s
+
+
+def resnet_init(in_nc: int, out_nc: int, nf: int, seed: int) -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator().manual_seed(seed)
+    p = OrderedDict()
+    for name, shp in resnet_param_shapes(in_nc, out_nc, nf).items():
+        if name.endswith(".bias"):
+            p[name] = torch.zeros(shp)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            p[name] = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in) * 0.1
+    return p
+
+
+def resnet_forward(p: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """arch_unet.py:349-409 (blindspot=False)."""
+    act = lambda t: F.leaky_relu(t, 0.2)
+    c3 = lambda t, n: F.conv2d(t, p[n + ".weight"], p[n + ".bias"], padding=1)
+    c1 = lambda t, n: F.conv2d(t, p[n + ".weight"], p[n + ".bias"])
+    pool0 = x
+    t = act(c3(x, "enc_conv0"))
+    t = act(c3(t, "enc_conv1")); pool1 = t
+    t = act(c3(t, "enc_conv2")); pool2 = t
+    t = act(c3(t, "enc_conv3")); pool3 = t
+    t = act(c3(t, "enc_conv4")); pool4 = t
+    t = act(c3(t, "enc_conv5"))
+    t = act(c3(t, "enc_conv6"))
+    for lvl, skip in ((5, pool4), (4, pool3), (3, pool2), (2, pool1), (1, pool0)):
+        t = torch.cat([t, skip], 1)
+        t = act(c3(t, f"dec_conv{lvl}a"))
+        t = act(c3(t, f"dec_conv{lvl}b"))
+    t = act(c1(t, "nin_a"))
+    t = act(c1(t, "nin_b"))
+    return c1(t, "nin_c") + x

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU pass 2: fused up-conv parity, network/fullsize suites, bench, per-layer table
 mkdir -p gpurun_out
-for f in test_gpu_upfuse test_gpu_network test_gpu_fullsize test_gpu_baseline_shapes; do
+for f in test_gpu_upfuse test_gpu_live_step test_gpu_network test_gpu_fullsize test_gpu_baseline_shapes; do
   timeout 900 python -m pytest tests/$f.py -q -s -m gpu --timeout 600 -x > gpurun_out/$f.log 2>&1
   echo "$f rc=$?"; grep -E "passed|failed" gpurun_out/$f.log | tail -1; grep -E "^FAILED|^ERROR|^E  " gpurun_out/$f.log | head -30
 done

@@ -94,3 +94,27 @@ def test_tile_weight_and_origins_match_oracle():
     from oracle import n2n_oracle as O
     assert np.array_equal(evaluate.tile_weight(352), O.tile_weight(352))
     assert evaluate.tile_origins(704, 704) == [(r, c) for r in (0, 288, 576) for c in (0, 288, 576)]
+
+
+def test_resnet_state_dict_layout_and_init_stream():
+    """arch_unet.RESNET (arch_unet.py:263-347): 42 tensors in the reference's order, up5.deconv.* included."""
+    from image_denoising_b200 import RESNET
+    from oracle import n2n_oracle as O
+    net = RESNET(in_nc=1, out_nc=1, n_feature=8)
+    shapes = O.resnet_param_shapes(1, 1, 8)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()) and len(sd) == 42
+    assert all(tuple(v.shape) == shapes[k] for k, v in sd.items())
+    with pytest.raises(ValueError):
+        RESNET(in_nc=1, out_nc=3)
+    ref_dir = os.environ.get("N2N_REFERENCE", "/root/reference")
+    if os.path.exists(os.path.join(ref_dir, "arch_unet.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_arch_unet2", os.path.join(ref_dir, "arch_unet.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        torch.manual_seed(7)
+        a = ref.RESNET(in_nc=3, out_nc=3, n_feature=8).state_dict()
+        torch.manual_seed(7)
+        b = RESNET(in_nc=3, out_nc=3, n_feature=8).state_dict()
+        assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)

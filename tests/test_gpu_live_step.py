@@ -1,0 +1,148 @@
+"""§8f rows N1 / N3 on the GPU: the fork's live supervised training step (train.py:354-368: network(noisy) and
+network(clean) with grad, util.Structure_loss, Adam) and arch_unet.RESNET, through the drop-in modules, against golden
+vectors produced by the unmodified reference (oracle/make_golden_r2.py) and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import n2n_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _rand_bias(p, seed):
+    g = torch.Generator().manual_seed(seed)
+    for k in p:
+        if k.endswith(".bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.05
+    return p
+
+
+def _csum(t):
+    t = t.detach().double().cpu()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+
+
+def test_structure_loss_kernel_matches_reference_golden(dev, golden):
+    from image_denoising_b200 import Structure_loss
+    z = golden("r2_misc")
+    crit = Structure_loss()
+    for i in range(3):
+        pred = torch.from_numpy(z[f"sl_pred{i}"]).to(dev).requires_grad_(True)
+        pred2 = torch.from_numpy(z[f"sl_pred2{i}"]).to(dev).requires_grad_(True)
+        tgt = torch.from_numpy(z[f"sl_tgt{i}"]).to(dev)
+        loss = crit(pred, pred2, tgt)
+        (3.0 * loss).backward()
+        assert np.allclose(crit.last_terms.cpu().numpy(), z[f"sl_loss{i}"], rtol=2e-6)
+        assert np.allclose(pred.grad.cpu().numpy(), 3.0 * z[f"sl_g1_{i}"], rtol=1e-5, atol=1e-9)
+        assert np.allclose(pred2.grad.cpu().numpy(), 3.0 * z[f"sl_g2_{i}"], rtol=1e-5, atol=1e-9)
+    with pytest.raises(NotImplementedError):
+        Structure_loss(reduction='sum')
+
+
+def test_structure_loss_large_vs_oracle(dev):
+    from image_denoising_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    a, b, t = (torch.rand(4, 1, 256, 256, generator=g) for _ in range(3))
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lo, px, tv, cs = O.structure_loss(ar, br, t, 1.0, 0.5, 0.5)
+    lo.backward()
+    loss4, g1, g2 = ops.structure_loss_fwdbwd(a.to(dev), b.to(dev), t.to(dev), 1.0, 0.5, 0.5)
+    assert np.allclose(loss4.cpu().numpy(), [lo.item(), px.item(), tv.item(), cs.item()], rtol=1e-5)
+    assert torch.allclose(g1.cpu(), ar.grad, atol=1e-10, rtol=1e-5) and torch.allclose(g2.cpu(), br.grad, atol=1e-10, rtol=1e-5)
+
+
+def test_space_to_depth_matches_reference_golden(dev, golden):
+    from image_denoising_b200 import space_to_depth
+    z = golden("r2_misc")
+    for i in range(4):
+        y = space_to_depth(torch.from_numpy(z[f"s2d_x{i}"]).to(dev), int(z[f"s2d_bs{i}"]))
+        assert np.array_equal(y.cpu().numpy(), z[f"s2d_y{i}"])
+
+
+def test_unet_live_supervised_step_fp32_matches_reference_golden(dev, golden):
+    """train.py:361-368 on UNet: two forwards with grad before one backward, Structure_loss, Adam — 3 iterations."""
+    from image_denoising_b200 import FusedAdam, Structure_loss, UNet
+    z = golden("r2_live_step")
+    net = UNet(in_nc=1, out_nc=1, n_feature=4)
+    net.load_state_dict(_rand_bias(O.unet_init(1, 1, 4, 3), 103))
+    net = net.to(dev).set_precision("fp32")
+    noisy = torch.from_numpy(z["noisy"]).to(dev); clean = torch.from_numpy(z["clean"]).to(dev)
+    opt = FusedAdam(net.parameters(), lr=3e-4)
+    crit = Structure_loss()
+    losses = []
+    for it in range(3):
+        opt.zero_grad()
+        noisy_output, clean_ = net(noisy), net(clean)
+        loss = crit(noisy_output, clean_, clean)
+        loss.backward()
+        if it == 0:
+            for k, v in net.named_parameters():
+                assert np.allclose(_csum(v.grad), z["gsum/" + k], rtol=2e-4, atol=1e-9), k
+                if ("grad/" + k) in z.files:
+                    ref = z["grad/" + k]
+                    assert np.abs(v.grad.cpu().numpy() - ref).max() <= 1e-7 + 3e-4 * np.abs(ref).max(), k
+        opt.step()
+        losses.append([float(crit.last_terms[0]), float(crit.last_terms[1])])
+    assert np.allclose(losses, z["losses"], rtol=2e-5)
+    for k, v in net.state_dict().items():
+        assert np.allclose(_csum(v), z["w3sum/" + k], rtol=1e-4, atol=1e-8), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,in_nc,nf", [("g1", 1, 4), ("c3", 3, 8)])
+def test_resnet_forward_and_live_step_match_reference_golden(dev, golden, tag, in_nc, nf, precision):
+    from image_denoising_b200 import RESNET, Structure_loss
+    z = golden("r2_resnet")
+    seed = int(z[f"{tag}_seed"])
+    p = _rand_bias(O.resnet_init(in_nc, in_nc, nf, seed), seed + 100)
+    net = RESNET(in_nc=in_nc, out_nc=in_nc, n_feature=nf)
+    assert list(net.state_dict().keys()) == list(p.keys())
+    net.load_state_dict(p)
+    net = net.to(dev).set_precision(precision)
+    noisy = torch.from_numpy(z[f"{tag}_noisy"]).to(dev); clean = torch.from_numpy(z[f"{tag}_clean"]).to(dev)
+    with torch.no_grad():
+        y = net(noisy)
+    err = np.abs(y.cpu().numpy() - z[f"{tag}_y"]).max()
+    assert err < (3e-6 if precision == "fp32" else 3e-2), err
+    crit = Structure_loss()
+    loss = crit(net(noisy), net(clean), clean)
+    loss.backward()
+    assert abs(float(loss) - float(z[f"{tag}_loss"])) <= (2e-5 if precision == "fp32" else 2e-2) * float(z[f"{tag}_loss"])
+    for k, v in net.named_parameters():
+        if not bool(z[f"{tag}_hasgrad/{k}"]):
+            assert v.grad is None, k                       # up5 is registered but unused (arch_unet.py:303)
+            continue
+        if ("%s_grad/%s" % (tag, k)) in z.files:
+            ref = z[f"{tag}_grad/{k}"].astype(np.float64); got = v.grad.cpu().numpy().astype(np.float64)
+            if precision == "fp32":
+                assert np.abs(got - ref).max() <= 1e-8 + 3e-4 * np.abs(ref).max(), k
+            else:
+                cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
+                assert cos > 0.97, (k, cos)
+        if precision == "fp32":
+            assert np.allclose(_csum(v.grad), z[f"{tag}_gsum/{k}"], rtol=5e-4, atol=1e-9), k
+
+
+def test_resnet_nf48_bf16_vs_oracle(dev):
+    from image_denoising_b200 import RESNET
+    p = _rand_bias(O.resnet_init(1, 1, 48, 9), 10)
+    g = torch.Generator().manual_seed(4)
+    clean = torch.rand(2, 1, 64, 96, generator=g)
+    x = clean + torch.randn(clean.shape, generator=g) * (25 / 255)
+    net = RESNET(1, 1, 48)
+    net.load_state_dict(p)
+    with torch.no_grad():
+        ref = O.resnet_forward(p, x)
+        y32 = net.to(dev).set_precision("fp32")(x.to(dev)).cpu()
+        y16 = net.set_precision("bf16")(x.to(dev)).cpu()
+    assert float((y32 - ref).abs().max()) < 2e-5
+    psnr = lambda a: 10 * np.log10(1.0 / float(((a - clean) ** 2).mean()))
+    assert abs(psnr(y16) - psnr(ref)) < 0.01

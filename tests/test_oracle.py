@@ -149,3 +149,50 @@ def test_oracle_ref_modules_agree_with_the_restatement():
     assert np.array_equal(m1.numpy(), o1) and np.array_equal(m2.numpy(), o2)
     assert np.array_equal(tf.generate_subimages(x, m1).numpy(), O.subimage_from_mask(x.numpy(), o1))
     assert np.array_equal(tf.space_to_depth(x, 2).numpy(), O.space_to_depth(x.numpy(), 2))
+
+
+def _rand_bias(p, seed):
+    g = torch.Generator().manual_seed(seed)
+    for k in p:
+        if k.endswith(".bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.05
+    return p
+
+
+def test_space_to_depth_and_structure_loss_match_reference(golden):
+    z = golden("r2_misc")
+    for i in range(4):
+        assert np.array_equal(O.space_to_depth(z[f"s2d_x{i}"], int(z[f"s2d_bs{i}"])), z[f"s2d_y{i}"])
+    for i in range(3):
+        pred = torch.from_numpy(z[f"sl_pred{i}"]).requires_grad_(True)
+        pred2 = torch.from_numpy(z[f"sl_pred2{i}"]).requires_grad_(True)
+        loss, px, tv, cs = O.structure_loss(pred, pred2, torch.from_numpy(z[f"sl_tgt{i}"]))
+        loss.backward()
+        assert np.allclose([loss.item(), px.item(), tv.item(), cs.item()], z[f"sl_loss{i}"], rtol=1e-6)
+        assert np.allclose(pred.grad.numpy(), z[f"sl_g1_{i}"], atol=1e-8) and np.allclose(pred2.grad.numpy(), z[f"sl_g2_{i}"], atol=1e-8)
+
+
+def test_resnet_forward_and_live_step_match_reference(golden):
+    """arch_unet.RESNET (arch_unet.py:263-409) + the fork's live supervised step (train.py:361-368)."""
+    z = golden("r2_resnet")
+    for tag, (in_nc, nf) in {"g1": (1, 4), "c3": (3, 8)}.items():
+        seed = int(z[f"{tag}_seed"])
+        p = _rand_bias(O.resnet_init(in_nc, in_nc, nf, seed), seed + 100)
+        noisy = torch.from_numpy(z[f"{tag}_noisy"]); clean = torch.from_numpy(z[f"{tag}_clean"])
+        with torch.no_grad():
+            assert np.abs(O.resnet_forward(p, noisy).numpy() - z[f"{tag}_y"]).max() < 1e-6
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        loss, _, _, _ = O.structure_loss(O.resnet_forward(pr, noisy), O.resnet_forward(pr, clean), clean)
+        loss.backward()
+        assert abs(loss.item() - float(z[f"{tag}_loss"])) < 1e-6
+        for k, v in pr.items():
+            assert bool(z[f"{tag}_hasgrad/{k}"]) == (v.grad is not None), k          # up5 is constructed but unused
+            if v.grad is not None:
+                assert np.allclose(_csum(v.grad), z[f"{tag}_gsum/{k}"], rtol=1e-4, atol=1e-9), k
+    z = golden("r2_live_step")
+    p = _rand_bias(O.unet_init(1, 1, 4, 3), 103)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    noisy = torch.from_numpy(z["noisy"]); clean = torch.from_numpy(z["clean"])
+    out = O.unet_forward(pr, noisy)
+    loss, px, _, _ = O.structure_loss(out, O.unet_forward(pr, clean), clean)
+    assert np.allclose([loss.item(), px.item()], z["losses"][0], rtol=1e-6)
