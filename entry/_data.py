@@ -29,6 +29,12 @@ def save_image(arr_u8: np.ndarray, path: str) -> None:
     Image.fromarray(np.squeeze(arr_u8)).save(path)
 
 
+def save_rgb(arr_u8: np.ndarray, path: str) -> None:
+    """train.py:413-430: Image.fromarray(x).convert('RGB').save(path)."""
+    from PIL import Image
+    Image.fromarray(np.squeeze(arr_u8)).convert('RGB').save(path)
+
+
 def synthetic_images(count: int, h: int, w: int, channels: int, sigma: float = 25.0, seed: int = 2025):
     """SEM-like smooth random fields + Gaussian noise, uint8."""
     from scipy.ndimage import gaussian_filter

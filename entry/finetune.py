@@ -12,8 +12,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from entry import _data  # noqa: E402
-from image_denoising_b200 import DenoiserWithAdapter, FusedAdam, UNet, l1_grad_loss  # noqa: E402
+from entry import _data, _models  # noqa: E402
+from image_denoising_b200 import DenoiserWithAdapter, FusedAdam, l1_grad_loss, ops  # noqa: E402
+from image_denoising_b200.data import DevicePatchSource  # noqa: E402
 
 parser = argparse.ArgumentParser()
 parser.add_argument('--data_dir', type=str, default=None)
@@ -40,8 +41,8 @@ parser.add_argument('--synthetic', type=int, default=0)
 
 def main():
     args, _ = parser.parse_known_args()
-    if args.arch != 'UNet':
-        raise SystemExit("only --arch UNet is on the B200 path (SURVEY.md §8f)")
+    import datetime
+    systime = datetime.datetime.now().strftime('%Y-%m-%d-%H-%M')
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     if args.synthetic:
@@ -50,43 +51,72 @@ def main():
     else:
         cf, nf = _data.list_pairs(args.data_dir, limit=5)           # finetune.py:109-110
         clean = [_data.load_image(f) for f in cf]; noise = [_data.load_image(f) for f in nf]
-    chw = lambda a: a[None] if a.ndim == 2 else np.transpose(a, (2, 0, 1))
-    clean = [chw(a) for a in clean]; noise = [chw(a) for a in noise]
+    # the (up to five) image pairs live on the device; patches are cut there (image_denoising_b200.data)
+    source = DevicePatchSource(clean, noise, device=dev)
+    valid_clean, valid_noise = clean, noise                       # finetune.py:231: validation = the same pairs, whole images
 
-    base = UNet(in_nc=args.n_channel, out_nc=args.n_channel, n_feature=args.n_feature)
+    base = _models.build_base_model(args.arch, args.n_channel, args.n_feature)                # finetune.py:189-204
     if args.pretrained_ckpt:
-        state = torch.load(args.pretrained_ckpt, map_location="cpu")
-        state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}     # finetune.py:207-218
-        base.load_state_dict(state, strict=False)
+        state = _models.strip_module_prefix(torch.load(args.pretrained_ckpt, map_location="cpu"))   # finetune.py:207-218
+        missing, unexpected = base.load_state_dict(state, strict=False)
+        if missing:
+            print(f'[Warning] Missing keys when loading base model: {missing}')
+        if unexpected:
+            print(f'[Warning] Unexpected keys when loading base model: {unexpected}')
     model = DenoiserWithAdapter(base, in_channels=args.n_channel, hidden_channels=args.adapter_hidden,
                                 freeze_base=True, use_no_grad_for_base=True).to(dev)
     model.set_precision(args.precision)
     opt = FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=args.lr)
     out_dir = os.path.join(args.save_model_path, args.log_name)
     os.makedirs(out_dir, exist_ok=True)
-    rng = np.random.default_rng(0)
+    rng = np.random.RandomState(0)
     ps = args.patch_size
-    samples = len(clean) * args.patches_per_image
+    samples = len(source) * args.patches_per_image               # finetune.py:123-124
     for epoch in range(1, args.n_epoch + 1):
-        order = rng.permutation(samples)
-        tot = 0.0
-        for b0 in range(0, samples - args.batchsize + 1, args.batchsize):
-            cb = np.empty((args.batchsize, args.n_channel, ps, ps), np.float32); nb = np.empty_like(cb)
-            for j, s in enumerate(order[b0:b0 + args.batchsize]):
-                i = s // args.patches_per_image
-                top = rng.integers(0, clean[i].shape[1] - ps + 1); left = rng.integers(0, clean[i].shape[2] - ps + 1)
-                cb[j] = clean[i][:, top:top + ps, left:left + ps]; nb[j] = noise[i][:, top:top + ps, left:left + ps]
-            c = torch.from_numpy(cb).to(dev) / 255.0; n = torch.from_numpy(nb).to(dev) / 255.0
+        order = rng.permutation(samples)                           # DataLoader(shuffle=True, drop_last=False), finetune.py:224-231
+        losses = []
+        for it, b0 in enumerate(range(0, samples, args.batchsize)):
+            sel = source.draw([int(s) // args.patches_per_image for s in order[b0:b0 + args.batchsize]], ps, rng)
+            c, n = source.crop(sel, ps)                            # same (top, left) for clean and noise, /255 (finetune.py:136-147)
             opt.zero_grad(set_to_none=True)
-            loss, _loss3 = l1_grad_loss(model(n), c, args.lambda_grad)
+            loss, loss3 = l1_grad_loss(model(n), c, args.lambda_grad)
             loss.backward()
             opt.step()
-            tot += float(loss)
-        print(f"[Epoch {epoch:03d}] loss {tot / max(samples // args.batchsize, 1):.6f}")
+            if it % 10 == 0:
+                l = loss3.tolist()
+                losses.append(l[1])
+                print(f'[Epoch {epoch:03d} | Iter {it:04d}] L1={l[1]:.6f} Grad={l[2]:.6f} Total={l[0]:.6f}')
+        print(f'End of epoch {epoch}, mean L1 loss={float(np.mean(losses)):.6f}')
         if epoch % args.save_every == 0 or epoch == args.n_epoch:
             path = os.path.join(out_dir, 'epoch_adapter_{:03d}.pth'.format(epoch))
             torch.save(model.state_dict(), path)
             print('Checkpoint saved to {}'.format(path))
+            # finetune.py:305-343: whole-image validation PSNR (clip(p*255+0.5), 99.0 when identical), PNGs of image 0
+            save_dir = os.path.join(args.save_model_path, args.log_name, f'val_{systime}_ep{epoch:03d}')
+            os.makedirs(save_dir, exist_ok=True)
+            model.eval()
+            psnrs = []
+            with torch.no_grad():
+                for i, (clean_np, noisy_np) in enumerate(zip(valid_clean, valid_noise)):
+                    noisy_im = np.asarray(noisy_np, np.float32) / 255.0
+                    t = torch.from_numpy(noisy_im[None] if noisy_im.ndim == 2 else np.transpose(noisy_im, (2, 0, 1))).unsqueeze(0).to(dev)
+                    try:
+                        pred = model(t)
+                    except ValueError as e:
+                        print(f"validation skipped: {e}")
+                        break
+                    pred255 = np.squeeze(ops.quantize_u8(pred, 0.5).squeeze(0).permute(1, 2, 0).cpu().numpy())
+                    diff = pred255.astype(np.float32) - np.asarray(clean_np, np.float32)
+                    mse = float(np.mean(np.square(diff)))
+                    psnrs.append(99.0 if mse == 0 else 10.0 * np.log10(255.0 * 255.0 / mse))
+                    if i == 0:
+                        _data.save_image(np.asarray(clean_np).astype(np.uint8), os.path.join(save_dir, f'clean_{i:03d}.png'))
+                        _data.save_image(np.asarray(noisy_np).astype(np.uint8), os.path.join(save_dir, f'noisy_{i:03d}.png'))
+                        _data.save_image(pred255, os.path.join(save_dir, f'denoised_ep{epoch:03d}.png'))
+            if psnrs:
+                print(f'Val ep{epoch}: PSNR {float(np.mean(psnrs)):.2f} dB over {len(psnrs)} images')
+            model.train()
+    print('Finetuning complete.')
 
 
 if __name__ == "__main__":

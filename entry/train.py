@@ -1,12 +1,20 @@
 #!/usr/bin/env python
-"""Neighbor2Neighbor training entry point — the flags of the reference's train.py:23-41, the loop of
-training_script.md:128-156 (the fork's train.py carries the ingredients but runs a supervised loop,
-SURVEY.md §0.2), checkpoints as train.py:47-53 (`epoch_model_XXX.pth`, epoch 0 included), Adam +
-MultiStepLR as train.py:332-340.  Multi-GPU: `torchrun --nproc-per-node N entry/train.py --parallel ...`
-(one process per GPU, NCCL) replaces the reference's nn.DataParallel (train.py:324-325).
+"""Training entry point — the flags of the reference's train.py:23-41, checkpoints as train.py:47-53
+(`epoch_model_XXX.pth`, epoch 0 included), Adam + MultiStepLR as train.py:332-340, per-snapshot validation PNGs and
+`A_log.csv` as train.py:391-434.
+
+Two loops (`--loop`):
+  n2n         the Neighbor2Neighbor iteration of training_script.md:128-156 (the path BASELINE.json names; the fork's
+              train.py carries its ingredients at :134-190 but no longer calls them) through the fused
+              N2NTrainer: clean images only, noise added on the device;
+  supervised  the fork's live loop, train.py:354-368: network(noisy), network(clean) with grad, util.Structure_loss,
+              on <data_dir>/clean + <data_dir>/noise pairs.
+The network family is picked from --log_name as train.py:298-314 does ('UNET' / 'RESNET').  Multi-GPU:
+`torchrun --nproc-per-node N entry/train.py --parallel ...` (one process per GPU, NCCL) replaces nn.DataParallel
+(train.py:324-325).  Patches are cut on the device from images uploaded once (image_denoising_b200.data).
 
     python entry/train.py --data_dir data --log_name UNET_gauss25 --n_epoch 100 --batchsize 4
-    python entry/train.py --synthetic 256 --n_epoch 2 --batchsize 64       # no dataset needed
+    python entry/train.py --synthetic 8 --n_epoch 2 --batchsize 64                  # no dataset needed
 """
 import argparse
 import datetime
@@ -18,10 +26,10 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from entry import _data  # noqa: E402
-from image_denoising_b200 import AugmentNoise, N2NTrainer, UNet, checkpoint, dp  # noqa: E402
+from entry import _data, _models  # noqa: E402
+from image_denoising_b200 import AugmentNoise, FusedAdam, N2NTrainer, Structure_loss, UNet, checkpoint, dp, ops  # noqa: E402
+from image_denoising_b200.data import DevicePatchSource  # noqa: E402
 from image_denoising_b200.optim import multistep_lr  # noqa: E402
-from image_denoising_b200.prefetch import DevicePrefetcher  # noqa: E402
 
 parser = argparse.ArgumentParser()
 parser.add_argument("--noisetype", type=str, default="gauss25")
@@ -41,69 +49,126 @@ parser.add_argument("--Lambda1", type=float, default=1.0)
 parser.add_argument("--Lambda2", type=float, default=1.0)
 parser.add_argument("--increase_ratio", type=float, default=2.0)
 # additions (not in the reference)
+parser.add_argument("--loop", default="n2n", choices=["n2n", "supervised"])
 parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
 parser.add_argument("--patch", type=int, default=256, help="random-crop size of the training patches")
-parser.add_argument("--synthetic", type=int, default=0, help="train on this many synthetic clean images instead of --data_dir")
+parser.add_argument("--patches_per_image", type=int, default=16)
+parser.add_argument("--synthetic", type=int, default=0, help="train on this many synthetic image pairs instead of --data_dir")
+
+
+def validate(network, valid, epoch, opt, validation_path, dev):
+    """train.py:391-430: whole-image forward of every validation image, clip(p*255+0.5) -> uint8; PNGs of image 0."""
+    clean_imgs, noisy_imgs, clean_paths, noise_paths = valid
+    os.makedirs(validation_path, exist_ok=True)
+    for i in range(len(clean_imgs)):
+        clean_name = os.path.basename(clean_paths[i]).split('.')[0]
+        noise_name = os.path.basename(noise_paths[i]).split('.')[0]
+        noisy_im = np.asarray(noisy_imgs[i], dtype=np.float32) / 255.0
+        t = torch.from_numpy(noisy_im[None] if noisy_im.ndim == 2 else np.transpose(noisy_im, (2, 0, 1))).unsqueeze(0).to(dev)
+        with torch.no_grad():
+            prediction = network(t)
+        pred255 = np.squeeze(ops.quantize_u8(prediction, 0.5).permute(0, 2, 3, 1).cpu().numpy())
+        if i == 0 and epoch == opt.n_snapshot:
+            _data.save_rgb(np.asarray(clean_imgs[i]).astype(np.uint8), os.path.join(validation_path, "{}_{:03d}-{:03d}_clean.png".format(clean_name, i, epoch)))
+            _data.save_rgb(np.asarray(noisy_imgs[i]).astype(np.uint8), os.path.join(validation_path, "{}_{:03d}-{:03d}_noisy.png".format(noise_name, i, epoch)))
+        if i == 0:
+            _data.save_rgb(pred255, os.path.join(validation_path, "{}_{:03d}-{:03d}_denoised.png".format(noise_name, i, epoch)))
 
 
 def main():
     opt, _ = parser.parse_known_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if 'UNET' not in opt.log_name and 'unet' not in opt.log_name.lower():
-        raise SystemExit("only the UNet family (log_name containing 'UNET', train.py:298-314) is on the B200 path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     systime = datetime.datetime.now().strftime('%Y-%m-%d-%H-%M')
 
-    # ---- data: clean images in 0..255 float32 (train.py:208-228); noise is added on the device ----
+    # ---- data: images as the reference holds them (float32 0..255, train.py:208-228), resident on the device ----
     if opt.synthetic:
-        clean_u8, _ = _data.synthetic_images(opt.synthetic, max(opt.patch, 256), max(opt.patch, 256), opt.n_channel)
-        images = [c.astype(np.float32) for c in clean_u8]
+        size = max(opt.patch, 256)
+        clean_u8, noisy_u8 = _data.synthetic_images(opt.synthetic, size, size, opt.n_channel)
+        clean = [c.astype(np.float32) for c in clean_u8]; noise = [n.astype(np.float32) for n in noisy_u8]
+        clean_paths = noise_paths = [f"synthetic_{i:03d}.png" for i in range(opt.synthetic)]
     else:
-        clean_files, _ = _data.list_pairs(opt.data_dir)
-        images = [_data.load_image(f) for f in clean_files]
-    images = [im[None] if im.ndim == 2 else np.transpose(im, (2, 0, 1)) for im in images]
-    rng = np.random.default_rng(1234 + rank)
+        clean_paths, noise_paths = _data.list_pairs(opt.data_dir)
+        clean = [_data.load_image(f) for f in clean_paths]; noise = [_data.load_image(f) for f in noise_paths]
+    valid = (clean, noise, clean_paths, noise_paths)                      # train.py:292: validation = the training pairs
+    source = DevicePatchSource(clean, noise if opt.loop == "supervised" else None, device=dev)
+    rng = np.random.RandomState(1234 + rank)
     per_rank = opt.batchsize if not opt.parallel else max(opt.batchsize // world, 1)
 
-    def next_batch():
-        out = np.empty((per_rank, opt.n_channel, opt.patch, opt.patch), np.float32)
-        for i in range(per_rank):
-            im = images[rng.integers(len(images))]
-            top = rng.integers(0, im.shape[1] - opt.patch + 1); left = rng.integers(0, im.shape[2] - opt.patch + 1)
-            out[i] = im[:, top:top + opt.patch, left:left + opt.patch]
-        return torch.from_numpy(out).pin_memory()
-
     torch.manual_seed(0)
-    network = UNet(in_nc=opt.n_channel, out_nc=opt.n_channel, n_feature=opt.n_feature).to(dev).set_precision(opt.precision)
-    noise_adder = AugmentNoise(style=opt.noisetype, rank=rank, world=world)      # global-batch noise, this rank's slice
-    trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)
+    network = _models.network_from_log_name(opt.log_name, opt.n_channel, opt.n_feature).to(dev).set_precision(opt.precision)
+    if opt.loop == "n2n":
+        if not isinstance(network, UNet) or type(network) is not UNet:
+            raise SystemExit("--loop n2n runs the fused N2N trainer, which is built for arch_unet.UNet (log_name containing 'UNET')")
+        noise_adder = AugmentNoise(style=opt.noisetype, rank=rank, world=world)      # global-batch noise, this rank's slice
+        trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)
+    else:
+        if world > 1:
+            dp.broadcast_params(torch.nn.utils.parameters_to_vector(network.parameters()).detach(), 0)
+        optimizer = FusedAdam(network.parameters(), lr=opt.lr)
+        criterion = Structure_loss()                                                 # train.py:322
     if rank == 0:
-        checkpoint(network, 0, "model", opt.save_model_path, opt.log_name, systime)      # train.py:343
-    staged = DevicePrefetcher(torch.empty((per_rank, opt.n_channel, opt.patch, opt.patch), dtype=torch.float32, device=dev))
-    staged.put(next_batch())
-    steps_per_epoch = max(len(images) * 16 // (per_rank * world), 1)
-    print(f"rank {rank}/{world}: {len(images)} images, {steps_per_epoch} steps/epoch, batch {per_rank}/GPU")
+        checkpoint(network, 0, "model", opt.save_model_path, opt.log_name, systime)  # train.py:343
+    steps_per_epoch = max(len(source) * opt.patches_per_image // (per_rank * world), 1)
+    print(f"rank {rank}/{world}: {len(source)} images, {steps_per_epoch} steps/epoch, batch {per_rank}/GPU, loop {opt.loop}")
     for epoch in range(1, opt.n_epoch + 1):
-        lr = multistep_lr(opt.lr, epoch, opt.n_epoch, opt.gamma)      # train.py:333-340, :375
-        Lambda = epoch / opt.n_epoch * opt.increase_ratio                                   # training_script.md:148
-        st = time.time()
+        epoch_st = time.time()
+        lr = multistep_lr(opt.lr, epoch, opt.n_epoch, opt.gamma)                     # train.py:333-340, :375
+        if rank == 0:
+            print("LearningRate of Epoch {} = {}".format(epoch, lr))
+        l1_loss = []
         for it in range(steps_per_epoch):
-            # batch i+1 is cropped on the host and copied H2D (copy stream) while step i runs
-            clean = staged.get() / 255.0
-            staged.release()
-            staged.put(next_batch())
-            noisy = noise_adder.add_train_noise(clean)
-            loss3 = trainer.step(noisy, Lambda, lr=lr)
-            if it % 50 == 0 and rank == 0:
-                l = loss3.tolist()
-                print('{:04d} {:05d} Loss1={:.6f}, Lambda={}, Loss2={:.6f}, Loss_Full={:.6f}, Time={:.4f}'.format(
-                    epoch, it, l[1], Lambda, l[2], l[0], time.time() - st))
+            st = time.time()
+            sel = source.draw(rng.randint(0, len(source), size=per_rank), opt.patch, rng)
+            clean_b, noisy_b = source.crop(sel, opt.patch)                           # /255 on the device (train.py:358)
+            if opt.loop == "n2n":
+                Lambda = epoch / opt.n_epoch * opt.increase_ratio                    # training_script.md:148
+                noisy_b = noise_adder.add_train_noise(clean_b)
+                loss3 = trainer.step(noisy_b, Lambda, lr=lr)
+                if it % 50 == 0:
+                    l = loss3.tolist()
+                    l1_loss.append(l[1])
+                    if rank == 0:
+                        print('{:04d} {:05d} Loss1={:.6f}, Lambda={}, Loss2={:.6f}, Loss_Full={:.6f}, Time={:.4f}'.format(
+                            epoch, it, l[1], Lambda, l[2], l[0], time.time() - st))
+            else:
+                for group in optimizer.param_groups:
+                    group['lr'] = lr
+                optimizer.zero_grad()
+                noisy_output, clean_ = network(noisy_b), network(clean_b)            # train.py:361
+                loss = criterion(noisy_output, clean_, clean_b)
+                loss.backward()
+                if world > 1:
+                    for prm in network.parameters():
+                        if prm.grad is not None:
+                            torch.distributed.all_reduce(prm.grad)
+                            prm.grad.div_(world)
+                optimizer.step()
+                if it % 50 == 0:
+                    terms = criterion.last_terms.tolist()                            # [loss, L1(noisy_output, clean), TV, cst]
+                    l1_loss.append(terms[1])
+                    if rank == 0:
+                        print('{:04d} {:05d} Loss1={:.6f}, Loss_Full={:.6f}, Time={:.4f}'.format(epoch, it, terms[1], terms[0], time.time() - st))
+        train_time = time.time() - epoch_st
+        mean_loss = float(np.mean(l1_loss)) if l1_loss else float("nan")
+        if rank == 0:
+            print(f'Training Time/Epoch:{train_time} \n Mean loss:{mean_loss}')
         if rank == 0 and (epoch % opt.n_snapshot == 0 or epoch == opt.n_epoch):
+            eval_st = time.time()
             checkpoint(network, epoch, "model", opt.save_model_path, opt.log_name, systime)
+            validation_path = os.path.join(opt.save_model_path, opt.log_name, systime, "validation")
+            try:
+                validate(network, valid, epoch, opt, validation_path, dev)
+            except ValueError as e:            # e.g. image sizes that are not multiples of 32 (the reference UNet fails there too)
+                os.makedirs(validation_path, exist_ok=True)
+                print(f"validation skipped: {e}")
+            with open(os.path.join(validation_path, "A_log.csv"), "a") as f:       # train.py:431-434
+                f.writelines("epoch{}, loss_{}, train_time_{}\n".format(epoch, mean_loss, train_time))
+            print(f'Evaluation Time/Epoch:{time.time() - eval_st}')
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -354,3 +354,14 @@ extern "C" int n2n_maxpool2_bwd(const float* x, const float* dy, float* dx, int 
   N2N_TRY(launch_unpool_lrelu(xv, yv, gv, slope, dtype, st));
   return launch_c16_to_nchw(gv, dtype, dx, c, st);
 }
+
+// ------------------------------------------------------------------------------------------
+// Device-side data path (train.py:208-228, finetune.py:94-150)
+// ------------------------------------------------------------------------------------------
+extern "C" int n2n_crop_patches(const float* const* images, const int32_t* dims_hw, const int32_t* sel, int batch,
+                                int channels, int patch, float scale, float* out, void* stream) {
+  N2N_CHECK_ARG(batch >= 0 && channels >= 1 && patch >= 1, "crop_patches: bad geometry");
+  if (batch == 0) return 0;
+  N2N_CHECK_ARG(images && dims_hw && sel && out, "crop_patches: null pointer");
+  return launch_crop_patches(images, dims_hw, sel, batch, channels, patch, scale, out, (cudaStream_t)stream);
+}

@@ -340,6 +340,8 @@ int launch_maxpool(const View& src, const View& dst, int dtype, cudaStream_t st)
 int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, float slope, int dtype, cudaStream_t st);
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t st);
 int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
+int launch_crop_patches(const float* const* imgs, const int* dims, const int* sel, int batch, int C, int ps, float scale,
+                        float* out, cudaStream_t st);
 
 // bf16 tensor-core engine (tapgemm_umma.cu / wgrad_umma.cu)
 int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st);

@@ -304,6 +304,35 @@ int launch_unpool_lrelu(const View& act, const View& gpool, const View& gact, fl
   return 0;
 }
 
+// Device-side patch cropper (the data path of train.py:208-228 / finetune.py:94-150 moved off the host): the training
+// images stay resident in HBM as the reference holds them (float32 H x W x C, values 0..255); one launch cuts a batch
+// of patches out of them at (image, top, left) and writes the [B, C, ps, ps] network input scaled by `scale`
+// (1/255, train.py:358, finetune.py:146-147).  Clean and noisy tables share the crop coordinates, so the pair stays
+// registered.  sel = int32 [B][3] (image index, top, left); imgs = device pointer table; dims = int32 [nimg][2] (H, W).
+__global__ void crop_patches_kernel(const float* const* __restrict__ imgs, const int* __restrict__ dims,
+                                    const int* __restrict__ sel, int C, int ps, float scale, float* __restrict__ out,
+                                    long long items) {
+  pdl_enter();
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < items; t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int x = (int)(r % ps); r /= ps;
+    const int y = (int)(r % ps); r /= ps;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const int im = sel[3 * b], top = sel[3 * b + 1], left = sel[3 * b + 2];
+    const int W = dims[2 * im + 1];
+    out[t] = imgs[im][((long long)(top + y) * W + (left + x)) * C + c] * scale;
+  }
+}
+int launch_crop_patches(const float* const* imgs, const int* dims, const int* sel, int batch, int C, int ps, float scale,
+                        float* out, cudaStream_t st) {
+  const long long items = (long long)batch * C * ps * ps;
+  if (items <= 0) return 0;
+  (void)launch_pdl_v(crop_patches_kernel, dim3(grid_for(items, 256)), dim3(256), 0, st, imgs, dims, sel, C, ps, scale, out, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
 // y[i] += x[i] (fp32): the global residual of arch_unet.RESNET (arch_unet.py:409) and its input gradient
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
   pdl_enter();

@@ -187,42 +187,76 @@ __global__ void unpack_kernel(const __grid_constant__ UnpackBatch b) {
 // -> ky / kx = 0 outside, 2 = last -> ky / kx = 2 outside) is what the epilogue subtracts there.
 struct UpFuseBatch { UpFuseJob j[5]; int n; };
 
-__global__ void upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
+// One block = one (16 co x 16 ci) tile of ALL 16 composite matrices of a layer: the nine taps of W3[co][c][.] and the four
+// taps of Wd[ci][c][.] of a 16-channel chunk are staged in shared memory with contiguous (coalesced) global reads, and
+// every thread accumulates its (co, ci) entry of the 16 composites in registers: 36 FMAs per reduction channel.
+constexpr int kUfTile = 16;
+__global__ void __launch_bounds__(kUfTile * kUfTile)
+upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
   pdl_enter_no_release();   // its output is prefetched by the next GEMM's prologue
   const UpFuseJob& J = b.j[blockIdx.y];
+  __shared__ float sA[kUfTile][9][kUfTile];       // [c][tap][co]
+  __shared__ float sB[kUfTile][4][kUfTile];       // [c][a*2+b][ci]
   const int ci_pad = J.ngroups * kGroupBlocks * 16;        // whole groups (the bulk copy reads the padding too)
-  const long long total = 16LL * J.co_pad * ci_pad;
+  const int tiles_ci = ci_pad / kUfTile, tiles_co = J.co_pad / kUfTile;
   const int cin3 = J.Cu + J.Cs;                            // dec_conv a's input channels
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % ci_pad);
-    const int co = (int)((i / ci_pad) % J.co_pad);
-    const int u = (int)((i / ((long long)ci_pad * J.co_pad)) % 8);     // (px, syi, sxi)
-    const int py = (int)(i / (8LL * ci_pad * J.co_pad));
-    const int px = u >> 2, sy = ((u >> 1) & 1) + py - 1, sx = (u & 1) + px - 1;
-    float v = 0.f;
-    if (co < J.Co && ci < J.Ci) {
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yo = py + ky - 1;
-        if ((yo >= 0 ? yo >> 1 : -1) != sy) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xo = px + kx - 1;
-          if ((xo >= 0 ? xo >> 1 : -1) != sx) continue;
-          const float* w3 = J.w3 + ((long long)co * cin3 * 3 + ky) * 3 + kx;                  // + c * 9
-          const float* wd = J.wd + ((long long)ci * J.Cu * 2 + (yo & 1)) * 2 + (xo & 1);      // + c * 4
-          float acc = 0.f;
-          for (int c = 0; c < J.Cu; ++c) acc = fmaf(__ldg(w3 + c * 9), __ldg(wd + c * 4), acc);
-          v += acc;
-        }
+  if ((int)blockIdx.x < tiles_ci * tiles_co) {
+    const int co0 = ((int)blockIdx.x / tiles_ci) * kUfTile, ci0 = ((int)blockIdx.x % tiles_ci) * kUfTile;
+    const int tco = threadIdx.x / kUfTile, tci = threadIdx.x % kUfTile;
+    float acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+    for (int c0 = 0; c0 < J.Cu; c0 += kUfTile) {
+      __syncthreads();
+      // W3[co0 + r][c0 + c][t]: for a fixed co the 16 x 9 values are contiguous in global memory
+      for (int i = threadIdx.x; i < kUfTile * kUfTile * 9; i += kUfTile * kUfTile) {
+        const int r = i / (kUfTile * 9), rem = i - r * (kUfTile * 9);
+        const int c = rem / 9, t = rem - c * 9;
+        const int co = co0 + r, cc = c0 + c;
+        sA[c][t][r] = (co < J.Co && cc < J.Cu) ? __ldg(J.w3 + ((long long)co * cin3 + cc) * 9 + t) : 0.f;
+      }
+      // Wd[ci0 + r][c0 + c][ab]: 16 x 4 contiguous values per ci
+      for (int i = threadIdx.x; i < kUfTile * kUfTile * 4; i += kUfTile * kUfTile) {
+        const int r = i / (kUfTile * 4), rem = i - r * (kUfTile * 4);
+        const int c = rem / 4, ab = rem - c * 4;
+        const int ci = ci0 + r, cc = c0 + c;
+        sB[c][ab][r] = (ci < J.Ci && cc < J.Cu) ? __ldg(J.wd + ((long long)ci * J.Cu + cc) * 4 + ab) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int c = 0; c < kUfTile; ++c) {
+        float a[9], w[4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a[t] = sA[c][t][tco];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = sB[c][q][tci];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int yo = py + ky - 1, xo = px + kx - 1;
+                const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1), sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
+                const int u = ((py * 2 + px) * 2 + syi) * 2 + sxi;
+                acc[u] = fmaf(a[ky * 3 + kx], w[(yo & 1) * 2 + (xo & 1)], acc[u]);
+              }
       }
     }
+    const int co = co0 + tco, ci = ci0 + tci;
     const int cb = ci >> 4, e = ci & 15;
     const int g = cb / kGroupBlocks, jj = cb - g * kGroupBlocks;
-    const size_t byte = ((size_t)((u * J.ngroups + g) * kGroupBlocks + jj) * J.co_pad + co) * 32 +
-                        ((((e >> 3) ^ ((co >> 2) & 1))) << 4) + (e & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>((char*)J.dst[py] + byte) = __float2bfloat16_rn(v);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int py = u >> 3, u8 = u & 7;                   // region per output-row parity; slab (px, syi, sxi) inside it
+      const size_t byte = ((size_t)((u8 * J.ngroups + g) * kGroupBlocks + jj) * J.co_pad + co) * 32 +
+                          ((((e >> 3) ^ ((co >> 2) & 1))) << 4) + (e & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>((char*)J.dst[py] + byte) = __float2bfloat16_rn(acc[u]);
+    }
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == gridDim.x - 1) {
     for (int co = threadIdx.x; co < J.co_pad; co += blockDim.x) {
       float tap[9];
       float full = 0.f;
@@ -252,14 +286,14 @@ int launch_upfuse_pack(const UpFuseJob* jobs, int njobs, cudaStream_t st) {
   N2N_CHECK_ARG(njobs <= 5, "upfuse_pack: too many jobs");
   UpFuseBatch b;
   b.n = njobs;
-  long long maxtotal = 1;
+  int maxtiles = 1;
   for (int i = 0; i < njobs; ++i) {
     b.j[i] = jobs[i];
-    const long long tot = 16LL * jobs[i].co_pad * jobs[i].ngroups * kGroupBlocks * 16;
-    if (tot > maxtotal) maxtotal = tot;
+    const int tiles = (jobs[i].co_pad / kUfTile) * (jobs[i].ngroups * kGroupBlocks * 16 / kUfTile);
+    if (tiles > maxtiles) maxtiles = tiles;
   }
-  dim3 grid(grid_for(maxtotal, 256, 4), njobs);
-  (void)launch_pdl_v(upfuse_pack_kernel, grid, dim3(256), 0, st, b);
+  dim3 grid(maxtiles + 1, njobs);            // + one block per layer for the bias / border tables
+  (void)launch_pdl_v(upfuse_pack_kernel, grid, dim3(kUfTile * kUfTile), 0, st, b);
   N2N_LAUNCH_CHECK();
   return 0;
 }

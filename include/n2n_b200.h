@@ -259,6 +259,18 @@ int n2n_psnr_ssim_u8(const uint8_t* a, const uint8_t* b, int batch, int h, int w
                      double* result, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Device-side data path — train.py:208-228 (DenoiseDataset), finetune.py:94-150
+ * (DenoisePatchDataset): the training images stay resident in device memory as the
+ * reference holds them (float32 H x W x C, 0..255); one launch cuts `batch` patches
+ * out[b][c][y][x] = images[sel[b][0]][(sel[b][1]+y) * W + sel[b][2]+x][c] * scale.
+ * images: device array of device pointers; dims_hw: int32 [nimg][2]; sel: int32
+ * [batch][3] = (image, top, left) — the caller draws the coordinates (host RNG as
+ * the reference's np.random.randint) and guarantees they are in range.
+ * ------------------------------------------------------------------------- */
+int n2n_crop_patches(const float* const* images, const int32_t* dims_hw, const int32_t* sel, int batch,
+                     int channels, int patch, float scale, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Probes (test / bring-up only): a bare tcgen05 GEMM used to validate the
  * shared-memory descriptor encodings the convolution kernels rely on.
  * ------------------------------------------------------------------------- */

@@ -44,3 +44,44 @@ def test_train_finetune_eval_roundtrip(tmp_path):
     _run([os.path.join(ROOT, "entry", "evaluation.py"), "--synthetic", "1", "--adapter_ckpt", os.path.join(out, "ft", "epoch_adapter_001.pth"),
           "--save_dir", ev2], ROOT)
     assert "PSNR=" in open(os.path.join(ev2, "metrics.txt")).read()
+    # per-snapshot validation + A_log.csv (train.py:391-434)
+    logs = glob.glob(os.path.join(out, "UNET_test", "*", "validation", "A_log.csv"))
+    assert len(logs) == 1 and open(logs[0]).read().count("epoch") == 2
+    assert glob.glob(os.path.join(out, "UNET_test", "*", "validation", "*_denoised.png"))
+
+
+def test_reference_named_eval_entry_points(tmp_path):
+    """evaluation_704.py / evaluation_adapter.py under the reference's own names and flags (eval_704.sh:21-25,
+    evaluation_adapter.py:17-44), and the fork's live supervised loop on RESNET (train.py:298-314, :354-368)."""
+    import numpy as np
+    from PIL import Image
+    out = str(tmp_path)
+    _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "2", "--patch", "64", "--batchsize", "2", "--n_epoch", "1",
+          "--loop", "supervised", "--save_model_path", out, "--log_name", "RESNET_sup", "--patches_per_image", "2"], ROOT)
+    ck = sorted(glob.glob(os.path.join(out, "RESNET_sup", "*", "epoch_model_*.pth")))
+    assert len(ck) == 2 and len(torch.load(ck[-1], map_location="cpu")) == 42
+    _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "2", "--patch", "64", "--batchsize", "2", "--n_epoch", "1",
+          "--save_model_path", out, "--log_name", "UNET_n2n", "--patches_per_image", "2"], ROOT)
+    ck = sorted(glob.glob(os.path.join(out, "UNET_n2n", "*", "epoch_model_*.pth")))
+    ev = os.path.join(out, "eval704")
+    txt = _run([os.path.join(ROOT, "entry", "evaluation_704.py"), "--synthetic", "2", "--checkpoint", ck[-1], "--save_dir", ev,
+                "--log_name", "UNET_n2n"], ROOT)
+    m = open(os.path.join(ev, "metrics.txt")).read()
+    assert m.startswith("Average PSNR:") and "Average SSIM:" in m and "Average L1 Loss:" in m
+    assert len(glob.glob(os.path.join(ev, "*_denoised.png"))) == 2
+    d0 = np.array(Image.open(sorted(glob.glob(os.path.join(ev, "*_denoised.png")))[0]))
+    assert (d0[0, :] == 0).all() and (d0[:, 0] == 0).all()          # evaluation_704.py's zero border weight (SURVEY §0.5)
+    # adapter inference: data_dir/noise (+ clean), --ckpt, --arch
+    _run([os.path.join(ROOT, "entry", "finetune.py"), "--synthetic", "2", "--pretrained_ckpt", ck[-1], "--n_epoch", "1",
+          "--batchsize", "2", "--patch_size", "64", "--patches_per_image", "2", "--save_model_path", out, "--log_name", "ft2"], ROOT)
+    dd = os.path.join(out, "data")
+    os.makedirs(os.path.join(dd, "noise")); os.makedirs(os.path.join(dd, "clean"))
+    rng = np.random.RandomState(0)
+    for i in range(2):
+        c = rng.randint(0, 256, (64, 96)).astype(np.uint8)
+        Image.fromarray(c).save(os.path.join(dd, "clean", f"im{i}.png"))
+        Image.fromarray(np.clip(c + rng.randn(64, 96) * 25, 0, 255).astype(np.uint8)).save(os.path.join(dd, "noise", f"im{i}.png"))
+    ev3 = os.path.join(out, "infer_adapter")
+    txt = _run([os.path.join(ROOT, "entry", "evaluation_adapter.py"), "--data_dir", dd, "--ckpt", os.path.join(out, "ft2", "epoch_adapter_001.pth"),
+                "--arch", "UNet", "--save_dir", ev3], ROOT)
+    assert txt.count("PSNR=") == 2 and len(glob.glob(os.path.join(ev3, "*_denoised.png"))) == 2
