@@ -110,6 +110,7 @@ _SIGS = {
     "n2n_unet_plan_destroy": (None, [c_void_p]),
     "n2n_unet_workspace_bytes": (c_size_t, [c_void_p]),
     "n2n_unet_launches": (c_int, [c_void_p, c_int]),
+    "n2n_unet_read_activation": (ctypes.c_longlong, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int), c_void_p]),
     "n2n_unet_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_unet_share_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "n2n_unet_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p), c_void_p,

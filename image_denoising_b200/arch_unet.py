@@ -205,8 +205,28 @@ class UNet(nn.Module):
         y = torch.empty((x.shape[0], self.out_nc, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
         check(lib().n2n_unet_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
         self.last_launches = lib().n2n_unet_launches(plan, 0)
+        self._last = (plan, ws)
         self._cache.give_back(key, x.device, ws)
         return y
+
+    ACTIVATION_BUFFERS = {"cat0": 0, "cat1": 1, "cat2": 2, "cat3": 3, "cat4": 4, "enc_conv0": 5, "enc_conv1": 6, "enc_conv2": 7,
+                          "enc_conv3": 8, "enc_conv4": 9, "enc_conv5": 10, "pool5": 11, "enc_conv6": 12, "dec_conv5a": 13,
+                          "dec_conv5b": 14, "dec_conv4a": 15, "dec_conv4b": 16, "dec_conv3a": 17, "dec_conv3b": 18,
+                          "dec_conv2a": 19, "dec_conv2b": 20, "dec_conv1a": 21, "dec_conv1b": 22, "nin_a": 23, "nin_b": 24}
+
+    def read_activation(self, name: str):
+        """Layer-level parity hook: an intermediate tensor of the most recent no-grad forward as fp32 NCHW (all 16-channel
+        blocks of the engine's buffer, zero / im2col padding included) — valid until the next forward of this module."""
+        plan, ws = self._last
+        dims = (_ext.ctypes.c_int * 3)()
+        n = lib().n2n_unet_read_activation(plan, ptr(ws), self.ACTIVATION_BUFFERS[name], None, dims, stream_ptr())
+        if n <= 0:
+            raise ValueError(f"{name}: buffer not used by this plan")
+        out = torch.empty((n // (dims[0] * dims[1] * dims[2]), dims[0], dims[1], dims[2]), dtype=torch.float32, device=ws.device)
+        rc = lib().n2n_unet_read_activation(plan, ptr(ws), self.ACTIVATION_BUFFERS[name], ptr(out), dims, stream_ptr())
+        if rc < 0:
+            check(int(rc))
+        return out
 
 
 class RESNET(UNet):

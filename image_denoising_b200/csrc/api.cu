@@ -269,10 +269,17 @@ extern "C" int n2n_deconv2x2_fwd(const float* x, const float* w, const float* b,
   View xv = make_view(ws.xa, dtype, n, h, w_, L.cin_blocks(), 0, L.cin_blocks());
   View yv = make_view(ws.ya, dtype, n, 2 * h, 2 * w_, L.cout_blocks(), 0, L.cout_blocks());
   N2N_TRY(launch_nchw_to_c16(x, cin, xv, dtype, st));
-  PackJob pj = make_fwd_pack(L, w, ws.wp);
-  N2N_TRY(launch_pack(&pj, 1, dtype, st));
   BiasPadJob bj{b, ws.bias, cout, L.cout_blocks() * 16};
   N2N_TRY(launch_bias_pad(&bj, 1, st));
+  if (slab_deconv_pair_ok(dtype, h, w_, L.cin_blocks(), L.cout_blocks())) {
+    // the launch form the network plans use: one N = 2*Cout GEMM per output-row parity
+    PackJob pj = make_deconv_pair_pack(L, w, ws.wp);
+    N2N_TRY(launch_pack(&pj, 1, dtype, st));
+    for (int a = 0; a < 2; ++a) N2N_TRY(launch_tapgemm(make_deconv_fwd_pair(L, dtype, xv, yv, a, ws.wp, ws.bias), st));
+    return launch_c16_to_nchw(yv, dtype, y, cout, st);
+  }
+  PackJob pj = make_fwd_pack(L, w, ws.wp);
+  N2N_TRY(launch_pack(&pj, 1, dtype, st));
   for (int ab = 0; ab < 4; ++ab) {
     TapGemm g = make_deconv_fwd(L, dtype, xv, yv, ab / 2, ab % 2, ws.wp, ws.bias);
     N2N_TRY(launch_tapgemm(g, st));

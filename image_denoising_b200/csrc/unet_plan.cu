@@ -172,6 +172,8 @@ static void plan_layout(n2n_unet_plan* p) {
     U.ci_blocks = p->L[dc].cin_blocks(); U.co_blocks = p->L[dc + 1].cout_blocks();
     U.skip_im2col = dc == 19 && p->im2col;
     U.skip_blocks = dc == 19 ? p->skipb : nfb;
+    { const char* e = getenv("N2N_UPFUSE_LEVELS");      // diagnostic: bit (dc - 7) / 3 enables the fusion of that level
+      if (e && !((atoi(e) >> ((dc - 7) / 3)) & 1)) { p->upfuse[dc] = false; continue; } }
     p->upfuse[dc] = !p->bwd && p->dtype == N2N_BF16 && !p->ksplit[dc + 1] &&
                     slab_upconv_ok(p->dtype, p->N, p->lh(lv), p->lw(lv), U.ci_blocks, U.skip_blocks, U.co_blocks, U.region_bytes());
   }
@@ -184,7 +186,16 @@ static void plan_layout(n2n_unet_plan* p) {
     p->act[b].off = take((size_t)p->N * p->act[b].Cb * p->lh(p->act[b].lvl) * p->lw(p->act[b].lvl) * 16 * es);
   }
   for (int i = 0; i < 25; ++i) {
-    p->off_wp[i] = take(p->L[i].fwd_pack_bytes(p->dtype));
+    size_t wbytes = p->L[i].fwd_pack_bytes(p->dtype);
+    if (p->im2col && i == 20) {
+      // im2col form of dec_conv1a: nine tap slabs over the c2b upsampled blocks, then ONE more slab (the im2col tap of
+      // the raw input) at slab index 9 — its own group of three blocks.  Sizing this by the layer's nominal
+      // (c2b + inb) blocks is one slab short whenever c2b + inb needs no more groups than c2b (n_feature 4, 16, 32, ...).
+      const size_t im2col_form = packed_weight_bytes(p->dtype, 9, p->L[i].cout_blocks() * 16, c2b) +
+                                 packed_weight_bytes(p->dtype, 1, p->L[i].cout_blocks() * 16, p->kb);
+      if (im2col_form > wbytes) wbytes = im2col_form;
+    }
+    p->off_wp[i] = take(wbytes);
     p->off_bias[i] = take(p->L[i].cout_blocks() * 16 * sizeof(float));
   }
   for (int dc = 7; dc <= 19; dc += 3) {
@@ -276,6 +287,20 @@ extern "C" int n2n_unet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc,
 }
 extern "C" void n2n_unet_plan_destroy(n2n_unet_plan* plan) { delete plan; }
 extern "C" size_t n2n_unet_workspace_bytes(const n2n_unet_plan* plan) { return plan ? plan->total : 0; }
+// Diagnostic / layer-level parity: copy one activation buffer of the last forward on `ws` out as fp32 NCHW
+// [N][16 * blocks][H_l][W_l] (all channel blocks of the buffer, padding included).  buffer: 0..4 = concat buffers of
+// levels 0..4, 5.. = enc_conv0..5 outputs, pool5, enc_conv6, dec_conv5a, 5b, 4a, 4b, 3a, 3b, 2a, 2b, 1a, 1b, nin_a, nin_b.
+// dims (may be NULL) receives {channels, H_l, W_l}.  Returns the element count, 0 for an empty buffer, < 0 on error.
+extern "C" long long n2n_unet_read_activation(const n2n_unet_plan* p, void* ws, int buffer, float* out, int* dims, void* stream) {
+  if (!p || !ws || buffer < 0 || buffer >= B_COUNT || buffer == B_OUT) { set_error("unet_read_activation: bad arguments"); return N2N_ERR_ARG; }
+  const Buf& B = p->act[buffer];
+  const int h = p->lh(B.lvl), w = p->lw(B.lvl);
+  if (dims) { dims[0] = B.Cb * 16; dims[1] = h; dims[2] = w; }
+  const long long count = (long long)p->N * B.Cb * 16 * h * w;
+  if (count == 0 || !out) return count;
+  const int r = launch_c16_to_nchw(p->view(p->act, ws, buffer, 0, B.Cb), p->dtype, out, B.Cb * 16, (cudaStream_t)stream);
+  return r < 0 ? r : count;
+}
 extern "C" int n2n_unet_launches(const n2n_unet_plan* plan, int backward) {
   return plan ? (backward ? plan->bwd_launches : plan->fwd_launches) : 0;
 }

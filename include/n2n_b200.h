@@ -151,6 +151,12 @@ int n2n_resnet_plan_create(n2n_unet_plan** plan, int in_nc, int out_nc, int n_fe
                            int n, int h, int w, int dtype, int with_backward);
 void n2n_unet_plan_destroy(n2n_unet_plan* plan);
 size_t n2n_unet_workspace_bytes(const n2n_unet_plan* plan);
+/* Diagnostic / layer-level parity tests: copy activation buffer `buffer` of the last forward on `workspace` out as fp32
+ * NCHW [N][16*blocks][H_l][W_l] (padding channels included).  buffer: 0..4 = concat buffers of levels 0..4 ([up | skip]),
+ * 5..10 = enc_conv0..5 outputs, 11 = pool5, 12 = enc_conv6, 13.. = dec_conv5a, 5b, 4a, 4b, 3a, 3b, 2a, 2b, 1a, 1b,
+ * 23 = nin_a, 24 = nin_b.  dims (may be NULL) = {channels, H_l, W_l}; out may be NULL (size query).  Returns the element
+ * count (0: the buffer is not used by this plan), < 0 on error.  Buffers a fused launch skips hold stale data. */
+long long n2n_unet_read_activation(const n2n_unet_plan* plan, void* workspace, int buffer, float* out, int* dims, void* stream);
 /* number of kernel launches one forward / backward issues (for gpu_launches). */
 int n2n_unet_launches(const n2n_unet_plan* plan, int backward);
 /* y = UNet(x): x [N,in_nc,H,W] fp32, y [N,out_nc,H,W] fp32.  With a

@@ -37,7 +37,8 @@ def _net(dev, in_nc, nf, params):
     return net.to(dev).set_precision("bf16")
 
 
-@pytest.mark.parametrize("in_nc,nf,shape", [(1, 48, (2, 64, 96)), (3, 48, (1, 96, 160)), (1, 48, (1, 352, 352)), (1, 16, (3, 32, 64))])
+@pytest.mark.parametrize("in_nc,nf,shape", [(1, 48, (2, 64, 96)), (3, 48, (1, 96, 160)), (1, 48, (1, 352, 352)), (1, 16, (3, 32, 64)),
+                                            (1, 32, (2, 64, 64)), (3, 32, (1, 64, 96)), (1, 4, (2, 64, 64))])
 def test_fused_upconv_matches_layerwise_and_oracle(dev, monkeypatch, in_nc, nf, shape):
     p = _weights(in_nc, nf, 11)
     n, h, w = shape
@@ -86,3 +87,27 @@ def test_fused_upconv_border_correction_is_needed(dev):
     border_err = float(torch.cat([(y - ref)[..., 0, :].flatten(), (y - ref)[..., -1, :].flatten(),
                                   (y - ref)[..., :, 0].flatten(), (y - ref)[..., :, -1].flatten()]).abs().mean())
     assert border_err <= 3.0 * interior_err + 1e-4, (border_err, interior_err)
+
+
+@pytest.mark.parametrize("nf", [4, 16, 32])
+def test_bf16_training_step_other_widths_vs_oracle(dev, nf):
+    """Widths whose decoder concat is not a whole number of 48-channel groups (n_feature 4 / 16 / 32): the im2col form of
+    dec_conv1a keeps its extra weight slab behind nine partially filled tap slabs — a workspace sizing bug once let the
+    next layer's pack overwrite it (garbage / NaN activations from dec_conv1a on)."""
+    from image_denoising_b200 import N2NTrainer, UNet
+    p = _weights(1, nf, 21, bias_scale=0.02)
+    g = torch.Generator().manual_seed(9)
+    clean = torch.rand(2, 1, 64, 64, generator=g)
+    noisy = clean + torch.randn(clean.shape, generator=g) * (25 / 255)
+    rd = O.draw_rd_idx(2, 64, 64, 1)
+    m1, m2 = O.masks_from_rd_idx(rd)
+    loss, _, _, grads, _, _ = O.n2n_step_grads(p, noisy, m1, m2, 1.0)
+    net = UNet(1, 1, nf); net.load_state_dict(p); net = net.to(dev).set_precision("bf16")
+    tr = N2NTrainer(net, lr=0.0, precision="bf16")
+    loss3 = tr.step(noisy.to(dev), 1.0, rd_idx=torch.from_numpy(rd).to(dev)).cpu().numpy()
+    assert np.isfinite(loss3).all() and abs(loss3[0] - loss) <= 3e-2 * abs(loss), (loss3, loss)
+    for (k, ref), gv in zip(grads.items(), tr.grads):
+        a, b = gv.cpu().double().flatten(), ref.double().flatten()
+        assert torch.isfinite(a).all(), k
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-300))
+        assert cos > 0.97, (k, cos)
