@@ -69,21 +69,14 @@ struct SgStage {
   uint8_t pad8[3];
   uint32_t b_off16[9];       // start of each tap's weight slab inside the resident weights (bytes/16)
   uint32_t tx_bytes;         // bytes the TMA box delivers
-  // the MMA issuer reads these straight from the constant bank with warp-uniform indices, so that descriptor
-  // arithmetic stays in uniform registers (the shared-memory copy cost ~13 SASS instructions per tcgen05.mma,
-  // most of them R2UR moves; measured: the lone issuing lane, not the tensor pipe, bounded the narrow layers)
-  uint32_t ta[9];            // a_off16 | accumulator column (/16) << 20
-  uint32_t tb[9];            // b_off16 / CG | "first MMA into these columns" << 31
-  uint32_t a_hi;             // A descriptor high word (SBO | version | SWIZZLE_32B)
-  uint32_t nt0;              // taps [0, nt0) start at accumulator column 0 (issuer 0), [nt0, ntaps) at column mma_n (issuer 1)
 };
 
 struct SgParams {
   // hot (epilogue / loop) fields first: they stay in the first constant-cache lines
   int nst, nout, ring, dbg_flags, nbuf;
-  int dual;                  // column-range form with exactly two ranges: a second issuer warp (the idle third epilogue group's
-                             // first warp) issues the taps of the upper range — the lone issuing lane, not the tensor pipe,
-                             // bounded the fused up-conv launches (ncu: tensor pipe 35 % active, issuer busy)
+  int esplit;                // 3: every tile's accumulator columns are drained by ALL THREE epilogue groups (a third each), used
+                             // when only two accumulators fit in TMEM (N = 144 / 192): with one group per tile the MMAs of tile
+                             // i+2 wait for the whole 12-block epilogue of tile i (ncu: tensor pipe 35 % active, third group idle)
   int mma_n, up_py;          // MMA width (= nout unless the launch is in column-range form); fused up-conv: output-row parity
   const float* corr;         // fused up-conv: border bias correction [9][mma_n] (see TapGemm::border_corr)
   int tiles_x, tiles_y, ntiles;
@@ -343,10 +336,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.dual ? 2 : 1); }
+    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
     mbar_init(wready_bar, CG);
-    for (int b = 0; b < 3; ++b) { mbar_init(tfull_bar(b), p.dual ? 2 : 1); mbar_init(tempty_bar(b), 4 * CG); }
+    for (int b = 0; b < 3; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG * (p.esplit == 3 ? 3 : 1)); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
@@ -454,19 +447,16 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (++slot == p.ring) { slot = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 || (p.dual && warp == 2 + 4 * 2)) {
-    // ---- MMA issuer(s): warp 1, plus the first warp of the (idle, nbuf == 2) third epilogue group in dual mode ----
-    const uint32_t q = warp == 1 ? 0u : 1u;
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
     int slot = 0; uint32_t phase = 0;
     pdl_wait();
-    if (q == 0) pdl_release();          // our own dependents may begin their prologue
+    pdl_release();                      // our own dependents may begin their prologue
     sg_wait(wfull_bar, 0);
     if (CG == 2) {
       // tell the leader that this CTA's weight half is in place; only the leader issues MMAs
-      if (q == 0) {
-        if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
-        __syncwarp();
-      }
+      if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
+      __syncwarp();
       if (rank == 0) sg_wait(wready_bar, 0);
     }
     const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
@@ -480,29 +470,39 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
       uint32_t acc = 0;
       for (int s = 0; s < p.nst; ++s) {
-        const SgStage& S = p.st[s];                            // constant bank, warp-uniform index
-        const uint32_t nb = (uint32_t)S.nb, cbz = (uint32_t)S.cb_bytes16, a_hi = S.a_hi;
-        const uint32_t t_begin = q ? S.nt0 : 0u, t_end = (p.dual && !q) ? S.nt0 : (uint32_t)S.ntaps;
+        const uint4 mm = s_mm[s];                            // ntaps, nb, cb_bytes16, a_hi
         const uint32_t a_lo = (((slots0 + slot * p.slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        // the stage's tap table goes to registers up front (5 LDS.128), so the issue loop below is
+        // two integer adds per tcgen05.mma
+        uint2 tp[10];
+        {
+          const uint4* t4 = reinterpret_cast<const uint4*>(&s_tap[s * 10]);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const uint4 t = t4[q];
+            tp[2 * q] = make_uint2(t.x, t.y); tp[2 * q + 1] = make_uint2(t.z, t.w);
+          }
+        }
         sg_wait(full_bar(slot), phase);
         fence_after_sync();
         if (elect_one_sync()) {
           if (!skip) {
-#pragma unroll 1
-            for (uint32_t t = t_begin; t < t_end; ++t) {
-              // ta: A offset (bits 0..19) | accumulator column / 16 (bits 20..); tb: B offset | "first MMA into these columns"
-              const uint32_t xa = S.ta[t], xb = S.tb[t];
-              const uint32_t al = a_lo + (xa & 0xFFFFFu), bl = w_lo + (xb & 0x7FFFFFFFu);
-              const uint32_t dt = d_tmem + (xa >> 20) * 16u;
-              const uint32_t a1 = acc | ((xb >> 31) ^ 1u);
-              if (CG == 2) {
-                sg_mma2(dt, al, a_hi, bl, b_hi, idesc, a1);
-                if (nb > 1) sg_mma2(dt, al + cbz, a_hi, bl + b_sub16, b_hi, idesc, 1);
-                if (nb > 2) sg_mma2(dt, al + 2 * cbz, a_hi, bl + 2 * b_sub16, b_hi, idesc, 1);
-              } else {
-                sg_mma(dt, al, a_hi, bl, b_hi, idesc, a1);
-                if (nb > 1) sg_mma(dt, al + cbz, a_hi, bl + b_sub16, b_hi, idesc, 1);
-                if (nb > 2) sg_mma(dt, al + 2 * cbz, a_hi, bl + 2 * b_sub16, b_hi, idesc, 1);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (t < (int)mm.x) {
+                // x: A offset (bits 0..19) | accumulator column (bits 20..); y: B offset | "first MMA into these columns"
+                const uint32_t al = a_lo + (tp[t].x & 0xFFFFFu), bl = w_lo + (tp[t].y & 0x7FFFFFFFu);
+                const uint32_t dt = d_tmem + (tp[t].x >> 20) * 16u;
+                const uint32_t a1 = acc | ((tp[t].y >> 31) ^ 1u);
+                if (CG == 2) {
+                  sg_mma2(dt, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma2(dt, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma2(dt, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                } else {
+                  sg_mma(dt, al, mm.w, bl, b_hi, idesc, a1);
+                  if (mm.y > 1) sg_mma(dt, al + mm.z, mm.w, bl + b_sub16, b_hi, idesc, 1);
+                  if (mm.y > 2) sg_mma(dt, al + 2 * mm.z, mm.w, bl + 2 * b_sub16, b_hi, idesc, 1);
+                }
               }
             }
           }
@@ -516,8 +516,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (p.bias_off && !skip) {
           const uint32_t one_lo = (((smem0 + p.bias_off) & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t bia_lo = (((smem0 + p.bias_off + 4096u) & 0x3FFFFu) >> 4) | (1u << 16);
-          // column-range form: the same bias rows serve every column range (dual mode: each issuer its own range)
-          for (int col = p.dual ? (int)q * p.mma_n : 0; col < (p.dual ? ((int)q + 1) * p.mma_n : p.nout); col += p.mma_n) {
+          for (int col = 0; col < p.nout; col += p.mma_n) {      // column-range form: the same bias rows serve every column range
             if (CG == 2) sg_mma2(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1); else sg_mma(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1);
           }
         }
@@ -534,8 +533,11 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const int py = m >> 3, px = m & 7;
     const int group = (warp - 2) >> 2;
     pdl_wait();                         // mask / addend reads and all stores touch the predecessor's data
-    const int cb_lo = 0;
-    const int nblk = p.nout >> 4;
+    const bool split = p.esplit == 3;
+    const int nblk_all = p.nout >> 4;
+    // split: this group's third of the columns of EVERY tile; else all columns of every nbuf-th tile
+    const int cb_lo = split ? group * (nblk_all / 3) : 0;
+    const int nblk = split ? cb_lo + nblk_all / 3 : nblk_all;
     const bool skip = (p.dbg_flags & 4) != 0;
     // group g <-> accumulator g: a group only ever waits on consecutive phases of its own barriers (with more
     // groups than accumulators a group could run two phases ahead, which a parity wait cannot tell apart)
@@ -543,15 +545,15 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     // on the narrow layers): one division up front, then carries
     int t_img, t_ty, t_tx;
     {
-      const int tile0 = first_tile + (group < p.nbuf ? group : 0) * tile_step;
+      const int tile0 = first_tile + ((!split && group < p.nbuf) ? group : 0) * tile_step;
       t_img = tile0 / tiles_per_img;
       const int r0 = tile0 - t_img * tiles_per_img;
       t_ty = r0 / p.tiles_x; t_tx = r0 - t_ty * p.tiles_x;
     }
-    const int adv = p.nbuf * tile_step;
+    const int adv = (split ? 1 : p.nbuf) * tile_step;
     const int adv_img = adv / tiles_per_img, adv_r = adv - adv_img * tiles_per_img;
     const int adv_ty = adv_r / p.tiles_x, adv_tx = adv_r - adv_ty * p.tiles_x;
-    for (int lt = group < p.nbuf ? group : npair_iters; lt < npair_iters; lt += p.nbuf) {
+    for (int lt = split ? 0 : (group < p.nbuf ? group : npair_iters); lt < npair_iters; lt += split ? 1 : p.nbuf) {
       int tile = first_tile + lt * tile_step;
       const bool tile_ok = tile < p.ntiles;                 // odd tile count: the peer's last accumulator is a duplicate
       SgPix c;
@@ -805,27 +807,10 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   // that is still draining tile i (two groups on alternate tiles); else two
   p.nbuf = 3 * g.nout <= 512 ? 3 : 2;
   { const char* e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
+  { const char* e = getenv("N2N_NO_ESPLIT");
+    p.esplit = (p.nbuf == 2 && (g.nout >> 4) % 3 == 0 && !(e && atoi(e))) ? 3 : 1; }
   p.tmem_cols = tmem_cols_for(p.nbuf * g.nout);
   p.idesc = make_idesc_bf16(128 * cg, mma_n, false, false);
-  bool dual_ok = true;
-  for (int si = 0; si < nst; ++si) {
-    SgStage& S = p.st[si];
-    for (int k = 0; k < S.ntaps; ++k) {
-      S.ta[k] = (uint32_t)S.a_off16[k] | ((uint32_t)S.col16[k] << 20);
-      S.tb[k] = (S.b_off16[k] / (uint32_t)cg) | ((((uint32_t)S.first >> k) & 1u) << 31);
-    }
-    S.a_hi = (uint32_t)S.sbo16 | (1u << 14) | (kSwizzle32 << 29);
-    // taps are listed lower column range first (make_upconv_fwd); nt0 = where the upper range starts
-    uint32_t nt0 = 0;
-    bool sorted = true;
-    for (int k = 0; k < S.ntaps; ++k) {
-      if (S.col16[k] == 0) { if (nt0 != (uint32_t)k) sorted = false; ++nt0; }
-    }
-    S.nt0 = nt0;
-    if (!sorted) dual_ok = false;
-  }
-  { const char* e = getenv("N2N_NO_DUAL_ISSUE");
-    p.dual = (dual_ok && g.mma_n && g.nout == 2 * mma_n && p.nbuf == 2 && !(e && atoi(e))) ? 1 : 0; }
   { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
   if (!attr_set) {
