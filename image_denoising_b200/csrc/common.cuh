@@ -316,8 +316,30 @@ struct UpFuseJob {
   void* dst[2] = {nullptr, nullptr};   // per output-row parity: 8 composite slabs [(px, sy, sx)][group][3][co_pad][32 B]
   float* bias_full = nullptr;     // [co_pad]
   float* corr = nullptr;          // [9][co_pad]
+  // training plans: the same 16 composites TRANSPOSED for the fused input gradient (rows = ci, K = co):
+  // [(py, px, sy, sx)][co group][3][ci_rows][32 B]
+  void* dst_t = nullptr;
+  int gco = 1, ci_rows = 16;
 };
 int launch_upfuse_pack(const UpFuseJob* jobs, int njobs, cudaStream_t st);
+
+// Backward of the fused up-conv (pack.cu: upfuse_grad_kernel): chain rule from the composite weight gradients
+// dWc[(py,px,sy,sx)][ci][co] (dense fp32, already reduced over the pixel splits) to the two layers' own gradients.
+struct UpFuseGradJob {
+  const float* dwc = nullptr;     // [16][ci_pad][co_pad]
+  const float* w3 = nullptr;      // [Co][Cu + Cs][3][3]
+  const float* wd = nullptr;      // [Ci][Cu][2][2]
+  const float* bd = nullptr;      // [Cu]
+  const float* border = nullptr;  // [8][co_pad]: sums of dL/dy over the first / last row, first / last column, four corners
+  const float* db3 = nullptr;     // [Co] = sum of dL/dy over all pixels (the conv's bias gradient, already reduced)
+  float* dw3 = nullptr;           // [Co][Cu + Cs][3][3]: channels [0, Cu) are written
+  float* dwd = nullptr;           // [Ci][Cu][2][2]
+  float* dbd = nullptr;           // [Cu]
+  int Ci = 0, Cu = 0, Cs = 0, Co = 0, ci_pad = 16, co_pad = 16;
+};
+int launch_upfuse_grad(const UpFuseGradJob* jobs, int njobs, cudaStream_t st);
+// border[8][co_pad] of a C16 bf16 gradient tensor (see UpFuseGradJob::border); deterministic block reductions
+int launch_border_sums(const View& g, float* border, int co_pad, cudaStream_t st);
 
 size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks);
 

@@ -199,6 +199,45 @@ inline TapGemm make_upconv_fwd(const UpConvGeom& U, int dtype, const View& x, co
   return g;
 }
 
+// Training plans: input gradient of the fused up-conv w.r.t. the ConvTranspose's input — one launch over the four
+// parity views of dL/dy (the conv's pre-activation output gradient, 2x resolution) with the transposed composites:
+//   g_x[i, j] = sum_{py,px,sy,sx} Wc[py,px,sy,sx]^T  dL/dy[2(i - sy) + py, 2(j - sx) + px]
+inline size_t upconv_wt_bytes(const UpConvGeom& U) {
+  return (size_t)16 * ((U.co_blocks + 2) / 3) * 3 * U.ci_blocks * 16 * 32;
+}
+inline TapGemm make_upconv_dgrad(const UpConvGeom& U, int dtype, const View& gy_full, const View& gx, const void* wt) {
+  TapGemm g;
+  g.dtype = dtype; g.cin_blocks = U.co_blocks; g.nout = U.ci_blocks * 16; g.w = wt; g.bias = nullptr; g.y = gx;
+  int t = 0;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      g.x[py * 2 + px] = parity_view(gy_full, dtype, py, px);
+      for (int syi = 0; syi < 2; ++syi)
+        for (int sxi = 0; sxi < 2; ++sxi) {
+          g.tap_view[t] = py * 2 + px;
+          g.tap_dy[t] = -(syi + py - 1); g.tap_dx[t] = -(sxi + px - 1);
+          g.tap_slab[t] = ((py * 2 + px) * 2 + syi) * 2 + sxi;
+          ++t;
+        }
+    }
+  g.ntaps = t;
+  return g;
+}
+// ... and the composite weight gradient of one output parity: dWc[py,px,sy,sx][ci][co] = sum_p dL/dy[2i+py, 2j+px][co] x[i+sy, j+sx][ci]
+inline TapWgrad make_upconv_wgrad(const UpConvGeom& U, int dtype, const View& x, const View& gy_full, int py, int px,
+                                  float* partial, int splits) {
+  TapWgrad g;
+  g.dtype = dtype; g.dy[0] = parity_view(gy_full, dtype, py, px); g.x[0] = x; g.npairs = 4;
+  for (int syi = 0; syi < 2; ++syi)
+    for (int sxi = 0; sxi < 2; ++sxi) {
+      const int t = syi * 2 + sxi;
+      g.pair_dyv[t] = 0; g.pair_xv[t] = 0; g.pair_dy[t] = syi + py - 1; g.pair_dx[t] = sxi + px - 1;
+    }
+  g.n_blocks = U.co_blocks; g.c_blocks = U.ci_blocks;
+  g.partial = partial; g.bias_partial = nullptr; g.ndyviews = 1; g.splits = splits;
+  return g;
+}
+
 bool slab_deconv_pair_ok(int dtype, int h, int w, int cin_blocks, int cout_blocks);
 bool slab_weights_fit(int ntaps, int cin_blocks, int nout, bool halo);
 bool slab_geometry_ok(int dtype, int h, int w);

@@ -198,7 +198,8 @@ upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
   __shared__ float sA[kUfTile][9][kUfTile];       // [c][tap][co]
   __shared__ float sB[kUfTile][4][kUfTile];       // [c][a*2+b][ci]
   const int ci_pad = J.ngroups * kGroupBlocks * 16;        // whole groups (the bulk copy reads the padding too)
-  const int tiles_ci = ci_pad / kUfTile, tiles_co = J.co_pad / kUfTile;
+  const int co_span = (J.dst_t && J.gco * kGroupBlocks * 16 > J.co_pad) ? J.gco * kGroupBlocks * 16 : J.co_pad;
+  const int tiles_ci = ci_pad / kUfTile, tiles_co = co_span / kUfTile;
   const int cin3 = J.Cu + J.Cs;                            // dec_conv a's input channels
   if ((int)blockIdx.x < tiles_ci * tiles_co) {
     const int co0 = ((int)blockIdx.x / tiles_ci) * kUfTile, ci0 = ((int)blockIdx.x % tiles_ci) * kUfTile;
@@ -248,12 +249,25 @@ upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
     const int co = co0 + tco, ci = ci0 + tci;
     const int cb = ci >> 4, e = ci & 15;
     const int g = cb / kGroupBlocks, jj = cb - g * kGroupBlocks;
+    if (co < J.co_pad) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int py = u >> 3, u8 = u & 7;                   // region per output-row parity; slab (px, syi, sxi) inside it
-      const size_t byte = ((size_t)((u8 * J.ngroups + g) * kGroupBlocks + jj) * J.co_pad + co) * 32 +
-                          ((((e >> 3) ^ ((co >> 2) & 1))) << 4) + (e & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>((char*)J.dst[py] + byte) = __float2bfloat16_rn(acc[u]);
+      for (int u = 0; u < 16; ++u) {
+        const int py = u >> 3, u8 = u & 7;                 // region per output-row parity; slab (px, syi, sxi) inside it
+        const size_t byte = ((size_t)((u8 * J.ngroups + g) * kGroupBlocks + jj) * J.co_pad + co) * 32 +
+                            ((((e >> 3) ^ ((co >> 2) & 1))) << 4) + (e & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>((char*)J.dst[py] + byte) = __float2bfloat16_rn(acc[u]);
+      }
+    }
+    if (J.dst_t && ci < J.ci_rows) {
+      // transposed pack for the fused input gradient: row = ci, contraction index = co
+      const int cbo = co >> 4, eo = co & 15;
+      const int go = cbo / kGroupBlocks, jo = cbo - go * kGroupBlocks;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const size_t byte = ((size_t)((u * J.gco + go) * kGroupBlocks + jo) * J.ci_rows + ci) * 32 +
+                            ((((eo >> 3) ^ ((ci >> 2) & 1))) << 4) + (eo & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>((char*)J.dst_t + byte) = __float2bfloat16_rn(acc[u]);
+      }
     }
   }
   if (blockIdx.x == gridDim.x - 1) {
@@ -289,11 +303,158 @@ int launch_upfuse_pack(const UpFuseJob* jobs, int njobs, cudaStream_t st) {
   int maxtiles = 1;
   for (int i = 0; i < njobs; ++i) {
     b.j[i] = jobs[i];
-    const int tiles = (jobs[i].co_pad / kUfTile) * (jobs[i].ngroups * kGroupBlocks * 16 / kUfTile);
+    const int co_span = (jobs[i].dst_t && jobs[i].gco * kGroupBlocks * 16 > jobs[i].co_pad) ? jobs[i].gco * kGroupBlocks * 16 : jobs[i].co_pad;
+    const int tiles = (co_span / kUfTile) * (jobs[i].ngroups * kGroupBlocks * 16 / kUfTile);
     if (tiles > maxtiles) maxtiles = tiles;
   }
   dim3 grid(maxtiles + 1, njobs);            // + one block per layer for the bias / border tables
   (void)launch_pdl_v(upfuse_pack_kernel, grid, dim3(kUfTile * kUfTile), 0, st, b);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- backward of the fused up-conv: chain rule (see UpFuseGradJob) -----------------------------------------------
+// Wc[u][co][ci] = sum over the taps (ky,kx) landing on source offset (sy,sx) of W3[co][c][ky][kx] Wd[ci][c][a][b], so
+//   dW3[co][c][ky][kx] = sum_{py,px} sum_ci dWc[u(py,px,ky,kx)][ci][co] Wd[ci][c][a][b]  +  S_{ky,kx}[co] bd[c]
+//   dWd[ci][c][a][b]   = sum_{(py,ky): a, (px,kx): b} sum_co dWc[u][ci][co] W3[co][c][ky][kx]
+//   dbd[c]             = sum_{ky,kx} sum_co W3[co][c][ky][kx] S_{ky,kx}[co]
+// S_t[co] = sum of dL/dy[co] over the output pixels whose tap t lies inside the upsampled image (the 3x3 conv zero-pads
+// it): total minus the excluded border row / column plus the doubly excluded corner.
+struct UpFuseGradBatch { UpFuseGradJob j[5]; int n; };
+
+__device__ __forceinline__ float upfuse_S(const UpFuseGradJob& J, int ky, int kx, int co) {
+  const float* B = J.border;
+  float s = J.db3[co];
+  if (ky == 0) s -= B[0 * J.co_pad + co];
+  if (ky == 2) s -= B[1 * J.co_pad + co];
+  if (kx == 0) s -= B[2 * J.co_pad + co];
+  if (kx == 2) s -= B[3 * J.co_pad + co];
+  if (ky != 1 && kx != 1) s += B[(4 + (ky >> 1) * 2 + (kx >> 1)) * J.co_pad + co];
+  return s;
+}
+
+__global__ void upfuse_grad_kernel(const __grid_constant__ UpFuseGradBatch b) {
+  pdl_enter();
+  const UpFuseGradJob& J = b.j[blockIdx.y];
+  const int cin3 = J.Cu + J.Cs;
+  const long long plane = (long long)J.ci_pad * J.co_pad;
+  const long long n3 = (long long)J.Co * J.Cu * 9, nd = (long long)J.Ci * J.Cu * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3 + nd + J.Cu;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n3) {
+      // dW3: co fastest -> dWc reads coalesced over co, Wd read is a warp broadcast
+      const int co = (int)(i % J.Co);
+      const int c = (int)((i / J.Co) % J.Cu);
+      const int t = (int)(i / ((long long)J.Co * J.Cu));
+      const int ky = t / 3, kx = t - ky * 3;
+      float acc = upfuse_S(J, ky, kx, co) * J.bd[c];
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int yo = py + ky - 1, xo = px + kx - 1;
+          const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1), sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
+          const int u = ((py * 2 + px) * 2 + syi) * 2 + sxi;
+          const float* d = J.dwc + u * plane + co;
+          const float* w = J.wd + (long long)c * 4 + (yo & 1) * 2 + (xo & 1);
+          float a = 0.f;
+          for (int ci = 0; ci < J.Ci; ++ci) a = fmaf(__ldg(d + (long long)ci * J.co_pad), __ldg(w + (long long)ci * J.Cu * 4), a);
+          acc += a;
+        }
+      J.dw3[((long long)co * cin3 + c) * 9 + t] = acc;
+    } else if (i < n3 + nd) {
+      // dWd: c fastest -> dWc read is a warp broadcast, W3 read strided by 9 floats
+      const long long r = i - n3;
+      const int c = (int)(r % J.Cu);
+      const int ci = (int)((r / J.Cu) % J.Ci);
+      const int ab = (int)(r / ((long long)J.Cu * J.Ci));
+      const int a = ab >> 1, bb = ab & 1;
+      float acc = 0.f;
+      for (int py = 0; py < 2; ++py)
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yo = py + ky - 1;
+          if ((yo & 1) != a) continue;
+          const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1);
+          for (int px = 0; px < 2; ++px)
+            for (int kx = 0; kx < 3; ++kx) {
+              const int xo = px + kx - 1;
+              if ((xo & 1) != bb) continue;
+              const int sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
+              const int u = ((py * 2 + px) * 2 + syi) * 2 + sxi;
+              const float* d = J.dwc + u * plane + (long long)ci * J.co_pad;
+              const float* w = J.w3 + (long long)c * 9 + ky * 3 + kx;
+              float s = 0.f;
+              for (int co = 0; co < J.Co; ++co) s = fmaf(__ldg(d + co), __ldg(w + (long long)co * cin3 * 9), s);
+              acc += s;
+            }
+        }
+      J.dwd[((long long)ci * J.Cu + c) * 4 + ab] = acc;
+    } else {
+      const int c = (int)(i - n3 - nd);
+      float acc = 0.f;
+      for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < J.Co; ++co) acc = fmaf(J.w3[((long long)co * cin3 + c) * 9 + t], upfuse_S(J, t / 3, t % 3, co), acc);
+      J.dbd[c] = acc;
+    }
+  }
+}
+
+int launch_upfuse_grad(const UpFuseGradJob* jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  N2N_CHECK_ARG(njobs <= 5, "upfuse_grad: too many jobs");
+  UpFuseGradBatch b;
+  b.n = njobs;
+  long long maxtotal = 1;
+  for (int i = 0; i < njobs; ++i) {
+    b.j[i] = jobs[i];
+    const long long tot = (long long)jobs[i].Co * jobs[i].Cu * 9 + (long long)jobs[i].Ci * jobs[i].Cu * 4 + jobs[i].Cu;
+    if (tot > maxtotal) maxtotal = tot;
+  }
+  dim3 grid(grid_for(maxtotal, 128, 8), njobs);
+  (void)launch_pdl_v(upfuse_grad_kernel, grid, dim3(128), 0, st, b);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+// border[k][co_pad], k = 0: first row, 1: last row, 2: first column, 3: last column, 4..7: corners (top-left, top-right,
+// bottom-left, bottom-right) of a C16 bf16 tensor, summed over the batch.  One block per (k, channel block): fixed-order sums.
+__global__ void __launch_bounds__(256) border_sums_kernel(View g, float* __restrict__ border, int co_pad) {
+  pdl_enter();
+  __shared__ float red[8][16];
+  const int k = blockIdx.x, cb = blockIdx.y;
+  const int H = g.H, W = g.W;
+  const long long count = k < 2 ? (long long)g.N * W : (k < 4 ? (long long)g.N * H : g.N);
+  float acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+  const __nv_bfloat16* base = (const __nv_bfloat16*)g.ptr + (long long)cb * g.sCb;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+    int n, y, x;
+    if (k < 2) { n = (int)(i / W); x = (int)(i - (long long)n * W); y = k == 0 ? 0 : H - 1; }
+    else if (k < 4) { n = (int)(i / H); y = (int)(i - (long long)n * H); x = k == 2 ? 0 : W - 1; }
+    else { n = (int)i; y = (k - 4) >> 1 ? H - 1 : 0; x = (k - 4) & 1 ? W - 1 : 0; }
+    float v[16];
+    Block16<__nv_bfloat16>::load(base + (long long)n * g.sN + (long long)y * g.sY + (long long)x * g.sX, v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] += v[q];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    float v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    border[(long long)k * co_pad + cb * 16 + threadIdx.x] = s;
+  }
+}
+
+int launch_border_sums(const View& g, float* border, int co_pad, cudaStream_t st) {
+  N2N_CHECK_ARG(g.Cb * 16 <= co_pad, "border_sums: bad channel count");
+  (void)launch_pdl_v(border_sums_kernel, dim3(8, g.Cb), dim3(256), 0, st, g, border, co_pad);
   N2N_LAUNCH_CHECK();
   return 0;
 }

@@ -63,6 +63,11 @@ struct n2n_unet_plan {
   bool upfuse[25] = {false};
   UpConvGeom ug[25];
   size_t off_upw[25][2] = {{0}}, off_upbias[25] = {0}, off_upcorr[25] = {0};
+  // training plans: transposed composites (fused input gradient), per-parity split-K partials of the composite weight
+  // gradient, their dense reduction, border sums of dL/dy (chain rule back to the two layers' own gradients)
+  size_t off_upwt[25] = {0}, off_dwcp[25][4] = {{0}}, off_dwc[25] = {0}, off_border[25] = {0};
+  int splits_up[25] = {0};
+  bool share_up[25] = {false};           // borrow the donor's forward composites of this level
   bool fused_layer(int i) const { return (L[i].kind == L_DECONV && upfuse[i]) || (i > 0 && L[i - 1].kind == L_DECONV && upfuse[i - 1]); }
   Buf act[B_COUNT], grd[B_COUNT];
   size_t off_wp[25], off_wd[25], off_bias[25], off_partial[25], off_bpartial[25];
@@ -174,8 +179,17 @@ static void plan_layout(n2n_unet_plan* p) {
     U.skip_blocks = dc == 19 ? p->skipb : nfb;
     { const char* e = getenv("N2N_UPFUSE_LEVELS");      // diagnostic: bit (dc - 7) / 3 enables the fusion of that level
       if (e && !((atoi(e) >> ((dc - 7) / 3)) & 1)) { p->upfuse[dc] = false; continue; } }
-    p->upfuse[dc] = !p->bwd && p->dtype == N2N_BF16 && !p->ksplit[dc + 1] &&
+    p->upfuse[dc] = p->dtype == N2N_BF16 && !p->ksplit[dc + 1] &&
                     slab_upconv_ok(p->dtype, p->N, p->lh(lv), p->lw(lv), U.ci_blocks, U.skip_blocks, U.co_blocks, U.region_bytes());
+    if (p->upfuse[dc] && p->bwd) {
+      // the backward runs in composite form too: transposed composites resident for the input gradient, the slab
+      // weight-gradient engine for the four parity launches
+      const char* e = getenv("N2N_NO_UPFUSE_TRAIN");
+      p->splits_up[dc] = wgrad_slab_splits(4, U.ci_blocks, U.co_blocks, false,
+                                           (long long)p->N * ((p->lh(lv) + 15) / 16) * ((p->lw(lv) + 7) / 8));
+      p->upfuse[dc] = !(e && atoi(e)) && p->splits_up[dc] > 0 &&
+                      slab_upconv_ok(p->dtype, p->N, p->lh(lv), p->lw(lv), U.co_blocks, 0, U.ci_blocks, upconv_wt_bytes(U));
+    }
   }
   // ---- workspace layout ----
   size_t off = 0;
@@ -205,6 +219,15 @@ static void plan_layout(n2n_unet_plan* p) {
     p->off_upcorr[dc] = take(9 * p->ug[dc].co_blocks * 16 * sizeof(float));
   }
   if (p->bwd) {
+    for (int dc = 7; dc <= 19; dc += 3) {
+      if (!p->upfuse[dc]) continue;
+      const UpConvGeom& U = p->ug[dc];
+      const size_t plane = (size_t)U.ci_blocks * 16 * U.co_blocks * 16 * sizeof(float);
+      p->off_upwt[dc] = take(upconv_wt_bytes(U));
+      for (int q = 0; q < 4; ++q) p->off_dwcp[dc][q] = take((size_t)p->splits_up[dc] * 4 * plane);
+      p->off_dwc[dc] = take(16 * plane);
+      p->off_border[dc] = take(8 * U.co_blocks * 16 * sizeof(float));
+    }
     p->head_splits = head_bwd_splits(p->dtype, p->hb, p->out_nc, p->N, p->H, p->W);
     for (int b = 0; b < B_COUNT; ++b)
       p->grd[b].off = take((size_t)p->N * p->grd[b].Cb * p->lh(p->grd[b].lvl) * p->lw(p->grd[b].lvl) * 16 * es);
@@ -227,10 +250,16 @@ static void plan_layout(n2n_unet_plan* p) {
           p->off_wd20_full = take(p->L[i].dgrad_pack_bytes(p->dtype, p->L[i].cin_blocks()));   // only used when dL/dx is wanted
         }
       }
+      if (i >= 8 && p->L[i - 1].kind == L_DECONV && p->upfuse[i - 1] && !(p->im2col && i == 20)) {
+        // fused up-conv: this conv's own weight-gradient launch only covers its skip channels
+        LayerGeom S = p->L[i]; S.cin = chan1(p->L[i].cin.cnt[1]);
+        p->splits[i] = layer_wgrad_splits(S, p->dtype, p->N, p->lh(p->act[io.in_buf].lvl), p->lw(p->act[io.in_buf].lvl));
+      }
       // nin_a / nin_b: their weight gradients come out of the fused head backward, one partial per CTA of it
       if ((i == 22 || i == 23) && p->head_splits > 0) p->splits[i] = p->head_splits;
       p->off_partial[i] = take(p->L[i].partial_bytes(p->splits[i]));
-      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes(p->splits[i]));
+      // (the fused level-1 backward sums dec_conv1a's bias gradient in its im2col launch: splits_skip rows)
+      p->off_bpartial[i] = take(p->L[i].bias_partial_bytes((i == 20 && p->splits_skip > p->splits[i]) ? p->splits_skip : p->splits[i]));
     }
   }
   p->total = off;
@@ -313,6 +342,7 @@ extern "C" int n2n_unet_launches(const n2n_unet_plan* plan, int backward) {
 extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* donor, const void* donor_ws) {
   N2N_CHECK_ARG(plan != nullptr, "unet_share_weights: plan is NULL");
   plan->donor = nullptr; plan->donor_ws = nullptr;
+  for (int i = 0; i < 25; ++i) plan->share_up[i] = false;
   if (!donor) return 0;
   if (plan->arch != ARCH_UNET || donor->arch != ARCH_UNET) return 1;
   N2N_CHECK_ARG(donor_ws != nullptr && donor != plan, "unet_share_weights: bad donor");
@@ -325,6 +355,11 @@ extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* 
     plan->share[i] = !donor->fused_layer(i) && !plan->fused_layer(i) &&
                      donor->ksplit[i] == plan->ksplit[i] && donor->deconv_pair[i] == plan->deconv_pair[i] &&
                      donor->L[i].fwd_pack_bytes(donor->dtype) == plan->L[i].fwd_pack_bytes(plan->dtype);
+  // forward composites of a fused level could be borrowed too, but the borrower of a training step is the plan with
+  // the backward pass, which has to run the composite pack anyway (it also emits the transposed composites)
+  for (int dc = 7; dc <= 19; dc += 3)
+    plan->share_up[dc] = !plan->bwd && donor->upfuse[dc] && plan->upfuse[dc] &&
+                         donor->ug[dc].region_bytes() == plan->ug[dc].region_bytes() && donor->ug[dc].skip_im2col == plan->ug[dc].skip_im2col;
   plan->donor = donor; plan->donor_ws = donor_ws;
   return 0;
 }
@@ -348,15 +383,24 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     int nuj = 0;
     for (int dc = 7; dc <= 19; dc += 3) {
       if (!p->upfuse[dc]) continue;
+      if (p->donor && p->share_up[dc] && !p->bwd) continue;         // forward composites borrowed, nothing else to pack
       const UpConvGeom& U = p->ug[dc];
       const LayerGeom& D = p->L[dc]; const LayerGeom& A = p->L[dc + 1];
+      if (p->bwd && !U.skip_im2col) {
+        // input gradient of the conv's skip channels: its own transposed weights, skip segment only
+        PackJob k = make_dgrad_pack(A, params[2 * (dc + 1)], (char*)ws + p->off_wd[dc + 1], U.skip_blocks);
+        k.nseg.n = 1; k.nseg.src0[0] = D.cout; k.nseg.cnt[0] = A.cin.real() - D.cout; k.nseg.dst0[0] = 0;
+        jobs.push_back(k);
+      }
       UpFuseJob& j = uj[nuj++];
+      if (p->bwd) { j.dst_t = (char*)ws + p->off_upwt[dc]; j.gco = (U.co_blocks + 2) / 3; j.ci_rows = U.ci_blocks * 16; }
       j.w3 = params[2 * (dc + 1)]; j.b3 = params[2 * (dc + 1) + 1]; j.wd = params[2 * dc]; j.bd = params[2 * dc + 1];
       j.Ci = D.cin.real(); j.Cu = D.cout; j.Cs = A.cin.real() - D.cout; j.Co = A.cout;
       j.ngroups = U.gu(); j.co_pad = U.co_blocks * 16;
       j.bias_full = (float*)((char*)ws + p->off_upbias[dc]); j.corr = (float*)((char*)ws + p->off_upcorr[dc]);
       for (int py = 0; py < 2; ++py) {
         j.dst[py] = (char*)ws + p->off_upw[dc][py];
+        if (p->donor && p->share_up[dc]) continue;                  // skip slabs live in the donor's regions
         // the conv's skip-channel slabs behind the composite slabs of each parity's region
         PackJob k = make_fwd_pack(A, params[2 * (dc + 1)], (char*)ws + p->off_upw[dc][py] + U.skip_base());
         k.cin_blocks = U.skip_blocks;
@@ -397,7 +441,9 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
       } else {
         jobs.push_back(make_fwd_pack(p->L[i], params[2 * i], (char*)ws + p->off_wp[i]));
       }
-      if (p->bwd && p->ksplit[i]) {
+      if (p->bwd && p->fused_layer(i)) {
+        // composite backward: no per-layer input-gradient pack (the skip segment's was queued above)
+      } else if (p->bwd && p->ksplit[i]) {
         const LayerGeom& G = p->L[i];
         const int b0 = cblocks(G.cin.cnt[0]), b1 = cblocks(G.cin.cnt[1]);
         PackJob j = make_dgrad_pack(G, params[2 * i], (char*)ws + p->off_wd[i], b0);      // rows = first segment's channels
@@ -447,10 +493,13 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
       View xsrc = p->view(p->act, ws, dio.in_buf, dio.in_cb0, dio.in_cb);
       View skip = p->view(p->act, ws, io.in_buf, p->L[dc].cout_blocks(), U.skip_blocks);
       View yfull = p->view(p->act, ws, io.out_buf, io.out_cb0, L.cout_blocks());
+      const bool borrowed = p->donor && p->share_up[dc];
+      const char* wbase = borrowed ? (const char*)p->donor_ws : (const char*)ws;
+      const n2n_unet_plan* wp_plan = borrowed ? p->donor : p;
       for (int py = 0; py < 2; ++py) {
-        TapGemm g = make_upconv_fwd(U, dt, xsrc, skip, yfull, py, (const char*)ws + p->off_upw[dc][py],
-                                    (const float*)((const char*)ws + p->off_upbias[dc]),
-                                    (const float*)((const char*)ws + p->off_upcorr[dc]));
+        TapGemm g = make_upconv_fwd(U, dt, xsrc, skip, yfull, py, wbase + wp_plan->off_upw[dc][py],
+                                    (const float*)(wbase + wp_plan->off_upbias[dc]),
+                                    (const float*)(wbase + wp_plan->off_upcorr[dc]));
         if (io.act) { g.act = 1; g.slope = 0.2f; }
         const int r = launch_tapgemm(g, st);
         if (r != 0) return r;
@@ -624,6 +673,59 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
                                p->view(p->grd, ws, act_buf, 0, p->nfb), 0.2f, dt, st);
   };
 
+  // Fused up-conv level (deconv dc + conv dc + 1) in composite form: four parity launches of the weight-gradient engine
+  // (dWc partials), the conv's own weight-gradient launch restricted to its skip channels (it also sums the bias
+  // gradient), ONE input-gradient launch with the transposed composites, the skip channels' input gradient, and the
+  // border sums the chain rule needs (reduced / chained after the join, see below).
+  auto fused_bwd = [&](int dc) -> int {
+    const UpConvGeom& U = p->ug[dc];
+    const int ca = dc + 1;
+    const LayerIO& dio = p->io[dc];
+    const LayerIO& aio = p->io[ca];
+    const LayerGeom& A = p->L[ca];
+    View xsrc = p->view(p->act, ws, dio.in_buf, dio.in_cb0, dio.in_cb);
+    View gy = p->view(p->grd, ws, aio.out_buf, aio.out_cb0, A.cout_blocks());
+    const int upb = p->L[dc].cout_blocks();
+    View skip_act = p->view(p->act, ws, aio.in_buf, upb, U.skip_blocks);
+    {
+      cudaStream_t wst = main_st;
+      if (use_side) {
+        N2N_CUDA(cudaEventRecord(p->ev_ready, main_st));
+        N2N_CUDA(cudaStreamWaitEvent(p->side, p->ev_ready, 0));
+        wst = p->side;
+      }
+      for (int q = 0; q < 4; ++q)
+        N2N_TRY(launch_tapwgrad(make_upconv_wgrad(U, dt, xsrc, gy, q >> 1, q & 1, (float*)((char*)ws + p->off_dwcp[dc][q]),
+                                                  p->splits_up[dc]), wst));
+      if (U.skip_im2col) {
+        LayerGeom S = A; S.kind = L_CONV1; S.cin = chan1(16 * p->kb);
+        N2N_TRY(launch_tapwgrad(make_conv_wgrad(S, dt, skip_act, gy, (float*)((char*)ws + p->off_partial_skip),
+                                                (float*)((char*)ws + p->off_bpartial[ca]), p->splits_skip), wst));
+      } else {
+        LayerGeom S = A; S.cin = chan1(A.cin.cnt[1]);
+        N2N_TRY(launch_tapwgrad(make_conv_wgrad(S, dt, skip_act, gy, (float*)((char*)ws + p->off_partial[ca]),
+                                                (float*)((char*)ws + p->off_bpartial[ca]), p->splits[ca]), wst));
+      }
+      N2N_TRY(launch_border_sums(gy, (float*)((char*)ws + p->off_border[dc]), U.co_blocks * 16, wst));
+    }
+    // input gradients (main stream)
+    TapGemm g = make_upconv_dgrad(U, dt, gy, p->view(p->grd, ws, dio.in_buf, dio.in_cb0, U.ci_blocks), (const char*)ws + p->off_upwt[dc]);
+    g.has_mask = true; g.mask = xsrc; g.slope = 0.2f;          // the deconv's input is an activated conv output
+    N2N_TRY(launch_tapgemm(g, st));
+    if (!U.skip_im2col) {
+      TapGemm gs = make_conv_dgrad(A, dt, gy, p->view(p->grd, ws, aio.in_buf, upb, U.skip_blocks), (const char*)ws + p->off_wd[ca], U.skip_blocks);
+      N2N_TRY(launch_tapgemm(gs, st));
+    } else if (want_dx) {
+      // dL/dx requested: the raw-input channels of dec_conv1a's concat (packed on the spot; not on the training path)
+      PackJob j = make_dgrad_pack(A, params[2 * ca], (char*)ws + p->off_wd20_full, p->inb);
+      j.nseg.n = 1; j.nseg.src0[0] = p->L[dc].cout; j.nseg.cnt[0] = p->in_nc; j.nseg.dst0[0] = 0;
+      N2N_TRY(launch_pack(&j, 1, dt, st));
+      TapGemm gs = make_conv_dgrad(A, dt, gy, p->view(p->grd, ws, B_CAT0, p->c2b, p->inb), (const char*)ws + p->off_wd20_full, p->inb);
+      N2N_TRY(launch_tapgemm(gs, st));
+    }
+    return 0;
+  };
+
   // head + level-0 decoder
   if (p->head_splits > 0) {
     // input gradients of the three 1x1 layers and the weight gradients of nin_a / nin_b in one kernel
@@ -648,15 +750,18 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
     }
   }
   N2N_TRY(wgrad(21)); N2N_TRY(dgrad(21, p->L[21].cin_blocks(), true, false));
-  N2N_TRY(wgrad(20));
-  N2N_TRY(dgrad(20, (want_dx || !p->im2col) ? p->c2b + p->inb : p->c2b, false, false));
-  // decoder levels 1..4: up{k} then dec_conv{k+1}b / a
-  for (int base = 19; base >= 10; base -= 3) {
-    N2N_TRY(wgrad(base));     N2N_TRY(dgrad(base, p->c2b, true, false));          // up_k: input is dec_conv_{k+1}b output
-    N2N_TRY(wgrad(base - 1)); N2N_TRY(dgrad(base - 1, p->c2b, true, false));      // dec_conv b
-    N2N_TRY(wgrad(base - 2)); N2N_TRY(dgrad(base - 2, p->L[base - 2].cin_blocks(), false, false));  // dec_conv a -> concat
+  // decoder levels 1..5: dec_conv{k}a then up{k} (one fused composite level when the plan fused them), dec_conv{k+1}b
+  for (int dc = 19; dc >= 7; dc -= 3) {
+    if (p->upfuse[dc]) {
+      N2N_TRY(fused_bwd(dc));
+    } else {
+      N2N_TRY(wgrad(dc + 1));                                                      // dec_conv a -> concat
+      if (dc == 19) N2N_TRY(dgrad(20, (want_dx || !p->im2col) ? p->c2b + p->inb : p->c2b, false, false));
+      else N2N_TRY(dgrad(dc + 1, p->L[dc + 1].cin_blocks(), false, false));
+      N2N_TRY(wgrad(dc)); N2N_TRY(dgrad(dc, p->L[dc].cin_blocks(), true, false));  // up_k: input is an activated conv output
+    }
+    if (dc > 7) { N2N_TRY(wgrad(dc - 1)); N2N_TRY(dgrad(dc - 1, p->c2b, true, false)); }   // dec_conv{k+1}b
   }
-  N2N_TRY(wgrad(7)); N2N_TRY(dgrad(7, p->nfb, true, false));                      // up5: input is enc_conv6 output
   N2N_TRY(wgrad(6)); N2N_TRY(dgrad(6, p->nfb, false, false));                     // enc_conv6: input is pool5 (no act)
   N2N_TRY(unpool(B_E5, B_P5, 0));
   // encoder: the pooled tensors also feed the skip connections, whose grads are already in the
@@ -677,11 +782,46 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   }
   // partials -> PyTorch-layout fp32 gradients
   {
-    UnpackJob jobs[26];
-    int nj = 0;
+    std::vector<UnpackJob> jobs;
+    UpFuseGradJob gj[5];
+    int ngj = 0;
     for (int i = 0; i < 25; ++i) {
+      if (p->L[i].kind == L_DECONV && p->upfuse[i]) continue;                 // gradients come out of the chain-rule kernel
       UnpackJob j = make_unpack(p->L[i], (const float*)((char*)ws + p->off_partial[i]),
                                 (const float*)((char*)ws + p->off_bpartial[i]), p->splits[i], grads[2 * i], grads[2 * i + 1]);
+      if (i > 0 && p->L[i - 1].kind == L_DECONV && p->upfuse[i - 1]) {
+        // fused up-conv level: (1) the four parity partials of the composite weight gradient -> one dense [16][ci][co]
+        // buffer, (2) this conv's skip-channel weights + its bias, (3) queue the chain rule for after the reductions
+        const int dc = i - 1;
+        const UpConvGeom& U = p->ug[dc];
+        const int cip = U.ci_blocks * 16, cop = U.co_blocks * 16;
+        float* dense = (float*)((char*)ws + p->off_dwc[dc]);
+        for (int q = 0; q < 4; ++q) {
+          UnpackJob d;
+          d.partial = (const float*)((char*)ws + p->off_dwcp[dc][q]); d.bias_partial = nullptr;
+          d.dst_w = dense + (size_t)q * 4 * cip * cop; d.dst_b = nullptr;
+          d.splits = p->splits_up[dc]; d.ntaps = 4; d.npad = cop; d.cpad = cip; d.bias_rows = 0;
+          d.s_t = (long long)cip * cop; d.s_n = 1; d.s_c = cop;
+          d.nseg.n = 1; d.nseg.src0[0] = 0; d.nseg.cnt[0] = cop; d.nseg.dst0[0] = 0;
+          d.cseg.n = 1; d.cseg.src0[0] = 0; d.cseg.cnt[0] = cip; d.cseg.dst0[0] = 0;
+          jobs.push_back(d);
+        }
+        if (U.skip_im2col) {
+          j.partial = (const float*)((char*)ws + p->off_partial_skip); j.splits = p->splits_skip; j.bias_rows = p->splits_skip;
+          j.ntaps = 1; j.cpad = 16 * p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = p->L[dc].cout;
+        } else {
+          j.cpad = U.skip_blocks * 16;
+          j.cseg.n = 1; j.cseg.src0[0] = p->L[dc].cout; j.cseg.cnt[0] = p->L[i].cin.cnt[1]; j.cseg.dst0[0] = 0;
+        }
+        jobs.push_back(j);
+        UpFuseGradJob& g = gj[ngj++];
+        g.dwc = dense; g.w3 = params[2 * i]; g.wd = params[2 * dc]; g.bd = params[2 * dc + 1];
+        g.border = (const float*)((char*)ws + p->off_border[dc]); g.db3 = grads[2 * i + 1];
+        g.dw3 = grads[2 * i]; g.dwd = grads[2 * dc]; g.dbd = grads[2 * dc + 1];
+        g.Ci = p->L[dc].cin.real(); g.Cu = p->L[dc].cout; g.Cs = p->L[i].cin.real() - p->L[dc].cout; g.Co = p->L[i].cout;
+        g.ci_pad = cip; g.co_pad = cop;
+        continue;
+      }
       if (p->im2col && i == 0) {
         j.ntaps = 1; j.cpad = 16 * p->kb; j.im2col_nc = p->in_nc; j.im2col_c0 = 0;
       } else if (p->im2col && i == 20) {
@@ -689,11 +829,12 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
         UnpackJob k = j;
         k.partial = (const float*)((char*)ws + p->off_partial_skip); k.bias_partial = nullptr; k.dst_b = nullptr;
         k.splits = p->splits_skip; k.ntaps = 1; k.cpad = 16 * p->kb; k.im2col_nc = p->in_nc; k.im2col_c0 = 2 * p->nf;
-        jobs[nj++] = k;
+        jobs.push_back(k);
       }
-      jobs[nj++] = j;
+      jobs.push_back(j);
     }
-    N2N_TRY(launch_unpack(jobs, nj, st));
+    N2N_TRY(launch_unpack(jobs.data(), (int)jobs.size(), st));
+    N2N_TRY(launch_upfuse_grad(gj, ngj, st));
   }
   p->bwd_launches = (int)(g_launch_count - launches0);
   return 0;

@@ -111,3 +111,46 @@ def test_bf16_training_step_other_widths_vs_oracle(dev, nf):
         assert torch.isfinite(a).all(), k
         cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-300))
         assert cos > 0.97, (k, cos)
+
+
+@pytest.mark.parametrize("in_nc,nf,shape", [(1, 48, (3, 64, 96)), (1, 48, (5, 128, 128)), (3, 48, (2, 64, 64)), (1, 32, (2, 64, 64))])
+def test_composite_backward_matches_layerwise_and_oracle(dev, monkeypatch, in_nc, nf, shape):
+    """Training pass with the fused up-conv levels: forward on composite weights, input gradient with the transposed
+    composites, composite weight gradient + chain rule back to dec_conv{k}a / up{k} (incl. the ConvTranspose bias gradient
+    through border-aware sums of dL/dy) — every parameter gradient against the layer-by-layer bf16 backward
+    (N2N_NO_UPFUSE_TRAIN=1) and the fp32 oracle, with non-zero biases everywhere."""
+    p = _weights(in_nc, nf, 7, bias_scale=0.05)
+    n, h, w = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(n, in_nc, h, w, generator=g)
+    tgt = torch.rand(n, in_nc, h, w, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    (O.unet_forward(pr, x) - tgt).square().mean().backward()
+    res = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("N2N_NO_UPFUSE_TRAIN", raising=False)
+        else:
+            monkeypatch.setenv("N2N_NO_UPFUSE_TRAIN", "1")
+        net = _net(dev, in_nc, nf, p)
+        xd = x.to(dev).requires_grad_(in_nc == 3)
+        loss = (net(xd) - tgt.to(dev)).square().mean()
+        loss.backward()
+        res[fused] = ({k: v.grad.detach().cpu().double() for k, v in net.named_parameters()}, float(loss),
+                      xd.grad.detach().cpu().double() if in_nc == 3 else None)
+    assert abs(res[True][1] - res[False][1]) <= 2e-3 * abs(res[False][1])
+    worst = 1.0
+    for k in res[True][0]:
+        a, b, r = res[True][0][k].flatten(), res[False][0][k].flatten(), pr[k].grad.double().flatten()
+        assert torch.isfinite(a).all(), k
+        cos_ab = float((a * b).sum() / (a.norm() * b.norm() + 1e-300))
+        cos_ar = float((a * r).sum() / (a.norm() * r.norm() + 1e-300))
+        cos_br = float((b * r).sum() / (b.norm() * r.norm() + 1e-300))
+        worst = min(worst, cos_ar)
+        # as close to the fp32 oracle as the layer-by-layer bf16 backward is (both carry bf16 activations / gradients)
+        assert cos_ar >= min(0.98, cos_br - 0.01), (k, cos_ar, cos_br, cos_ab)
+        assert abs(float(a.norm() / (r.norm() + 1e-300)) - 1.0) < 0.05, (k, float(a.norm()), float(r.norm()))
+    if in_nc == 3:
+        a, b = res[True][2].flatten(), res[False][2].flatten()
+        assert float((a * b).sum() / (a.norm() * b.norm())) > 0.995
+    print(f"composite backward: worst cosine vs fp32 oracle {worst:.5f}")
