@@ -339,7 +339,7 @@ struct UpFuseGradJob {
 };
 int launch_upfuse_grad(const UpFuseGradJob* jobs, int njobs, cudaStream_t st);
 // border[8][co_pad] of a C16 bf16 gradient tensor (see UpFuseGradJob::border); deterministic block reductions
-int launch_border_sums(const View& g, float* border, int co_pad, cudaStream_t st);
+int launch_border_sums(const View* g, float* const* border, const int* co_pad, int n, cudaStream_t st);
 
 size_t packed_weight_bytes(int dtype, int ntaps, int nout_pad, int cin_blocks);
 

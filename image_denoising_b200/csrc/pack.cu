@@ -32,7 +32,7 @@ __device__ __forceinline__ int seg_lookup(const Segs& s, int dst, long long* ext
 }
 
 struct PackBatch { PackJob j[8]; int n; };
-struct UnpackBatch { UnpackJob j[8]; int n; };
+struct UnpackBatch { UnpackJob j[16]; int n; };
 
 template <bool BF16>
 __global__ void pack_kernel(const __grid_constant__ PackBatch b) {
@@ -274,12 +274,17 @@ upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
     for (int co = threadIdx.x; co < J.co_pad; co += blockDim.x) {
       float tap[9];
       float full = 0.f;
-      for (int t = 0; t < 9; ++t) {
-        float acc = 0.f;
-        if (co < J.Co)
-          for (int c = 0; c < J.Cu; ++c) acc = fmaf(J.w3[((long long)co * cin3 + c) * 9 + t], J.bd[c], acc);
-        tap[t] = acc; full += acc;
-      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap[t] = 0.f;
+      if (co < J.Co)
+        for (int c = 0; c < J.Cu; ++c) {                  // the nine taps of (co, c) are contiguous
+          const float bdc = J.bd[c];
+          const float* w = J.w3 + ((long long)co * cin3 + c) * 9;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) tap[t] = fmaf(__ldg(w + t), bdc, tap[t]);
+        }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) full += tap[t];
       J.bias_full[co] = co < J.Co ? J.b3[co] + full : 0.f;
       for (int cls = 0; cls < 9; ++cls) {
         const int yc = cls / 3, xc = cls % 3;
@@ -333,65 +338,110 @@ __device__ __forceinline__ float upfuse_S(const UpFuseGradJob& J, int ky, int kx
   return s;
 }
 
-__global__ void upfuse_grad_kernel(const __grid_constant__ UpFuseGradBatch b) {
+// Tiled like the pack kernel (a one-thread-per-output version spent 470 us per step on strided global reads):
+//   blocks [0, T3):      (16 co x 16 c) tiles of dW3 — all nine taps per thread, reduction over ci in chunks of 16
+//   blocks [T3, T3+Td):  (16 ci x 16 c) tiles of dWd — all four (a, b) per thread, reduction over co in chunks of 16
+//   last block:          dbd
+__global__ void __launch_bounds__(kUfTile * kUfTile)
+upfuse_grad_kernel(const __grid_constant__ UpFuseGradBatch b) {
   pdl_enter();
   const UpFuseGradJob& J = b.j[blockIdx.y];
+  __shared__ float sD[kUfTile][16][kUfTile + 1];     // [reduction index][composite u][co or ci]
+  __shared__ float sW[kUfTile][9][kUfTile];          // [reduction index][tap or ab][c]
   const int cin3 = J.Cu + J.Cs;
   const long long plane = (long long)J.ci_pad * J.co_pad;
-  const long long n3 = (long long)J.Co * J.Cu * 9, nd = (long long)J.Ci * J.Cu * 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3 + nd + J.Cu;
-       i += (long long)gridDim.x * blockDim.x) {
-    if (i < n3) {
-      // dW3: co fastest -> dWc reads coalesced over co, Wd read is a warp broadcast
-      const int co = (int)(i % J.Co);
-      const int c = (int)((i / J.Co) % J.Cu);
-      const int t = (int)(i / ((long long)J.Co * J.Cu));
-      const int ky = t / 3, kx = t - ky * 3;
-      float acc = upfuse_S(J, ky, kx, co) * J.bd[c];
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-          const int yo = py + ky - 1, xo = px + kx - 1;
-          const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1), sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
-          const int u = ((py * 2 + px) * 2 + syi) * 2 + sxi;
-          const float* d = J.dwc + u * plane + co;
-          const float* w = J.wd + (long long)c * 4 + (yo & 1) * 2 + (xo & 1);
-          float a = 0.f;
-          for (int ci = 0; ci < J.Ci; ++ci) a = fmaf(__ldg(d + (long long)ci * J.co_pad), __ldg(w + (long long)ci * J.Cu * 4), a);
-          acc += a;
-        }
-      J.dw3[((long long)co * cin3 + c) * 9 + t] = acc;
-    } else if (i < n3 + nd) {
-      // dWd: c fastest -> dWc read is a warp broadcast, W3 read strided by 9 floats
-      const long long r = i - n3;
-      const int c = (int)(r % J.Cu);
-      const int ci = (int)((r / J.Cu) % J.Ci);
-      const int ab = (int)(r / ((long long)J.Cu * J.Ci));
-      const int a = ab >> 1, bb = ab & 1;
-      float acc = 0.f;
-      for (int py = 0; py < 2; ++py)
-        for (int ky = 0; ky < 3; ++ky) {
-          const int yo = py + ky - 1;
-          if ((yo & 1) != a) continue;
-          const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1);
+  const int tco = (J.Co + kUfTile - 1) / kUfTile, tc = (J.Cu + kUfTile - 1) / kUfTile, tci = (J.Ci + kUfTile - 1) / kUfTile;
+  const int T3 = tco * tc, Td = tci * tc;
+  const int tr = threadIdx.x / kUfTile, tcx = threadIdx.x % kUfTile;      // tile row (co or ci), tile column (c)
+  if ((int)blockIdx.x < T3) {
+    const int co0 = ((int)blockIdx.x / tc) * kUfTile, c0 = ((int)blockIdx.x % tc) * kUfTile;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    for (int i0 = 0; i0 < J.Ci; i0 += kUfTile) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kUfTile * 16 * kUfTile; i += kUfTile * kUfTile) {
+        const int co = i % kUfTile, u = (i / kUfTile) % 16, ci = i / (kUfTile * 16);
+        sD[ci][u][co] = (i0 + ci < J.Ci && co0 + co < J.Co) ? __ldg(J.dwc + u * plane + (long long)(i0 + ci) * J.co_pad + co0 + co) : 0.f;
+      }
+      for (int i = threadIdx.x; i < kUfTile * kUfTile * 4; i += kUfTile * kUfTile) {
+        const int ab = i % 4, c = (i / 4) % kUfTile, ci = i / (4 * kUfTile);
+        sW[ci][ab][c] = (i0 + ci < J.Ci && c0 + c < J.Cu) ? __ldg(J.wd + ((long long)(i0 + ci) * J.Cu + c0 + c) * 4 + ab) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int ci = 0; ci < kUfTile; ++ci) {
+        float d[16], w[4];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) d[u] = sD[ci][u][tr];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = sW[ci][q][tcx];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
           for (int px = 0; px < 2; ++px)
-            for (int kx = 0; kx < 3; ++kx) {
-              const int xo = px + kx - 1;
-              if ((xo & 1) != bb) continue;
-              const int sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
-              const int u = ((py * 2 + px) * 2 + syi) * 2 + sxi;
-              const float* d = J.dwc + u * plane + (long long)ci * J.co_pad;
-              const float* w = J.w3 + (long long)c * 9 + ky * 3 + kx;
-              float s = 0.f;
-              for (int co = 0; co < J.Co; ++co) s = fmaf(__ldg(d + co), __ldg(w + (long long)co * cin3 * 9), s);
-              acc += s;
-            }
-        }
-      J.dwd[((long long)ci * J.Cu + c) * 4 + ab] = acc;
-    } else {
-      const int c = (int)(i - n3 - nd);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int yo = py + ky - 1, xo = px + kx - 1;
+                const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1), sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
+                acc[ky * 3 + kx] = fmaf(d[((py * 2 + px) * 2 + syi) * 2 + sxi], w[(yo & 1) * 2 + (xo & 1)], acc[ky * 3 + kx]);
+              }
+      }
+    }
+    const int co = co0 + tr, c = c0 + tcx;
+    if (co < J.Co && c < J.Cu) {
+      const float bdc = J.bd[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) J.dw3[((long long)co * cin3 + c) * 9 + t] = acc[t] + upfuse_S(J, t / 3, t % 3, co) * bdc;
+    }
+  } else if ((int)blockIdx.x < T3 + Td) {
+    const int bi = (int)blockIdx.x - T3;
+    const int ci0 = (bi / tc) * kUfTile, c0 = (bi % tc) * kUfTile;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int o0 = 0; o0 < J.Co; o0 += kUfTile) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kUfTile * 16 * kUfTile; i += kUfTile * kUfTile) {
+        const int co = i % kUfTile, ci = (i / kUfTile) % kUfTile, u = i / (kUfTile * kUfTile);      // co fastest: coalesced
+        sD[co][u][ci] = (o0 + co < J.Co && ci0 + ci < J.Ci) ? __ldg(J.dwc + u * plane + (long long)(ci0 + ci) * J.co_pad + o0 + co) : 0.f;
+      }
+      for (int i = threadIdx.x; i < kUfTile * kUfTile * 9; i += kUfTile * kUfTile) {
+        const int t = i % 9, c = (i / 9) % kUfTile, co = i / (9 * kUfTile);
+        sW[co][t][c] = (o0 + co < J.Co && c0 + c < J.Cu) ? __ldg(J.w3 + ((long long)(o0 + co) * cin3 + c0 + c) * 9 + t) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int co = 0; co < kUfTile; ++co) {
+        float d[16], w[9];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) d[u] = sD[co][u][tr];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t] = sW[co][t][tcx];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int yo = py + ky - 1, xo = px + kx - 1;
+                const int syi = (yo >= 0 ? yo >> 1 : -1) - (py - 1), sxi = (xo >= 0 ? xo >> 1 : -1) - (px - 1);
+                acc[(yo & 1) * 2 + (xo & 1)] = fmaf(d[((py * 2 + px) * 2 + syi) * 2 + sxi], w[ky * 3 + kx], acc[(yo & 1) * 2 + (xo & 1)]);
+              }
+      }
+    }
+    const int ci = ci0 + tr, c = c0 + tcx;
+    if (ci < J.Ci && c < J.Cu) {
+#pragma unroll
+      for (int ab = 0; ab < 4; ++ab) J.dwd[((long long)ci * J.Cu + c) * 4 + ab] = acc[ab];
+    }
+  } else if ((int)blockIdx.x == T3 + Td) {
+    for (int c = threadIdx.x; c < J.Cu; c += blockDim.x) {
       float acc = 0.f;
-      for (int t = 0; t < 9; ++t)
-        for (int co = 0; co < J.Co; ++co) acc = fmaf(J.w3[((long long)co * cin3 + c) * 9 + t], upfuse_S(J, t / 3, t % 3, co), acc);
+      for (int co = 0; co < J.Co; ++co)
+        for (int t = 0; t < 9; ++t) acc = fmaf(J.w3[((long long)co * cin3 + c) * 9 + t], upfuse_S(J, t / 3, t % 3, co), acc);
       J.dbd[c] = acc;
     }
   }
@@ -402,24 +452,28 @@ int launch_upfuse_grad(const UpFuseGradJob* jobs, int njobs, cudaStream_t st) {
   N2N_CHECK_ARG(njobs <= 5, "upfuse_grad: too many jobs");
   UpFuseGradBatch b;
   b.n = njobs;
-  long long maxtotal = 1;
+  int maxblocks = 1;
   for (int i = 0; i < njobs; ++i) {
     b.j[i] = jobs[i];
-    const long long tot = (long long)jobs[i].Co * jobs[i].Cu * 9 + (long long)jobs[i].Ci * jobs[i].Cu * 4 + jobs[i].Cu;
-    if (tot > maxtotal) maxtotal = tot;
+    const int tco = (jobs[i].Co + kUfTile - 1) / kUfTile, tc = (jobs[i].Cu + kUfTile - 1) / kUfTile, tci = (jobs[i].Ci + kUfTile - 1) / kUfTile;
+    const int blocks = tco * tc + tci * tc + 1;
+    if (blocks > maxblocks) maxblocks = blocks;
   }
-  dim3 grid(grid_for(maxtotal, 128, 8), njobs);
-  (void)launch_pdl_v(upfuse_grad_kernel, grid, dim3(128), 0, st, b);
+  (void)launch_pdl_v(upfuse_grad_kernel, dim3(maxblocks, njobs), dim3(kUfTile * kUfTile), 0, st, b);
   N2N_LAUNCH_CHECK();
   return 0;
 }
 
 // border[k][co_pad], k = 0: first row, 1: last row, 2: first column, 3: last column, 4..7: corners (top-left, top-right,
 // bottom-left, bottom-right) of a C16 bf16 tensor, summed over the batch.  One block per (k, channel block): fixed-order sums.
-__global__ void __launch_bounds__(256) border_sums_kernel(View g, float* __restrict__ border, int co_pad) {
+struct BorderBatch { View g[5]; float* out[5]; int co_pad[5]; int n; };
+
+__global__ void __launch_bounds__(256) border_sums_kernel(const __grid_constant__ BorderBatch b) {
   pdl_enter();
   __shared__ float red[8][16];
+  const View& g = b.g[blockIdx.z];
   const int k = blockIdx.x, cb = blockIdx.y;
+  if (cb >= g.Cb) return;
   const int H = g.H, W = g.W;
   const long long count = k < 2 ? (long long)g.N * W : (k < 4 ? (long long)g.N * H : g.N);
   float acc[16];
@@ -448,13 +502,23 @@ __global__ void __launch_bounds__(256) border_sums_kernel(View g, float* __restr
   if (threadIdx.x < 16) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    border[(long long)k * co_pad + cb * 16 + threadIdx.x] = s;
+    b.out[blockIdx.z][(long long)k * b.co_pad[blockIdx.z] + cb * 16 + threadIdx.x] = s;
   }
 }
 
-int launch_border_sums(const View& g, float* border, int co_pad, cudaStream_t st) {
-  N2N_CHECK_ARG(g.Cb * 16 <= co_pad, "border_sums: bad channel count");
-  (void)launch_pdl_v(border_sums_kernel, dim3(8, g.Cb), dim3(256), 0, st, g, border, co_pad);
+// one launch for up to five tensors (the fused levels of a backward pass)
+int launch_border_sums(const View* g, float* const* border, const int* co_pad, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  N2N_CHECK_ARG(n <= 5, "border_sums: too many tensors");
+  BorderBatch b;
+  b.n = n;
+  int maxcb = 1;
+  for (int i = 0; i < n; ++i) {
+    N2N_CHECK_ARG(g[i].Cb * 16 <= co_pad[i], "border_sums: bad channel count");
+    b.g[i] = g[i]; b.out[i] = border[i]; b.co_pad[i] = co_pad[i];
+    if (g[i].Cb > maxcb) maxcb = g[i].Cb;
+  }
+  (void)launch_pdl_v(border_sums_kernel, dim3(8, maxcb, n), dim3(256), 0, st, b);
   N2N_LAUNCH_CHECK();
   return 0;
 }
@@ -478,9 +542,9 @@ int launch_pack(const PackJob* jobs, int njobs, int dtype, cudaStream_t st) {
 }
 
 int launch_unpack(const UnpackJob* jobs, int njobs, cudaStream_t st) {
-  for (int base = 0; base < njobs; base += 8) {
+  for (int base = 0; base < njobs; base += 16) {
     UnpackBatch b;
-    b.n = njobs - base < 8 ? njobs - base : 8;
+    b.n = njobs - base < 16 ? njobs - base : 16;
     long long maxtotal = 1;
     for (int i = 0; i < b.n; ++i) {
       b.j[i] = jobs[base + i];

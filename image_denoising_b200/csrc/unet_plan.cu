@@ -677,6 +677,7 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
   // (dWc partials), the conv's own weight-gradient launch restricted to its skip channels (it also sums the bias
   // gradient), ONE input-gradient launch with the transposed composites, the skip channels' input gradient, and the
   // border sums the chain rule needs (reduced / chained after the join, see below).
+  View bviews[5]; float* bouts[5]; int bpads[5]; int nborder = 0;      // border sums of dL/dy of the fused levels: one launch at the end
   auto fused_bwd = [&](int dc) -> int {
     const UpConvGeom& U = p->ug[dc];
     const int ca = dc + 1;
@@ -706,8 +707,8 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
         N2N_TRY(launch_tapwgrad(make_conv_wgrad(S, dt, skip_act, gy, (float*)((char*)ws + p->off_partial[ca]),
                                                 (float*)((char*)ws + p->off_bpartial[ca]), p->splits[ca]), wst));
       }
-      N2N_TRY(launch_border_sums(gy, (float*)((char*)ws + p->off_border[dc]), U.co_blocks * 16, wst));
     }
+    bviews[nborder] = gy; bouts[nborder] = (float*)((char*)ws + p->off_border[dc]); bpads[nborder] = U.co_blocks * 16; ++nborder;
     // input gradients (main stream)
     TapGemm g = make_upconv_dgrad(U, dt, gy, p->view(p->grd, ws, dio.in_buf, dio.in_cb0, U.ci_blocks), (const char*)ws + p->off_upwt[dc]);
     g.has_mask = true; g.mask = xsrc; g.slope = 0.2f;          // the deconv's input is an activated conv output
@@ -780,6 +781,7 @@ extern "C" int n2n_unet_backward(n2n_unet_plan* p, const float* const* params, c
     N2N_CUDA(cudaEventRecord(p->ev_done, p->side));
     N2N_CUDA(cudaStreamWaitEvent(st, p->ev_done, 0));
   }
+  N2N_TRY(launch_border_sums(bviews, bouts, bpads, nborder, st));
   // partials -> PyTorch-layout fp32 gradients
   {
     std::vector<UnpackJob> jobs;
