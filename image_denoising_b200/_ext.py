@@ -138,6 +138,8 @@ _SIGS = {
     "n2n_tile_accumulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
     "n2n_tile_finalize_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "n2n_tile_gather_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "n2n_tile_blend_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "n2n_psnr_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "n2n_psnr_ssim_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "n2n_crop_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

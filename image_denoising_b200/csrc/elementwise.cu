@@ -391,9 +391,84 @@ __global__ void tile_finalize_kernel(const float* __restrict__ acc, const float*
   }
 }
 
+// evaluation_704.py:82-101 on the device: tile t = (ty, tx) of image b starts at (ty * stride, tx * stride), is cut to the
+// image, scaled by 1/255 and extended to ps x ps exactly as np.pad(patch, ((0, ps-th), (0, ps-tw)), mode='reflect') does
+// (numpy's reflect continues periodically, period 2 (n - 1), when the pad exceeds the patch — the 128-pixel edge tiles of
+// a 704 x 704 image are padded by 224).  tiles: fp32 [B * T][1][ps][ps], T = tiles_y * tiles_x, row-major tile order.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  if (i < n) return i;
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  const int m = i % period;
+  return m < n ? m : period - m;
+}
+__global__ void tile_gather_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int ps, int stride, int tiles_y, int tiles_x,
+                                      float* __restrict__ tiles, long long items) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int x = (int)(r % ps); r /= ps;
+    const int y = (int)(r % ps); r /= ps;
+    const int tx = (int)(r % tiles_x); r /= tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const long long b = r / tiles_y;
+    const int r0 = ty * stride, c0 = tx * stride;
+    const int th = min(ps, H - r0), tw = min(ps, W - c0);
+    const int sy = r0 + reflect_index(y, th), sx = c0 + reflect_index(x, tw);
+    tiles[i] = __fdiv_rn((float)img[(b * H + sy) * W + sx], 255.0f);         // evaluation_704.py:89: astype(float32) / 255.0
+  }
+}
+// evaluation_704.py:103-120: out = clip(acc / cnt * 255) with acc = sum_t clamp(pred_t, 0, 1) * w, cnt = sum_t w over the
+// tiles covering the pixel, accumulated in the reference's tile order (fp32, same rounding as its sequential loop).
+__global__ void tile_blend_u8_kernel(const float* __restrict__ pred, const float* __restrict__ wm, int H, int W, int ps, int stride,
+                                     int tiles_y, int tiles_x, uint8_t* __restrict__ out, long long items) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const long long b = i / ((long long)W * H);
+    float acc = 0.f, cnt = 0.f;
+    for (int ty = 0; ty < tiles_y; ++ty) {
+      const int r0 = ty * stride;
+      if (y < r0 || y >= min(r0 + ps, H)) continue;
+      for (int tx = 0; tx < tiles_x; ++tx) {
+        const int c0 = tx * stride;
+        if (x < c0 || x >= min(c0 + ps, W)) continue;
+        const long long t = (b * tiles_y + ty) * tiles_x + tx;
+        const long long o = (long long)(y - r0) * ps + (x - c0);
+        const float p = fminf(fmaxf(pred[t * ps * ps + o], 0.f), 1.f);
+        const float w = wm[o];
+        acc = __fadd_rn(acc, __fmul_rn(p, w));
+        cnt = __fadd_rn(cnt, w);
+      }
+    }
+    if (cnt == 0.f) cnt = 1.f;
+    float v = __fmul_rn(__fdiv_rn(acc, cnt), 255.0f);
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = (uint8_t)v;
+  }
+}
+
 }  // namespace n2n
 
 using namespace n2n;
+
+extern "C" int n2n_tile_gather_u8(const uint8_t* images, int batch, int h, int w, int ps, int stride, float* tiles, void* stream) {
+  N2N_CHECK_ARG(images && tiles && batch >= 1 && h >= 1 && w >= 1 && ps >= 1 && stride >= 1, "tile_gather_u8: bad arguments");
+  const int ty = (h + stride - 1) / stride, tx = (w + stride - 1) / stride;
+  const long long items = (long long)batch * ty * tx * ps * ps;
+  tile_gather_u8_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(images, h, w, ps, stride, ty, tx, tiles, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int n2n_tile_blend_u8(const float* pred_tiles, const float* weight_mask, int batch, int h, int w, int ps, int stride,
+                                 uint8_t* out, void* stream) {
+  N2N_CHECK_ARG(pred_tiles && weight_mask && out && batch >= 1 && h >= 1 && w >= 1 && ps >= 1 && stride >= 1, "tile_blend_u8: bad arguments");
+  const int ty = (h + stride - 1) / stride, tx = (w + stride - 1) / stride;
+  const long long items = (long long)batch * h * w;
+  tile_blend_u8_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(pred_tiles, weight_mask, h, w, ps, stride, ty, tx, out, items);
+  N2N_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int n2n_quantize_u8(const float* pred, uint8_t* out, int64_t count, float bias, void* stream) {
   N2N_CHECK_ARG(pred && out && count >= 0, "quantize_u8: bad arguments");

@@ -56,34 +56,29 @@ def tile_origins(h: int, w: int, ps: int = 352, overlap: int = 64):
 
 @torch.no_grad()
 def denoise_tiled(network, noisy_imgs: Sequence[np.ndarray], ps: int = 352, overlap: int = 64, device="cuda",
-                  images_per_batch: int = 8) -> Tuple[List[np.ndarray], List[float]]:
-    """evaluation_704.py:70-120 for a list of equally-sized 2-D uint8 images."""
-    wm_host = tile_weight(ps)
-    wm = torch.from_numpy(wm_host).to(device)
+                  images_per_batch: int = 8, return_device: bool = False) -> Tuple[List[np.ndarray], List[float]]:
+    """evaluation_704.py:70-120 for a list of equally-sized 2-D uint8 images.  The images are uploaded as uint8; tiling
+    (cut, /255, numpy-style reflect padding), the forward of all tiles of ``images_per_batch`` images as ONE batch, the
+    triangular blend in the reference's tile order and the truncating quantiser all run on the device."""
+    stride = ps - overlap
+    wm = torch.from_numpy(tile_weight(ps)).to(device)
     outs, l1s = [], []
     h, w = np.asarray(noisy_imgs[0]).shape
-    origins = tile_origins(h, w, ps, overlap)
+    nt = len(tile_origins(h, w, ps, overlap))
     for b0 in range(0, len(noisy_imgs), images_per_batch):
-        chunk = [np.asarray(n).astype(np.uint8) for n in noisy_imgs[b0:b0 + images_per_batch]]
-        tiles, geo = [], []
-        for noisy in chunk:
-            for (r0, c0) in origins:
-                r1, c1 = min(r0 + ps, h), min(c0 + ps, w)
-                patch = noisy[r0:r1, c0:c1].astype(np.float32) / 255.0
-                tiles.append(np.pad(patch, ((0, ps - patch.shape[0]), (0, ps - patch.shape[1])), mode='reflect'))
-                geo.append((r0, c0, r1 - r0, c1 - c0))
-        x = torch.from_numpy(np.stack(tiles)[:, None]).to(device)
+        chunk = noisy_imgs[b0:b0 + images_per_batch]
+        if isinstance(chunk[0], torch.Tensor):
+            imgs = torch.stack([c.to(device=device, dtype=torch.uint8) for c in chunk])
+        else:
+            imgs = torch.from_numpy(np.stack([np.asarray(n).astype(np.uint8) for n in chunk])).to(device)
+        x = ops.tile_gather_u8(imgs, ps, stride)                      # [B*nt, 1, ps, ps]
         pred = network(x)
-        nt = len(origins)
-        for i in range(len(chunk)):
-            acc = torch.zeros((h, w), dtype=torch.float32, device=device)
-            cnt = torch.zeros((h, w), dtype=torch.float32, device=device)
-            for t in range(nt):
-                r0, c0, th, tw = geo[i * nt + t]
-                ops.tile_accumulate(pred[i * nt + t, 0], wm, acc, cnt, r0, c0, th, tw)
-            outs.append(ops.tile_finalize_u8(acc, cnt))
+        out = ops.tile_blend_u8(pred, wm, imgs.shape[0], h, w, ps, stride)
+        outs.append(out)
+        for i in range(imgs.shape[0]):                                # L1(pred tile, noisy tile), evaluation_704.py:99-101
             loss3, _ = ops.l1grad_loss_fwdbwd(pred[i * nt:(i + 1) * nt], x[i * nt:(i + 1) * nt], 0.0, 1.0, want_grad=False)
             l1s.append(loss3)
-    outs = [o.cpu().numpy() for o in outs]
     l1s = [float(t[1]) for t in torch.stack(l1s).cpu()]
-    return outs, l1s
+    if return_device:
+        return [o for batch in outs for o in batch], l1s
+    return [o for batch in outs for o in batch.cpu().numpy()], l1s

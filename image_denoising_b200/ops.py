@@ -262,6 +262,28 @@ def tile_finalize_u8(acc, cnt) -> torch.Tensor:
     return out
 
 
+def tile_gather_u8(images: torch.Tensor, ps: int, stride: int) -> torch.Tensor:
+    """uint8 [B,H,W] (CUDA) -> fp32 tiles [B*T,1,ps,ps] (evaluation_704.py:82-96: cut, /255, reflect-pad)."""
+    require_cuda(images, "tile_gather_u8")
+    if images.dtype != torch.uint8 or images.dim() != 3:
+        raise ValueError("tile_gather_u8 takes a uint8 [B,H,W] tensor")
+    images = images.contiguous()
+    b, h, w = images.shape
+    t = ((h + stride - 1) // stride) * ((w + stride - 1) // stride)
+    tiles = torch.empty((b * t, 1, ps, ps), dtype=torch.float32, device=images.device)
+    check(lib().n2n_tile_gather_u8(ptr(images), b, h, w, ps, stride, ptr(tiles), stream_ptr()))
+    return tiles
+
+
+def tile_blend_u8(pred_tiles: torch.Tensor, weight_mask: torch.Tensor, batch: int, h: int, w: int, ps: int, stride: int) -> torch.Tensor:
+    """fp32 tiles [B*T,1,ps,ps] -> uint8 [B,H,W] (evaluation_704.py:103-120: triangular blend, truncating quantiser)."""
+    require_cuda(pred_tiles, "tile_blend_u8")
+    pred_tiles = _f32c(pred_tiles); weight_mask = _f32c(weight_mask)
+    out = torch.empty((batch, h, w), dtype=torch.uint8, device=pred_tiles.device)
+    check(lib().n2n_tile_blend_u8(ptr(pred_tiles), ptr(weight_mask), batch, h, w, ps, stride, ptr(out), stream_ptr()))
+    return out
+
+
 def psnr_ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a, b: uint8 CUDA tensors [B,H,W] or [B,H,W,C] (C in {1,3}) -> float64 [B,2] = (psnr, ssim)."""
     require_cuda(a, "psnr_ssim")

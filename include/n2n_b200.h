@@ -257,6 +257,14 @@ int n2n_tile_accumulate(const float* pred_tile, int ps, const float* weight_mask
 /* evaluation_704.py:114-120: out = clip(acc / (cnt==0 ? 1 : cnt) * 255, 0, 255) truncated. */
 int n2n_tile_finalize_u8(const float* acc, const float* cnt, uint8_t* out, int64_t count, void* stream);
 
+/* Batched device form of the same tiling (evaluation_704.py:82-120) for `batch` equally sized uint8 images [batch][H][W]:
+ * gather = cut tile (ty, tx) at (ty*stride, tx*stride), /255, extend to ps x ps as np.pad(mode='reflect') does (periodic
+ * when the pad exceeds the patch) -> tiles fp32 [batch * T][ps][ps], T = ceil(H/stride) * ceil(W/stride), row-major;
+ * blend = per output pixel, the weighted sum over its covering tiles in that order, / weight sum, *255, truncated. */
+int n2n_tile_gather_u8(const uint8_t* images, int batch, int h, int w, int ps, int stride, float* tiles, void* stream);
+int n2n_tile_blend_u8(const float* pred_tiles, const float* weight_mask, int batch, int h, int w, int ps, int stride,
+                      uint8_t* out, void* stream);
+
 size_t n2n_psnr_ssim_workspace_bytes(int batch, int h, int w, int channels);
 /* utils_eval.py:19-53 on `batch` pairs of H x W x C uint8 images (interleaved
  * HWC as PIL/numpy hold them, C in {1,3}).  result: [batch][2] doubles =
