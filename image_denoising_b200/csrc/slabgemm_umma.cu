@@ -38,7 +38,8 @@ namespace n2n {
 using namespace umma;
 
 constexpr int kSgEpiGroups = 3;           // groups of four epilogue warps, each takes every third tile
-constexpr int kSgThreads = 64 + 128 * kSgEpiGroups;   // TMA warp, MMA warp, epilogue warps
+constexpr int kSgThreads = 64 + 128 * kSgEpiGroups + 32;   // TMA warp, MMA warp, epilogue warps, second MMA issuer (dual mode)
+constexpr int kSgIssuer2 = 2 + 4 * kSgEpiGroups;           // warp index of the second issuer
 constexpr int kSgMaxStages = 12;          // pipeline stages (TMA boxes) per tile
 constexpr int kSgMaxRing = 8;
 constexpr int kSgGroup = 3;               // channel blocks per stage = one packed-weight group
@@ -69,11 +70,14 @@ struct SgStage {
   uint8_t pad8[3];
   uint32_t b_off16[9];       // start of each tap's weight slab inside the resident weights (bytes/16)
   uint32_t tx_bytes;         // bytes the TMA box delivers
+  uint32_t nt0;              // taps [0, nt0) start at accumulator column 0 (issuer 0), [nt0, ntaps) at column mma_n (issuer 1)
 };
 
 struct SgParams {
   // hot (epilogue / loop) fields first: they stay in the first constant-cache lines
   int nst, nout, ring, dbg_flags, nbuf;
+  int dual;                  // column-range form with two ranges: warp kSgIssuer2 issues the taps of the upper range (disjoint
+                             // accumulator columns, so the two issuers need no ordering between them)
   int esplit;                // 3: every tile's accumulator columns are drained by ALL THREE epilogue groups (a third each), used
                              // when only two accumulators fit in TMEM (N = 144 / 192): with one group per tile the MMAs of tile
                              // i+2 wait for the whole 12-block epilogue of tile i (ncu: tensor pipe 35 % active, third group idle)
@@ -336,10 +340,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kSgMaxRing; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.dual ? 2 : 1); }
     mbar_init(wfull_bar, 1);
     mbar_init(wready_bar, CG);
-    for (int b = 0; b < 3; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4 * CG * (p.esplit == 3 ? 3 : 1)); }
+    for (int b = 0; b < 3; ++b) { mbar_init(tfull_bar(b), p.dual ? 2 : 1); mbar_init(tempty_bar(b), 4 * CG * (p.esplit == 3 ? 3 : 1)); }
     fence_barrier_init();
   }
   // per-CTA schedule tables
@@ -378,7 +382,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
   if (threadIdx.x < p.nst) {
     const SgStage& S = p.st[threadIdx.x];
     s_ld[threadIdx.x] = make_int4(S.view, S.cb0, (int)(uint16_t)S.ox | ((int)(uint16_t)S.oy << 16), (int)S.tx_bytes);
-    s_mm[threadIdx.x] = make_uint4((uint32_t)S.ntaps, (uint32_t)S.nb, (uint32_t)S.cb_bytes16,
+    s_mm[threadIdx.x] = make_uint4((uint32_t)S.ntaps | (S.nt0 << 16), (uint32_t)S.nb, (uint32_t)S.cb_bytes16,
                                    (uint32_t)S.sbo16 | (1u << 14) | (kSwizzle32 << 29));
   }
   if (warp == 1) {
@@ -447,16 +451,19 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (++slot == p.ring) { slot = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer ----
+  } else if (warp == 1 || (warp == kSgIssuer2 && p.dual)) {
+    // ---- MMA issuer(s) ----
+    const uint32_t q = warp == 1 ? 0u : 1u;
     int slot = 0; uint32_t phase = 0;
     pdl_wait();
-    pdl_release();                      // our own dependents may begin their prologue
+    if (q == 0) pdl_release();          // our own dependents may begin their prologue
     sg_wait(wfull_bar, 0);
     if (CG == 2) {
       // tell the leader that this CTA's weight half is in place; only the leader issues MMAs
-      if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
-      __syncwarp();
+      if (q == 0) {
+        if (elect_one_sync()) mbar_arrive_cluster(wready_bar & kPeerMask);
+        __syncwarp();
+      }
       if (rank == 0) sg_wait(wready_bar, 0);
     }
     const uint32_t b_hi = (256u >> 4) | (1u << 14) | (kSwizzle32 << 29);
@@ -470,7 +477,10 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nout);
       uint32_t acc = 0;
       for (int s = 0; s < p.nst; ++s) {
-        const uint4 mm = s_mm[s];                            // ntaps, nb, cb_bytes16, a_hi
+        const uint4 mm = s_mm[s];                            // ntaps | nt0 << 16, nb, cb_bytes16, a_hi
+        // dual mode: issuer 0 takes the taps of the lower column range [0, nt0), issuer 1 the rest
+        const int nt_all = (int)(mm.x & 0xffffu), nt0 = (int)(mm.x >> 16);
+        const int t_begin = q ? nt0 : 0, t_end = (p.dual && !q) ? nt0 : nt_all;
         const uint32_t a_lo = (((slots0 + slot * p.slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
         // the stage's tap table goes to registers up front (5 LDS.128), so the issue loop below is
         // two integer adds per tcgen05.mma
@@ -489,7 +499,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
           if (!skip) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              if (t < (int)mm.x) {
+              if (t >= t_begin && t < t_end) {
                 // x: A offset (bits 0..19) | accumulator column (bits 20..); y: B offset | "first MMA into these columns"
                 const uint32_t al = a_lo + (tp[t].x & 0xFFFFFu), bl = w_lo + (tp[t].y & 0x7FFFFFFFu);
                 const uint32_t dt = d_tmem + (tp[t].x >> 20) * 16u;
@@ -516,7 +526,8 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         if (p.bias_off && !skip) {
           const uint32_t one_lo = (((smem0 + p.bias_off) & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t bia_lo = (((smem0 + p.bias_off + 4096u) & 0x3FFFFu) >> 4) | (1u << 16);
-          for (int col = 0; col < p.nout; col += p.mma_n) {      // column-range form: the same bias rows serve every column range
+          // column-range form: the same bias rows serve every column range (dual mode: each issuer its own range)
+          for (int col = p.dual ? (int)q * p.mma_n : 0; col < (p.dual ? ((int)q + 1) * p.mma_n : p.nout); col += p.mma_n) {
             if (CG == 2) sg_mma2(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1); else sg_mma(d_tmem + col, one_lo, b_hi, bia_lo, b_hi, idesc, 1);
           }
         }
@@ -524,7 +535,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2 && warp < kSgIssuer2) {
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = image rows 4*(w%4) .. +3 of the tile;
     //      groups of four warps take tiles round-robin (group g <-> accumulator buffer g), so the
     //      per-tile bookkeeping is paid once per group and all accumulators drain concurrently ----
@@ -807,6 +818,18 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   // that is still draining tile i (two groups on alternate tiles); else two
   p.nbuf = 3 * g.nout <= 512 ? 3 : 2;
   { const char* e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
+  {
+    bool dual_ok = g.mma_n != 0 && g.nout == 2 * mma_n;
+    for (int si = 0; si < nst; ++si) {
+      SgStage& S = p.st[si];
+      uint32_t nt0 = 0;
+      for (int k = 0; k < S.ntaps; ++k)
+        if (S.col16[k] == 0) { if (nt0 != (uint32_t)k) dual_ok = false; ++nt0; }      // lower range first
+      S.nt0 = nt0;
+    }
+    const char* e = getenv("N2N_NO_DUAL_ISSUE");
+    p.dual = (dual_ok && !(e && atoi(e))) ? 1 : 0;
+  }
   { const char* e = getenv("N2N_NO_ESPLIT");
     p.esplit = (p.nbuf == 2 && (g.nout >> 4) % 3 == 0 && !(e && atoi(e))) ? 3 : 1; }
   p.tmem_cols = tmem_cols_for(p.nbuf * g.nout);

@@ -63,7 +63,7 @@ def denoise_tiled(network, noisy_imgs: Sequence[np.ndarray], ps: int = 352, over
     stride = ps - overlap
     wm = torch.from_numpy(tile_weight(ps)).to(device)
     outs, l1s = [], []
-    h, w = np.asarray(noisy_imgs[0]).shape
+    h, w = (int(v) for v in noisy_imgs[0].shape)
     nt = len(tile_origins(h, w, ps, overlap))
     for b0 in range(0, len(noisy_imgs), images_per_batch):
         chunk = noisy_imgs[b0:b0 + images_per_batch]
