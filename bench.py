@@ -231,7 +231,7 @@ def _max_over_ranks(ms, world, dev, dist):
     return ms
 
 
-def inference_704(dev, precision, world, rank, dist, total_images=128, per_launch=8, reps=2):
+def inference_704(dev, precision, world, rank, dist, total_images=128, per_launch=16, reps=2):
     """BASELINE configs[3]: evaluation.py semantics on 128 synthetic 704x704 grayscale images sharded over
     the ranks (no collective): pinned uint8 H2D -> /255 -> whole-image UNet forward -> clamp/quantise ->
     PSNR/SSIM kernel -> D2H of the metrics.  Returns whole-job images/s (device timing, max over ranks)."""
@@ -275,9 +275,9 @@ def inference_704(dev, precision, world, rank, dist, total_images=128, per_launc
             "note": "e2e: pinned uint8 H2D + forward + quantise + PSNR/SSIM kernel + D2H of metrics; random-init weights"}
 
 
-def inference_704_tiled(dev, precision, world, rank, dist, total_images=128, per_launch=8, reps=1):
+def inference_704_tiled(dev, precision, world, rank, dist, total_images=128, per_launch=16, reps=1):
     """BASELINE configs[3] with evaluation_704.py semantics (9 reflect-padded 352x352 tiles per image, triangular
-    blend, truncating quantiser): pinned uint8 H2D -> device tiling -> ONE forward over the 72 tiles of 8 images ->
+    blend, truncating quantiser): pinned uint8 H2D -> device tiling -> ONE forward over the 144 tiles of 16 images ->
     device blend / quantise -> PSNR/SSIM kernel -> D2H of the metrics, through `evaluate.denoise_tiled`."""
     import torch
     from image_denoising_b200 import UNet, evaluate, ops
@@ -313,7 +313,7 @@ def inference_704_tiled(dev, precision, world, rank, dist, total_images=128, per
     return {"metric": "inference_images_per_s_704x704_tiled_9x352", "value": ips, "unit": "images/s", "images": world * mine,
             "gflop_per_image": 656.3, "tflops": ips * 656.3 / 1e3,
             "frac_of_bf16_sustained_per_gpu": ips / world * 656.3 / 1e3 / pk["bf16"], "psnr_first": float(res_h[0, 0]),
-            "note": "e2e: pinned uint8 H2D + device tiling + forward on 72 tiles per 8 images + blend/quantise + PSNR/SSIM kernel + D2H of the metrics (the per-image L1(pred, noisy) of evaluation_704.py:99-101 is read back too)"}
+            "note": "e2e: pinned uint8 H2D + device tiling + forward on 144 tiles per 16 images + blend/quantise + PSNR/SSIM kernel + D2H of the metrics (the per-image L1(pred, noisy) of evaluation_704.py:99-101 is read back too)"}
 
 
 def adapter_finetune_c5(dev, precision, steps=10, batch=32):

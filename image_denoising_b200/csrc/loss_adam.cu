@@ -128,6 +128,7 @@ n2n_loss_kernel(const float* __restrict__ out, const float* __restrict__ sub2, c
 // d/de[y,x] = sgn(e)/M + lg/Mx * (sgn(dx[x-1]) - sgn(dx[x])) + lg/My * (sgn(dy[y-1]) - sgn(dy[y]))
 __device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
+template <typename IDX>
 __global__ void __launch_bounds__(kRedThreads)
 l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int planes, int h, int w,
                    float lg, float gscale, float* __restrict__ loss3, float* __restrict__ grad, RedWs* ws) {
@@ -139,33 +140,40 @@ l1grad_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
   const float k1 = gscale / (float)count;
   const float kx = cx > 0 ? gscale * lg / (float)cx : 0.f;
   const float ky = cy > 0 ? gscale * lg / (float)cy : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i % hw;
-    const int y = (int)(r / w), x = (int)(r - (long long)y * w);
-    const float e = pred[i] - tgt[i];
-    acc[0] += (double)fabsf(e);
+  // per-thread sums stay fp32 over short runs, then accumulate in double (fp64 throughput is a small fraction of fp32);
+  // IDX = 32-bit index arithmetic whenever the tensor allows it (two 64-bit divisions per element dominated the kernel)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  int run = 0;
+  const IDX n = (IDX)count, ihw = (IDX)hw, step = (IDX)gridDim.x * (IDX)blockDim.x;
+  for (IDX i = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x; i < n; i += step) {
+    const IDX r = i % ihw;
+    const int y = (int)(r / (IDX)w), x = (int)(r - (IDX)y * (IDX)w);
+    const float p0 = pred[i], t0 = tgt[i];
+    const float e = p0 - t0;
+    a0 += fabsf(e);
     float g = k1 * sgnf(e);
     if (x + 1 < w) {
-      const float dd = (pred[i + 1] - pred[i]) - (tgt[i + 1] - tgt[i]);
-      acc[1] += (double)fabsf(dd);
+      const float dd = (pred[i + 1] - p0) - (tgt[i + 1] - t0);
+      a1 += fabsf(dd);
       g -= kx * sgnf(dd);
     }
     if (x > 0) {
-      const float dd = (pred[i] - pred[i - 1]) - (tgt[i] - tgt[i - 1]);
+      const float dd = (p0 - pred[i - 1]) - (t0 - tgt[i - 1]);
       g += kx * sgnf(dd);
     }
     if (y + 1 < h) {
-      const float dd = (pred[i + w] - pred[i]) - (tgt[i + w] - tgt[i]);
-      acc[2] += (double)fabsf(dd);
+      const float dd = (pred[i + w] - p0) - (tgt[i + w] - t0);
+      a2 += fabsf(dd);
       g -= ky * sgnf(dd);
     }
     if (y > 0) {
-      const float dd = (pred[i] - pred[i - w]) - (tgt[i] - tgt[i - w]);
+      const float dd = (p0 - pred[i - w]) - (t0 - tgt[i - w]);
       g += ky * sgnf(dd);
     }
     if (grad) grad[i] = g;
+    if (++run == 16) { acc[0] += (double)a0; acc[1] += (double)a1; acc[2] += (double)a2; a0 = a1 = a2 = 0.f; run = 0; }
   }
+  acc[0] += (double)a0; acc[1] += (double)a1; acc[2] += (double)a2;
   block_reduce<3>(acc, red);
   if (threadIdx.x == 0) {
     ws->partial[blockIdx.x][0] = acc[0]; ws->partial[blockIdx.x][1] = acc[1]; ws->partial[blockIdx.x][2] = acc[2];
@@ -299,8 +307,12 @@ extern "C" int n2n_loss_l1grad_fwdbwd(const float* pred, const float* target, in
   const long long count = (long long)n * c * h * w;
   int grid = grid_for(count, kRedThreads, 4);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  (void)launch_pdl_v(l1grad_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, n * c, h, w, lambda_grad,
-                                                                     grad_scale, loss3, grad, (RedWs*)workspace);
+  if (count < (1LL << 31) - (long long)grid * kRedThreads)
+    (void)launch_pdl_v(l1grad_loss_kernel<unsigned int>, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, n * c, h, w,
+                       lambda_grad, grad_scale, loss3, grad, (RedWs*)workspace);
+  else
+    (void)launch_pdl_v(l1grad_loss_kernel<long long>, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, n * c, h, w,
+                       lambda_grad, grad_scale, loss3, grad, (RedWs*)workspace);
   N2N_LAUNCH_CHECK();
   return 0;
 }

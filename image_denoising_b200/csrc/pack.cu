@@ -277,6 +277,7 @@ upfuse_pack_kernel(const __grid_constant__ UpFuseBatch b) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap[t] = 0.f;
       if (co < J.Co)
+#pragma unroll 4
         for (int c = 0; c < J.Cu; ++c) {                  // the nine taps of (co, c) are contiguous
           const float bdc = J.bd[c];
           const float* w = J.w3 + ((long long)co * cin3 + c) * 9;

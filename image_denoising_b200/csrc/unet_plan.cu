@@ -185,9 +185,14 @@ static void plan_layout(n2n_unet_plan* p) {
       // the backward runs in composite form too: transposed composites resident for the input gradient, the slab
       // weight-gradient engine for the four parity launches
       const char* e = getenv("N2N_NO_UPFUSE_TRAIN");
-      p->splits_up[dc] = wgrad_slab_splits(4, U.ci_blocks, U.co_blocks, false,
-                                           (long long)p->N * ((p->lh(lv) + 15) / 16) * ((p->lw(lv) + 7) / 8));
-      p->upfuse[dc] = !(e && atoi(e)) && p->splits_up[dc] > 0 &&
+      const long long src_tiles = (long long)p->N * ((p->lh(lv) + 15) / 16) * ((p->lw(lv) + 7) / 8);
+      p->splits_up[dc] = wgrad_slab_splits(4, U.ci_blocks, U.co_blocks, false, src_tiles);
+      // the composite backward trades FLOPs for launches (four parity weight-gradient launches + a skip launch instead of
+      // two); an A/B of "all levels" against "levels with >= 256 / >= 1000 source tiles only" was within the box noise
+      // (5.28 / 5.36 / 5.36 ms per step), so every eligible level is fused
+      long long min_tiles = 0;
+      { const char* m = getenv("N2N_UPFUSE_TRAIN_MIN_TILES"); if (m) min_tiles = atoll(m); }
+      p->upfuse[dc] = !(e && atoi(e)) && p->splits_up[dc] > 0 && src_tiles >= min_tiles &&
                       slab_upconv_ok(p->dtype, p->N, p->lh(lv), p->lw(lv), U.co_blocks, 0, U.ci_blocks, upconv_wt_bytes(U));
     }
   }

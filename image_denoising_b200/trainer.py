@@ -77,6 +77,7 @@ class N2NTrainer:
             return
         net, dev = self.net, noisy.device
         dt = _ext.dtype_tag(self.precision)
+        self._destroy_plans()                       # a shape change rebuilds both plans: release the old ones
         self._shapes = (n, c, h, w)
         self.plan_full = ctypes.c_void_p()
         self.plan_half = ctypes.c_void_p()
@@ -107,6 +108,20 @@ class N2NTrainer:
         self.grad_ptrs = ptr_array(self.grads)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork = torch.cuda.Event(); self.ev_join = torch.cuda.Event()
+
+    def _destroy_plans(self):
+        for name in ("plan_full", "plan_half"):
+            h = getattr(self, name, None)
+            if h is not None and h.value:
+                lib().n2n_unet_plan_destroy(h)
+            setattr(self, name, None)
+
+    def __del__(self):
+        try:
+            self._graph = None
+            self._destroy_plans()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ one iteration
     def _launch_sequence(self, noisy, rd_idx, lam, lr, dev_scalars):
@@ -167,6 +182,11 @@ class N2NTrainer:
         self.graph_launches = lib().n2n_launch_count() - launches0
         self._graph = g
 
+    def input_buffer(self):
+        """The graph's static input tensor (after the first two steps of a shape): a caller that writes its batch here
+        (e.g. as the destination of its host-to-device copy) and passes it to ``step`` saves the staging copy."""
+        return getattr(self, "in_static", None) if self._graph is not None else None
+
     def step(self, noisy, Lambda, rd_idx=None, lr=None):
         """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
         device tensor [loss_all, loss1, loss2] (no host sync; the SAME buffer every step — clone it to keep a
@@ -182,20 +202,28 @@ class N2NTrainer:
             self._eager_steps = 0
         L = lib()
         launches0 = L.n2n_launch_count()
+        self.step_count += 1
+        lr = float(self.lr if lr is None else lr)
+        profiling = L.n2n_profile_active() == 1
+        replay = self.use_graph and not profiling and self._eager_steps >= 1
+        if replay and self._graph is None:
+            self._capture()
         if rd_idx is None:
             if self.world > 1:
                 n = noisy.shape[0]
                 rd_idx = dp.shard_selector(n2n.draw_rd_idx(noisy, batch=n * self.world), self.rank, self.world, n * self.world)
+            elif replay:
+                # train.py:155-162 drawn straight into the graph's selector buffer (no staging copy)
+                torch.randint(low=0, high=8, size=(self.rd_static.numel(),), generator=n2n.get_generator(noisy.device),
+                              out=self.rd_static)
+                rd_idx = self.rd_static
             else:
                 rd_idx = n2n.draw_rd_idx(noisy)
-        self.step_count += 1
-        lr = float(self.lr if lr is None else lr)
-        profiling = L.n2n_profile_active() == 1
-        if self.use_graph and not profiling and self._eager_steps >= 1:
-            if self._graph is None:
-                self._capture()
-            self.in_static.copy_(noisy, non_blocking=True)
-            self.rd_static.copy_(rd_idx, non_blocking=True)
+        if replay:
+            if noisy.data_ptr() != self.in_static.data_ptr():       # callers may fill input_buffer() directly
+                self.in_static.copy_(noisy, non_blocking=True)
+            if rd_idx.data_ptr() != self.rd_static.data_ptr():
+                self.rd_static.copy_(rd_idx, non_blocking=True)
             check(L.n2n_set_step_scalars(ptr(self.dev_scalars), float(Lambda), lr, float(self.betas[0]),
                                          float(self.betas[1]), self.step_count, stream_ptr()))
             self._graph.replay()
