@@ -258,14 +258,33 @@ adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ b
   const long long n = row[4];
   const long long base = (long long)chunk * N2N_ADAM_CHUNK;
   const float w1 = 1.0f - b1, w2 = 1.0f - b2;
-  for (long long i = base + threadIdx.x; i < base + N2N_ADAM_CHUNK && i < n; i += blockDim.x) {
-    const float gi = g[i] * gscale;
-    float mi = m[i], vi = v[i];
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
     mi = mi + w1 * (gi - mi);
     vi = vi * b2 + w2 * gi * gi;
     const float denom = sqrtf(vi) / inv_sqrt_bc2_recip + eps;
-    p[i] = p[i] - step_size * (mi / denom);
-    m[i] = mi; v[i] = vi;
+    pi = pi - step_size * (mi / denom);
+  };
+  // whole, 16-byte aligned chunk: two float4 per thread and array, all eight loads in flight before the first use
+  // (the scalar loop was a chain of eight dependent 4-byte round trips per thread: 14 us for 35 MB)
+  if (base + N2N_ADAM_CHUNK <= n && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0)) {
+    static_assert(N2N_ADAM_CHUNK == 2048, "two float4 per thread at 256 threads");
+    const long long i0 = base / 4 + threadIdx.x, i1 = i0 + 256;
+    float4 P0 = reinterpret_cast<float4*>(p)[i0], P1 = reinterpret_cast<float4*>(p)[i1];
+    const float4 G0 = reinterpret_cast<const float4*>(g)[i0], G1 = reinterpret_cast<const float4*>(g)[i1];
+    float4 M0 = reinterpret_cast<float4*>(m)[i0], M1 = reinterpret_cast<float4*>(m)[i1];
+    float4 V0 = reinterpret_cast<float4*>(v)[i0], V1 = reinterpret_cast<float4*>(v)[i1];
+    update(P0.x, G0.x, M0.x, V0.x); update(P0.y, G0.y, M0.y, V0.y); update(P0.z, G0.z, M0.z, V0.z); update(P0.w, G0.w, M0.w, V0.w);
+    update(P1.x, G1.x, M1.x, V1.x); update(P1.y, G1.y, M1.y, V1.y); update(P1.z, G1.z, M1.z, V1.z); update(P1.w, G1.w, M1.w, V1.w);
+    reinterpret_cast<float4*>(p)[i0] = P0; reinterpret_cast<float4*>(p)[i1] = P1;
+    reinterpret_cast<float4*>(m)[i0] = M0; reinterpret_cast<float4*>(m)[i1] = M1;
+    reinterpret_cast<float4*>(v)[i0] = V0; reinterpret_cast<float4*>(v)[i1] = V1;
+    return;
+  }
+  for (long long i = base + threadIdx.x; i < base + N2N_ADAM_CHUNK && i < n; i += blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    update(pi, g[i], mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 

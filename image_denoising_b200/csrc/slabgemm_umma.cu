@@ -54,9 +54,14 @@ static int sg_pair_mode() {
   const char* e = getenv("N2N_PAIR");
   return e ? atoi(e) : kSgPairDefault;
 }
+static long long sg_pair_min_tiles() {
+  static long long v = -1;
+  if (v < 0) { const char* e = getenv("N2N_PAIR_MIN_TILES"); v = e ? atoll(e) : 2; }
+  return v;
+}
 static bool sg_use_pair(int nout, long long tiles) {
   const int mode = sg_pair_mode();
-  return tiles >= 2 && nout % 16 == 0 && ((nout <= 64 && (mode & 1)) || (nout > 64 && (mode & 2)));
+  return tiles >= sg_pair_min_tiles() && nout % 16 == 0 && ((nout <= 64 && (mode & 1)) || (nout > 64 && (mode & 2)));
 }
 constexpr size_t kSgStaticSlack = 6144;   // static shared memory of the kernel, rounded up
 
