@@ -13,7 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from entry import _data, _models  # noqa: E402
-from image_denoising_b200 import DenoiserWithAdapter, FusedAdam, l1_grad_loss, ops  # noqa: E402
+from image_denoising_b200 import DenoiserWithAdapter, FusedAdam, iqsl_loss, l1_grad_loss, ops  # noqa: E402
 from image_denoising_b200.data import DevicePatchSource  # noqa: E402
 
 parser = argparse.ArgumentParser()
@@ -39,8 +39,12 @@ parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
 parser.add_argument('--synthetic', type=int, default=0)
 
 
-def main():
-    args, _ = parser.parse_known_args()
+def main(args=None, iqsl=False):
+    """``iqsl`` = the finetune_iqsl.py variant of the same loop (entry/finetune_iqsl.py): adds lambda_iqsl * iqsl_loss
+    (finetune_iqsl.py:469-483) with thresholds estimated from the clean images (:258-288) and saves the ADAPTER's
+    state_dict only as `epoch_adapter_only_XXX.pth` (:114-132)."""
+    if args is None:
+        args, _ = parser.parse_known_args()
     import datetime
     systime = datetime.datetime.now().strftime('%Y-%m-%d-%H-%M')
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -54,6 +58,19 @@ def main():
     # the (up to five) image pairs live on the device; patches are cut there (image_denoising_b200.data)
     source = DevicePatchSource(clean, noise, device=dev)
     valid_clean, valid_noise = clean, noise                       # finetune.py:231: validation = the same pairs, whole images
+    t1 = t2 = None
+    if iqsl and args.lambda_iqsl > 0.0:
+        # finetune_iqsl.py:258-288: quantiles of the pooled clean pixels in [0,1] (all clean files up to iqsl_max_images)
+        if args.synthetic:
+            pool = clean
+        else:
+            pool = [_data.load_image(f) for f in _data.list_pairs(args.data_dir, limit=args.iqsl_max_images)[0]]
+        assert 0.0 < args.iqsl_q1 < args.iqsl_q2 < 1.0, 'iqsl_q1, iqsl_q2 must satisfy 0 < q1 < q2 < 1.'
+        px = np.concatenate([np.asarray(c, np.float32).reshape(-1) / 255.0 for c in pool])
+        t1, t2 = float(np.quantile(px, args.iqsl_q1)), float(np.quantile(px, args.iqsl_q2))
+        print(f'[IQSL] Estimated thresholds from clean/: t1={t1:.4f}, t2={t2:.4f}')
+    elif iqsl:
+        print('[IQSL] lambda_iqsl=0 → IQSL disabled.')
 
     base = _models.build_base_model(args.arch, args.n_channel, args.n_feature)                # finetune.py:189-204
     if args.pretrained_ckpt:
@@ -79,18 +96,33 @@ def main():
             sel = source.draw([int(s) // args.patches_per_image for s in order[b0:b0 + args.batchsize]], ps, rng)
             c, n = source.crop(sel, ps)                            # same (top, left) for clean and noise, /255 (finetune.py:136-147)
             opt.zero_grad(set_to_none=True)
-            loss, loss3 = l1_grad_loss(model(n), c, args.lambda_grad)
+            pred = model(n)
+            loss, loss3 = l1_grad_loss(pred, c, args.lambda_grad)
+            loss_iq = None
+            if t1 is not None:
+                loss_iq = iqsl_loss(pred, c, t1=t1, t2=t2, tau=args.iqsl_tau, margin=args.iqsl_margin,
+                                    ce_factor=args.iqsl_ce_factor)
+                loss = loss + args.lambda_iqsl * loss_iq                # finetune_iqsl.py:483
             loss.backward()
             opt.step()
             if it % 10 == 0:
                 l = loss3.tolist()
                 losses.append(l[1])
-                print(f'[Epoch {epoch:03d} | Iter {it:04d}] L1={l[1]:.6f} Grad={l[2]:.6f} Total={l[0]:.6f}')
+                if loss_iq is not None:
+                    print(f'[Epoch {epoch:03d} | Iter {it:04d}] L1={l[1]:.6f} Grad={l[2]:.6f} IQSL={loss_iq.item():.6f} '
+                          f'Total={loss.item():.6f}')
+                else:
+                    print(f'[Epoch {epoch:03d} | Iter {it:04d}] L1={l[1]:.6f} Grad={l[2]:.6f} Total={l[0]:.6f}')
         print(f'End of epoch {epoch}, mean L1 loss={float(np.mean(losses)):.6f}')
         if epoch % args.save_every == 0 or epoch == args.n_epoch:
-            path = os.path.join(out_dir, 'epoch_adapter_{:03d}.pth'.format(epoch))
-            torch.save(model.state_dict(), path)
-            print('Checkpoint saved to {}'.format(path))
+            if iqsl:                                                   # finetune_iqsl.py:114-132: the adapter alone
+                path = os.path.join(out_dir, 'epoch_adapter_only_{:03d}.pth'.format(epoch))
+                torch.save(model.adapter.state_dict(), path)
+                print('Adapter checkpoint saved to {}'.format(path))
+            else:
+                path = os.path.join(out_dir, 'epoch_adapter_{:03d}.pth'.format(epoch))
+                torch.save(model.state_dict(), path)
+                print('Checkpoint saved to {}'.format(path))
             # finetune.py:305-343: whole-image validation PSNR (clip(p*255+0.5), 99.0 when identical), PNGs of image 0
             save_dir = os.path.join(args.save_model_path, args.log_name, f'val_{systime}_ep{epoch:03d}')
             os.makedirs(save_dir, exist_ok=True)

@@ -127,6 +127,9 @@ _SIGS = {
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_loss_structure_fwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                           c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_loss_iqsl_workspace_bytes": (c_size_t, []),
+    "n2n_loss_iqsl_fwdbwd": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_adam_multi": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_float, c_float, c_int,
                                c_float, c_void_p]),
     "n2n_set_step_scalars": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p]),

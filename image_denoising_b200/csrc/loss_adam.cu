@@ -239,6 +239,122 @@ structure_loss_kernel(const float* __restrict__ pred, const float* __restrict__ 
   }
 }
 
+// ---- IQSL: intensity-quantised structural loss (finetune_iqsl.py:291-383) ----------------------------------------
+// Three soft classes (dark / mid / bright) around the centres c = {t1/2, (t1+t2)/2, (t2+1)/2}: p = softmax(-|yhat - c| / tau);
+// target one-hot from the thresholds t1, t2 (an optional margin around them is "don't care"); loss = multi-class Dice over the
+// whole batch + ce_factor * soft cross-entropy.  Dice couples every pixel through nine global sums, so the gradient needs
+// them first: pass 1 reduces {I_k, P_k, T_k, CE, V} (deterministic two-stage) and writes the loss, pass 2 writes dL/dyhat.
+struct IqslWs {
+  unsigned int counter;
+  unsigned int pad[3];
+  double sums[12];                 // I[3], P[3], T[3], ce_sum, valid_count, (unused)
+  double partial[kMaxRedBlocks][11];
+};
+struct IqslParams { float t1, t2, inv_tau, margin, ce_factor, eps, gscale; };
+
+__device__ __forceinline__ void iqsl_pixel(const IqslParams& q, float yh, float y, float (&p)[3], float (&t)[3], float& valid) {
+  valid = 1.f;
+  if (q.margin > 0.f)
+    valid = ((y <= q.t1 - q.margin) || (y >= q.t1 + q.margin && y <= q.t2 - q.margin) || (y >= q.t2 + q.margin)) ? 1.f : 0.f;
+  t[0] = (y <= q.t1) ? valid : 0.f;
+  t[1] = (y > q.t1 && y < q.t2) ? valid : 0.f;
+  t[2] = (y >= q.t2) ? valid : 0.f;
+  const float c0 = q.t1 / 2.0f, c1 = (q.t1 + q.t2) / 2.0f, c2 = (q.t2 + 1.0f) / 2.0f;
+  const float l0 = -fabsf(yh - c0) * q.inv_tau, l1 = -fabsf(yh - c1) * q.inv_tau, l2 = -fabsf(yh - c2) * q.inv_tau;
+  const float mx = fmaxf(l0, fmaxf(l1, l2));
+  const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+  const float inv = 1.0f / (e0 + e1 + e2);
+  p[0] = e0 * inv * valid; p[1] = e1 * inv * valid; p[2] = e2 * inv * valid;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+iqsl_sums_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long count, IqslParams q,
+                 float* __restrict__ loss3, IqslWs* ws) {
+  pdl_enter();
+  __shared__ double red[11 * 8];
+  double acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0.0;
+  float a[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) a[k] = 0.f;
+  int run = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float p[3], t[3], valid;
+    iqsl_pixel(q, pred[i], tgt[i], p, t, valid);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      a[k] += p[k] * t[k]; a[3 + k] += p[k]; a[6 + k] += t[k];
+      a[9] -= t[k] * logf(p[k] + q.eps);
+    }
+    a[10] += valid;
+    if (++run == 16) {
+#pragma unroll
+      for (int k = 0; k < 11; ++k) { acc[k] += (double)a[k]; a[k] = 0.f; }
+      run = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] += (double)a[k];
+  block_reduce<11>(acc, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 11; ++k) ws->partial[blockIdx.x][k] = acc[k];
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&ws->counter, 1u) == gridDim.x - 1;
+    if (last) __threadfence();
+  }
+  __syncthreads();
+  if (!last) return;
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kRedThreads)
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] += __ldcg(&ws->partial[b][k]);
+  __syncthreads();
+  block_reduce<11>(acc, red);
+  if (threadIdx.x == 0) {
+    double dice_mean = 0.0;
+    for (int k = 0; k < 3; ++k) dice_mean += (2.0 * acc[k] + q.eps) / (acc[3 + k] + acc[6 + k] + q.eps);
+    dice_mean /= 3.0;
+    const double ce = acc[9] / (acc[10] * 3.0 + q.eps);
+    const float ld = (float)(1.0 - dice_mean), lc = (float)ce;
+    loss3[0] = ld + q.ce_factor * lc; loss3[1] = ld; loss3[2] = lc;
+    for (int k = 0; k < 11; ++k) ws->sums[k] = acc[k];
+    ws->counter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+iqsl_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long count, IqslParams q,
+                 float* __restrict__ grad, const IqslWs* ws) {
+  pdl_enter();
+  // d total / d prob_k = -(1/3) (2 t_k D_k - N_k) / D_k^2  -  ce_factor t_k / (prob_k + eps) / (3 V + eps)
+  float N[3], D[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { N[k] = (float)(2.0 * ws->sums[k] + q.eps); D[k] = (float)(ws->sums[3 + k] + ws->sums[6 + k] + q.eps); }
+  const float ce_w = q.ce_factor / (float)(ws->sums[10] * 3.0 + q.eps);
+  const float c[3] = {q.t1 / 2.0f, (q.t1 + q.t2) / 2.0f, (q.t2 + 1.0f) / 2.0f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float p[3], t[3], valid;
+    const float yh = pred[i];
+    iqsl_pixel(q, yh, tgt[i], p, t, valid);
+    float G[3], gp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      G[k] = valid * (-(2.0f * t[k] * D[k] - N[k]) / (3.0f * D[k] * D[k]) - ce_w * t[k] / (p[k] + q.eps));
+      gp += G[k] * p[k];
+    }
+    // softmax: d total / d l_j = p_j (G_j - sum_k G_k p_k) (p already carries `valid`; for valid = 0 everything is 0);
+    // l_j = -|yhat - c_j| / tau
+    float g = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g -= p[j] * (G[j] - gp) * sgnf(yh - c[j]) * q.inv_tau;
+    grad[i] = q.gscale * g;
+  }
+}
+
 // ---- multi-tensor Adam ---------------------------------------------------------------------
 // torch.optim.Adam (defaults, no amsgrad / weight decay), same operation order as
 // torch/optim/adam.py: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
@@ -346,6 +462,29 @@ extern "C" int n2n_loss_structure_fwdbwd(const float* pred, const float* pred2, 
   (void)launch_pdl_v(structure_loss_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, pred2, target, n * c, h, w,
                      alpha, beta, gamma, grad_scale, loss4, grad_pred, grad_pred2, (RedWs*)workspace);
   N2N_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t n2n_loss_iqsl_workspace_bytes(void) { return sizeof(IqslWs); }
+
+extern "C" int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, float t1, float t2, float tau, float margin,
+                                    float ce_factor, float eps, float grad_scale, float* loss3, float* grad, void* workspace,
+                                    void* stream) {
+  N2N_CHECK_ARG(pred && target && loss3 && workspace && count > 0, "loss_iqsl: bad arguments");
+  N2N_CHECK_ARG(t1 < t2, "loss_iqsl: need t1 < t2");
+  IqslParams q;
+  q.t1 = t1; q.t2 = t2; q.inv_tau = 1.0f / (tau > 1e-6f ? tau : 1e-6f); q.margin = margin; q.ce_factor = ce_factor; q.eps = eps;
+  q.gscale = grad_scale;
+  int grid = grid_for(count, kRedThreads, 4);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  (void)launch_pdl_v(iqsl_sums_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, (long long)count, q, loss3,
+                     (IqslWs*)workspace);
+  N2N_LAUNCH_CHECK();
+  if (grad) {
+    (void)launch_pdl_v(iqsl_grad_kernel, dim3(grid), dim3(kRedThreads), 0, (cudaStream_t)stream, pred, target, (long long)count, q, grad,
+                       (const IqslWs*)workspace);
+    N2N_LAUNCH_CHECK();
+  }
   return 0;
 }
 

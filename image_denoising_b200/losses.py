@@ -79,3 +79,29 @@ class Structure_loss(torch.nn.Module):
         loss, self.last_terms = _StructureLoss.apply(pred, pred2, target.detach(), float(self.alpha), float(self.beta),
                                                       float(self.gamma))
         return loss
+
+
+class _IqslLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, t1, t2, tau, margin, ce_factor, eps):
+        loss3, grad = ops.iqsl_loss_fwdbwd(pred, target, t1, t2, tau, margin, ce_factor, eps, 1.0, want_grad=True)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(loss3)
+        return loss3[0].clone(), loss3
+
+    @staticmethod
+    def backward(ctx, g, _g3):
+        (grad,) = ctx.saved_tensors
+        return (grad * g,) + (None,) * 7
+
+
+def iqsl_loss(pred, target, t1, t2, tau=0.1, margin=0.0, ce_factor=0.5, eps=1e-6):
+    """finetune_iqsl.py:291-383 (same signature): Intensity-Quantized Structural Loss — 3-class surrogate segmentation
+    (dark / mid / bright by the thresholds t1, t2), multi-class Dice over the batch + ce_factor * soft cross-entropy.
+    Forward and gradient w.r.t. ``pred`` in two fused kernels (the Dice couples all pixels through nine global sums)."""
+    if pred.dim() == 3:
+        pred = pred.unsqueeze(1)
+    if target.dim() == 3:
+        target = target.unsqueeze(1)
+    loss, _terms = _IqslLoss.apply(pred, target.detach(), float(t1), float(t2), float(tau), float(margin), float(ce_factor), float(eps))
+    return loss

@@ -240,6 +240,29 @@ def structure_loss_fwdbwd(pred, pred2, target, alpha: float, beta: float, gamma:
     return loss4, g1, g2
 
 
+_iqsl_ws = {}
+
+
+def iqsl_loss_fwdbwd(pred, target, t1: float, t2: float, tau: float = 0.1, margin: float = 0.0, ce_factor: float = 0.5,
+                     eps: float = 1e-6, grad_scale: float = 1.0, want_grad: bool = True):
+    """finetune_iqsl.py:291-383 -> (loss3 [total, dice, ce], dloss/dpred or None); single-channel tensors in [0,1]."""
+    require_cuda(pred, "iqsl_loss")
+    pred = _f32c(pred); target = _f32c(target)
+    if pred.shape != target.shape:
+        raise ValueError("pred and target must have the same shape.")
+    if pred.dim() == 4 and pred.shape[1] != 1:
+        raise ValueError("IQSL currently assumes single-channel grayscale input.")
+    key = (pred.device.type, pred.device.index)
+    if key not in _iqsl_ws:
+        _iqsl_ws[key] = torch.zeros(lib().n2n_loss_iqsl_workspace_bytes(), dtype=torch.uint8, device=pred.device)
+    loss3 = torch.empty(3, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib().n2n_loss_iqsl_fwdbwd(ptr(pred), ptr(target), pred.numel(), float(t1), float(t2), float(tau), float(margin),
+                                     float(ce_factor), float(eps), float(grad_scale), ptr(loss3), ptr(grad), ptr(_iqsl_ws[key]),
+                                     stream_ptr()))
+    return loss3, grad
+
+
 # ----------------------------------------------------------------------------- evaluation
 def quantize_u8(pred: torch.Tensor, bias: float) -> torch.Tensor:
     require_cuda(pred, "quantize_u8")

@@ -61,3 +61,28 @@ def calculate_ssim(target, ref):
 def calculate_psnr(target, ref):
     """utils_eval.py:49-53."""
     return float(psnr_ssim_batch([np.asarray(target)], [np.asarray(ref)])[0, 0])
+
+
+def compute_iq_iou(pred255, clean255, low_q: float, high_q: float):
+    """evaluation_704_iqsl.py:53-83: per-class IoU (dark / mid / bright) of the 3-level intensity quantisation of ``pred255``
+    against ``clean255``, thresholds = the (low_q, high_q) quantiles of the clean image.  Host numpy, as in the reference."""
+    def gray01(img):
+        arr = np.asarray(img).astype(np.float32)
+        if arr.ndim == 3:
+            arr = arr.mean(axis=2)
+        return arr / 255.0
+    gt, pr = gray01(clean255), gray01(pred255)
+    t1, t2 = np.quantile(gt, [low_q, high_q])
+    def quant(g):
+        lab = np.zeros_like(g, dtype=np.int32)
+        lab[g <= t1] = 0
+        lab[(g > t1) & (g < t2)] = 1
+        lab[g >= t2] = 2
+        return lab
+    gl, pl = quant(gt), quant(pr)
+    ious = []
+    for k in range(3):
+        inter = np.logical_and(gl == k, pl == k).sum()
+        union = np.logical_or(gl == k, pl == k).sum()
+        ious.append(float("nan") if union == 0 else float(inter) / float(union))
+    return ious

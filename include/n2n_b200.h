@@ -218,6 +218,13 @@ int n2n_loss_structure_fwdbwd(const float* pred, const float* pred2, const float
                               float alpha, float beta, float gamma, float grad_scale, float* loss4,
                               float* grad_pred, float* grad_pred2, void* workspace, void* stream);
 
+/* finetune_iqsl.py:291-383 (iqsl_loss): 3-class intensity-quantised Dice + ce_factor * soft CE on
+ * single-channel pred / target in [0,1] (count = all elements).  workspace: n2n_loss_iqsl_workspace_bytes() bytes, zero on
+ * first use.  loss3 = {total, dice term, CE term}; grad (may be NULL) = grad_scale * dloss/dpred. */
+size_t n2n_loss_iqsl_workspace_bytes(void);
+int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, float t1, float t2, float tau, float margin,
+                         float ce_factor, float eps, float grad_scale, float* loss3, float* grad, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Adam — train.py:332 (torch.optim.Adam defaults), finetune.py:260-263.
  * One launch over a table of tensors.  table (device, int64) holds, per tensor t

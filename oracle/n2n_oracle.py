@@ -420,3 +420,26 @@ def resnet_forward(p: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
     t = act(c1(t, "nin_a"))
     t = act(c1(t, "nin_b"))
     return c1(t, "nin_c") + x
+
+
+# ----------------------------------------------------------------------------
+# N4: IQSL — intensity-quantised structural loss (finetune_iqsl.py:291-383)
+# ----------------------------------------------------------------------------
+def iqsl_loss(pred, target, t1: float, t2: float, tau: float = 0.1, margin: float = 0.0, ce_factor: float = 0.5,
+              eps: float = 1e-6):
+    """finetune_iqsl.py:291-383 on [B,1,H,W] tensors.  Returns (total, dice term, CE term)."""
+    y_s, yh = target[:, 0], pred[:, 0]
+    if margin > 0.0:
+        valid = ((y_s <= (t1 - margin)) | ((y_s >= (t1 + margin)) & (y_s <= (t2 - margin))) | (y_s >= (t2 + margin))).float()
+    else:
+        valid = torch.ones_like(y_s)
+    oh = torch.stack([(y_s <= t1).float(), ((y_s > t1) & (y_s < t2)).float(), (y_s >= t2).float()], dim=1)
+    centers = torch.tensor([t1 / 2.0, (t1 + t2) / 2.0, (t2 + 1.0) / 2.0], dtype=pred.dtype).view(1, 3, 1, 1)
+    prob = torch.softmax(-torch.abs(yh.unsqueeze(1) - centers) / max(float(tau), 1e-6), dim=1)
+    vb = valid.unsqueeze(1)
+    prob = prob * vb
+    oh = oh * vb
+    inter = (prob * oh).sum(dim=(0, 2, 3)); ps = prob.sum(dim=(0, 2, 3)); ts = oh.sum(dim=(0, 2, 3))
+    loss_dice = 1.0 - ((2.0 * inter + eps) / (ps + ts + eps)).mean()
+    ce = -(oh * torch.log(prob + eps)).sum() / (vb.sum() * 3 + eps)
+    return loss_dice + ce_factor * ce, loss_dice, ce

@@ -85,3 +85,18 @@ def test_reference_named_eval_entry_points(tmp_path):
     txt = _run([os.path.join(ROOT, "entry", "evaluation_adapter.py"), "--data_dir", dd, "--ckpt", os.path.join(out, "ft2", "epoch_adapter_001.pth"),
                 "--arch", "UNet", "--save_dir", ev3], ROOT)
     assert txt.count("PSNR=") == 2 and len(glob.glob(os.path.join(ev3, "*_denoised.png"))) == 2
+
+
+def test_finetune_iqsl_entry_point(tmp_path):
+    """finetune_iqsl.py under its own name and flags: IQSL term in the loss, adapter-only checkpoint (finetune_iqsl.py:114-132)."""
+    out = str(tmp_path)
+    _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "2", "--patch", "64", "--batchsize", "2", "--n_epoch", "1",
+          "--save_model_path", out, "--log_name", "UNET_b", "--patches_per_image", "2"], ROOT)
+    ck = sorted(glob.glob(os.path.join(out, "UNET_b", "*", "epoch_model_*.pth")))
+    txt = _run([os.path.join(ROOT, "entry", "finetune_iqsl.py"), "--synthetic", "2", "--arch", "UNet", "--pretrained_ckpt", ck[-1],
+                "--n_epoch", "1", "--batchsize", "2", "--patch_size", "64", "--patches_per_image", "2", "--save_model_path", out,
+                "--log_name", "ftq", "--lambda_iqsl", "0.2", "--iqsl_margin", "0.01"], ROOT)
+    assert "[IQSL] Estimated thresholds" in txt and "IQSL=" in txt
+    ad = torch.load(os.path.join(out, "ftq", "epoch_adapter_only_001.pth"), map_location="cpu")
+    assert sorted(ad.keys()) == ["net.0.bias", "net.0.weight", "net.2.bias", "net.2.weight"]
+    assert all(torch.isfinite(v).all() for v in ad.values())

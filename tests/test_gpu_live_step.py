@@ -59,6 +59,44 @@ def test_structure_loss_large_vs_oracle(dev):
     assert torch.allclose(g1.cpu(), ar.grad, atol=1e-9, rtol=1e-5) and torch.allclose(g2.cpu(), br.grad, atol=1e-9, rtol=1e-5)
 
 
+def test_iqsl_loss_kernel_matches_reference_golden(dev, golden):
+    """finetune_iqsl.py:291-383: loss terms and dL/dpred of the fused kernels vs the reference's own function."""
+    from image_denoising_b200 import iqsl_loss
+    z = golden("r2_misc")
+    for i in range(3):
+        t1, t2, tau, margin, cef = (float(v) for v in z[f"iq_cfg{i}"])
+        pred = torch.from_numpy(z[f"iq_pred{i}"]).to(dev).requires_grad_(True)
+        tgt = torch.from_numpy(z[f"iq_tgt{i}"]).to(dev)
+        loss = iqsl_loss(pred, tgt, t1=t1, t2=t2, tau=tau, margin=margin, ce_factor=cef)
+        (2.0 * loss).backward()
+        assert abs(loss.item() - z[f"iq_loss{i}"][0]) <= 2e-6 * abs(z[f"iq_loss{i}"][0])
+        assert np.allclose(pred.grad.cpu().numpy(), 2.0 * z[f"iq_grad{i}"], rtol=2e-4, atol=2e-8)
+    # [B,H,W] inputs are accepted like the reference; multi-channel input and mismatched shapes are rejected
+    p3 = torch.rand(2, 16, 16, device=dev)
+    assert iqsl_loss(p3, p3.clone(), 0.3, 0.7).dim() == 0
+    with pytest.raises(ValueError):
+        iqsl_loss(torch.rand(1, 3, 8, 8, device=dev), torch.rand(1, 3, 8, 8, device=dev), 0.3, 0.7)
+    with pytest.raises(ValueError):
+        iqsl_loss(torch.rand(1, 1, 8, 8, device=dev), torch.rand(1, 1, 8, 4, device=dev), 0.3, 0.7)
+
+
+def test_iqsl_loss_large_vs_oracle(dev):
+    """Finetune shape (32 x 1 x 256 x 256): the nine global Dice sums couple 2 M pixels; fp64 two-stage reduction."""
+    from image_denoising_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    a, t = torch.rand(32, 1, 256, 256, generator=g), torch.rand(32, 1, 256, 256, generator=g)
+    for margin, cef in ((0.0, 0.5), (0.02, 1.0)):
+        ar = a.clone().double().requires_grad_(True)
+        lo, ld, lc = O.iqsl_loss(ar, t.double(), 0.35, 0.66, 0.1, margin, cef)
+        lo.backward()
+        loss3, grad = ops.iqsl_loss_fwdbwd(a.to(dev), t.to(dev), 0.35, 0.66, 0.1, margin, cef)
+        assert np.allclose(loss3.cpu().numpy(), [lo.item(), ld.item(), lc.item()], rtol=2e-5)
+        gr = ar.grad.float()
+        assert (grad.cpu() - gr).abs().max().item() <= 2e-4 * gr.abs().max().item()
+        loss3b, none = ops.iqsl_loss_fwdbwd(a.to(dev), t.to(dev), 0.35, 0.66, 0.1, margin, cef, want_grad=False)
+        assert none is None and torch.equal(loss3b, loss3)          # deterministic, workspace counter reset
+
+
 def test_space_to_depth_matches_reference_golden(dev, golden):
     from image_denoising_b200 import space_to_depth
     z = golden("r2_misc")

@@ -172,6 +172,18 @@ def test_space_to_depth_and_structure_loss_match_reference(golden):
         assert np.allclose(pred.grad.numpy(), z[f"sl_g1_{i}"], atol=1e-8) and np.allclose(pred2.grad.numpy(), z[f"sl_g2_{i}"], atol=1e-8)
 
 
+def test_iqsl_loss_matches_reference(golden):
+    """finetune_iqsl.py:291-383, golden made by executing the reference's own function (oracle/make_golden_r2.py)."""
+    z = golden("r2_misc")
+    for i in range(3):
+        t1, t2, tau, margin, cef = (float(v) for v in z[f"iq_cfg{i}"])
+        pred = torch.from_numpy(z[f"iq_pred{i}"]).requires_grad_(True)
+        loss, ld, lc = O.iqsl_loss(pred, torch.from_numpy(z[f"iq_tgt{i}"]), t1, t2, tau, margin, cef)
+        loss.backward()
+        assert np.allclose([loss.item(), ld.item(), lc.item()], z[f"iq_loss{i}"], rtol=1e-6)
+        assert np.allclose(pred.grad.numpy(), z[f"iq_grad{i}"], atol=1e-9, rtol=1e-5)
+
+
 def test_resnet_forward_and_live_step_match_reference(golden):
     """arch_unet.RESNET (arch_unet.py:263-409) + the fork's live supervised step (train.py:361-368)."""
     z = golden("r2_resnet")
