@@ -12,8 +12,8 @@ def network_from_log_name(log_name: str, n_channel: int, n_feature: int):
     if 'RESNET' in log_name:
         return RESNET(in_nc=n_channel, out_nc=n_channel, n_feature=n_feature)
     if 'UNetImproved' in log_name:
-        return ImprovedUNet(in_nc=n_channel, out_nc=n_channel, n_feature=n_feature)             # raises: §8f N2
-    raise SystemExit(f"--log_name {log_name!r} selects no network (it must contain 'UNET' or 'RESNET'; the reference "
+        return ImprovedUNet(in_nc=n_channel, out_nc=n_channel, n_feature=n_feature)             # §8f N2 (image_denoising_b200/improved.py)
+    raise SystemExit(f"--log_name {log_name!r} selects no network (it must contain 'UNET', 'RESNET' or 'UNetImproved'; the reference "
                      "leaves `network` undefined in this case, train.py:298-314)")
 
 

@@ -290,5 +290,4 @@ class RESNET(UNet):
         self.last_launches = 0
 
 
-def ImprovedUNet(*a, **k):  # arch_unet.py:475-531 — "next" row N2
-    raise NotImplementedError("ImprovedUNet is outside the B200 hot-path scope (SURVEY.md §8f N2)")
+from .improved import ImprovedUNet  # noqa: E402,F401  (arch_unet.py:475-531 — §8f N2, image_denoising_b200/improved.py)

@@ -27,7 +27,7 @@ constexpr int kMaxStages = 8;
 constexpr int kGroupBlocks = 3;
 constexpr int kThreads = 192;
 constexpr int kSlabRows = 136;                    // 128 pixels + left/right halo, padded to a multiple of 8 rows
-constexpr int kMaxEntries = 32;
+constexpr int kMaxEntries = 160;      // 9 taps x 16 channel-block groups (the 768-channel layers of ImprovedUNet) fit
 constexpr size_t kSmemBudget = 232448 - 4096;     // 227 KB per CTA minus static/alignment slack
 
 // One pipeline stage of the main loop: one staged activation tile (<= 3 channel blocks of one view

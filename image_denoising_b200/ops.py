@@ -263,6 +263,86 @@ def iqsl_loss_fwdbwd(pred, target, t1: float, t2: float, tau: float = 0.1, margi
     return loss3, grad
 
 
+# ----------------------------------------------------------------------------- ImprovedUNet operators (arch_unet.py:420-531)
+def groupnorm_groups(channels: int, groups: int = 32) -> int:
+    """arch_unet.py:11-15: the largest g <= min(groups, channels) that divides channels."""
+    return int(lib().n2n_groupnorm_groups(int(channels), int(groups)))
+
+
+def groupnorm_fwd(x, gamma, beta, groups: int, eps: float = 1e-5, act_slope: float = -1.0, residual=None, want_stats: bool = True):
+    """-> (y, mean_rstd [n, groups, 2] or None).  y = GN(x)*gamma + beta, then LeakyReLU(act_slope) if act_slope >= 0, + residual if given."""
+    require_cuda(x, "groupnorm_fwd")
+    x = _f32c(x); gamma = _f32c(gamma); beta = _f32c(beta)
+    residual = None if residual is None else _f32c(residual)
+    n, c, h, w = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device) if want_stats else None
+    ws = _ws(lib().n2n_groupnorm_workspace_bytes(n, c), x.device)
+    check(lib().n2n_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(residual), ptr(y), ptr(stats), n, c, h * w, int(groups),
+                                  float(eps), float(act_slope), ptr(ws), stream_ptr()))
+    return y, stats
+
+
+def groupnorm_bwd(x, gamma, y, dy, stats, groups: int, act_slope: float = -1.0):
+    """-> (dx, dgamma, dbeta); ``y`` (forward output) is only read when an activation was fused."""
+    require_cuda(x, "groupnorm_bwd")
+    x = _f32c(x); gamma = _f32c(gamma); dy = _f32c(dy)
+    n, c, h, w = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty_like(gamma); dbeta = torch.empty_like(gamma)
+    ws = _ws(lib().n2n_groupnorm_workspace_bytes(n, c), x.device)
+    check(lib().n2n_groupnorm_bwd(ptr(x), ptr(gamma), ptr(y), ptr(dy), ptr(stats), ptr(dx), ptr(dgamma), ptr(dbeta), n, c, h * w,
+                                  int(groups), float(act_slope), ptr(ws), stream_ptr()))
+    return dx, dgamma, dbeta
+
+
+ACT_LRELU, ACT_SIGMOID = 1, 2
+
+
+def act_fwd(x, kind: int, slope: float = 0.2):
+    require_cuda(x, "act_fwd")
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    check(lib().n2n_act_fwd(ptr(x), ptr(y), x.numel(), int(kind), float(slope), stream_ptr()))
+    return y
+
+
+def act_bwd(y, dy, kind: int, slope: float = 0.2):
+    require_cuda(y, "act_bwd")
+    y = _f32c(y); dy = _f32c(dy)
+    dx = torch.empty_like(y)
+    check(lib().n2n_act_bwd(ptr(y), ptr(dy), ptr(dx), y.numel(), int(kind), float(slope), stream_ptr()))
+    return dx
+
+
+def add(a, b):
+    require_cuda(a, "add")
+    a = _f32c(a); b = _f32c(b)
+    if a.shape != b.shape:
+        raise ValueError("add: shape mismatch")
+    out = torch.empty_like(a)
+    check(lib().n2n_add_f32(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
+    return out
+
+
+def pixel_shuffle2(x, inverse: bool = False):
+    """nn.PixelShuffle(2) ([n,4c,h,w] -> [n,c,2h,2w]) or, with inverse=True, its gradient map ([n,c,2h,2w] -> [n,4c,h,w])."""
+    require_cuda(x, "pixel_shuffle2")
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    if inverse:
+        if h % 2 or w % 2:
+            raise ValueError("pixel_shuffle2(inverse): H and W must be even")
+        y = torch.empty((n, 4 * c, h // 2, w // 2), dtype=torch.float32, device=x.device)
+        check(lib().n2n_pixel_shuffle2(ptr(x), ptr(y), n, c, h // 2, w // 2, 1, stream_ptr()))
+    else:
+        if c % 4:
+            raise ValueError("pixel_shuffle2: channels must be a multiple of 4")
+        y = torch.empty((n, c // 4, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+        check(lib().n2n_pixel_shuffle2(ptr(x), ptr(y), n, c // 4, h, w, 0, stream_ptr()))
+    return y
+
+
 # ----------------------------------------------------------------------------- evaluation
 def quantize_u8(pred: torch.Tensor, bias: float) -> torch.Tensor:
     require_cuda(pred, "quantize_u8")

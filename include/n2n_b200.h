@@ -226,6 +226,33 @@ int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, 
                          float ce_factor, float eps, float grad_scale, float* loss3, float* grad, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Non-GEMM operators of arch_unet.ImprovedUNet — arch_unet.py:420-531, fp32 NCHW.
+ * GroupNorm = norm2d('gn', c, 32) (arch_unet.py:7-15): n2n_groupnorm_groups() applies the reference's
+ * "largest divisor of c that is <= groups" rule.  y = GN(x) * gamma + beta, then LeakyReLU(act_slope) when
+ * act_slope >= 0, or + residual when given (the two forms ResBlock uses, :421-432; exclusive).  mean_rstd
+ * [n][groups][2] (may be NULL in no-grad passes) is what the backward needs; biased variance, eps inside the
+ * square root (torch.nn.GroupNorm).  workspace: n2n_groupnorm_workspace_bytes(n, c).  Backward: dy is the
+ * gradient w.r.t. the (activated) output, y the forward output (only read when act_slope >= 0).
+ * ------------------------------------------------------------------------- */
+int n2n_groupnorm_groups(int channels, int groups);
+size_t n2n_groupnorm_workspace_bytes(int n, int c);
+int n2n_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                      float* mean_rstd, int n, int c, int hw, int groups, float eps, float act_slope,
+                      void* workspace, void* stream);
+int n2n_groupnorm_bwd(const float* x, const float* gamma, const float* y, const float* dy, const float* mean_rstd,
+                      float* dx, float* dgamma, float* dbeta, int n, int c, int hw, int groups, float act_slope,
+                      void* workspace, void* stream);
+/* kind 1: LeakyReLU(slope) (arch_unet.py:424, :441, :464), kind 2: Sigmoid (:486, :530).  The backward reads the
+ * OUTPUT (the reference's activations are in place): dx = dy * (y > 0 ? 1 : slope) or dy * y * (1 - y). */
+int n2n_act_fwd(const float* x, float* y, int64_t count, int kind, float slope, void* stream);
+int n2n_act_bwd(const float* y, const float* dy, float* dx, int64_t count, int kind, float slope, void* stream);
+/* out = a + b — the residual connections of RDB / ResBlock (arch_unet.py:432, :449). */
+int n2n_add_f32(const float* a, const float* b, float* out, int64_t count, void* stream);
+/* nn.PixelShuffle(2) (arch_unet.py:456, :461): src [n][4*c_out][h][w] -> dst [n][c_out][2h][2w] with
+ * dst[n,c,2y+i,2x+j] = src[n,4c+2i+j,y,x]; inverse != 0 runs the same map backwards (its gradient). */
+int n2n_pixel_shuffle2(const float* src, float* dst, int n, int c_out, int h, int w, int inverse, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Adam — train.py:332 (torch.optim.Adam defaults), finetune.py:260-263.
  * One launch over a table of tensors.  table (device, int64) holds, per tensor t
  * of ntensors: [p_ptr, g_ptr, m_ptr, v_ptr, numel]; blocks (device, int32) holds

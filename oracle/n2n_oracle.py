@@ -443,3 +443,112 @@ def iqsl_loss(pred, target, t1: float, t2: float, tau: float = 0.1, margin: floa
     loss_dice = 1.0 - ((2.0 * inter + eps) / (ps + ts + eps)).mean()
     ce = -(oh * torch.log(prob + eps)).sum() / (vb.sum() * 3 + eps)
     return loss_dice + ce_factor * ce, loss_dice, ce
+
+
+# ----------------------------------------------------------------------------
+# N2: ImprovedUNet (arch_unet.py:420-531)
+# ----------------------------------------------------------------------------
+def gn_groups(channels: int, groups: int = 32) -> int:
+    """arch_unet.py:11-15 (norm2d 'gn')."""
+    g = min(groups, channels)
+    while channels % g != 0 and g > 1:
+        g -= 1
+    return g
+
+
+def improved_param_shapes(in_nc: int, out_nc: int, nf0: int, depth: int = 4, noise: bool = True) -> "OrderedDict[str, tuple]":
+    """state_dict keys / shapes of arch_unet.ImprovedUNet in registration order (arch_unet.py:476-513)."""
+    s = OrderedDict()
+
+    def conv(name, co, ci, k, bias=True):
+        s[name + ".weight"] = (co, ci, k, k)
+        if bias:
+            s[name + ".bias"] = (co,)
+
+    def rdb(pre, c):
+        ci = c
+        for i in range(4):
+            conv(f"{pre}.convs.{i}", 32, ci, 3)
+            ci += 32
+        conv(f"{pre}.lff", c, ci, 1)
+
+    def res(pre, c):
+        for j in (0, 3):
+            conv(f"{pre}.block.{j}", c, c, 3, bias=False)
+            s[f"{pre}.block.{j + 1}.weight"] = (c,)
+            s[f"{pre}.block.{j + 1}.bias"] = (c,)
+
+    if noise:
+        conv("noise_estimator.0", nf0, in_nc, 3)
+        conv("noise_estimator.2", 1, nf0, 3)
+    nf = nf0
+    for i in range(depth):
+        inc = (in_nc + 1 if noise else 1) if i == 0 else nf // 2
+        conv(f"downs.{i}.0", nf, inc, 3)
+        rdb(f"downs.{i}.2", nf)
+        res(f"downs.{i}.3", nf)
+        nf *= 2
+    rdb("bottle.0", nf // 2)
+    res("bottle.1", nf // 2)
+    nf //= 2
+    for i in range(depth):
+        conv(f"ups.{i}.conv_ps", 2 * nf, nf, 3)          # out_ch * 4 = (nf // 2) * 4
+        conv(f"ups.{i}.fuse", nf // 2, 3 * (nf // 2), 3)
+        rdb(f"ups.{i}.rdb", nf // 2)
+        res(f"ups.{i}.res", nf // 2)
+        nf //= 2
+    conv("final", out_nc, nf0 // 2 + in_nc, 3)
+    return s
+
+
+def improved_init(in_nc: int, out_nc: int, nf: int, seed: int, depth: int = 4, noise: bool = True) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded test weights (NOT the reference's default init): convs ~ N(0, 1/fan_in), biases ~ 0.05 N, GroupNorm gain ~ 1 + 0.1 N."""
+    g = torch.Generator().manual_seed(seed)
+    p = OrderedDict()
+    for name, shp in improved_param_shapes(in_nc, out_nc, nf, depth, noise).items():
+        if len(shp) == 4:
+            p[name] = torch.randn(shp, generator=g) * math.sqrt(1.0 / (shp[1] * shp[2] * shp[3]))
+        elif name.endswith(".weight"):
+            p[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            p[name] = 0.05 * torch.randn(shp, generator=g)
+    return p
+
+
+def improved_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, depth: int = 4, noise: bool = True) -> torch.Tensor:
+    """arch_unet.py:515-531."""
+    act = lambda t: F.leaky_relu(t, 0.2)
+    in_nc = x.shape[1]
+
+    def conv(t, n):
+        w = p[n + ".weight"]
+        return F.conv2d(t, w, p.get(n + ".bias"), padding=w.shape[2] // 2)
+
+    def gn(t, n):
+        return F.group_norm(t, gn_groups(t.shape[1]), p[n + ".weight"], p[n + ".bias"], 1e-5)
+
+    def rdb(t, pre):
+        feats = [t]
+        for i in range(4):
+            feats.append(act(conv(torch.cat(feats, 1), f"{pre}.convs.{i}")))
+        return t + conv(torch.cat(feats, 1), f"{pre}.lff")
+
+    def res(t, pre):
+        u = act(gn(conv(t, f"{pre}.block.0"), f"{pre}.block.1"))
+        return t + gn(conv(u, f"{pre}.block.3"), f"{pre}.block.4")
+
+    if noise:
+        sigma = torch.sigmoid(conv(act(conv(x, "noise_estimator.0")), "noise_estimator.2"))
+        x = torch.cat([x, sigma], 1)
+    orig = x[:, :in_nc]
+    skips = []
+    for i in range(depth):
+        x = res(rdb(act(conv(x, f"downs.{i}.0")), f"downs.{i}.2"), f"downs.{i}.3")
+        skips.append(x)
+        x = F.max_pool2d(x, 2)
+    x = res(rdb(x, "bottle.0"), "bottle.1")
+    for i, skip in enumerate(reversed(skips)):
+        x = F.pixel_shuffle(conv(x, f"ups.{i}.conv_ps"), 2)
+        x = act(conv(torch.cat([x, skip], 1), f"ups.{i}.fuse"))
+        x = res(rdb(x, f"ups.{i}.rdb"), f"ups.{i}.res")
+    return torch.sigmoid(conv(torch.cat([x, orig], 1), "final"))

@@ -100,3 +100,19 @@ def test_finetune_iqsl_entry_point(tmp_path):
     ad = torch.load(os.path.join(out, "ftq", "epoch_adapter_only_001.pth"), map_location="cpu")
     assert sorted(ad.keys()) == ["net.0.bias", "net.0.weight", "net.2.bias", "net.2.weight"]
     assert all(torch.isfinite(v).all() for v in ad.values())
+
+
+def test_improved_unet_through_the_entry_points(tmp_path):
+    """train.sh:3 / eval_704.sh launch the 'UNetImproved' family (arch_unet.ImprovedUNet): the fork's live supervised loop,
+    then evaluation_704.py on its checkpoint (reference state_dict keys)."""
+    out = str(tmp_path)
+    _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "2", "--patch", "64", "--batchsize", "2", "--n_epoch", "1",
+          "--loop", "supervised", "--save_model_path", out, "--log_name", "UNetImproved_t", "--patches_per_image", "2",
+          "--n_feature", "16"], ROOT)
+    ck = sorted(glob.glob(os.path.join(out, "UNetImproved_t", "*", "epoch_model_*.pth")))
+    sd = torch.load(ck[-1], map_location="cpu")
+    assert "ups.3.res.block.4.bias" in sd and "noise_estimator.2.weight" in sd and sd["final.weight"].shape == (1, 9, 3, 3)
+    ev = os.path.join(out, "eval704")
+    _run([os.path.join(ROOT, "entry", "evaluation_704.py"), "--synthetic", "1", "--checkpoint", ck[-1], "--save_dir", ev,
+          "--log_name", "UNetImproved_t", "--n_feature", "16"], ROOT)
+    assert "Average PSNR:" in open(os.path.join(ev, "metrics.txt")).read()

@@ -208,3 +208,27 @@ def test_resnet_forward_and_live_step_match_reference(golden):
     out = O.unet_forward(pr, noisy)
     loss, px, _, _ = O.structure_loss(out, O.unet_forward(pr, clean), clean)
     assert np.allclose([loss.item(), px.item()], z["losses"][0], rtol=1e-6)
+
+
+def test_improved_unet_oracle_matches_reference(golden):
+    """arch_unet.ImprovedUNet (arch_unet.py:420-531): forward, live-step loss and gradient checksums vs the unmodified reference;
+    the drop-in module registers the reference's parameters (names, shapes, order)."""
+    from image_denoising_b200 import ImprovedUNet
+    z = golden("r2_improved")
+    for tag in ("g16", "c48"):
+        in_nc, nf, seed = (int(v) for v in z[f"{tag}_cfg"])
+        p = O.improved_init(in_nc, in_nc, nf, seed)
+        net = ImprovedUNet(in_nc=in_nc, out_nc=in_nc, n_feature=nf)
+        assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(v.shape)) for k, v in p.items()]
+        noisy = torch.from_numpy(z[f"{tag}_noisy"]); clean = torch.from_numpy(z[f"{tag}_clean"])
+        with torch.no_grad():
+            assert np.abs(O.improved_forward(p, noisy).numpy() - z[f"{tag}_y"]).max() < 1e-6
+        if tag == "g16":
+            pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+            loss, _, _, _ = O.structure_loss(O.improved_forward(pr, noisy), O.improved_forward(pr, clean), clean)
+            loss.backward()
+            assert abs(loss.item() - float(z[f"{tag}_loss"])) < 1e-6
+            for k, v in pr.items():
+                assert np.allclose(_csum(v.grad), z[f"{tag}_gsum/{k}"], rtol=1e-3, atol=1e-8), k
+    assert sum(v.numel() for v in ImprovedUNet(1, 1, 48).state_dict().values()) == sum(
+        int(np.prod(s)) for s in O.improved_param_shapes(1, 1, 48).values())
