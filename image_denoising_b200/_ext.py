@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libn2n_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "subsample.cu", "loss_adam.cu", "metrics.cu", "pack.cu",
-           "improved_ops.cu", "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "headbwd_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
+           "improved_ops.cu", "adapter_fused.cu", "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "headbwd_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -119,7 +119,7 @@ _SIGS = {
     "n2n_adapter_plan_destroy": (None, [c_void_p]),
     "n2n_adapter_workspace_bytes": (c_size_t, [c_void_p]),
     "n2n_adapter_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "n2n_adapter_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p), c_void_p, c_void_p]),
+    "n2n_adapter_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p]),
     "n2n_loss_workspace_bytes": (c_size_t, [c_int64]),
     "n2n_loss_n2n_fwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int64,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),

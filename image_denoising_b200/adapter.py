@@ -25,15 +25,17 @@ class _AdapterFunction(torch.autograd.Function):
         out = torch.empty_like(base_out)
         check(lib().n2n_adapter_forward(plan, ptr_array(params), ptr(noisy), ptr(base_out), ptr(out), ptr(ws), stream_ptr()))
         ctx.mod, ctx.key, ctx.plan, ctx.ws, ctx.params = mod, key, plan, ws, params
+        ctx.inputs = (noisy, base_out)           # conv1's weight gradient reads the concat operand again
         return out
 
     @staticmethod
     def backward(ctx, dout):
         dout = dout.contiguous().float()
         grads = [torch.empty_like(p) for p in ctx.params]
-        check(lib().n2n_adapter_backward(ctx.plan, ptr_array(ctx.params), ptr(dout), ptr_array(grads), ptr(ctx.ws), stream_ptr()))
+        check(lib().n2n_adapter_backward(ctx.plan, ptr_array(ctx.params), ptr(ctx.inputs[0]), ptr(ctx.inputs[1]), ptr(dout),
+                                         ptr_array(grads), ptr(ctx.ws), stream_ptr()))
         ctx.mod._give_back(ctx.key, ctx.ws)
-        ctx.ws = None
+        ctx.ws = ctx.inputs = None
         return (None, None, None) + tuple(grads)
 
 

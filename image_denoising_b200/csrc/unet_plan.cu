@@ -1077,8 +1077,19 @@ static int resnet_backward(n2n_unet_plan* p, const float* const* params, const f
 // ------------------------------------------------------------------------------------------
 // Output adapter (adapter.py:5-26)
 // ------------------------------------------------------------------------------------------
+namespace n2n {      // adapter_fused.cu: CUDA-core direct convolutions for C in {1, 3}, hidden 16
+struct AdapterFusedWs { size_t off_const, off_h, off_gh, off_p1, off_p2, total; };
+AdapterFusedWs adapter_fused_layout(int C, int n, int h, int w, bool bwd);
+bool adapter_fused_ok(int C, int hid, int w);
+int adapter_fused_forward(int C, int dtype, const float* const* params, const float* noisy, const float* base_out, float* out, void* ws,
+                          int n, int h, int w, bool bwd, cudaStream_t st);
+int adapter_fused_backward(int C, int dtype, const float* const* params, const float* noisy, const float* base_out, const float* dout,
+                           float* const* grads, void* ws, int n, int h, int w, cudaStream_t st);
+}  // namespace n2n
+
 struct n2n_adapter_plan {
   int C, hid, N, H, W, dtype; bool bwd;
+  bool fused = false;      // adapter_fused.cu path (fp32 math in both precision modes)
   LayerGeom L[2];
   size_t off_cat, off_h, off_gout, off_gh, off_wp[2], off_wd1, off_bias[2], off_partial[2], off_bpartial[2];
   int splits[2];
@@ -1092,6 +1103,12 @@ extern "C" int n2n_adapter_plan_create(n2n_adapter_plan** plan, int channels, in
   N2N_CHECK_ARG(dtype == N2N_F32 || dtype == N2N_BF16, "adapter_plan_create: bad dtype");
   n2n_adapter_plan* p = new n2n_adapter_plan();
   p->C = channels; p->hid = hidden; p->N = n; p->H = h; p->W = w; p->dtype = dtype; p->bwd = with_backward != 0;
+  { const char* e = getenv("N2N_NO_ADAPTER_FUSED"); p->fused = adapter_fused_ok(channels, hidden, w) && !(e && atoi(e)); }
+  if (p->fused) {
+    p->total = adapter_fused_layout(channels, n, h, w, p->bwd).total;
+    *plan = p;
+    return 0;
+  }
   p->L[0].kind = L_CONV3; p->L[0].cin = chan2(channels, channels); p->L[0].cout = hidden;   // cat[noisy, base_out]
   p->L[1].kind = L_CONV3; p->L[1].cin = chan1(hidden); p->L[1].cout = channels;
   size_t off = 0;
@@ -1124,6 +1141,7 @@ extern "C" int n2n_adapter_forward(n2n_adapter_plan* p, const float* const* para
                                    const float* base_out, float* out, void* ws, void* stream) {
   N2N_CHECK_ARG(p && params && noisy && base_out && out && ws, "adapter_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->fused) return adapter_fused_forward(p->C, p->dtype, params, noisy, base_out, out, ws, p->N, p->H, p->W, p->bwd, st);
   const int dt = p->dtype;
   const int hb = cblocks(p->hid);
   View cat = make_view((char*)ws + p->off_cat, dt, p->N, p->H, p->W, 2, 0, 2);
@@ -1149,11 +1167,12 @@ extern "C" int n2n_adapter_forward(n2n_adapter_plan* p, const float* const* para
   return launch_tapgemm(g1, st);
 }
 
-extern "C" int n2n_adapter_backward(n2n_adapter_plan* p, const float* const* params, const float* dout,
-                                    float* const* grads, void* ws, void* stream) {
-  N2N_CHECK_ARG(p && params && dout && grads && ws, "adapter_backward: null argument");
+extern "C" int n2n_adapter_backward(n2n_adapter_plan* p, const float* const* params, const float* noisy, const float* base_out,
+                                    const float* dout, float* const* grads, void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && noisy && base_out && dout && grads && ws, "adapter_backward: null argument");
   N2N_CHECK_ARG(p->bwd, "adapter_backward: plan was created without with_backward");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->fused) return adapter_fused_backward(p->C, p->dtype, params, noisy, base_out, dout, grads, ws, p->N, p->H, p->W, st);
   const int dt = p->dtype;
   const int hb = cblocks(p->hid);
   View cat = make_view((char*)ws + p->off_cat, dt, p->N, p->H, p->W, 2, 0, 2);

@@ -182,6 +182,11 @@ int n2n_unet_backward(n2n_unet_plan* plan, const float* const* params, const flo
  * Output adapter — adapter.py:5-26 (OutputAdapter.forward), :59-67.
  * out = base_out + conv3x3(relu(conv3x3(cat[noisy, base_out]))).
  * params/grads: net.0.weight [hid,2C,3,3], net.0.bias, net.2.weight [C,hid,3,3], net.2.bias.
+ * C in {1, 3} with hid = 16 and W % 4 == 0 (the reference's configurations) runs as direct fp32
+ * convolutions on the CUDA cores (csrc/adapter_fused.cu: weights in the constant bank, exact in both
+ * precision modes); other shapes run as 16-channel-block tap GEMMs on the engine `dtype` selects.
+ * The backward reads the hidden activations the forward of the SAME plan + workspace left behind and
+ * takes the forward's inputs again (noisy, base_out: the concat operand of conv1's weight gradient).
  * ------------------------------------------------------------------------- */
 typedef struct n2n_adapter_plan n2n_adapter_plan;
 int n2n_adapter_plan_create(n2n_adapter_plan** plan, int channels, int hidden,
@@ -191,8 +196,9 @@ size_t n2n_adapter_workspace_bytes(const n2n_adapter_plan* plan);
 int n2n_adapter_forward(n2n_adapter_plan* plan, const float* const* params,
                         const float* noisy, const float* base_out, float* out,
                         void* workspace, void* stream);
-int n2n_adapter_backward(n2n_adapter_plan* plan, const float* const* params, const float* dout,
-                         float* const* grads, void* workspace, void* stream);
+int n2n_adapter_backward(n2n_adapter_plan* plan, const float* const* params, const float* noisy,
+                         const float* base_out, const float* dout, float* const* grads, void* workspace,
+                         void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Losses
