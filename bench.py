@@ -358,6 +358,51 @@ def adapter_finetune_c5(dev, precision, steps=10, batch=32):
             "inputs": "4 device-resident batches (151 MB each side) rotated; activations >> L2"}
 
 
+def improved_unet_leg(dev, precision):
+    """arch_unet.ImprovedUNet(1, 1, 48) (what train.sh:3 launches; 90.2 GFLOP forward per 256x256 patch)
+    through the drop-in module — no-grad forward on 8 x 1x256x256 and the fork's live supervised step (train.py:354-368: two
+    forwards with grad, Structure_loss, backward, Adam) on 4 x 1x128x128.  A "next" row: functional + parity-tested, not tuned."""
+    import torch
+    from image_denoising_b200 import FusedAdam, ImprovedUNet, Structure_loss
+    torch.manual_seed(5)
+    net = ImprovedUNet(1, 1, NF).to(dev).set_precision(precision)
+    x = torch.rand(8, 1, 256, 256, device=dev)
+
+    def timed(fn, warm, it):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(it):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / it
+
+    with torch.no_grad():
+        fwd_ms = timed(lambda: net(x), 2, 5)
+    opt = FusedAdam(net.parameters(), lr=1e-4)
+    crit = Structure_loss()
+    clean = torch.rand(4, 1, 128, 128, device=dev)
+    noisy = (clean + 0.1 * torch.randn_like(clean)).clamp(0, 1)
+
+    def step():
+        opt.zero_grad()
+        loss = crit(net(noisy), net(clean), clean)
+        loss.backward()
+        opt.step()
+
+    train_ms = timed(step, 2, 4)
+    del net, opt
+    torch.cuda.empty_cache()
+    return {"metric": "improved_unet48_forward_images_per_s_1x256x256", "value": 8 / (fwd_ms / 1e3), "unit": "images/s", "batch": 8,
+            "ms_per_forward": fwd_ms, "gflop_per_image": 90.2, "tflops": 8 * 90.2 / fwd_ms,
+            "supervised_step_4x1x128x128_ms": train_ms,
+            "note": "layers cross the C-ABI one call at a time as fp32 NCHW (conversions inside each call); stock PyTorch bf16 "
+                    "autocast runs the same forward in 10.5 ms on this GPU (scripts/improved_bench.py)"}
+
+
 def hbm_kernels(dev):
     """HBM-bound rows: achieved GB/s = ALGORITHMIC bytes per launch / average launch duration
     (CUDA events around R back-to-back launches on the launching stream, rotating over buffer sets whose total
@@ -420,6 +465,17 @@ def hbm_kernels(dev):
     us = timed(lambda i: check(L.n2n_loss_n2n_fwdbwd(ptr(bufs[i][0]), ptr(bufs[i][1]), ptr(bufs[i][2]), ptr(bufs[i][3]), 0.5, 1.0, m,
                                                      ptr(loss3), ptr(bufs[i][4]), ptr(lws), st)), nsets, 140)
     row("n2n_loss_fwdbwd_64x128x128", 5 * m * 4, us, "out, sub2, den1, den2 read + dL/dout written, fp64 two-stage reduction")
+    del bufs
+
+    # ---- IQSL loss fwd+bwd at the finetune shape (32 x 1 x 256 x 256 fp32): pred + target read by both passes, grad written
+    m2 = 32 * 256 * 256
+    nsets = 10
+    bufs = [[torch.rand(m2, generator=g, device=dev) for _ in range(3)] for _ in range(nsets)]
+    iq3 = torch.zeros(3, device=dev)
+    iqws = torch.zeros(L.n2n_loss_iqsl_workspace_bytes(), dtype=torch.uint8, device=dev)
+    us = timed(lambda i: check(L.n2n_loss_iqsl_fwdbwd(ptr(bufs[i][0]), ptr(bufs[i][1]), m2, 0.3, 0.7, 0.1, 0.0, 0.5, 1e-6, 1.0, ptr(iq3),
+                                                      ptr(bufs[i][2]), ptr(iqws), st)), nsets, 100)
+    row("iqsl_loss_fwdbwd_32x256x256", 5 * m2 * 4, us, "two launches (global Dice sums, then the gradient): 4 reads + 1 write; expf/logf per class")
     del bufs
 
     # ---- Adam over the UNet's 1 256 689 parameters: read p,g,m,v + write p,m,v = 35.2 MB
@@ -682,9 +738,10 @@ def run_b200(args):
         infer = inference_704(dev, args.precision, world, rank, dist)
         infer_tiled = inference_704_tiled(dev, args.precision, world, rank, dist)
 
-    cpu = adapter = hbm = torch_gpu = None
+    cpu = adapter = hbm = torch_gpu = improved = None
     if rank == 0 and world == 1 and not args.no_extra:
         adapter = adapter_finetune_c5(dev, args.precision)
+        improved = improved_unet_leg(dev, args.precision)
         hbm = hbm_kernels(dev)
         torch_gpu = torch_gpu_baseline(dev, B)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -718,6 +775,7 @@ def run_b200(args):
             "inference_704": infer,
             "inference_704_tiled": infer_tiled,
             "adapter_finetune": adapter,
+            "improved_unet": improved,
             "hbm_kernels": hbm,
             "torch_gpu_baseline": torch_gpu,
             "final_loss": final_loss,
