@@ -113,6 +113,7 @@ _SIGS = {
     "n2n_unet_read_activation": (ctypes.c_longlong, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int), c_void_p]),
     "n2n_unet_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_unet_share_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "n2n_unet_pack_weights": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p]),
     "n2n_unet_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, POINTER(c_void_p), c_void_p,
                                   c_void_p, c_void_p]),
     "n2n_adapter_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

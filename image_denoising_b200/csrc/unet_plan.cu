@@ -75,6 +75,7 @@ struct n2n_unet_plan {
   int fwd_launches = 0, bwd_launches = 0;
   // forward weights / padded biases may be borrowed from another plan of the same network that has already
   // packed them for this step (n2n_unet_share_weights): the pack is a function of the parameters only
+  bool prepacked = false;                // n2n_unet_pack_weights ran for the next n2n_unet_forward (which then skips its pack step)
   const n2n_unet_plan* donor = nullptr;
   const void* donor_ws = nullptr;
   bool share[25] = {false};              // per layer: the donor packs this layer exactly as this plan would
@@ -369,18 +370,10 @@ extern "C" int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* 
   return 0;
 }
 
-extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y,
-                                void* ws, void* stream) {
-  N2N_CHECK_ARG(p && params && x && y && ws, "unet_forward: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long launches0 = g_launch_count;
-  if (p->arch == ARCH_RESNET) {
-    N2N_TRY(resnet_forward(p, params, x, y, ws, st));
-    p->fwd_launches = (int)(g_launch_count - launches0);
-    return 0;
-  }
+// The pack step of n2n_unet_forward: PyTorch-layout fp32 parameters -> the engines' packed weight images, padded biases
+// and (fused levels) the composite up-conv weights.  A function of the parameters only.
+static int unet_pack_weights(n2n_unet_plan* p, const float* const* params, void* ws, cudaStream_t st) {
   const int dt = p->dtype;
-  // weights -> engine layout (fwd; dgrad copies too when a backward will follow)
   {
     std::vector<PackJob> jobs;
     BiasPadJob bj[25];
@@ -466,6 +459,32 @@ extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, co
     N2N_TRY(launch_upfuse_pack(uj, nuj, st));
     if (!p->donor) N2N_TRY(launch_bias_pad(bj, 25, st));
   }
+  return 0;
+}
+
+extern "C" int n2n_unet_pack_weights(n2n_unet_plan* p, const float* const* params, void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && ws, "unet_pack_weights: null argument");
+  if (p->arch != ARCH_UNET) return 0;                       // the RESNET plan packs inside its forward
+  N2N_TRY(unet_pack_weights(p, params, ws, (cudaStream_t)stream));
+  p->prepacked = true;
+  return 0;
+}
+
+extern "C" int n2n_unet_forward(n2n_unet_plan* p, const float* const* params, const float* x, float* y,
+                                void* ws, void* stream) {
+  N2N_CHECK_ARG(p && params && x && y && ws, "unet_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long launches0 = g_launch_count;
+  if (p->arch == ARCH_RESNET) {
+    N2N_TRY(resnet_forward(p, params, x, y, ws, st));
+    p->fwd_launches = (int)(g_launch_count - launches0);
+    return 0;
+  }
+  const int dt = p->dtype;
+  // weights -> engine layout (fwd; dgrad copies too when a backward will follow) — unless n2n_unet_pack_weights already
+  // did it for this call
+  if (p->prepacked) p->prepacked = false;
+  else N2N_TRY(unet_pack_weights(p, params, ws, st));
   // input image -> skip block of the level-0 concat buffer (pool0 = x, arch_unet.py:200)
   bool enc0_done = false;     // the fused input stage also produced enc_conv0's output
   if (p->im2col) {

@@ -62,9 +62,9 @@ class N2NTrainer:
         if use_graph is None:
             use_graph = os.environ.get("N2N_NO_GRAPH", "0") != "1"
         self.use_graph = bool(use_graph)
-        # optional: run the two forward passes on two streams (measured: no gain — the persistent
-        # one-CTA-per-SM kernels leave no room to co-schedule — so it is off by default)
-        self.overlap_forwards = os.environ.get("N2N_OVERLAP", "0") == "1"
+        # the no-grad full-resolution pass and the training forward are independent: two streams (the launch-bound deep
+        # levels of one pass fill the SMs the other leaves idle; measured 5.27 -> 5.14 ms/step).  N2N_OVERLAP=0: one stream
+        self.overlap_forwards = os.environ.get("N2N_OVERLAP", "1") == "1"
         self._graph = None
         self._eager_steps = 0
         if self.world > 1:
@@ -86,10 +86,10 @@ class N2NTrainer:
                                          h // 2, w // 2, dt, 1))
         self.ws_full = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_full), dtype=torch.uint8, device=dev)
         self.ws_half = torch.empty(lib().n2n_unet_workspace_bytes(self.plan_half), dtype=torch.uint8, device=dev)
-        # the half-resolution pass runs right behind the full-resolution one on the same weights: borrow its packed
-        # forward weights instead of repacking them (not when the two passes run on different streams)
+        # the half-resolution pass runs on the same weights as the full-resolution one: borrow its packed forward weights
+        # instead of repacking them (two streams: the full plan packs BEFORE the fork, n2n_unet_pack_weights)
         self.shared_weights = False
-        if not self.overlap_forwards and os.environ.get("N2N_NO_SHARE", "0") != "1":
+        if os.environ.get("N2N_NO_SHARE", "0") != "1":
             rc = lib().n2n_unet_share_weights(self.plan_half, self.plan_full, ptr(self.ws_full))
             if rc < 0:
                 check(rc)
@@ -135,8 +135,10 @@ class N2NTrainer:
         # The no-grad full-resolution pass and the half-resolution training forward are independent
         # (training_script.md:139-146): run the latter on a side stream so that its launch-bound deep
         # levels fill the SMs the other pass leaves idle (and vice versa); joined before the loss.
-        side = self.side_stream if self.overlap_forwards else None
+        side = self.side_stream if (self.overlap_forwards and L.n2n_profile_active() != 1) else None   # per-launch timing: one stream
         if side is not None:
+            if self.shared_weights:
+                check(L.n2n_unet_pack_weights(self.plan_full, self.param_ptrs, ptr(self.ws_full), st))
             self.ev_fork.record()
             side.wait_event(self.ev_fork)
             with torch.cuda.stream(side):

@@ -173,6 +173,11 @@ int n2n_unet_forward(n2n_unet_plan* plan, const float* const* params, const floa
  * (deepest levels of small inputs) is still packed locally.  Returns 0 when shared,
  * 1 when the plans are not the same network (nothing changed); donor = NULL ends it. */
 int n2n_unet_share_weights(n2n_unet_plan* plan, const n2n_unet_plan* donor, const void* donor_workspace);
+/* The pack step of n2n_unet_forward on its own (parameters -> packed weights / padded biases in `workspace`); the NEXT
+ * n2n_unet_forward of this plan then skips it.  Lets a caller that runs two plans on two streams (the no-grad
+ * full-resolution pass and the training forward of one N2N iteration, training_script.md:139-146, are independent) pack
+ * once, fork, and still share the packed weights (n2n_unet_share_weights).  No-op for the RESNET plan. */
+int n2n_unet_pack_weights(n2n_unet_plan* plan, const float* const* params, void* workspace, void* stream);
 /* grads[i] (fp32, same shapes as params) are OVERWRITTEN with dL/dparam for the
  * last forward; dy is dL/dy [N,out_nc,H,W].  dx (may be NULL) receives dL/dx. */
 int n2n_unet_backward(n2n_unet_plan* plan, const float* const* params, const float* dy,
