@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libn2n_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "subsample.cu", "loss_adam.cu", "metrics.cu", "pack.cu",
-           "improved_ops.cu", "adapter_fused.cu", "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "headbwd_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
+           "improved_ops.cu", "improved_plan.cu", "adapter_fused.cu", "tapgemm_simt.cu", "tapgemm_umma.cu", "slabgemm_umma.cu", "wgrad_slab_umma.cu", "head_umma.cu", "headbwd_umma.cu", "wgrad_umma.cu", "unet_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -131,6 +131,12 @@ _SIGS = {
     "n2n_loss_iqsl_workspace_bytes": (c_size_t, []),
     "n2n_loss_iqsl_fwdbwd": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_improved_plan_create": (c_int, [POINTER(c_void_p)] + [c_int] * 9),
+    "n2n_improved_plan_destroy": (None, [c_void_p]),
+    "n2n_improved_workspace_bytes": (c_size_t, [c_void_p]),
+    "n2n_improved_num_params": (c_int, [c_void_p]),
+    "n2n_improved_launches": (c_int, [c_void_p]),
+    "n2n_improved_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
     "n2n_groupnorm_groups": (c_int, [c_int, c_int]),
     "n2n_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "n2n_groupnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -11,15 +11,25 @@ a kernel of libn2n_b200 reached through the C-ABI (include/n2n_b200.h):
 * GroupNorm (+ fused LeakyReLU or residual add), LeakyReLU / Sigmoid, PixelShuffle(2), MaxPool2d(2), residual adds:
   ``n2n_groupnorm_{fwd,bwd}``, ``n2n_act_{fwd,bwd}``, ``n2n_pixel_shuffle2``, ``n2n_maxpool2_{fwd,bwd}``, ``n2n_add_f32``.
 
-PyTorch supplies the autograd tape, ``torch.cat`` / slicing of the dense-concat features and the memory.  This row is a
-"next" row: it is functional and parity-tested, not tuned (activations cross the C-ABI as fp32 NCHW)."""
+No-grad calls (evaluation*.py, validation) run the native executor ``n2n_improved_forward`` (csrc/improved_plan.cu): one C
+call, activations resident in the engines' blocked layout, dense / skip concats written in place.  With autograd enabled
+the network is composed from the per-layer calls above; PyTorch supplies the tape, ``torch.cat`` / slicing of the
+dense-concat features and the memory (activations cross the C-ABI as fp32 NCHW there — functional and parity-tested, not
+tuned)."""
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 import torch.nn as nn
 
+
 from . import _ext, ops
-from ._ext import require_cuda
+from ._ext import check, lib, ptr, ptr_array, require_cuda, stream_ptr
+
+
+_NATIVE_NOGRAD = os.environ.get("N2N_IMPROVED_NATIVE", "1") != "0"      # 0: no-grad calls also take the layer-by-layer path
 
 
 # ----------------------------------------------------------------------------- channel chunking of wide layers
@@ -255,6 +265,39 @@ class ImprovedUNet(nn.Module):
         self.precision = precision
         return self
 
+    def _native_forward(self, x):
+        """n2n_improved_forward on a (plan, workspace) cached per shape / precision."""
+        n, _, h, w = x.shape
+        key = (n, h, w, _ext.dtype_tag(self.precision), x.device.index)
+        plans = self.__dict__.setdefault("_plans", {})
+        if key not in plans:
+            if len(plans) >= 4:
+                _, (old, _ws) = plans.popitem()
+                lib().n2n_improved_plan_destroy(old)
+            handle = ctypes.c_void_p()
+            check(lib().n2n_improved_plan_create(ctypes.byref(handle), self.in_nc, self.out_nc, self.n_feature, self.depth,
+                                                 int(self.noise), n, h, w, key[3]))
+            plans[key] = (handle, torch.empty(lib().n2n_improved_workspace_bytes(handle), dtype=torch.uint8, device=x.device))
+        plan, ws = plans[key]
+        params = list(self.parameters())
+        if len(params) != lib().n2n_improved_num_params(plan):
+            raise RuntimeError("ImprovedUNet: parameter list does not match the native plan")
+        for q in params:
+            require_cuda(q, "ImprovedUNet parameters")
+            if q.dtype != torch.float32 or not q.is_contiguous():
+                raise RuntimeError("ImprovedUNet parameters must be contiguous float32 tensors")
+        y = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=x.device)
+        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
+        self.last_launches = lib().n2n_improved_launches(plan)
+        return y
+
+    def __del__(self):
+        try:
+            for plan, _ws in self.__dict__.get("_plans", {}).values():
+                lib().n2n_improved_plan_destroy(plan)
+        except Exception:
+            pass
+
     def forward(self, x):
         require_cuda(x, "ImprovedUNet.forward")
         if x.dim() != 4 or x.shape[1] != self.in_nc:
@@ -264,6 +307,8 @@ class ImprovedUNet(nn.Module):
             raise ValueError(f"H and W must be multiples of {m} ({self.depth} 2x2 poolings, arch_unet.py:521-523)")
         p = self.precision
         x = x.contiguous().float()
+        if _NATIVE_NOGRAD and not (torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in self.parameters()))):
+            return self._native_forward(x)
         if self.noise:
             ne = self.noise_estimator
             sigma = _Act.apply(_conv(_conv(x, ne[0], p, slope=0.2), ne[2], p), ops.ACT_SIGMOID, 0.0)

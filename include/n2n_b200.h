@@ -237,6 +237,24 @@ int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, 
                          float ce_factor, float eps, float grad_scale, float* loss3, float* grad, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * ImprovedUNet no-grad executor — arch_unet.py:475-531 (ImprovedUNet.forward with its RDB / ResBlock / UpBlock
+ * sub-modules, :420-472).  One call runs the whole network with the activations resident in the engines' blocked
+ * layout (dense concats and skip concats are block ranges written in place).  params: the module's parameters in
+ * state_dict order (n2n_improved_num_params() of them; noise_estimator.*, downs.*, bottle.*, ups.*, final.*).
+ * x: [n, in_nc, h, w] fp32, y: [n, out_nc, h, w] fp32; h, w multiples of 2^depth.  Workspace: caller-owned,
+ * n2n_improved_workspace_bytes(plan) bytes.
+ * ------------------------------------------------------------------------- */
+typedef struct n2n_improved_plan n2n_improved_plan;
+int n2n_improved_plan_create(n2n_improved_plan** plan, int in_nc, int out_nc, int n_feature, int depth, int noise,
+                             int n, int h, int w, int dtype);
+void n2n_improved_plan_destroy(n2n_improved_plan* plan);
+size_t n2n_improved_workspace_bytes(const n2n_improved_plan* plan);
+int n2n_improved_num_params(const n2n_improved_plan* plan);
+int n2n_improved_launches(const n2n_improved_plan* plan);
+int n2n_improved_forward(n2n_improved_plan* plan, const float* const* params, const float* x, float* y,
+                         void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Non-GEMM operators of arch_unet.ImprovedUNet — arch_unet.py:420-531, fp32 NCHW.
  * GroupNorm = norm2d('gn', c, 32) (arch_unet.py:7-15): n2n_groupnorm_groups() applies the reference's
  * "largest divisor of c that is <= groups" rule.  y = GN(x) * gamma + beta, then LeakyReLU(act_slope) when

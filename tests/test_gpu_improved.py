@@ -95,8 +95,10 @@ def test_improved_unet_fp32_matches_reference_golden(dev, golden, tag):
     net = net.to(dev).set_precision("fp32")
     noisy = torch.from_numpy(z[f"{tag}_noisy"]).to(dev); clean = torch.from_numpy(z[f"{tag}_clean"]).to(dev)
     with torch.no_grad():
-        y = net(noisy)
+        y = net(noisy)                                  # native executor (csrc/improved_plan.cu)
     assert np.abs(y.cpu().numpy() - z[f"{tag}_y"]).max() < 2e-5
+    y_layers = net(noisy)                               # autograd composition of the per-layer calls
+    assert y_layers.requires_grad and (y_layers.detach() - y).abs().max().item() < 2e-5
     loss = _live_step(net, noisy, clean)
     assert abs(loss - float(z[f"{tag}_loss"])) < 2e-6
     # every parameter gradient against the pinned oracle (full tensors) and the reference's checksums
