@@ -101,10 +101,12 @@ int launch_nchw_to_im2col9(const float* src, int C, const View& dst, int dtype, 
 // pixel), so it runs on the CUDA cores in fp32 straight from the fp32 weights instead of going
 // through a K=16-padded tensor-core GEMM and a second pass over the im2col block.
 // ------------------------------------------------------------------------------------------
-template <int C>
+// PX horizontally adjacent pixels per thread: every weight quad fetched from shared memory (one LDS.128) feeds 4 * PX FMAs.
+// With one pixel per thread the RGB form (K = 27) was bound by those loads (4 LDS.128 per 16 FMAs), not by the HBM writes.
+template <int C, int PX>
 __global__ void __launch_bounds__(128)
 input_stage_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                   View col, View e0, float slope, long long pixels) {
+                   View col, View e0, float slope, long long groups) {
   pdl_enter();
   constexpr int K = 9 * C;
   __shared__ __align__(16) float s_w[K * 64];      // [k = tap*C + c][co], co padded to 64
@@ -116,46 +118,65 @@ input_stage_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = i < Cout ? bias[i] : 0.f;
   __syncthreads();
-  const int H = e0.H, W = e0.W;
-  const long long hw = (long long)H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(p / hw);
-    const int r = (int)(p - (long long)n * hw);
-    const int y = r / W, xx = r - y * W;
-    float t[K];
+  const int H = e0.H, W = e0.W, WG = W / PX;
+  const long long hw = (long long)H * W, ghw = (long long)H * WG;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(g / ghw);
+    const int r = (int)(g - (long long)n * ghw);
+    const int y = r / WG, x0 = (r - y * WG) * PX;
+    float win[C][3][PX + 2];                          // the (PX + 2) x 3 input window of the group, zero outside the image
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int sy = y + tap / 3 - 1, sx = xx + tap % 3 - 1;
-      const bool in = sy >= 0 && sy < H && sx >= 0 && sx < W;
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        t[tap * C + c] = in ? x[((long long)n * C + c) * hw + (long long)sy * W + sx] : 0.f;
-    }
-    // im2col block(s)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int sy = y + ky - 1;
+        const float* row = x + ((long long)n * C + c) * hw + (long long)sy * W;
 #pragma unroll
-    for (int cb = 0; cb < (K + 15) / 16; ++cb) {
-      float v[16];
+        for (int j = 0; j < PX + 2; ++j) {
+          const int sx = x0 + j - 1;
+          win[c][ky][j] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(row + sx) : 0.f;
+        }
+      }
+    // im2col block(s): element k = tap * C + c of pixel px is win[c][tap / 3][px + tap % 3]
 #pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] = (cb * 16 + q < K) ? t[(cb * 16 + q < K) ? cb * 16 + q : 0] : 0.f;
-      Block16<__nv_bfloat16>::store((__nv_bfloat16*)col.ptr + n * col.sN + cb * col.sCb + y * col.sY + xx * col.sX, v);
-    }
+    for (int px = 0; px < PX; ++px)
+#pragma unroll
+      for (int cb = 0; cb < (K + 15) / 16; ++cb) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int k = cb * 16 + q, kk = k < K ? k : 0;
+          v[q] = k < K ? win[kk % C][(kk / C) / 3][px + (kk / C) % 3] : 0.f;
+        }
+        Block16<__nv_bfloat16>::store((__nv_bfloat16*)col.ptr + n * col.sN + cb * col.sCb + y * col.sY + (x0 + px) * col.sX, v);
+      }
     // enc_conv0 + bias + LeakyReLU
     for (int cb = 0; cb < e0.Cb; ++cb) {
-      float acc[16];
+      float acc[PX][16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = s_b[cb * 16 + q];
+      for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[px][q] = s_b[cb * 16 + q];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const float4* wr = reinterpret_cast<const float4*>(&s_w[k * 64 + cb * 16]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 wv = wr[q];
-          acc[4 * q] += t[k] * wv.x; acc[4 * q + 1] += t[k] * wv.y; acc[4 * q + 2] += t[k] * wv.z; acc[4 * q + 3] += t[k] * wv.w;
+#pragma unroll
+          for (int px = 0; px < PX; ++px) {
+            const float a = win[k % C][(k / C) / 3][px + (k / C) % 3];
+            acc[px][4 * q] = fmaf(a, wv.x, acc[px][4 * q]); acc[px][4 * q + 1] = fmaf(a, wv.y, acc[px][4 * q + 1]);
+            acc[px][4 * q + 2] = fmaf(a, wv.z, acc[px][4 * q + 2]); acc[px][4 * q + 3] = fmaf(a, wv.w, acc[px][4 * q + 3]);
+          }
         }
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = acc[q] > 0.f ? acc[q] : acc[q] * slope;
-      Block16<__nv_bfloat16>::store((__nv_bfloat16*)e0.ptr + n * e0.sN + cb * e0.sCb + y * e0.sY + xx * e0.sX, acc);
+      for (int px = 0; px < PX; ++px) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[px][q] = acc[px][q] > 0.f ? acc[px][q] : acc[px][q] * slope;
+        Block16<__nv_bfloat16>::store((__nv_bfloat16*)e0.ptr + n * e0.sN + cb * e0.sCb + y * e0.sY + (x0 + px) * e0.sX, acc[px]);
+      }
     }
   }
 }
@@ -166,9 +187,18 @@ int launch_input_stage(const float* x, int C, const float* w, const float* bias,
   if ((C != 1 && C != 3) || Cout > 64 || e0.Cb * 16 < Cout || col.Cb != (9 * C + 15) / 16) return kSgNotEligible;
   { const char* e = getenv("N2N_NO_INPUT_STAGE"); if (e && atoi(e)) return kSgNotEligible; }
   const long long pixels = (long long)e0.N * e0.H * e0.W;
-  const int grid = grid_for(pixels, 128, 16);
-  if (C == 1) (void)launch_pdl_v(input_stage_kernel<1>, dim3(grid), dim3(128), 0, st, x, w, bias, Cout, col, e0, slope, pixels);
-  else (void)launch_pdl_v(input_stage_kernel<3>, dim3(grid), dim3(128), 0, st, x, w, bias, Cout, col, e0, slope, pixels);
+  static int px_knob = -1;
+  if (px_knob < 0) { const char* e = getenv("N2N_INPUT_STAGE_PX"); px_knob = e ? atoi(e) : 0; }
+  // measured (64 x 1 x 256 x 256 / 32 x 3 x 256 x 256): C = 1 is bound by its HBM writes at any PX (PX = 4 is slower: registers);
+  // C = 3 (27 taps) was bound by the weight loads: PX = 2 takes 40 us off the launch
+  const int want = px_knob > 0 ? px_knob : (C == 1 ? 1 : 2);
+  const int px = (want >= 4 && C == 1 && e0.W % 4 == 0) ? 4 : ((want >= 2 && e0.W % 2 == 0) ? 2 : 1);
+  const long long groups = pixels / px;
+  const int grid = grid_for(groups, 128, 16);
+#define N2N_IS_LAUNCH(CC, PP) (void)launch_pdl_v(input_stage_kernel<CC, PP>, dim3(grid), dim3(128), 0, st, x, w, bias, Cout, col, e0, slope, groups)
+  if (C == 1) { if (px == 4) N2N_IS_LAUNCH(1, 4); else if (px == 2) N2N_IS_LAUNCH(1, 2); else N2N_IS_LAUNCH(1, 1); }
+  else { if (px == 2) N2N_IS_LAUNCH(3, 2); else N2N_IS_LAUNCH(3, 1); }
+#undef N2N_IS_LAUNCH
   N2N_LAUNCH_CHECK();
   return 0;
 }
