@@ -54,7 +54,7 @@ class N2NTrainer:
         self.table, self.blocks = build_adam_tables([self.flat_p], [self.flat_g], [self.flat_m], [self.flat_v], dev)
         # gradient buckets in reverse-autograd order: the head / full-resolution decoder tensors
         # sit at the END of the state_dict order, so bucket 0 is the tail of the flat buffer.
-        self.bucket_slices = dp.bucket_slices(sizes, buckets)
+        self.bucket_slices = dp.bucket_slices(sizes, int(os.environ.get("N2N_BUCKETS", buckets)))
         self._shapes = None
         self.last_launches = 0
         # CUDA-graph replay of the whole iteration (one graph launch instead of ~190 kernel launches);
