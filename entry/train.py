@@ -9,7 +9,8 @@ Two loops (`--loop`):
               N2NTrainer: clean images only, noise added on the device;
   supervised  the fork's live loop, train.py:354-368: network(noisy), network(clean) with grad, util.Structure_loss,
               on <data_dir>/clean + <data_dir>/noise pairs.
-The network family is picked from --log_name as train.py:298-314 does ('UNET' / 'RESNET').  Multi-GPU:
+The network family is picked from --log_name as train.py:298-314 does ('UNET' / 'RESNET' / 'UNetImproved'; under --loop n2n the
+UNet runs the fused trainer, the other families the same iteration through autograd).  Multi-GPU:
 `torchrun --nproc-per-node N entry/train.py --parallel ...` (one process per GPU, NCCL) replaces nn.DataParallel
 (train.py:324-325).  Patches are cut on the device from images uploaded once (image_denoising_b200.data).
 
@@ -27,7 +28,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from entry import _data, _models  # noqa: E402
-from image_denoising_b200 import AugmentNoise, FusedAdam, N2NTrainer, Structure_loss, UNet, checkpoint, dp, ops  # noqa: E402
+from image_denoising_b200 import (AugmentNoise, FusedAdam, N2NTrainer, Structure_loss, UNet, checkpoint, dp,  # noqa: E402
+                                   generate_mask_pair, generate_subimage_pair, n2n_loss, ops)
 from image_denoising_b200.data import DevicePatchSource  # noqa: E402
 from image_denoising_b200.optim import multistep_lr  # noqa: E402
 
@@ -101,12 +103,14 @@ def main():
 
     torch.manual_seed(0)
     network = _models.network_from_log_name(opt.log_name, opt.n_channel, opt.n_feature).to(dev).set_precision(opt.precision)
+    fused_n2n = opt.loop == "n2n" and type(network) is UNet
     if opt.loop == "n2n":
-        if not isinstance(network, UNet) or type(network) is not UNet:
-            raise SystemExit("--loop n2n runs the fused N2N trainer, which is built for arch_unet.UNet (log_name containing 'UNET')")
         noise_adder = AugmentNoise(style=opt.noisetype, rank=rank, world=world)      # global-batch noise, this rank's slice
-        trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)
+    if fused_n2n:
+        trainer = N2NTrainer(network, lr=opt.lr, precision=opt.precision)            # the whole iteration as one CUDA graph
     else:
+        # RESNET / ImprovedUNet under --loop n2n: the same iteration (training_script.md:137-156) written out on the drop-in
+        # functions with autograd; the supervised loop below shares the optimiser / criterion
         if world > 1:
             dp.broadcast_params(torch.nn.utils.parameters_to_vector(network.parameters()).detach(), 0)
         optimizer = FusedAdam(network.parameters(), lr=opt.lr)
@@ -128,7 +132,25 @@ def main():
             if opt.loop == "n2n":
                 Lambda = epoch / opt.n_epoch * opt.increase_ratio                    # training_script.md:148
                 noisy_b = noise_adder.add_train_noise(clean_b)
-                loss3 = trainer.step(noisy_b, Lambda, lr=lr)
+                if fused_n2n:
+                    loss3 = trainer.step(noisy_b, Lambda, lr=lr)
+                else:
+                    for group in optimizer.param_groups:
+                        group['lr'] = lr
+                    optimizer.zero_grad()
+                    mask1, mask2 = generate_mask_pair(noisy_b)                       # training_script.md:137-144
+                    noisy_sub1, noisy_sub2 = generate_subimage_pair(noisy_b, mask1, mask2)
+                    with torch.no_grad():
+                        noisy_denoised = network(noisy_b)
+                    den_sub1, den_sub2 = generate_subimage_pair(noisy_denoised, mask1, mask2)
+                    loss, loss3 = n2n_loss(network(noisy_sub1), noisy_sub2, den_sub1, den_sub2, Lambda)   # :146-153
+                    loss.backward()
+                    if world > 1:
+                        for prm in network.parameters():
+                            if prm.grad is not None:
+                                torch.distributed.all_reduce(prm.grad)
+                                prm.grad.div_(world)
+                    optimizer.step()
                 if it % 50 == 0:
                     l = loss3.tolist()
                     l1_loss.append(l[1])

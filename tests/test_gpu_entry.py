@@ -116,3 +116,17 @@ def test_improved_unet_through_the_entry_points(tmp_path):
     _run([os.path.join(ROOT, "entry", "evaluation_704.py"), "--synthetic", "1", "--checkpoint", ck[-1], "--save_dir", ev,
           "--log_name", "UNetImproved_t", "--n_feature", "16"], ROOT)
     assert "Average PSNR:" in open(os.path.join(ev, "metrics.txt")).read()
+
+
+def test_n2n_loop_on_other_network_families(tmp_path):
+    """--loop n2n with RESNET / UNetImproved: the iteration of training_script.md:137-156 through the drop-in functions and
+    autograd (the fused N2NTrainer is built for arch_unet.UNet)."""
+    out = str(tmp_path)
+    for log_name, extra, nkeys in (("RESNET_n2n", [], 42), ("UNetImproved_n2n", ["--n_feature", "16"], None)):
+        txt = _run([os.path.join(ROOT, "entry", "train.py"), "--synthetic", "2", "--patch", "64", "--batchsize", "2", "--n_epoch", "1",
+                    "--save_model_path", out, "--log_name", log_name, "--patches_per_image", "2"] + extra, ROOT)
+        assert "Loss_Full=" in txt and "Lambda=" in txt
+        ck = sorted(glob.glob(os.path.join(out, log_name, "*", "epoch_model_*.pth")))
+        a, b = torch.load(ck[0], map_location="cpu"), torch.load(ck[-1], map_location="cpu")
+        assert len(ck) == 2 and (nkeys is None or len(b) == nkeys)
+        assert all(torch.isfinite(v).all() for v in b.values()) and any(not torch.equal(a[k], b[k]) for k in a)
