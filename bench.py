@@ -405,8 +405,8 @@ def improved_unet_leg(dev, precision):
             "supervised_step_4x1x128x128_ms": train_ms,
             "note": "no-grad forward = native executor n2n_improved_forward (activations resident in the blocked layout, ~160 "
                     "launches, launch-bound at batch 8); stock PyTorch bf16 autocast runs the batch-8 forward in 10.5 ms on this "
-                    "GPU (scripts/improved_bench.py); the training step composes per-layer C-ABI calls under autograd (fp32 NCHW "
-                    "between layers) and is slower than stock PyTorch (30 ms)"}
+                    "GPU (scripts/improved_bench.py); the training step (two forwards + backward + Adam) runs forward and backward on the "
+                    "same executor (n2n_improved_backward); stock PyTorch bf16 autocast: 30 ms"}
 
 
 def hbm_kernels(dev):

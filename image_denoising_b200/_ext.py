@@ -131,12 +131,14 @@ _SIGS = {
     "n2n_loss_iqsl_workspace_bytes": (c_size_t, []),
     "n2n_loss_iqsl_fwdbwd": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
-    "n2n_improved_plan_create": (c_int, [POINTER(c_void_p)] + [c_int] * 9),
+    "n2n_improved_plan_create": (c_int, [POINTER(c_void_p)] + [c_int] * 10),
     "n2n_improved_plan_destroy": (None, [c_void_p]),
     "n2n_improved_workspace_bytes": (c_size_t, [c_void_p]),
     "n2n_improved_num_params": (c_int, [c_void_p]),
-    "n2n_improved_launches": (c_int, [c_void_p]),
+    "n2n_improved_launches": (c_int, [c_void_p, c_int]),
     "n2n_improved_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "n2n_improved_read_buffer": (ctypes.c_longlong, [c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),
+    "n2n_improved_backward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p]),
     "n2n_groupnorm_groups": (c_int, [c_int, c_int]),
     "n2n_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "n2n_groupnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -11,11 +11,10 @@ a kernel of libn2n_b200 reached through the C-ABI (include/n2n_b200.h):
 * GroupNorm (+ fused LeakyReLU or residual add), LeakyReLU / Sigmoid, PixelShuffle(2), MaxPool2d(2), residual adds:
   ``n2n_groupnorm_{fwd,bwd}``, ``n2n_act_{fwd,bwd}``, ``n2n_pixel_shuffle2``, ``n2n_maxpool2_{fwd,bwd}``, ``n2n_add_f32``.
 
-No-grad calls (evaluation*.py, validation) run the native executor ``n2n_improved_forward`` (csrc/improved_plan.cu): one C
-call, activations resident in the engines' blocked layout, dense / skip concats written in place.  With autograd enabled
-the network is composed from the per-layer calls above; PyTorch supplies the tape, ``torch.cat`` / slicing of the
-dense-concat features and the memory (activations cross the C-ABI as fp32 NCHW there — functional and parity-tested, not
-tuned)."""
+Forward and backward run on the native executor (csrc/improved_plan.cu: ``n2n_improved_forward`` / ``n2n_improved_backward``,
+one C call each, activations and gradients resident in the engines' blocked layout, dense / skip concats written in place).
+The per-layer composition above — PyTorch's tape over single-layer C-ABI calls, fp32 NCHW between layers — is kept as the
+cross-check of the executor (``net.native_train = False``) and serves inputs that require grad."""
 from __future__ import annotations
 
 import ctypes
@@ -29,7 +28,37 @@ from . import _ext, ops
 from ._ext import check, lib, ptr, ptr_array, require_cuda, stream_ptr
 
 
+_DEBUG_TAPE = None      # tests: a list that collects (name, tensor) of selected intermediates of the per-layer path
 _NATIVE_NOGRAD = os.environ.get("N2N_IMPROVED_NATIVE", "1") != "0"      # 0: no-grad calls also take the layer-by-layer path
+_NATIVE_TRAIN = os.environ.get("N2N_IMPROVED_NATIVE_TRAIN", "1") != "0"  # 0: training composes the per-layer calls under autograd
+
+
+class _ImprovedFunction(torch.autograd.Function):
+    """Forward + backward of the whole network on the native executor (csrc/improved_plan.cu); parameter gradients only
+    (a network input that requires grad takes the layer-by-layer path)."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        key, plan, ws = net._checkout(x, True)
+        net._param_list(plan)
+        y = torch.empty((x.shape[0], net.out_nc, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
+        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
+        net.last_launches = lib().n2n_improved_launches(plan, 0)
+        ctx.net, ctx.key, ctx.plan, ctx.ws, ctx.params = net, key, plan, ws, params
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        grads = [torch.empty_like(q) for q in ctx.params]
+        check(lib().n2n_improved_backward(ctx.plan, ptr_array(ctx.params), ptr(dy), ptr(y), ptr_array(grads), ptr(ctx.ws), stream_ptr()))
+        ctx.net.last_bwd_launches = lib().n2n_improved_launches(ctx.plan, 1)
+        ctx.net._last_train = (ctx.plan, ctx.ws)            # read_buffer() hook: valid until the workspace is reused
+        ctx.net._give_back(ctx.key, ctx.ws)
+        ctx.ws = None
+        return (None, None) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------- channel chunking of wide layers
@@ -187,8 +216,14 @@ class ResBlock(nn.Module):
 
     def run(self, x, precision):
         b = self.block
-        t = _gn(_conv(x, b[0], precision), b[1], slope=0.2)
-        return _gn(_conv(t, b[3], precision), b[4], residual=x)
+        t1 = _conv(x, b[0], precision)
+        t = _gn(t1, b[1], slope=0.2)
+        t3 = _conv(t, b[3], precision)
+        if _DEBUG_TAPE is not None and t.requires_grad:
+            for q in (t1, t, t3):
+                q.retain_grad()
+            _DEBUG_TAPE.append((t1, t, t3))
+        return _gn(t3, b[4], residual=x)
 
 
 class RDB(nn.Module):
@@ -258,6 +293,10 @@ class ImprovedUNet(nn.Module):
         self.final = nn.Conv2d(n_feature // 2 + in_nc, out_nc, 3, 1, 1, bias=True)
         self.sigmoid = nn.Sigmoid()
         self.precision = _ext.default_precision()
+        # native executor (csrc/improved_plan.cu) for no-grad calls / for forward + backward; False = compose the per-layer
+        # C-ABI calls under autograd (kept as the cross-check of the executor and for inputs that require grad)
+        self.native_nograd = _NATIVE_NOGRAD
+        self.native_train = _NATIVE_TRAIN
 
     def set_precision(self, precision: str):
         if precision not in ("bf16", "fp32"):
@@ -265,20 +304,33 @@ class ImprovedUNet(nn.Module):
         self.precision = precision
         return self
 
-    def _native_forward(self, x):
-        """n2n_improved_forward on a (plan, workspace) cached per shape / precision."""
+    def _checkout(self, x, train):
+        """(key, plan, workspace) for this shape / precision; training workspaces are held until the backward has run, so two
+        forwards before one backward (train.py:361) keep separate activations."""
         n, _, h, w = x.shape
-        key = (n, h, w, _ext.dtype_tag(self.precision), x.device.index)
+        key = (n, h, w, _ext.dtype_tag(self.precision), x.device.index, bool(train))
         plans = self.__dict__.setdefault("_plans", {})
+        pools = self.__dict__.setdefault("_free_ws", {})
         if key not in plans:
-            if len(plans) >= 4:
-                _, (old, _ws) = plans.popitem()
-                lib().n2n_improved_plan_destroy(old)
+            if len(plans) >= 6:
+                old_key = next(iter(plans))
+                lib().n2n_improved_plan_destroy(plans.pop(old_key))
+                pools.pop(old_key, None)
             handle = ctypes.c_void_p()
             check(lib().n2n_improved_plan_create(ctypes.byref(handle), self.in_nc, self.out_nc, self.n_feature, self.depth,
-                                                 int(self.noise), n, h, w, key[3]))
-            plans[key] = (handle, torch.empty(lib().n2n_improved_workspace_bytes(handle), dtype=torch.uint8, device=x.device))
-        plan, ws = plans[key]
+                                                 int(self.noise), n, h, w, key[3], int(train)))
+            plans[key] = handle
+        plan = plans[key]
+        pool = pools.setdefault(key, [])
+        ws = pool.pop() if pool else torch.empty(lib().n2n_improved_workspace_bytes(plan), dtype=torch.uint8, device=x.device)
+        return key, plan, ws
+
+    def _give_back(self, key, ws):
+        pool = self.__dict__.setdefault("_free_ws", {}).setdefault(key, [])
+        if len(pool) < 2:
+            pool.append(ws)
+
+    def _param_list(self, plan):
         params = list(self.parameters())
         if len(params) != lib().n2n_improved_num_params(plan):
             raise RuntimeError("ImprovedUNet: parameter list does not match the native plan")
@@ -286,14 +338,34 @@ class ImprovedUNet(nn.Module):
             require_cuda(q, "ImprovedUNet parameters")
             if q.dtype != torch.float32 or not q.is_contiguous():
                 raise RuntimeError("ImprovedUNet parameters must be contiguous float32 tensors")
-        y = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=x.device)
+        return params
+
+    def _native_forward(self, x):
+        """n2n_improved_forward on a (plan, workspace) cached per shape / precision."""
+        key, plan, ws = self._checkout(x, False)
+        params = self._param_list(plan)
+        y = torch.empty((x.shape[0], self.out_nc, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
         check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
-        self.last_launches = lib().n2n_improved_launches(plan)
+        self.last_launches = lib().n2n_improved_launches(plan, 0)
+        self._give_back(key, ws)
         return y
+
+    def read_buffer(self, buf: int, grad: bool = False):
+        """Layer-level parity hook: buffer ``buf`` of the last native training step (its gradient mirror with grad=True) as
+        fp32 NCHW, all 16-channel blocks (zero padding included)."""
+        plan, ws = self._last_train
+        dims = (ctypes.c_int * 3)()
+        n = lib().n2n_improved_read_buffer(plan, ptr(ws), buf, int(grad), None, dims, stream_ptr())
+        if n <= 0:
+            raise ValueError("no such buffer")
+        out = torch.empty((n // (dims[0] * dims[1] * dims[2]), dims[0], dims[1], dims[2]), dtype=torch.float32, device=ws.device)
+        if lib().n2n_improved_read_buffer(plan, ptr(ws), buf, int(grad), ptr(out), dims, stream_ptr()) < 0:
+            raise RuntimeError("read_buffer failed")
+        return out
 
     def __del__(self):
         try:
-            for plan, _ws in self.__dict__.get("_plans", {}).values():
+            for plan in self.__dict__.get("_plans", {}).values():
                 lib().n2n_improved_plan_destroy(plan)
         except Exception:
             pass
@@ -307,8 +379,11 @@ class ImprovedUNet(nn.Module):
             raise ValueError(f"H and W must be multiples of {m} ({self.depth} 2x2 poolings, arch_unet.py:521-523)")
         p = self.precision
         x = x.contiguous().float()
-        if _NATIVE_NOGRAD and not (torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in self.parameters()))):
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in self.parameters()))
+        if self.native_nograd and not need_grad:
             return self._native_forward(x)
+        if self.native_train and need_grad and not x.requires_grad:
+            return _ImprovedFunction.apply(self, x, *self.parameters())
         if self.noise:
             ne = self.noise_estimator
             sigma = _Act.apply(_conv(_conv(x, ne[0], p, slope=0.2), ne[2], p), ops.ACT_SIGMOID, 0.0)

@@ -237,7 +237,7 @@ int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, 
                          float ce_factor, float eps, float grad_scale, float* loss3, float* grad, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * ImprovedUNet no-grad executor — arch_unet.py:475-531 (ImprovedUNet.forward with its RDB / ResBlock / UpBlock
+ * ImprovedUNet executor — arch_unet.py:475-531 (ImprovedUNet.forward with its RDB / ResBlock / UpBlock
  * sub-modules, :420-472).  One call runs the whole network with the activations resident in the engines' blocked
  * layout (dense concats and skip concats are block ranges written in place).  params: the module's parameters in
  * state_dict order (n2n_improved_num_params() of them; noise_estimator.*, downs.*, bottle.*, ups.*, final.*).
@@ -246,13 +246,25 @@ int n2n_loss_iqsl_fwdbwd(const float* pred, const float* target, int64_t count, 
  * ------------------------------------------------------------------------- */
 typedef struct n2n_improved_plan n2n_improved_plan;
 int n2n_improved_plan_create(n2n_improved_plan** plan, int in_nc, int out_nc, int n_feature, int depth, int noise,
-                             int n, int h, int w, int dtype);
+                             int n, int h, int w, int dtype, int with_backward);
 void n2n_improved_plan_destroy(n2n_improved_plan* plan);
 size_t n2n_improved_workspace_bytes(const n2n_improved_plan* plan);
 int n2n_improved_num_params(const n2n_improved_plan* plan);
-int n2n_improved_launches(const n2n_improved_plan* plan);
+int n2n_improved_launches(const n2n_improved_plan* plan, int backward);
 int n2n_improved_forward(n2n_improved_plan* plan, const float* const* params, const float* x, float* y,
                          void* workspace, void* stream);
+/* Backward of the last n2n_improved_forward of a plan created with_backward (which keeps every intermediate tensor and the
+ * GroupNorm statistics in `workspace`): dy = dL/dy [n, out_nc, h, w], y = the forward's output (sigmoid'), grads[i] (fp32,
+ * shapes of params[i]) are OVERWRITTEN with dL/dparam.  The operators are walked in reverse; every gradient tensor is
+ * accumulated into a zero-initialised mirror of the activation buffers (dense concats collect the contributions of all
+ * their consumers), LeakyReLU' is applied once per tensor after its last consumer, weight gradients run as engine-sized
+ * channel chunks through one partial buffer (fixed-order reduction). */
+/* Layer-level parity hook (tests): buffer `buf` of the plan's workspace (or, grad != 0, its gradient mirror after a
+ * backward) as fp32 NCHW over all of its 16-channel blocks; out == NULL only returns the element count and dims. */
+long long n2n_improved_read_buffer(const n2n_improved_plan* plan, const void* workspace, int buf, int grad, float* out,
+                                   int* dims, void* stream);
+int n2n_improved_backward(n2n_improved_plan* plan, const float* const* params, const float* dy, const float* y,
+                          float* const* grads, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Non-GEMM operators of arch_unet.ImprovedUNet — arch_unet.py:420-531, fp32 NCHW.
