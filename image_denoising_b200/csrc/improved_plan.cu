@@ -420,6 +420,7 @@ struct ImpOp {                                          // one forward operator,
   int c0 = 0, c1 = 0, cout = 0, k = 3, pidx = 0;        // conv: input segments, outputs, kernel, first parameter
   float slope = -1.f;
   int C = 0, stat = -1;                                 // GroupNorm: channels, slot of the saved (mean, rstd)
+  int wg0 = 0, dg0 = 0;                                 // conv: first weight-gradient / input-gradient chunk in the plan's tables
 };
 
 struct n2n_improved_plan {
@@ -429,6 +430,20 @@ struct n2n_improved_plan {
   std::vector<size_t> conv_wp, conv_bias;     // per convolution chunk: offsets of its packed weights / padded bias
   std::vector<size_t> gn_stat;                // training: per GroupNorm, offset of its saved (mean, rstd) [N][Cb*16][2]
   std::vector<ImpOp> tape;                    // training: the forward operators in execution order
+  // training: per weight-gradient chunk (dY <= 8 blocks x X <= 9 blocks) its partial / bias-partial offsets (relative to
+  // off_partial / off_bpartial; chunks of ONE conv do not overlap, convs reuse the region) and pixel splits; per
+  // input-gradient chunk (<= 16 blocks of Cin) the offset of its packed transposed weights (all packed up front)
+  std::vector<size_t> wg_partial, wg_bpartial, dg_wd;
+  std::vector<int> wg_splits;
+  // executions captured as CUDA graphs, keyed by every pointer the launch sequence touches (a caller that keeps its
+  // buffers in place pays the ~170 / ~540 launches and their tensor-map encodes once)
+  struct Captured { unsigned long long key; cudaGraphExec_t exec; int launches; };
+  std::vector<Captured> graphs;
+  cudaStream_t cap_stream = nullptr;          // private stream the sequences are captured on (the caller's may be the legacy stream)
+  ~n2n_improved_plan() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
   size_t act_bytes = 0;                       // activations occupy [0, act_bytes); training: gradients [off_grad, off_grad + act_bytes)
   size_t off_wp = 0, off_bias = 0, off_gn_partial = 0, off_gn_ss = 0, off_f32 = 0, off_grad = 0, off_stat = 0, off_wd = 0,
          off_partial = 0, off_bpartial = 0, off_f32b = 0, total = 0;
@@ -722,19 +737,19 @@ struct Backward {
       N2N_LAUNCH_CHECK();
     }
     if (op.has_res) N2N_TRY(add_into(gy, grd(op.res)));
-    const float* w = prm[op.pidx];
     float* dw = grads[op.pidx];
     float* db = op.has_bias ? grads[op.pidx + 1] : nullptr;
-    const ImpBuf& B = p->bufs[op.x.buf];
-    // weight gradient, chunk by chunk through one partial buffer (launch -> fixed-order reduction -> next chunk)
+    // weight gradient: engine-sized chunks into disjoint partial regions, then ONE fixed-order reduction launch for the layer
+    std::vector<UnpackJob> jobs;
+    int wi = op.wg0;
     for (int o0 = 0; o0 < yb; o0 += kWgDyBlocks) {
       const int ob = yb - o0 < kWgDyBlocks ? yb - o0 : kWgDyBlocks;
-      for (int c0 = 0; c0 < xb; c0 += kWgXBlocks) {
+      for (int c0 = 0; c0 < xb; c0 += kWgXBlocks, ++wi) {
         const int cb = xb - c0 < kWgXBlocks ? xb - c0 : kWgXBlocks;
         LayerGeom L; L.kind = k == 3 ? L_CONV3 : L_CONV1; L.cin = chan1(cb * 16); L.cout = ob * 16;
-        const int splits = layer_wgrad_splits(L, dt, p->N, B.h, B.w);
-        float* partial = (float*)(ws + p->off_partial);
-        float* bpartial = (float*)(ws + p->off_bpartial);
+        const int splits = p->wg_splits[wi];
+        float* partial = (float*)(ws + p->off_partial + p->wg_partial[wi]);
+        float* bpartial = (float*)(ws + p->off_bpartial + p->wg_bpartial[wi]);
         const bool bias_here = db != nullptr && c0 == 0;
         TapWgrad g = make_conv_wgrad(L, dt, sub_blocks(x, dt, c0, cb), sub_blocks(gy, dt, o0, ob), partial, bias_here ? bpartial : nullptr, splits);
         N2N_TRY(launch_tapwgrad(g, st));
@@ -744,24 +759,38 @@ struct Backward {
         if (k == 3) { j.s_t = 1; j.s_n = (long long)cin_real * 9; j.s_c = 9; } else { j.s_t = 0; j.s_n = cin_real; j.s_c = 1; }
         j.nseg.n = 1; j.nseg.src0[0] = 16 * o0; j.nseg.cnt[0] = op.cout - 16 * o0 < 16 * ob ? op.cout - 16 * o0 : 16 * ob; j.nseg.dst0[0] = 0;
         j.cseg = chunk_segs(op.c0, op.c1, c0, cb);
-        N2N_TRY(launch_unpack(&j, 1, st));
+        jobs.push_back(j);
       }
     }
+    N2N_TRY(launch_unpack(jobs.data(), (int)jobs.size(), st));
     if (!op.want_dgrad) return 0;
     // input gradient, accumulated into the (zero-initialised / partly filled) gradient window of the input
     LayerGeom L; L.kind = k == 3 ? L_CONV3 : L_CONV1; L.cin = op.c1 > 0 ? chan2(op.c0, op.c1) : chan1(op.c0); L.cout = op.cout;
-    for (int b0 = 0; b0 < xb; b0 += kDgBlocks) {
+    int di = op.dg0;
+    for (int b0 = 0; b0 < xb; b0 += kDgBlocks, ++di) {
       const int nb = xb - b0 < kDgBlocks ? xb - b0 : kDgBlocks;
-      void* wd = ws + p->off_wd;
-      PackJob pj = make_dgrad_pack(L, w, wd, nb);
-      pj.nseg = chunk_segs(op.c0, op.c1, b0, nb);
-      N2N_TRY(launch_pack(&pj, 1, dt, st));
       const View dx = sub_blocks(gx, dt, b0, nb);
-      TapGemm g = make_conv_dgrad(L, dt, gy, dx, wd, nb);
+      TapGemm g = make_conv_dgrad(L, dt, gy, dx, ws + p->off_wd + p->dg_wd[di], nb);
       g.has_addend = true; g.addend = dx;
       N2N_TRY(launch_tapgemm(g, st));
     }
     return 0;
+  }
+  // all transposed weights of the input-gradient GEMMs -> engine layout, a few batched launches before the walk
+  int pack_dgrad_weights() {
+    std::vector<PackJob> jobs;
+    for (const ImpOp& op : p->tape) {
+      if (op.kind != OP_CONV || !op.want_dgrad) continue;
+      LayerGeom L; L.kind = op.k == 3 ? L_CONV3 : L_CONV1; L.cin = op.c1 > 0 ? chan2(op.c0, op.c1) : chan1(op.c0); L.cout = op.cout;
+      int di = op.dg0;
+      for (int b0 = 0; b0 < op.x.cb; b0 += kDgBlocks, ++di) {
+        const int nb = op.x.cb - b0 < kDgBlocks ? op.x.cb - b0 : kDgBlocks;
+        PackJob pj = make_dgrad_pack(L, prm[op.pidx], ws + p->off_wd + p->dg_wd[di], nb);
+        pj.nseg = chunk_segs(op.c0, op.c1, b0, nb);
+        jobs.push_back(pj);
+      }
+    }
+    return launch_pack(jobs.data(), (int)jobs.size(), p->dtype, st);
   }
 
   int groupnorm(const ImpOp& op) {
@@ -793,6 +822,7 @@ struct Backward {
   int run(const float* dy, const float* y_out) {
     const int dt = p->dtype, N = p->N, H = p->H, W = p->W;
     N2N_CUDA(cudaMemsetAsync(ws + p->off_grad, 0, p->act_bytes, st));
+    N2N_TRY(pack_dgrad_weights());
     for (int i = (int)p->tape.size() - 1; i >= 0; --i) {
       const ImpOp& op = p->tape[i];
       switch (op.kind) {
@@ -862,23 +892,33 @@ extern "C" int n2n_improved_plan_create(n2n_improved_plan** plan, int in_nc, int
     p->off_grad = take(p->act_bytes);
     p->off_stat = take(b.stat_total);
     p->off_f32b = take((size_t)n * (out_nc > 1 ? out_nc : 1) * h * w * sizeof(float));
-    // the widest chunks: weight-gradient partials (splits x taps x 144 x 128 fp32), input-gradient weights (taps x 256 rows x K = max Cout)
+    // weight-gradient chunks of one conv get disjoint partial regions (one reduction launch per conv), the region is reused by
+    // the next conv; every input-gradient chunk of the network keeps its own packed weights (packed in one batch up front)
     size_t partial = 0, bpartial = 0, wd = 0;
-    for (const ImpOp& op : p->tape) {
+    for (ImpOp& op : p->tape) {
       if (op.kind != OP_CONV) continue;
       const ImpBuf& B = p->bufs[op.x.buf];
       const int xb = op.x.cb, yb = cblocks(op.cout);
+      op.wg0 = (int)p->wg_splits.size();
+      size_t po = 0, bo = 0;
       for (int o0 = 0; o0 < yb; o0 += kWgDyBlocks)           // the same chunking as Backward::conv
         for (int c0 = 0; c0 < xb; c0 += kWgXBlocks) {
           LayerGeom L; L.kind = op.k == 3 ? L_CONV3 : L_CONV1;
           L.cin = chan1((xb - c0 < kWgXBlocks ? xb - c0 : kWgXBlocks) * 16); L.cout = (yb - o0 < kWgDyBlocks ? yb - o0 : kWgDyBlocks) * 16;
           const int splits = layer_wgrad_splits(L, dtype, n, B.h, B.w);
-          if (L.partial_bytes(splits) > partial) partial = L.partial_bytes(splits);
-          if (L.bias_partial_bytes(splits) > bpartial) bpartial = L.bias_partial_bytes(splits);
+          p->wg_splits.push_back(splits); p->wg_partial.push_back(po); p->wg_bpartial.push_back(bo);
+          po += align_up(L.partial_bytes(splits), 1024); bo += align_up(L.bias_partial_bytes(splits), 1024);
         }
-      LayerGeom G; G.kind = op.k == 3 ? L_CONV3 : L_CONV1; G.cin = chan1(op.c0 + op.c1); G.cout = op.cout;
-      const size_t wb = G.dgrad_pack_bytes(dtype, xb < kDgBlocks ? xb : kDgBlocks);
-      if (wb > wd) wd = wb;
+      if (po > partial) partial = po;
+      if (bo > bpartial) bpartial = bo;
+      op.dg0 = (int)p->dg_wd.size();
+      if (op.want_dgrad) {
+        LayerGeom G; G.kind = op.k == 3 ? L_CONV3 : L_CONV1; G.cin = chan1(op.c0 + op.c1); G.cout = op.cout;
+        for (int b0 = 0; b0 < xb; b0 += kDgBlocks) {
+          p->dg_wd.push_back(wd);
+          wd += align_up(G.dgrad_pack_bytes(dtype, xb - b0 < kDgBlocks ? xb - b0 : kDgBlocks), 1024);
+        }
+      }
     }
     p->off_partial = take(partial); p->off_bpartial = take(bpartial); p->off_wd = take(wd);
   }
@@ -892,10 +932,61 @@ extern "C" size_t n2n_improved_workspace_bytes(const n2n_improved_plan* plan) { 
 extern "C" int n2n_improved_num_params(const n2n_improved_plan* plan) { return plan ? plan->nparams : 0; }
 extern "C" int n2n_improved_launches(const n2n_improved_plan* plan, int backward) { return plan ? (backward ? plan->bwd_launches : plan->launches) : 0; }
 
+static int improved_forward_body(n2n_improved_plan* p, const float* const* params, const float* x, float* y, void* ws, cudaStream_t st);
+namespace {
+unsigned long long mix(unsigned long long h, const void* ptr) {
+  h ^= (unsigned long long)(uintptr_t)ptr + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  return h;
+}
+// Run `body` (a launch sequence on `st`) through a CUDA graph cached under `key`; falls back to plain launches when the
+// stream is already being captured, per-launch profiling is armed or N2N_IMPROVED_NO_GRAPH=1.
+template <typename Body>
+int run_captured(n2n_improved_plan* p, unsigned long long key, cudaStream_t st, int* launches, Body body) {
+  static const char* const off = getenv("N2N_IMPROVED_NO_GRAPH");
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  N2N_CUDA(cudaStreamIsCapturing(st, &cs));
+  if ((off && atoi(off)) || cs != cudaStreamCaptureStatusNone || profiling_active()) {
+    const long long l0 = g_launch_count;
+    N2N_TRY(body(st));
+    *launches = (int)(g_launch_count - l0);
+    return 0;
+  }
+  for (auto& g : p->graphs)
+    if (g.key == key) {
+      N2N_CUDA(cudaGraphLaunch(g.exec, st));
+      *launches = g.launches;
+      g_launch_count += g.launches;
+      return 0;
+    }
+  const long long l0 = g_launch_count;
+  if (!p->cap_stream) N2N_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+  N2N_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(p->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  N2N_CUDA(e);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  N2N_CUDA(ei);
+  if (p->graphs.size() >= 8) { cudaGraphExecDestroy(p->graphs.front().exec); p->graphs.erase(p->graphs.begin()); }
+  *launches = (int)(g_launch_count - l0);
+  p->graphs.push_back({key, exec, *launches});
+  N2N_CUDA(cudaGraphLaunch(exec, st));
+  return 0;
+}
+}  // namespace
+
 extern "C" int n2n_improved_forward(n2n_improved_plan* p, const float* const* params, const float* x, float* y, void* ws, void* stream) {
   N2N_CHECK_ARG(p && params && x && y && ws, "improved_forward: null argument");
-  const long long l0 = g_launch_count;
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long key = mix(mix(mix(1, ws), x), y);
+  for (int i = 0; i < p->nparams; ++i) key = mix(key, params[i]);
+  return run_captured(p, key, st, &p->launches, [&](cudaStream_t s) -> int { return improved_forward_body(p, params, x, y, ws, s); });
+}
+
+static int improved_forward_body(n2n_improved_plan* p, const float* const* params, const float* x, float* y, void* ws, cudaStream_t st) {
   {   // every layer's weights -> engine layout, biases -> padded rows: a few batched launches for the whole network
     Builder pk{p, params, (char*)ws, st};
     pk.mode = IMP_PACK;
@@ -907,7 +998,6 @@ extern "C" int n2n_improved_forward(n2n_improved_plan* p, const float* const* pa
   b.mode = IMP_EXEC;
   N2N_TRY(b.network(x, y));
   N2N_CHECK_ARG(b.pi == p->nparams, "improved_forward: walked %d parameters, plan has %d", b.pi, p->nparams);
-  p->launches = (int)(g_launch_count - l0);
   return 0;
 }
 
@@ -930,9 +1020,11 @@ extern "C" int n2n_improved_backward(n2n_improved_plan* p, const float* const* p
                                      float* const* grads, void* ws, void* stream) {
   N2N_CHECK_ARG(p && params && dy && y && grads && ws, "improved_backward: null argument");
   N2N_CHECK_ARG(p->train, "improved_backward: plan was created without with_backward");
-  const long long l0 = g_launch_count;
-  Backward b{p, params, grads, (char*)ws, (cudaStream_t)stream};
-  N2N_TRY(b.run(dy, y));
-  p->bwd_launches = (int)(g_launch_count - l0);
-  return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long key = mix(mix(mix(2, ws), dy), y);
+  for (int i = 0; i < p->nparams; ++i) key = mix(mix(key, params[i]), grads[i]);
+  return run_captured(p, key, st, &p->bwd_launches, [&](cudaStream_t s) -> int {
+    Backward b{p, params, grads, (char*)ws, s};
+    return b.run(dy, y);
+  });
 }

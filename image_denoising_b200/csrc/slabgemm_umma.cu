@@ -51,7 +51,7 @@ constexpr size_t kSgSmemMax = 232448;     // 227 KB per CTA (static + dynamic)
 // Cin = 144 convs — whose 249 KB of weights only fit when split over the pair — 177 -> 93 us (1.40 PFLOP/s).
 constexpr int kSgPairDefault = 3;
 static int sg_pair_mode() {
-  const char* e = getenv("N2N_PAIR");
+  static const char* const e = getenv("N2N_PAIR");
   return e ? atoi(e) : kSgPairDefault;
 }
 static long long sg_pair_min_tiles() {
@@ -799,12 +799,12 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   uint32_t bias_off = 0;
   {
     const size_t extra = 4096 + align_up((size_t)mma_n / cg * 32, 1024);
-    const char* e = getenv("N2N_NO_BIAS_MMA");
+    static const char* const e = getenv("N2N_NO_BIAS_MMA");
     if (g.bias && !(e && atoi(e)) && w_region + extra + 4 * slot_bytes <= budget) { bias_off = (uint32_t)w_region; w_region += extra; }
   }
   int ring = (int)((budget - w_region) / slot_bytes);
   if (ring > kSgMaxRing) ring = kSgMaxRing;
-  { const char* e = getenv("N2N_SG_RING"); if (e && atoi(e) >= 2 && atoi(e) < ring) ring = atoi(e); }
+  { static const char* const e = getenv("N2N_SG_RING"); if (e && atoi(e) >= 2 && atoi(e) < ring) ring = atoi(e); }
 
   p.nst = nst; p.nout = g.nout; p.mma_n = mma_n; p.corr = g.border_corr; p.up_py = g.up_py;
   p.w = (const uint8_t*)g.w; p.w_bytes = (uint32_t)w_bytes; p.w_region = (uint32_t)w_region; p.bias_off = bias_off;
@@ -822,7 +822,7 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
   // accumulators: three when they fit in TMEM, so the MMAs of tile i+2 need not wait for the epilogue group
   // that is still draining tile i (two groups on alternate tiles); else two
   p.nbuf = 3 * g.nout <= 512 ? 3 : 2;
-  { const char* e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
+  { static const char* const e = getenv("N2N_SG_NBUF"); if (e && atoi(e) == 2) p.nbuf = 2; }
   {
     bool dual_ok = g.mma_n != 0 && g.nout == 2 * mma_n;
     for (int si = 0; si < nst; ++si) {
@@ -832,14 +832,14 @@ int launch_slabgemm_umma(const TapGemm& g, cudaStream_t st) {
         if (S.col16[k] == 0) { if (nt0 != (uint32_t)k) dual_ok = false; ++nt0; }      // lower range first
       S.nt0 = nt0;
     }
-    const char* e = getenv("N2N_NO_DUAL_ISSUE");
+    static const char* const e = getenv("N2N_NO_DUAL_ISSUE");
     p.dual = (dual_ok && !(e && atoi(e))) ? 1 : 0;
   }
-  { const char* e = getenv("N2N_NO_ESPLIT");
+  { static const char* const e = getenv("N2N_NO_ESPLIT");
     p.esplit = (p.nbuf == 2 && (g.nout >> 4) % 3 == 0 && !(e && atoi(e))) ? 3 : 1; }
   p.tmem_cols = tmem_cols_for(p.nbuf * g.nout);
   p.idesc = make_idesc_bf16(128 * cg, mma_n, false, false);
-  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
+  { static const char* const df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   const size_t smem = 1024 + w_region + (size_t)ring * slot_bytes;
   if (!attr_set) {
     N2N_CUDA(cudaFuncSetAttribute(slabgemm_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -435,7 +435,7 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   }
   p.nentries = ne;
   {
-    const char* pd = getenv("N2N_PREFETCH_DIST");
+    static const char* const pd = getenv("N2N_PREFETCH_DIST");
     p.prefetch_dist = pd ? atoi(pd) : 2;
   }
   const int boxw = slab ? kSlabRows : bw;
@@ -478,8 +478,8 @@ int launch_tapgemm_umma(const TapGemm& g, cudaStream_t st) {
   N2N_CHECK_ARG(nst >= 2, "tapgemm_umma: not enough shared memory for a pipeline (nout=%d)", g.nout);
   p.nstages = nst;
   p.dbg = g_dbg_buf;
-  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
-  { const char* ns = getenv("N2N_STAGES"); if (ns && atoi(ns) >= 2 && atoi(ns) < nst) p.nstages = nst = atoi(ns); }
+  { static const char* const df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
+  { static const char* const ns = getenv("N2N_STAGES"); if (ns && atoi(ns) >= 2 && atoi(ns) < nst) p.nstages = nst = atoi(ns); }
   p.tmem_cols = tmem_cols_for(2 * g.nout);
   p.idesc = make_idesc_bf16(128, g.nout, false, false);
   const size_t smem = 1024 + (size_t)p.b_region_bytes + (size_t)nst * p.stage_bytes;

@@ -370,7 +370,7 @@ int launch_wgrad_slab_umma(const TapWgrad& g, cudaStream_t st) {
   p.npad = g.n_blocks * 16; p.cpad = g.c_blocks * 16;
   p.partial = g.partial;
   p.bias_partial = (g.bias_partial && (!swap || (box_per_tap && g.ndyviews == g.npairs && n_blocks <= 8))) ? g.bias_partial : nullptr;
-  { const char* df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
+  { static const char* const df = getenv("N2N_DBG_FLAGS"); p.dbg_flags = df ? atoi(df) : 0; }
   { const char* e = getenv("N2N_WS_RING"); if (e && atoi(e) >= 2) g_ring_override = atoi(e); }
   p.halo = halo ? 1 : 0; p.box_per_tap = box_per_tap ? 1 : 0;
   const int bw = halo ? kWsTileW + 2 : kWsTileW, bh = halo ? kWsTileH + 2 : kWsTileH;

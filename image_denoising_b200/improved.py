@@ -39,25 +39,33 @@ class _ImprovedFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, net, x, *params):
-        key, plan, ws = net._checkout(x, True)
+        key, plan, slot = net._checkout(x, True)
         net._param_list(plan)
-        y = torch.empty((x.shape[0], net.out_nc, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
-        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
+        slot["x"].copy_(x)
+        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(slot["x"]), ptr(slot["y"]), ptr(slot["ws"]), stream_ptr()))
         net.last_launches = lib().n2n_improved_launches(plan, 0)
-        ctx.net, ctx.key, ctx.plan, ctx.ws, ctx.params = net, key, plan, ws, params
-        ctx.save_for_backward(y)
-        return y
+        ctx.net, ctx.key, ctx.plan, ctx.slot, ctx.params = net, key, plan, slot, params
+        return slot["y"].clone()            # slot["y"] itself stays put for the backward (sigmoid')
 
     @staticmethod
     def backward(ctx, dy):
-        (y,) = ctx.saved_tensors
-        dy = dy.contiguous().float()
-        grads = [torch.empty_like(q) for q in ctx.params]
-        check(lib().n2n_improved_backward(ctx.plan, ptr_array(ctx.params), ptr(dy), ptr(y), ptr_array(grads), ptr(ctx.ws), stream_ptr()))
+        slot = ctx.slot
+        slot["dy"].copy_(dy)
+
+        def views_of(flat):
+            out, off = [], 0
+            for q, nq in zip(ctx.params, slot["sizes"]):
+                out.append(flat[off:off + nq].view(q.shape))
+                off += nq
+            return out
+
+        check(lib().n2n_improved_backward(ctx.plan, ptr_array(ctx.params), ptr(slot["dy"]), ptr(slot["y"]), ptr_array(views_of(slot["g"])),
+                                          ptr(slot["ws"]), stream_ptr()))
         ctx.net.last_bwd_launches = lib().n2n_improved_launches(ctx.plan, 1)
-        ctx.net._last_train = (ctx.plan, ctx.ws)            # read_buffer() hook: valid until the workspace is reused
-        ctx.net._give_back(ctx.key, ctx.ws)
-        ctx.ws = None
+        grads = views_of(slot["g"].clone())                  # one copy; the gradients handed to autograd are views of it
+        ctx.net._last_train = (ctx.plan, slot["ws"])         # read_buffer() hook: valid until the workspace is reused
+        ctx.net._give_back(ctx.key, slot)
+        ctx.slot = None
         return (None, None) + tuple(grads)
 
 
@@ -322,13 +330,23 @@ class ImprovedUNet(nn.Module):
             plans[key] = handle
         plan = plans[key]
         pool = pools.setdefault(key, [])
-        ws = pool.pop() if pool else torch.empty(lib().n2n_improved_workspace_bytes(plan), dtype=torch.uint8, device=x.device)
-        return key, plan, ws
+        if pool:
+            return key, plan, pool.pop()
+        # workspace + the call's boundary tensors kept IN PLACE (input, output, dL/dy, flat parameter gradients): the executor
+        # caches its launch sequence as a CUDA graph keyed by these pointers
+        f32 = dict(dtype=torch.float32, device=x.device)
+        slot = {"ws": torch.empty(lib().n2n_improved_workspace_bytes(plan), dtype=torch.uint8, device=x.device),
+                "x": torch.empty((n, self.in_nc, h, w), **f32), "y": torch.empty((n, self.out_nc, h, w), **f32)}
+        if train:
+            slot["dy"] = torch.empty((n, self.out_nc, h, w), **f32)
+            slot["sizes"] = [q.numel() for q in self.parameters()]
+            slot["g"] = torch.empty(sum(slot["sizes"]), **f32)
+        return key, plan, slot
 
-    def _give_back(self, key, ws):
+    def _give_back(self, key, slot):
         pool = self.__dict__.setdefault("_free_ws", {}).setdefault(key, [])
         if len(pool) < 2:
-            pool.append(ws)
+            pool.append(slot)
 
     def _param_list(self, plan):
         params = list(self.parameters())
@@ -342,12 +360,13 @@ class ImprovedUNet(nn.Module):
 
     def _native_forward(self, x):
         """n2n_improved_forward on a (plan, workspace) cached per shape / precision."""
-        key, plan, ws = self._checkout(x, False)
+        key, plan, slot = self._checkout(x, False)
         params = self._param_list(plan)
-        y = torch.empty((x.shape[0], self.out_nc, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
-        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(x), ptr(y), ptr(ws), stream_ptr()))
+        slot["x"].copy_(x)
+        check(lib().n2n_improved_forward(plan, ptr_array(params), ptr(slot["x"]), ptr(slot["y"]), ptr(slot["ws"]), stream_ptr()))
         self.last_launches = lib().n2n_improved_launches(plan, 0)
-        self._give_back(key, ws)
+        y = slot["y"].clone()
+        self._give_back(key, slot)
         return y
 
     def read_buffer(self, buf: int, grad: bool = False):

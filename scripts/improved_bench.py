@@ -50,6 +50,11 @@ def step():
 
 
 out["train_bf16_4x128_ms"] = timeit(step)
+out["launches_fwd"], out["launches_bwd"] = net.last_launches, getattr(net, "last_bwd_launches", None)
+clean_b, noisy_b = clean, noisy
+clean = torch.rand(4, 1, 256, 256, device=dev); noisy = (clean + 0.1 * torch.randn_like(clean)).clamp(0, 1)
+out["train_bf16_4x256_ms"] = timeit(step)
+clean, noisy = clean_b, noisy_b
 pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
 topt = torch.optim.Adam(pr.values(), lr=1e-4)
 
