@@ -409,6 +409,55 @@ def improved_unet_leg(dev, precision):
                     "same executor (n2n_improved_backward); stock PyTorch bf16 autocast: 30 ms"}
 
 
+def next_rows_leg(dev, precision):
+    """SURVEY.md §8f N1 / N3 through the drop-in modules: the fork's LIVE supervised step (train.py:354-368: network(noisy) and
+    network(clean) with grad, util.Structure_loss, backward, Adam) on UNet(1,1,48) at 16 x 1x256x256, and arch_unet.RESNET(1,1,48)
+    (every layer at full resolution) no-grad forward + the same live step at 4 x 1x256x256."""
+    import torch
+    from image_denoising_b200 import FusedAdam, RESNET, Structure_loss, UNet
+
+    def timed(fn, warm, it):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(it):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / it
+
+    out = {}
+    for name, ctor, batch in (("unet48_live_supervised_step", UNet, 16), ("resnet48_live_supervised_step", RESNET, 4)):
+        torch.manual_seed(3)
+        net = ctor(1, 1, NF).to(dev).set_precision(precision)
+        opt = FusedAdam(net.parameters(), lr=1e-4)
+        crit = Structure_loss()
+        clean = torch.rand(batch, 1, PATCH, PATCH, device=dev)
+        noisy = clean + torch.randn_like(clean) * (25.0 / 255.0)
+
+        def step():
+            opt.zero_grad()
+            loss = crit(net(noisy), net(clean), clean)
+            loss.backward()
+            opt.step()
+
+        ms = timed(step, 3, 6)
+        out[name] = {"batch": batch, "ms_per_step": ms, "patches_per_s": batch / (ms / 1e3)}
+        if ctor is RESNET:
+            with torch.no_grad():
+                fms = timed(lambda: net(noisy), 2, 5)
+            out["resnet48_forward_4x1x256x256_ms"] = fms
+        del net, opt
+        torch.cuda.empty_cache()
+    # per 256x256 patch the live UNet step is 2 forwards + 2 backwards at full resolution = 6 x 38.573 GFLOP
+    u = out["unet48_live_supervised_step"]
+    u["gflop_per_patch"] = 6 * 38.573
+    u["tflops"] = u["patches_per_s"] * u["gflop_per_patch"] / 1e3
+    return out
+
+
 def hbm_kernels(dev):
     """HBM-bound rows: achieved GB/s = ALGORITHMIC bytes per launch / average launch duration
     (CUDA events around R back-to-back launches on the launching stream, rotating over buffer sets whose total
@@ -744,10 +793,11 @@ def run_b200(args):
         infer = inference_704(dev, args.precision, world, rank, dist)
         infer_tiled = inference_704_tiled(dev, args.precision, world, rank, dist)
 
-    cpu = adapter = hbm = torch_gpu = improved = None
+    cpu = adapter = hbm = torch_gpu = improved = next_rows = None
     if rank == 0 and world == 1 and not args.no_extra:
         adapter = adapter_finetune_c5(dev, args.precision)
         improved = improved_unet_leg(dev, args.precision)
+        next_rows = next_rows_leg(dev, args.precision)
         hbm = hbm_kernels(dev)
         torch_gpu = torch_gpu_baseline(dev, B)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -782,6 +832,7 @@ def run_b200(args):
             "inference_704_tiled": infer_tiled,
             "adapter_finetune": adapter,
             "improved_unet": improved,
+            "next_rows": next_rows,
             "hbm_kernels": hbm,
             "torch_gpu_baseline": torch_gpu,
             "final_loss": final_loss,
