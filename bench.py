@@ -363,7 +363,7 @@ def improved_unet_leg(dev, precision):
     through the drop-in module — no-grad forward on 8 x 1x256x256 and the fork's live supervised step (train.py:354-368: two
     forwards with grad, Structure_loss, backward, Adam) on 4 x 1x128x128.  A "next" row: functional + parity-tested, not tuned."""
     import torch
-    from image_denoising_b200 import FusedAdam, ImprovedUNet, Structure_loss
+    from image_denoising_b200 import FusedAdam, ImprovedUNet, Structure_loss, forward_pair
     torch.manual_seed(5)
     net = ImprovedUNet(1, 1, NF).to(dev).set_precision(precision)
     x = torch.rand(8, 1, 256, 256, device=dev)
@@ -392,21 +392,28 @@ def improved_unet_leg(dev, precision):
 
     def step():
         opt.zero_grad()
+        loss = crit(*forward_pair(net, noisy, clean), clean)           # entry/train.py's form: one pass over [noisy | clean]
+        loss.backward()
+        opt.step()
+
+    def step_two_calls():
+        opt.zero_grad()
         loss = crit(net(noisy), net(clean), clean)
         loss.backward()
         opt.step()
 
     train_ms = timed(step, 2, 4)
+    train2_ms = timed(step_two_calls, 2, 4)
     del net, opt
     torch.cuda.empty_cache()
     return {"metric": "improved_unet48_forward_images_per_s_1x256x256", "value": 8 / (fwd_ms / 1e3), "unit": "images/s", "batch": 8,
             "ms_per_forward": fwd_ms, "gflop_per_image": 90.2, "tflops": 8 * 90.2 / fwd_ms,
             "batch32": {"ms_per_forward": fwd32_ms, "images_per_s": 32 / (fwd32_ms / 1e3), "tflops": 32 * 90.2 / fwd32_ms},
-            "supervised_step_4x1x128x128_ms": train_ms,
+            "supervised_step_4x1x128x128_ms": train_ms, "supervised_step_two_forward_calls_ms": train2_ms,
             "note": "no-grad forward = native executor n2n_improved_forward (activations resident in the blocked layout, ~160 "
                     "launches, launch-bound at batch 8); stock PyTorch bf16 autocast runs the batch-8 forward in 10.5 ms on this "
-                    "GPU (scripts/improved_bench.py); the training step (two forwards + backward + Adam) runs forward and backward on the "
-                    "same executor (n2n_improved_backward); stock PyTorch bf16 autocast: 30 ms"}
+                    "GPU (scripts/improved_bench.py); the live supervised step (forward over [noisy | clean], Structure_loss, backward, Adam) runs forward "
+                    "and backward on the same executor (n2n_improved_backward); stock PyTorch bf16 autocast (two forward calls): 30 ms"}
 
 
 def next_rows_leg(dev, precision):
@@ -414,7 +421,7 @@ def next_rows_leg(dev, precision):
     network(clean) with grad, util.Structure_loss, backward, Adam) on UNet(1,1,48) at 16 x 1x256x256, and arch_unet.RESNET(1,1,48)
     (every layer at full resolution) no-grad forward + the same live step at 4 x 1x256x256."""
     import torch
-    from image_denoising_b200 import FusedAdam, RESNET, Structure_loss, UNet
+    from image_denoising_b200 import FusedAdam, RESNET, Structure_loss, UNet, forward_pair
 
     def timed(fn, warm, it):
         for _ in range(warm):
@@ -439,12 +446,19 @@ def next_rows_leg(dev, precision):
 
         def step():
             opt.zero_grad()
+            loss = crit(*forward_pair(net, noisy, clean), clean)       # entry/train.py's form: one pass over [noisy | clean]
+            loss.backward()
+            opt.step()
+
+        def step_two_calls():
+            opt.zero_grad()
             loss = crit(net(noisy), net(clean), clean)
             loss.backward()
             opt.step()
 
         ms = timed(step, 3, 6)
-        out[name] = {"batch": batch, "ms_per_step": ms, "patches_per_s": batch / (ms / 1e3)}
+        out[name] = {"batch": batch, "ms_per_step": ms, "patches_per_s": batch / (ms / 1e3),
+                     "ms_per_step_two_forward_calls": timed(step_two_calls, 2, 4)}
         if ctor is RESNET:
             with torch.no_grad():
                 fms = timed(lambda: net(noisy), 2, 5)

@@ -29,7 +29,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from entry import _data, _models  # noqa: E402
 from image_denoising_b200 import (AugmentNoise, FusedAdam, N2NTrainer, Structure_loss, UNet, checkpoint, dp,  # noqa: E402
-                                   generate_mask_pair, generate_subimage_pair, n2n_loss, ops)
+                                   forward_pair, generate_mask_pair, generate_subimage_pair, n2n_loss, ops)
 from image_denoising_b200.data import DevicePatchSource  # noqa: E402
 from image_denoising_b200.optim import multistep_lr  # noqa: E402
 
@@ -161,7 +161,7 @@ def main():
                 for group in optimizer.param_groups:
                     group['lr'] = lr
                 optimizer.zero_grad()
-                noisy_output, clean_ = network(noisy_b), network(clean_b)            # train.py:361
+                noisy_output, clean_ = forward_pair(network, noisy_b, clean_b)       # train.py:361, one batched pass
                 loss = criterion(noisy_output, clean_, clean_b)
                 loss.backward()
                 if world > 1:

@@ -8,7 +8,7 @@ from . import _ext  # noqa: F401
 from . import dp  # noqa: F401
 from .arch_unet import RESNET, ImprovedUNet, UNet  # noqa: F401
 from .adapter import DenoiserWithAdapter, OutputAdapter  # noqa: F401
-from .n2n import (AugmentNoise, checkpoint, generate_mask_pair, generate_packed_selector,  # noqa: F401
+from .n2n import (AugmentNoise, checkpoint, forward_pair, generate_mask_pair, generate_packed_selector,  # noqa: F401
                   generate_subimage_pair, generate_subimages, get_generator, space_to_depth)
 from .losses import Structure_loss, iqsl_loss, l1_grad_loss, n2n_loss  # noqa: F401
 from .optim import FusedAdam, multistep_lr  # noqa: F401

@@ -184,3 +184,25 @@ def test_resnet_nf48_bf16_vs_oracle(dev):
     assert float((y32 - ref).abs().max()) < 2e-5
     psnr = lambda a: 10 * np.log10(1.0 / float(((a - clean) ** 2).mean()))
     assert abs(psnr(y16) - psnr(ref)) < 0.01
+
+
+@pytest.mark.parametrize("family", ["UNet", "RESNET", "ImprovedUNet"])
+def test_forward_pair_equals_two_calls(dev, family):
+    """entry/train.py runs train.py:361's network(noisy), network(clean) as one pass over the concatenated batch: outputs and
+    parameter gradients must be those of the two calls (every layer is per-sample)."""
+    import image_denoising_b200 as M
+    torch.manual_seed(1)
+    net = getattr(M, family)(1, 1, 16).to(dev).set_precision("fp32")
+    g = torch.Generator().manual_seed(2)
+    a = torch.rand(2, 1, 64, 64, generator=g).to(dev); b = torch.rand(2, 1, 64, 64, generator=g).to(dev)
+    crit = M.Structure_loss()
+    ya, yb = net(a), net(b)
+    crit(ya, yb, b).backward()
+    g2 = {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None}
+    net.zero_grad()
+    pa, pb = M.forward_pair(net, a, b)
+    assert (pa - ya).abs().max().item() < 1e-5 and (pb - yb).abs().max().item() < 1e-5
+    crit(pa, pb, b).backward()
+    for k, v in net.named_parameters():
+        if v.grad is not None:
+            assert (v.grad - g2[k]).abs().max().item() <= 2e-3 * g2[k].abs().max().item() + 1e-9, k
