@@ -146,10 +146,7 @@ def main():
                     loss, loss3 = n2n_loss(network(noisy_sub1), noisy_sub2, den_sub1, den_sub2, Lambda)   # :146-153
                     loss.backward()
                     if world > 1:
-                        for prm in network.parameters():
-                            if prm.grad is not None:
-                                torch.distributed.all_reduce(prm.grad)
-                                prm.grad.div_(world)
+                        dp.allreduce_mean_grads(network.parameters())
                     optimizer.step()
                 if it % 50 == 0:
                     l = loss3.tolist()
@@ -165,10 +162,7 @@ def main():
                 loss = criterion(noisy_output, clean_, clean_b)
                 loss.backward()
                 if world > 1:
-                    for prm in network.parameters():
-                        if prm.grad is not None:
-                            torch.distributed.all_reduce(prm.grad)
-                            prm.grad.div_(world)
+                    dp.allreduce_mean_grads(network.parameters())
                 optimizer.step()
                 if it % 50 == 0:
                     terms = criterion.last_terms.tolist()                            # [loss, L1(noisy_output, clean), TV, cst]

@@ -57,6 +57,12 @@ def _worker(rank, world, port, out):
         m = np.zeros(flat_p.numel(), np.float32); v = np.zeros_like(m)
         w = flat_p.numpy().copy()
         O.adam_update(w, flat_g.numpy(), m, v, 1, 3e-4)
+        # the autograd loops' helper: one flat all-reduce, mean over ranks, parameters without a gradient skipped
+        prm = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(4))]
+        prm[0].grad = torch.full((3, 2), float(rank + 1)); prm[2].grad = torch.arange(4.0) * (rank + 1)
+        dp.allreduce_mean_grads(prm)
+        assert torch.equal(prm[0].grad, torch.full((3, 2), 1.5)) and prm[1].grad is None
+        assert torch.equal(prm[2].grad, torch.arange(4.0) * 1.5)
         out[rank] = (flat_g.numpy().copy(), w, float(loss))
     finally:
         dist.destroy_process_group()
