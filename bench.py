@@ -404,16 +404,33 @@ def improved_unet_leg(dev, precision):
 
     train_ms = timed(step, 2, 4)
     train2_ms = timed(step_two_calls, 2, 4)
+    # the same forward / live step on stock PyTorch (cuDNN, bf16 autocast) on this GPU: the oracle's functional graph moved
+    # to CUDA — a baseline like torch_gpu_baseline, never the thing shipped
+    from oracle import n2n_oracle as O
+    pt = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    topt = torch.optim.Adam(pt.values(), lr=1e-4)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        torch_fwd_ms = timed(lambda: O.improved_forward(pt, x), 2, 4)
+
+    def torch_step():
+        topt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            a, b = O.improved_forward(pt, noisy), O.improved_forward(pt, clean)
+        O.structure_loss(a.float(), b.float(), clean)[0].backward()
+        topt.step()
+
+    torch_step_ms = timed(torch_step, 2, 4)
+    del pt, topt
     del net, opt
     torch.cuda.empty_cache()
     return {"metric": "improved_unet48_forward_images_per_s_1x256x256", "value": 8 / (fwd_ms / 1e3), "unit": "images/s", "batch": 8,
             "ms_per_forward": fwd_ms, "gflop_per_image": 90.2, "tflops": 8 * 90.2 / fwd_ms,
             "batch32": {"ms_per_forward": fwd32_ms, "images_per_s": 32 / (fwd32_ms / 1e3), "tflops": 32 * 90.2 / fwd32_ms},
             "supervised_step_4x1x128x128_ms": train_ms, "supervised_step_two_forward_calls_ms": train2_ms,
-            "note": "no-grad forward = native executor n2n_improved_forward (activations resident in the blocked layout, ~160 "
-                    "launches, launch-bound at batch 8); stock PyTorch bf16 autocast runs the batch-8 forward in 10.5 ms on this "
-                    "GPU (scripts/improved_bench.py); the live supervised step (forward over [noisy | clean], Structure_loss, backward, Adam) runs forward "
-                    "and backward on the same executor (n2n_improved_backward); stock PyTorch bf16 autocast (two forward calls): 30 ms"}
+            "torch_bf16_autocast": {"forward_8x1x256x256_ms": torch_fwd_ms, "supervised_step_4x1x128x128_ms": torch_step_ms},
+            "note": "no-grad forward = native executor n2n_improved_forward (activations resident in the blocked layout, ~170 "
+                    "launches, launch-bound at batch 8); the live supervised step (forward over [noisy | clean], Structure_loss, backward, Adam) runs forward "
+                    "and backward on the same executor (n2n_improved_backward); torch_bf16_autocast = the same graph on stock PyTorch / cuDNN"}
 
 
 def next_rows_leg(dev, precision):

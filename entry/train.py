@@ -186,7 +186,18 @@ def main():
                 f.writelines("epoch{}, loss_{}, train_time_{}\n".format(epoch, mean_loss, train_time))
             print(f'Evaluation Time/Epoch:{time.time() - eval_st}')
     if world > 1:
+        # the captured step graph holds NCCL work: drop it before the communicator goes away (destroy_process_group otherwise
+        # waits on it forever), line the ranks up, and never let a stuck teardown outlive a finished training run
+        trainer = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        import threading
+        t = threading.Timer(60.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":
