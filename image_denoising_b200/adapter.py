@@ -71,6 +71,12 @@ class OutputAdapter(nn.Module):
         if len(pool) < 2:
             pool.append(ws)
 
+    def __getstate__(self):
+        # plan handles / workspaces are per-process native objects: copies and pickles of the module start without them
+        state = self.__dict__.copy()
+        state["_plans"], state["_free_ws"] = {}, {}
+        return state
+
     def clear_plans(self):
         for h in self._plans.values():
             lib().n2n_adapter_plan_destroy(h)

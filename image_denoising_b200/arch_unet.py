@@ -84,6 +84,13 @@ class _PlanCache:
         self.plans.clear()
         self.free_ws.clear()
 
+    # plan handles are per-process native objects: a copied / unpickled module starts with an empty cache
+    def __deepcopy__(self, memo):
+        return _PlanCache()
+
+    def __reduce__(self):
+        return (_PlanCache, ())
+
 
 class _UNetFunction(torch.autograd.Function):
     @staticmethod

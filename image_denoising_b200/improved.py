@@ -369,6 +369,13 @@ class ImprovedUNet(nn.Module):
         self._give_back(key, slot)
         return y
 
+    def __getstate__(self):
+        # native plans / workspaces are per-process handles: copies and pickles of the module start without them
+        state = self.__dict__.copy()
+        for k in ("_plans", "_free_ws", "_last_train"):
+            state.pop(k, None)
+        return state
+
     def read_buffer(self, buf: int, grad: bool = False):
         """Layer-level parity hook: buffer ``buf`` of the last native training step (its gradient mirror with grad=True) as
         fp32 NCHW, all 16-channel blocks (zero padding included)."""
