@@ -104,3 +104,19 @@ def test_adapter_refuses_gradient_through_base_out():
     with pytest.raises(Exception) as e:
         ad(x, b)
     assert "not implemented" in str(e.value).lower() or "cuda" in str(e.value).lower()
+
+
+def test_modules_copy_and_pickle_without_native_handles():
+    """Plan handles / workspaces are per-process native objects: a deepcopy (EMA copies, DataParallel replicas) or a pickle
+    of a module carries the parameters and starts with empty plan caches."""
+    import copy
+    import pickle
+    from image_denoising_b200.adapter import OutputAdapter
+    from image_denoising_b200.arch_unet import RESNET, UNet
+    from image_denoising_b200.improved import ImprovedUNet
+    for m in (UNet(1, 1, 4), RESNET(1, 1, 4), ImprovedUNet(1, 1, 16), OutputAdapter(1)):
+        for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+            assert list(c.state_dict()) == list(m.state_dict())
+            for a, b in zip(m.state_dict().values(), c.state_dict().values()):
+                assert torch.equal(a, b)
+            assert not getattr(c, "_plans", {}) and not getattr(c, "_free_ws", {})
