@@ -743,7 +743,12 @@ def run_b200(args):
     from image_denoising_b200.prefetch import DevicePrefetcher
     host = [b.cpu().pin_memory() for b in batches[:4]]
     pf = DevicePrefetcher(batches[0])
-    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    # The loss of every step is copied D2H and read on the host (train.py:364 prints it every step); the read of step i
+    # waits on step i's own event AFTER step i + 1 has been enqueued, so the host runs one step ahead of the device
+    # instead of draining the stream at every step.
+    loss_host = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    losses_read = []
     barrier()
     t0 = time.perf_counter()
     pf.put(host[0])
@@ -753,9 +758,15 @@ def run_b200(args):
             pf.put(host[(i + 1) % len(host)])
         l3 = trainer.step(dbuf, lam)
         pf.release()
-        loss_host.copy_(l3, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step (train.py:364)
+        loss_host[i & 1].copy_(l3, non_blocking=True)
+        loss_ev[i & 1].record()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            losses_read.append(float(loss_host[(i - 1) & 1][0]))
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    losses_read.append(float(loss_host[(args.steps - 1) & 1][0]))
     barrier()
+    assert len(losses_read) == args.steps and all(v == v for v in losses_read)
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world, dev, dist)
     e2e_value = world * B * args.steps / e2e_s
 
