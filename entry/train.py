@@ -112,7 +112,13 @@ def main():
         # RESNET / ImprovedUNet under --loop n2n: the same iteration (training_script.md:137-156) written out on the drop-in
         # functions with autograd; the supervised loop below shares the optimiser / criterion
         if world > 1:
-            dp.broadcast_params(torch.nn.utils.parameters_to_vector(network.parameters()).detach(), 0)
+            # parameters_to_vector returns a COPY: broadcast it, then write rank 0's values back into the parameters
+            flat = torch.nn.utils.parameters_to_vector(network.parameters()).detach()
+            dp.broadcast_params(flat, 0)
+            off = 0
+            for prm in network.parameters():
+                prm.data.copy_(flat[off:off + prm.numel()].view_as(prm))
+                off += prm.numel()
         optimizer = FusedAdam(network.parameters(), lr=opt.lr)
         criterion = Structure_loss()                                                 # train.py:322
     if rank == 0:
