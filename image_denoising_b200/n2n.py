@@ -105,7 +105,7 @@ def draw_rd_idx(img: torch.Tensor, batch: int = None) -> torch.Tensor:
     if batch is not None:
         n = int(batch)
     cells = n * h // 2 * w // 2
-    rd_idx = torch.zeros(size=(cells,), dtype=torch.int64, device=img.device)
+    rd_idx = torch.empty(size=(cells,), dtype=torch.int64, device=img.device)     # randint(out=) writes every element
     torch.randint(low=0, high=8, size=(cells,), generator=get_generator(img.device), out=rd_idx)
     return rd_idx
 
