@@ -67,6 +67,8 @@ class N2NTrainer:
         self.overlap_forwards = os.environ.get("N2N_OVERLAP", "1") == "1"
         self._graph = None
         self._eager_steps = 0
+        self._rd_global = None          # world > 1: the global-batch selector is drawn on its own stream (see _draw_global_selector)
+        self._rd_borrowed = False
         if self.world > 1:
             dp.broadcast_params(self.flat_p, 0, self.pg)
 
@@ -189,6 +191,37 @@ class N2NTrainer:
         (e.g. as the destination of its host-to-device copy) and passes it to ``step`` saves the staging copy."""
         return getattr(self, "in_static", None) if self._graph is not None else None
 
+    def _draw_global_selector(self, noisy):
+        """train.py:155-162 for the GLOBAL batch of a W-rank run (same counter seed on every rank; this rank keeps its slice,
+        SURVEY.md §8e).  The draw is W times the size of a rank's own selector (67 MB of int64 at W = 8, 64 x 256 x 256 per rank)
+        and depends on nothing but the seed counter, so it is issued on its own stream: it runs under the tail of the previous
+        step instead of between two steps.  One persistent buffer; the next draw waits for the consumer of this one
+        (``_release_global_selector``)."""
+        n, c, h, w = noisy.shape
+        cells = n * self.world * (h // 2) * (w // 2)
+        if self._rd_global is None or self._rd_global.numel() != cells or self._rd_global.device != noisy.device:
+            self._rd_global = torch.empty(cells, dtype=torch.int64, device=noisy.device)
+            self._rng_stream = torch.cuda.Stream(device=noisy.device)
+            self._ev_drawn, self._ev_taken = torch.cuda.Event(), torch.cuda.Event()
+            self._rng_stream.wait_stream(torch.cuda.current_stream())       # the buffer's allocation / earlier users
+            self._rd_taken = False
+        gen = n2n.get_generator(noisy.device)                               # same call order as a 1-process run
+        with torch.cuda.stream(self._rng_stream):
+            if self._rd_taken:
+                self._rng_stream.wait_event(self._ev_taken)
+            torch.randint(low=0, high=8, size=(cells,), generator=gen, out=self._rd_global)
+            self._ev_drawn.record()
+        torch.cuda.current_stream().wait_event(self._ev_drawn)
+        self._rd_borrowed = True
+        return dp.shard_selector(self._rd_global, self.rank, self.world, n * self.world)
+
+    def _release_global_selector(self):
+        """The consumer of the last _draw_global_selector slice has been enqueued on the current stream."""
+        if self._rd_borrowed:
+            self._ev_taken.record()
+            self._rd_taken = True
+            self._rd_borrowed = False
+
     def step(self, noisy, Lambda, rd_idx=None, lr=None):
         """One N2N iteration on this rank's ``noisy`` batch [n,c,h,w] (fp32, CUDA).  Returns the
         device tensor [loss_all, loss1, loss2] (no host sync; the SAME buffer every step — clone it to keep a
@@ -212,8 +245,7 @@ class N2NTrainer:
             self._capture()
         if rd_idx is None:
             if self.world > 1:
-                n = noisy.shape[0]
-                rd_idx = dp.shard_selector(n2n.draw_rd_idx(noisy, batch=n * self.world), self.rank, self.world, n * self.world)
+                rd_idx = self._draw_global_selector(noisy)
             elif replay:
                 # train.py:155-162 drawn straight into the graph's selector buffer (no staging copy)
                 torch.randint(low=0, high=8, size=(self.rd_static.numel(),), generator=n2n.get_generator(noisy.device),
@@ -226,12 +258,14 @@ class N2NTrainer:
                 self.in_static.copy_(noisy, non_blocking=True)
             if rd_idx.data_ptr() != self.rd_static.data_ptr():
                 self.rd_static.copy_(rd_idx, non_blocking=True)
+            self._release_global_selector()
             check(L.n2n_set_step_scalars(ptr(self.dev_scalars), float(Lambda), lr, float(self.betas[0]),
                                          float(self.betas[1]), self.step_count, stream_ptr()))
             self._graph.replay()
             self.last_launches = self.graph_launches + 1
             return self.loss3
         self._launch_sequence(noisy, rd_idx, Lambda, lr, None)
+        self._release_global_selector()
         self._eager_steps += 1
         self.last_launches = L.n2n_launch_count() - launches0
         return self.loss3
