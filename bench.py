@@ -860,7 +860,10 @@ def run_b200(args):
                                % (soak_steps, args.soak_seconds),
                        "tflops_per_step_algorithmic": GFLOP_PER_PATCH * B / 1e3},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * PATCH * PATCH * 4, "d2h_bytes_per_step": 12},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * PATCH * PATCH * 4, "d2h_bytes_per_step": 12,
+                    "note": "N2NTrainer.step on pinned HOST batches: H2D of every batch (DevicePrefetcher, copy stream) and D2H + host read "
+                            "of every step's loss inside the wall-clock region; the read of step i follows the enqueue of step i+1, "
+                            "so it tracks `value` (same kernels) to within clock drift between the two timed regions"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
