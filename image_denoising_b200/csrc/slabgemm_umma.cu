@@ -263,7 +263,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
   }
   if (p.act && !(p.dbg_flags & 16)) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], v[q] * p.slope);     // LeakyReLU / ReLU, 0 <= slope <= 1
+    for (int q = 0; q < 16; q += 2) lrelu_pair(v[q], v[q + 1], p.slope);     // LeakyReLU / ReLU, 0 <= slope <= 1
   }
   if (p.has_mask) {
     uint32_t aw[8]; float t[16];

@@ -11,6 +11,14 @@
 namespace n2n {
 namespace umma {
 
+// LeakyReLU / ReLU with 0 <= slope <= 1 on two values: max(a, slope * a).  The two multiplies are ONE packed FMUL2
+// (sm_100 f32x2 arithmetic, same rounding as FMUL): the epilogues that use this are issue-slot bound.
+__device__ __forceinline__ void lrelu_pair(float& a, float& b, float slope) {
+  const float2 m = __fmul2_rn(make_float2(a, b), make_float2(slope, slope));
+  a = fmaxf(a, m.x);
+  b = fmaxf(b, m.y);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
