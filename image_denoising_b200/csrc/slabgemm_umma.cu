@@ -231,7 +231,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 b = b4[q];
-      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      add_pair(v[4 * q], v[4 * q + 1], b.x, b.y); add_pair(v[4 * q + 2], v[4 * q + 3], b.z, b.w);
     }
   }
   if (p.corr) {
@@ -259,14 +259,14 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     }
     unpack_bf16x16(aw, t);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] += t[q];
+    for (int q = 0; q < 16; q += 2) add_pair(v[q], v[q + 1], t[q], t[q + 1]);
   }
   if (p.act && !(p.dbg_flags & 16)) {
 #pragma unroll
     for (int q = 0; q < 16; q += 2) lrelu_pair(v[q], v[q + 1], p.slope);     // LeakyReLU / ReLU, 0 <= slope <= 1
   }
   if (p.has_mask) {
-    uint32_t aw[8]; float t[16];
+    uint32_t aw[8];
     if (aux) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) aw[q] = aux[q];
@@ -276,9 +276,8 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
 #pragma unroll
       for (int q = 0; q < 8; ++q) aw[q] = 0u;
     }
-    unpack_bf16x16(aw, t);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] *= (t[q] > 0.f ? 1.f : p.slope);
+    for (int j = 0; j < 8; ++j) lrelu_mask_pair(v[2 * j], v[2 * j + 1], aw[j], p.slope);
   }
   if (p.out_nchw) {
     const long long hw = (long long)p.y.H * p.y.W;
