@@ -17,6 +17,34 @@
 
 namespace n2n {
 
+// ---- packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2 issue one instruction for two lanes' worth of values; the
+// rounding of each half is that of the scalar instruction, so results are bit-identical) for issue-slot-bound epilogues ----
+// LeakyReLU / ReLU with 0 <= slope <= 1 on two values: max(a, slope * a).  The two multiplies are ONE packed FMUL2
+// (sm_100 f32x2 arithmetic, same rounding as FMUL): the epilogues that use this are issue-slot bound.
+__device__ __forceinline__ void lrelu_pair(float& a, float& b, float slope) {
+  const float2 m = __fmul2_rn(make_float2(a, b), make_float2(slope, slope));
+  a = fmaxf(a, m.x);
+  b = fmaxf(b, m.y);
+}
+
+// (a, b) += (x, y) as one packed FADD2 (same rounding as two FADDs).
+__device__ __forceinline__ void add_pair(float& a, float& b, float x, float y) {
+  const float2 r = __fadd2_rn(make_float2(a, b), make_float2(x, y));
+  a = r.x;
+  b = r.y;
+}
+
+// (a, b) *= lrelu'(activation): 1 where the bf16 activation (low / high half of `w`) is > 0, else slope.  One HSETP2 (two
+// predicates), one FMUL2 and two selects per pair; the same values as v * (t > 0 ? 1 : slope) (v * 1 is v, FMUL2 rounds as FMUL).
+__device__ __forceinline__ void lrelu_mask_pair(float& a, float& b, uint32_t w, float slope) {
+  const float2 s = __fmul2_rn(make_float2(a, b), make_float2(slope, slope));
+  const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  const __nv_bfloat16 z = __float2bfloat16(0.f);
+  const bool p0 = __hgt(__low2bfloat16(t), z), p1 = __hgt(__high2bfloat16(t), z);
+  a = p0 ? a : s.x;
+  b = p1 ? b : s.y;
+}
+
 void set_error(const char* fmt, ...);
 bool profiling_active();       // per-launch event timing armed (n2n_profile_begin): keep every launch on one stream
 extern thread_local long long g_launch_count;   // kernels launched by this host thread (for gpu_launches)
