@@ -218,14 +218,57 @@ struct SgPix {
   long long ypix, apix, mpix, ppix;
 };
 
+// Stores of one packed 16-channel block: the activation (when the launch keeps it) and the 2x2 max-pooled activation.
+__device__ __forceinline__ void sg_store_block(const SgParams& p, const SgPix& c, int cb, int lane, uint32_t w[8],
+                                               bool keep_y = true) {
+  if (p.store_y && c.valid && keep_y) {
+    long long o = c.ypix;
+    int cbr = cb;
+    if (p.n_split && cb >= p.n_split) { cbr = cb - p.n_split; o += p.split_stride; }
+    st_global_32B((__nv_bfloat16*)p.y.ptr + o + cbr * p.y.sCb, w);
+  }
+  if (p.has_pool) {
+    // 2x2 max over lanes {l, l^1 (x neighbour), l^8 (y neighbour)}; max commutes with bf16 rounding
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+      uint32_t o = __shfl_xor_sync(0xffffffffu, w[j], 1);
+      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+      uint32_t aw = *reinterpret_cast<uint32_t*>(&a);
+      o = __shfl_xor_sync(0xffffffffu, aw, 8);
+      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
+      w[j] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    if ((lane & 9) == 0 && c.valid) st_global_32B((__nv_bfloat16*)p.pool.ptr + c.ppix + cb * p.pool.sCb, w);
+  }
+}
+
 // One 16-channel block of one pixel: accumulator -> bias -> (+addend) -> act -> (*mask) -> stores.
 // `aux` (when non-null) holds the block's mask words (or addend words when there is no mask), loaded
 // from global memory before the accumulator wait so that their DRAM latency is off the critical path.
+// PLAIN (compile time): the launch has none of bias-in-epilogue / border correction / addend / mask / NCHW output / debug
+// flags — every forward convolution whose bias rides in the GEMM.  The generic form tests each of them per block with a
+// uniform branch (constant load + compare + branch, ~20 instructions per block on issue-slot-bound layers).
+template <bool PLAIN>
 __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix& c, int cb, const uint32_t r[16],
                                                   int lane, const float* s_bias, const uint32_t* aux) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+  if (PLAIN) {
+    if (p.act) {
+#pragma unroll
+      for (int q = 0; q < 16; q += 2) lrelu_pair(v[q], v[q + 1], p.slope);
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    sg_store_block(p, c, cb, lane, w);
+    return;
+  }
   if (!(p.dbg_flags & 8) && !p.bias_off) {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb * 16);   // shared-memory broadcast
 #pragma unroll
@@ -294,26 +337,7 @@ __device__ __forceinline__ void sg_epilogue_block(const SgParams& p, const SgPix
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     w[j] = *reinterpret_cast<uint32_t*>(&h);
   }
-  if (p.store_y && c.valid && !(p.dbg_flags & 32)) {
-    long long o = c.ypix;
-    int cbr = cb;
-    if (p.n_split && cb >= p.n_split) { cbr = cb - p.n_split; o += p.split_stride; }
-    st_global_32B((__nv_bfloat16*)p.y.ptr + o + cbr * p.y.sCb, w);
-  }
-  if (p.has_pool) {
-    // 2x2 max over lanes {l, l^1 (x neighbour), l^8 (y neighbour)}; max commutes with bf16 rounding
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
-      uint32_t o = __shfl_xor_sync(0xffffffffu, w[j], 1);
-      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-      uint32_t aw = *reinterpret_cast<uint32_t*>(&a);
-      o = __shfl_xor_sync(0xffffffffu, aw, 8);
-      a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o));
-      w[j] = *reinterpret_cast<uint32_t*>(&a);
-    }
-    if ((lane & 9) == 0 && c.valid) st_global_32B((__nv_bfloat16*)p.pool.ptr + c.ppix + cb * p.pool.sCb, w);
-  }
+  sg_store_block(p, c, cb, lane, w, !(p.dbg_flags & 32));       // flag 32 (diagnostic): no activation store
 }
 
 // CG = 1: one CTA per tile.  CG = 2: clusters of two CTAs, tcgen05 cta_group::2 — rank r of a pair owns
@@ -554,6 +578,7 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
     const int cb_lo = split ? group * (nblk_all / 3) : 0;
     const int nblk = split ? cb_lo + nblk_all / 3 : nblk_all;
     const bool skip = (p.dbg_flags & 4) != 0;
+    const bool plain = p.bias_off && !p.corr && !p.has_addend && !p.has_mask && !p.out_nchw && p.dbg_flags == 0;
     // group g <-> accumulator g: a group only ever waits on consecutive phases of its own barriers (with more
     // groups than accumulators a group could run two phases ahead, which a parity wait cannot tell apart)
     // tile coordinates advance incrementally (two integer divisions per tile were ~9 % of this warp's instructions
@@ -629,8 +654,13 @@ slabgemm_umma_kernel(const __grid_constant__ SgParams p) {
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (skip) continue;
-        sg_epilogue_block(p, c, cb, r0, lane, s_bias, pre ? ax0 : nullptr);
-        if (two) sg_epilogue_block(p, c, cb + 1, r1, lane, s_bias, pre ? ax1 : nullptr);
+        if (plain) {
+          sg_epilogue_block<true>(p, c, cb, r0, lane, s_bias, nullptr);
+          if (two) sg_epilogue_block<true>(p, c, cb + 1, r1, lane, s_bias, nullptr);
+        } else {
+          sg_epilogue_block<false>(p, c, cb, r0, lane, s_bias, pre ? ax0 : nullptr);
+          if (two) sg_epilogue_block<false>(p, c, cb + 1, r1, lane, s_bias, pre ? ax1 : nullptr);
+        }
         if (pre) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) { ax0[q] = nx0[q]; ax1[q] = nx1[q]; }
