@@ -120,3 +120,41 @@ def test_modules_copy_and_pickle_without_native_handles():
             for a, b in zip(m.state_dict().values(), c.state_dict().values()):
                 assert torch.equal(a, b)
             assert not getattr(c, "_plans", {}) and not getattr(c, "_free_ws", {})
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import or execute it.
+    The package, the entry points and the native sources must not mention it in code (comments / docstrings may cite it)."""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("image_denoising_b200", "entry"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                path = os.path.join(dirpath, f)
+                if f.endswith(".py"):
+                    tree = ast.parse(open(path).read())
+                    for node in ast.walk(tree):
+                        names = []
+                        if isinstance(node, ast.Import):
+                            names = [a.name for a in node.names]
+                        elif isinstance(node, ast.ImportFrom):
+                            names = [node.module or ""]
+                        if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                            offenders.append(path)
+                elif f.endswith((".cu", ".cuh", ".h")):
+                    if any("oracle/" in line and "#include" in line for line in open(path)):
+                        offenders.append(path)
+    assert not offenders, offenders
+    # bench.py may, in its BASELINE legs only: the CPU reference / port, and the oracle's functional graph run by stock PyTorch on
+    # the GPU (torch_gpu_baseline and the stock-PyTorch comparison inside improved_unet_leg) — never in the measured product step
+    src = open(os.path.join(root, "bench.py")).read()
+    tree = ast.parse(src)
+    users = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                users.add(fn.name)
+    assert users <= {"cpu_reference_steps", "torch_gpu_baseline", "improved_unet_leg"}, users
+    assert "run_b200" not in users
