@@ -732,6 +732,11 @@ def run_b200(args):
     ms, loss3 = timed_steps(args.steps)
     if rank == 0:
         sampler.stop_flag = True
+        if not sampler.samples:           # a very short timed region on a box with slow NVML calls: one sample right behind it
+            try:
+                sampler._sample_nvml() if sampler.nvml is not None else sampler._sample_smi()
+            except Exception:
+                pass
     launches = int(trainer.last_launches) * args.steps
     final_loss = float(loss3[0].item())
     value = world * B * args.steps / (ms / 1e3)
